@@ -1,0 +1,28 @@
+"""Pin oracle/port_*.py against the REAL reference (container only; skipped where
+/root/reference is absent, e.g. on the GPU box — there tests/golden/ carries the pin)."""
+import os
+import runpy
+import sys
+
+import pytest
+
+from oracle import ref_loader
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = [pytest.mark.ref,
+              pytest.mark.skipif(not ref_loader.reference_available(), reason="no /root/reference")]
+
+
+def test_port_modules_match_reference_modules():
+    """EncoderLSTM (3 configs), EnvDrop/Follower/Monitor decoders, Critic: eval + train(RNG-matched)."""
+    runpy.run_path(os.path.join(HERE, "_ref_check_modules.py"), run_name="__main__")
+
+
+def test_reference_env_matches_world_tables():
+    """The reference's own R2RBatch/make_candidate over FakeSim == World index tables, bit-exact."""
+    runpy.run_path(os.path.join(HERE, "_ref_check_env.py"), run_name="__main__")
+
+
+def test_port_rollouts_match_reference_agents():
+    """Real Follower/Monitor/EnvDrop agents' rollout + backward == port: loss, grads, trajectories."""
+    runpy.run_path(os.path.join(HERE, "_ref_check_rollout.py"), run_name="__main__")
