@@ -1,0 +1,90 @@
+"""ctypes binding of the C-ABI in include/vln_b200.h (csrc/libvln_b200.so).
+
+There is no CPU fallback: if the shared library is missing, loading raises, and every op that
+needs it fails loudly.  ``build()`` compiles the library in-tree with nvcc for sm_100a.
+"""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libvln_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "vln_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -shared -> csrc/libvln_b200.so"""
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(p) for p in deps)):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_PATH
+
+
+_lib = None
+
+_p = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_u64 = C.c_uint64
+_i64 = C.c_int64
+
+_SIGS = {
+    "vln_version": ([], _i),
+    "vln_last_error": ([], C.c_char_p),
+    "vln_ctx_create": ([C.POINTER(_p), _p, _i, _i], _i),
+    "vln_ctx_destroy": ([_p], None),
+    "vln_gather_pano": ([_p, _p, _p, _p, _p, _i, _p], _i),
+    "vln_gather_cand": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
+    "vln_pano_attn": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _u64, _i, _p], _i),
+    "vln_cand_logits_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _u64, _u64, _p], _i),
+    "vln_cand_logits_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _u64, _u64, _p], _i),
+    "vln_ctx_attn_fwd": ([_p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
+    "vln_ctx_attn_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
+    "vln_lstm_pointwise_fwd": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
+    "vln_lstm_pointwise_bwd": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
+    "vln_policy_fwd": ([_p, _p, _i, _u64, _u64, _p, _p, _p, _p, _p, _i, _p], _i),
+    "vln_policy_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _p], _i),
+    "vln_dropout": ([_p, _p, _i64, _f, _u64, _u64, _p], _i),
+    "vln_dropout_mask": ([_p, _i64, _f, _u64, _u64, _p], _i),
+    "vln_env_step": ([_p] * 16 + [_i, _p], _i),
+    "vln_env_observe": ([_p] * 11 + [_i, _p], _i),
+    "vln_grad_sqnorm": ([_p, C.POINTER(_i64), _i, _p, _f, _p], _i),
+    "vln_optim_step": ([_p, _p, _p, _p, C.POINTER(_i64), C.POINTER(_f), _i, _p, _f, _i, _f, _i, _p], _i),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback for its kernels.")
+        L = C.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(L, name)            # AttributeError here = header/library mismatch
+            fn.argtypes = args
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"{what or 'vln_b200 call'} failed (rc={rc}): {lib().vln_last_error().decode()}")

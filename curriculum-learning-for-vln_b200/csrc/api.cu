@@ -1,0 +1,77 @@
+// C-ABI plumbing: errors, context (feature table + TMA descriptor).
+#include <cstdarg>
+#include <cstdio>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void vln_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* vln_last_error(void) { return g_err; }
+extern "C" int vln_version(void) { return 100; }
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  return fn;
+}
+
+// Generic 2-D bf16 row-major tensor map; used by the feature table and by the GEMM operands.
+int vln_make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                     uint32_t box_cols, uint32_t box_rows, int swizzle128) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    vln_set_error("cuTensorMapEncodeTiled entry point not available");
+    return -4;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vln_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_cols,
+                  box_rows);
+    return -5;
+  }
+  return 0;
+}
+
+extern "C" int vln_ctx_create(vln_ctx** out, const void* table_bf16, int n_vp, int device) {
+  VLN_REQUIRE(out && table_bf16 && n_vp > 0, "null table or n_vp <= 0");
+  VLN_REQUIRE(((uintptr_t)table_bf16 & 15) == 0, "table must be 16-byte aligned");
+  VLN_CHECK_CUDA(cudaSetDevice(device));
+  vln_ctx* c = new vln_ctx();
+  c->table = (const __nv_bfloat16*)table_bf16;
+  c->n_vp = n_vp;
+  c->device = device;
+  cudaDeviceProp prop;
+  VLN_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  int rc = vln_make_tmap_2d(&c->tmap_tile, table_bf16, (uint64_t)n_vp * VLN_V, VLN_IMG, VLN_IMG, 256, VLN_V, 0);
+  if (rc) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" void vln_ctx_destroy(vln_ctx* ctx) { delete ctx; }

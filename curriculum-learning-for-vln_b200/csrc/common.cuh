@@ -1,0 +1,175 @@
+// Shared device helpers for the sm_100a kernels: Philox keep-masks, mbarrier/TMA/cluster PTX,
+// warp reductions, error plumbing for the C-ABI.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vln_b200.h"
+
+// ---- error plumbing -----------------------------------------------------------------------
+void vln_set_error(const char* fmt, ...);
+#define VLN_CHECK_CUDA(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      vln_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+#define VLN_REQUIRE(cond, msg)                                                        \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      vln_set_error("%s: requirement failed: %s", __func__, msg);                     \
+      return -1;                                                                      \
+    }                                                                                 \
+  } while (0)
+#define VLN_LAUNCH_OK()                                                               \
+  do {                                                                                \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      vln_set_error("%s: launch failed: %s", __func__, cudaGetErrorString(_e));       \
+      return -3;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+struct vln_ctx {
+  const __nv_bfloat16* table;
+  int n_vp;
+  int device;
+  int num_sms;
+  CUtensorMap tmap_tile;   // [n_vp*36, 2048] bf16, box {256 cols, 36 rows}: one panorama slice
+};
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------
+struct Philox8 {
+  uint32_t w[4];  // 8 x 16-bit lanes
+};
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifdef __CUDA_ARCH__
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+#else
+  uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+  uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+// 128 random bits for block `blk` (= element index / 8) of stream (seed, offset).
+__host__ __device__ __forceinline__ Philox8 philox8(uint64_t seed, uint64_t offset, uint64_t blk) {
+  uint32_t c[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)};
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  Philox8 o;
+  o.w[0] = c[0]; o.w[1] = c[1]; o.w[2] = c[2]; o.w[3] = c[3];
+  return o;
+}
+
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  float t = p * 65536.0f + 0.5f;
+  return t <= 0.f ? 0u : (t >= 65536.f ? 65536u : (uint32_t)t);
+}
+// lane j (0..7) of a Philox8 block: kept iff its 16-bit value >= thr
+__host__ __device__ __forceinline__ bool philox_keep(const Philox8& r, int j, uint32_t thr) {
+  uint32_t v = (r.w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+  return v >= thr;
+}
+// uniform in [0,1) from 24 bits of word j (0..3)
+__host__ __device__ __forceinline__ float philox_uniform(const Philox8& r, int j) {
+  return (float)(r.w[j] >> 8) * (1.0f / 16777216.0f);
+}
+
+#ifdef __CUDACC__
+// ---- warp helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- shared-memory addresses, mbarrier, TMA, cluster ----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 2-D tiled TMA load: box at (c0 = inner/column coordinate, c1 = row coordinate)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float from the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ float dsmem_ld_f32(const float* local_ptr, uint32_t rank) {
+  uint32_t a = smem_u32(local_ptr), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+#endif  // __CUDACC__

@@ -1,0 +1,369 @@
+// Small fused kernels: LSTM pointwise halves, the action head (masked log-softmax / CE / sampling /
+// entropy) with its backward, Philox dropout, the index-table environment step, and the fused
+// clip + optimiser pass.  All are launch/latency-bound at B=64; they exist to keep the rollout
+// on the device and to collapse ~20 ATen launches per decoder step into one each.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- nn.LSTMCell pointwise (gate order i, f, g, o) ----------------------------------------------
+__global__ void lstm_pw_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c0,
+                                   float* __restrict__ h1, float* __restrict__ c1, float* __restrict__ acts, int B,
+                                   int H) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, h = idx - b * H;
+  const float* gr = gates + (size_t)b * 4 * H;
+  const float i = sigmoidf_(gr[h]), f = sigmoidf_(gr[H + h]), g = tanhf(gr[2 * H + h]), o = sigmoidf_(gr[3 * H + h]);
+  const float c = f * c0[idx] + i * g;
+  c1[idx] = c;
+  h1[idx] = o * tanhf(c);
+  if (acts) {
+    float* ar = acts + (size_t)b * 4 * H;
+    ar[h] = i; ar[H + h] = f; ar[2 * H + h] = g; ar[3 * H + h] = o;
+  }
+}
+
+__global__ void lstm_pw_bwd_kernel(const float* __restrict__ acts, const float* __restrict__ c0,
+                                   const float* __restrict__ c1, const float* __restrict__ d_h1,
+                                   const float* __restrict__ d_c1, float* __restrict__ d_gates,
+                                   float* __restrict__ d_c0, int B, int H) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, h = idx - b * H;
+  const float* ar = acts + (size_t)b * 4 * H;
+  const float i = ar[h], f = ar[H + h], g = ar[2 * H + h], o = ar[3 * H + h];
+  const float tc = tanhf(c1[idx]);
+  const float dh = d_h1 ? d_h1[idx] : 0.f;
+  const float dc = (d_c1 ? d_c1[idx] : 0.f) + dh * o * (1.f - tc * tc);
+  float* dg = d_gates + (size_t)b * 4 * H;
+  dg[h] = dc * g * i * (1.f - i);
+  dg[H + h] = dc * c0[idx] * f * (1.f - f);
+  dg[2 * H + h] = dc * i * (1.f - g * g);
+  dg[3 * H + h] = dh * tc * o * (1.f - o);
+  d_c0[idx] = dc * f;
+}
+
+// ---- action head: one warp per episode, 16 slots -------------------------------------------------
+__global__ void policy_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ target, int feedback,
+                                  uint64_t seed, uint64_t offset, float* __restrict__ ce, int32_t* __restrict__ action,
+                                  float* __restrict__ logp, float* __restrict__ entropy, float* __restrict__ probs,
+                                  int B) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float x = lane < VLN_NSLOT ? logits[(size_t)b * VLN_NSLOT + lane] : -INFINITY;
+  const float m = warp_max(x);
+  const float e = (x == -INFINITY) ? 0.f : expf(x - m);
+  const float s = warp_sum(e);
+  const float p = e / s;
+  const float lp = x - m - logf(s);                       // log-softmax (−inf on masked slots)
+  const float ent = -warp_sum(p > 0.f ? p * lp : 0.f);
+  const int tg = target ? target[b] : -1;
+  int act;
+  if (feedback == 0) {
+    act = tg;
+  } else if (feedback == 1) {                             // first index attaining the maximum
+    const unsigned hit = __ballot_sync(0xffffffffu, x == m);
+    act = __ffs(hit) - 1;
+  } else {                                                // inverse-CDF sample, u ~ Philox(seed, offset, b)
+    const float u = philox_uniform(philox8(seed, offset, (uint64_t)b), 0);
+    float cdf = p;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, cdf, o);
+      if (lane >= o) cdf += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, p > 0.f && cdf > u);
+    const unsigned valid = __ballot_sync(0xffffffffu, p > 0.f);
+    act = hit ? __ffs(hit) - 1 : 31 - __clz(valid);
+  }
+  const float lp_t = __shfl_sync(0xffffffffu, lp, tg >= 0 ? tg : 0);
+  const float lp_a = __shfl_sync(0xffffffffu, lp, act >= 0 ? act : 0);
+  if (lane < VLN_NSLOT && probs) probs[(size_t)b * VLN_NSLOT + lane] = p;
+  if (lane == 0) {
+    if (ce) ce[b] = tg >= 0 ? -lp_t : 0.f;              // CrossEntropyLoss(ignore_index=-1, reduction='none')
+    if (action) action[b] = act;
+    if (logp) logp[b] = act >= 0 ? lp_a : 0.f;
+    if (entropy) entropy[b] = ent;
+  }
+}
+
+__global__ void policy_bwd_kernel(const float* __restrict__ probs, const int32_t* __restrict__ target,
+                                  const int32_t* __restrict__ action, const float* __restrict__ entropy,
+                                  const float* __restrict__ g_ce, const float* __restrict__ g_logp,
+                                  const float* __restrict__ g_ent, float* __restrict__ dlogits, int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * VLN_NSLOT) return;
+  const int b = idx / VLN_NSLOT, j = idx - b * VLN_NSLOT;
+  const float p = probs[idx];
+  float d = 0.f;
+  if (g_ce && target[b] >= 0) d += g_ce[b] * (p - (j == target[b] ? 1.f : 0.f));
+  if (g_logp && action[b] >= 0) d += g_logp[b] * ((j == action[b] ? 1.f : 0.f) - p);
+  if (g_ent && p > 0.f) d -= g_ent[b] * p * (logf(p) + entropy[b]);
+  dlogits[idx] = d;
+}
+
+// ---- dropout ----------------------------------------------------------------------------------
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p, uint64_t seed,
+                               uint64_t offset) {
+  const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = blk * 8;
+  if (e0 >= n) return;
+  const Philox8 r = philox8(seed, offset, (uint64_t)blk);
+  const uint32_t thr = drop_threshold(p);
+  const float sc = 1.0f / (1.0f - p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (e0 + j < n) y[e0 + j] = philox_keep(r, j, thr) ? x[e0 + j] * sc : 0.f;
+}
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
+  const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = blk * 8;
+  if (e0 >= n) return;
+  const Philox8 r = philox8(seed, offset, (uint64_t)blk);
+  const uint32_t thr = drop_threshold(p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (e0 + j < n) mask[e0 + j] = philox_keep(r, j, thr) ? 1 : 0;
+}
+
+// ---- environment on index tables -----------------------------------------------------------------
+__device__ __forceinline__ int teacher_slot(int cur, int goal, const int32_t* cand_vp, const int32_t* n_cand,
+                                            const int32_t* next_hop, const int64_t* sq_off, const int32_t* vp_local) {
+  const int n = n_cand[cur];
+  if (cur == goal) return n;                               // STOP (base.py:174-177)
+  const int nh = next_hop[sq_off[cur] + vp_local[goal]];
+  for (int j = 0; j < n; ++j)
+    if (cand_vp[(size_t)cur * VLN_CMAX + j] == nh) return j;
+  return n;
+}
+
+__global__ void env_observe_kernel(const int32_t* __restrict__ vp, const uint8_t* __restrict__ ended,
+                                   const int32_t* __restrict__ goal, const int32_t* __restrict__ cand_vp,
+                                   const int32_t* __restrict__ n_cand, const int32_t* __restrict__ next_hop,
+                                   const float* __restrict__ dist_tbl, const int64_t* __restrict__ sq_off,
+                                   const int32_t* __restrict__ vp_local, int32_t* __restrict__ teacher,
+                                   float* __restrict__ dist, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int cur = vp[b], g = goal[b];
+  if (teacher) teacher[b] = (ended && ended[b]) ? -1 : teacher_slot(cur, g, cand_vp, n_cand, next_hop, sq_off, vp_local);
+  if (dist) dist[b] = dist_tbl[sq_off[cur] + vp_local[g]];
+}
+
+__global__ void env_step_kernel(int32_t* __restrict__ vp, int32_t* __restrict__ view, uint8_t* __restrict__ ended,
+                                const int32_t* __restrict__ goal, const int32_t* __restrict__ action,
+                                const int32_t* __restrict__ cand_vp, const int32_t* __restrict__ cand_view,
+                                const int32_t* __restrict__ n_cand, const int32_t* __restrict__ next_hop,
+                                const float* __restrict__ dist_tbl, const int64_t* __restrict__ sq_off,
+                                const int32_t* __restrict__ vp_local, float* __restrict__ last_dist,
+                                int32_t* __restrict__ teacher, float* __restrict__ reward, float* __restrict__ mask,
+                                int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int cur = vp[b];
+  const int g = goal[b];
+  const bool was_ended = ended[b] != 0;
+  const int a = action[b];
+  const bool stop = was_ended || a < 0 || a >= n_cand[cur];       // envdrop.py:198-203
+  if (!stop) {
+    view[b] = cand_view[(size_t)cur * VLN_CMAX + a];              // agent turns to the view, then steps (misc.py:366-390)
+    cur = cand_vp[(size_t)cur * VLN_CMAX + a];
+    vp[b] = cur;
+  }
+  const float d = dist_tbl[sq_off[cur] + vp_local[g]];
+  if (reward) {                                                   // envdrop.py:207-213
+    float r = 0.f;
+    if (!was_ended) {
+      if (stop) r = d < 3.0f ? 2.f : -2.f;
+      else { const float dd = last_dist[b] - d; r = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f); }
+    }
+    reward[b] = r;
+  }
+  if (mask) mask[b] = was_ended ? 0.f : 1.f;
+  last_dist[b] = d;
+  const bool now_ended = was_ended || stop;
+  ended[b] = now_ended ? 1 : 0;
+  if (teacher) teacher[b] = now_ended ? -1 : teacher_slot(cur, g, cand_vp, n_cand, next_hop, sq_off, vp_local);
+}
+
+// ---- gradient clip + optimiser ----------------------------------------------------------------------
+struct Groups {
+  int64_t off[5];
+  float max_norm[4];
+  int n;
+};
+
+__global__ void sqnorm_kernel(const float* __restrict__ grad, Groups gr, float scale, float* __restrict__ sqnorm) {
+  __shared__ float red[4][32];
+  const int64_t n = gr.off[gr.n];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = grad[i] * scale;
+    int k = 0;
+    while (k + 1 < gr.n && i >= gr.off[k + 1]) ++k;
+    acc[k] += g * g;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float s = warp_sum(acc[k]);
+    if (lane == 0) red[k][warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float s = lane < (blockDim.x >> 5) ? red[k][lane] : 0.f;
+      s = warp_sum(s);
+      if (lane == 0 && k < gr.n) atomicAdd(sqnorm + k, s);
+    }
+  }
+}
+
+__global__ void optim_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ s1,
+                             float* __restrict__ s2, Groups gr, const float* __restrict__ sqnorm, float scale,
+                             int kind, float lr, float bc1, float bc2) {
+  const int64_t n = gr.off[gr.n];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < gr.n && i >= gr.off[k + 1]) ++k;
+    float g = grad[i] * scale;
+    if (gr.max_norm[k] > 0.f) {                                   // clip_grad_norm_: coef = max/(norm+1e-6), clamped to 1
+      const float coef = gr.max_norm[k] / (sqrtf(sqnorm[k]) + 1e-6f);
+      if (coef < 1.f) g *= coef;
+    }
+    if (kind == 0) {                                              // torch.optim.RMSprop defaults
+      const float sq = 0.99f * s1[i] + 0.01f * g * g;
+      s1[i] = sq;
+      param[i] -= lr * g / (sqrtf(sq) + 1e-8f);
+    } else {                                                      // torch.optim.Adam defaults
+      const float m = 0.9f * s1[i] + 0.1f * g;
+      const float v = 0.999f * s2[i] + 0.001f * g * g;
+      s1[i] = m;
+      s2[i] = v;
+      param[i] -= (lr / bc1) * m / (sqrtf(v) / sqrtf(bc2) + 1e-8f);
+    }
+  }
+}
+
+}  // namespace
+
+#define STREAM ((cudaStream_t)stream)
+
+extern "C" int vln_lstm_pointwise_fwd(const float* gates, const float* c0, float* h1, float* c1, float* acts, int B,
+                                      int H, void* stream) {
+  VLN_REQUIRE(gates && c0 && h1 && c1 && B > 0 && H > 0, "bad arguments");
+  lstm_pw_fwd_kernel<<<(B * H + 255) / 256, 256, 0, STREAM>>>(gates, c0, h1, c1, acts, B, H);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_lstm_pointwise_bwd(const float* acts, const float* c0, const float* c1, const float* d_h1,
+                                      const float* d_c1, float* d_gates, float* d_c0, int B, int H, void* stream) {
+  VLN_REQUIRE(acts && c0 && c1 && d_gates && d_c0 && B > 0 && H > 0, "bad arguments");
+  lstm_pw_bwd_kernel<<<(B * H + 255) / 256, 256, 0, STREAM>>>(acts, c0, c1, d_h1, d_c1, d_gates, d_c0, B, H);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_policy_fwd(const float* logits, const int32_t* target, int feedback, uint64_t seed,
+                              uint64_t offset, float* ce, int32_t* action, float* logp, float* entropy, float* probs,
+                              int B, void* stream) {
+  VLN_REQUIRE(logits && B > 0 && feedback >= 0 && feedback <= 2, "bad arguments");
+  VLN_REQUIRE(feedback != 0 || target, "teacher feedback needs targets");
+  policy_fwd_kernel<<<(B + 3) / 4, 128, 0, STREAM>>>(logits, target, feedback, seed, offset, ce, action, logp, entropy,
+                                                     probs, B);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_policy_bwd(const float* probs, const int32_t* target, const int32_t* action, const float* entropy,
+                              const float* g_ce, const float* g_logp, const float* g_ent, float* dlogits, int B,
+                              void* stream) {
+  VLN_REQUIRE(probs && dlogits && B > 0, "bad arguments");
+  VLN_REQUIRE(!g_ce || target, "g_ce needs targets");
+  VLN_REQUIRE(!g_logp || action, "g_logp needs actions");
+  VLN_REQUIRE(!g_ent || entropy, "g_ent needs entropy");
+  policy_bwd_kernel<<<(B * VLN_NSLOT + 255) / 256, 256, 0, STREAM>>>(probs, target, action, entropy, g_ce, g_logp,
+                                                                     g_ent, dlogits, B);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
+                           void* stream) {
+  VLN_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
+  const int64_t blks = (n + 7) / 8;
+  dropout_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(x, y, n, p, seed, offset);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  VLN_REQUIRE(mask && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
+  const int64_t blks = (n + 7) / 8;
+  dropout_mask_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(mask, n, p, seed, offset);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_env_observe(const int32_t* vp, const uint8_t* ended, const int32_t* goal, const int32_t* cand_vp,
+                               const int32_t* n_cand, const int32_t* next_hop, const float* dist_tbl,
+                               const int64_t* sq_off, const int32_t* vp_local, int32_t* teacher, float* dist, int B,
+                               void* stream) {
+  VLN_REQUIRE(vp && goal && cand_vp && n_cand && next_hop && dist_tbl && sq_off && vp_local && B > 0, "bad arguments");
+  env_observe_kernel<<<(B + 127) / 128, 128, 0, STREAM>>>(vp, ended, goal, cand_vp, n_cand, next_hop, dist_tbl, sq_off,
+                                                          vp_local, teacher, dist, B);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_env_step(int32_t* vp, int32_t* view, uint8_t* ended, const int32_t* goal, const int32_t* action,
+                            const int32_t* cand_vp, const int32_t* cand_view, const int32_t* n_cand,
+                            const int32_t* next_hop, const float* dist_tbl, const int64_t* sq_off,
+                            const int32_t* vp_local, float* last_dist, int32_t* teacher, float* reward, float* mask,
+                            int B, void* stream) {
+  VLN_REQUIRE(vp && view && ended && goal && action && cand_vp && cand_view && n_cand && next_hop && dist_tbl &&
+                  sq_off && vp_local && last_dist && B > 0,
+              "bad arguments");
+  env_step_kernel<<<(B + 127) / 128, 128, 0, STREAM>>>(vp, view, ended, goal, action, cand_vp, cand_view, n_cand,
+                                                       next_hop, dist_tbl, sq_off, vp_local, last_dist, teacher, reward,
+                                                       mask, B);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+static int make_groups(Groups* g, const int64_t* group_off, const float* max_norm, int n_groups) {
+  if (n_groups < 1 || n_groups > 4) return -1;
+  g->n = n_groups;
+  for (int i = 0; i <= n_groups; ++i) g->off[i] = group_off[i];
+  for (int i = 0; i < n_groups; ++i) g->max_norm[i] = max_norm ? max_norm[i] : 0.f;
+  return 0;
+}
+
+extern "C" int vln_grad_sqnorm(const float* grad, const int64_t* group_off, int n_groups, float* sqnorm,
+                               float grad_scale, void* stream) {
+  VLN_REQUIRE(grad && group_off && sqnorm, "bad arguments");
+  Groups g;
+  VLN_REQUIRE(make_groups(&g, group_off, nullptr, n_groups) == 0, "1..4 groups supported");
+  VLN_CHECK_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(float) * n_groups, STREAM));
+  sqnorm_kernel<<<296, 256, 0, STREAM>>>(grad, g, grad_scale, sqnorm);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_optim_step(float* param, const float* grad, float* state1, float* state2, const int64_t* group_off,
+                              const float* max_norm, int n_groups, const float* sqnorm, float grad_scale, int kind,
+                              float lr, int step, void* stream) {
+  VLN_REQUIRE(param && grad && state1 && group_off && sqnorm && (kind == 0 || (kind == 1 && state2)), "bad arguments");
+  Groups g;
+  VLN_REQUIRE(make_groups(&g, group_off, max_norm, n_groups) == 0, "1..4 groups supported");
+  const float bc1 = 1.0f - powf(0.9f, (float)step), bc2 = 1.0f - powf(0.999f, (float)step);
+  optim_kernel<<<592, 256, 0, STREAM>>>(param, grad, state1, state2, g, sqnorm, grad_scale, kind, lr, bc1, bc2);
+  VLN_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,160 @@
+/*
+ * vln_b200.h — C-ABI of the B200-native rollout hot path.
+ *
+ * The reference (IMNearth/Curriculum-Learning-For-VLN, tasks/R2R-judy/src) is pure
+ * Python/PyTorch and has no FFI of its own; its boundary for this path is the set of
+ * nn.Module.forward()/agent helper calls listed in SURVEY.md §8(a,b).  Each entry point
+ * below names the reference code it replaces.  Host code (Python, ctypes) sits on top and
+ * keeps the reference's module/agent signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (a torch tensor's data_ptr())
+ *     unless it says "host"; the library allocates nothing persistent except vln_ctx;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue, never synchronise;
+ *   - return 0 on success, a negative code on failure; vln_last_error() gives the text
+ *     (thread-local);  nothing throws or exits;
+ *   - layouts are row-major, innermost dimension last.  F = 2176 = 2048 image + 128 angle,
+ *     V = 36 views, CMAX = 15 neighbours (+1 END slot => 16 action slots).
+ *   - dropout: keep-mask bit for element e of a tensor = Philox4x32-10(seed, offset, e/8)
+ *     16-bit lane (e%8) >= round(p*65536); kept values are scaled by 1/(1-p) (nn.Dropout).
+ *     vln_dropout_mask() exposes the very same mask so the oracle can be fed identical masks.
+ */
+#ifndef VLN_B200_H_
+#define VLN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLN_V 36
+#define VLN_IMG 2048
+#define VLN_ANG 128
+#define VLN_F 2176
+#define VLN_CMAX 15
+#define VLN_NSLOT 16
+
+typedef struct vln_ctx vln_ctx;
+
+int vln_version(void);
+const char* vln_last_error(void);
+
+/* Feature store.  Replaces ImageFeatures.read_in's dict + EnvBatch.getStates lookup
+ * (misc.py:254-279, common_env.py:72-89): one HBM-resident bf16 table [n_vp,36,2048]
+ * described to the TMA unit as a 2-D tensor [n_vp*36, 2048]. */
+int vln_ctx_create(vln_ctx** out, const void* table_bf16, int n_vp, int device);
+void vln_ctx_destroy(vln_ctx* ctx);
+
+/* R2RBatch.observe feature concat + _feature_variable (common_env.py:309, base.py:141-147):
+ * out[b] = concat(table[vp[b]], loc4[view[b]] repeated x32) as fp32 [B,36,2176]. bit-exact. */
+int vln_gather_pano(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                    const float* loc4 /*[36,36,4]*/, float* out, int B, void* stream);
+
+/* make_candidate feature + _candidate_variable (common_env.py:283-291, base.py:149-157):
+ * out[b,j] = concat(table[vp[b], cand_view[vp[b],j]], cand_ang4[vp[b],j,view[b]%12] x32) for
+ * j < n_cand[vp[b]], zeros elsewhere (row n_cand = END).  fp32 [B,C,2176]; out_len[b]=n_cand+1. */
+int vln_gather_cand(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                    const int32_t* cand_view /*[n_vp,15]*/, const float* cand_ang4 /*[n_vp,15,12,4]*/,
+                    const int32_t* n_cand /*[n_vp]*/, float* out, int32_t* out_len, int B, int C,
+                    void* stream);
+
+/* Fused gather + soft-dot attention over the 36-view panorama (SoftDotAttention.forward,
+ * units.py:107-118, with EnvDropDecoder's in-place feature dropout policy.py:226-231 folded
+ * into the load).  One TMA read of the episode's tile; never materialises [B,36,2176].
+ *   mode 0 (forward):  vec = query q[B,2176];  attn_io <- softmax_v(x~_v . q) [B,36];
+ *                      out <- sum_v attn_v x~_v  [B,2176]
+ *   mode 1 (backward): vec = d(out) [B,2176], attn_io = saved attn (read);
+ *                      out <- dq = sum_v dlogit_v x~_v,  dlogit = attn*(r - attn.r), r_v = x~_v . vec
+ * x~ = dropout(table row) (+) angle embedding.  split in {1,2,4,8}: CTAs per episode (cluster). */
+int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
+                  const float* vec, float* attn_io, float* out, int B, int mode, float drop_p,
+                  uint64_t seed, uint64_t offset, int split, void* stream);
+
+/* Candidate logits (EnvDropDecoder.candidate_attn policy.py:199-206; also ActionScoring
+ * units.py:173-185 after folding its Linear layers into tgt/bias on the host side):
+ *   logits[b,j] = x~c[b,j] . tgt[b] + bias[b]   j <= n_cand (END row is all-zero features)
+ *   logits[b,j] = -inf                          j >  n_cand          (length2mask, misc.py:481-486)
+ * logits is [B,16].  bias may be NULL. */
+int vln_cand_logits_fwd(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                        const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
+                        const float* tgt, const float* bias, float* logits, int B, float drop_p,
+                        uint64_t seed, uint64_t offset, void* stream);
+/* d_tgt[b] = sum_j dlogits[b,j] x~c[b,j];  d_bias[b] = sum_{j<=n_cand} dlogits[b,j] (may be NULL). */
+int vln_cand_logits_bwd(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                        const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
+                        const float* dlogits, float* d_tgt, float* d_bias, int B, float drop_p,
+                        uint64_t seed, uint64_t offset, void* stream);
+
+/* Soft-dot attention over the instruction context (SoftDotAttention.forward units.py:107-118,
+ * the bmm/softmax/bmm part; linear_in/linear_out are GEMMs outside).  context fp32 [B,L,H],
+ * tgt [B,H], lengths[b] = number of unmasked rows (mask = position >= length). */
+int vln_ctx_attn_fwd(const float* context, const float* tgt, const int32_t* lengths, float* attn,
+                     float* weighted, int B, int L, int H, void* stream);
+/* d_tgt <- sum_l dlogit_l ctx_l ; d_context += attn_l*d_weighted + dlogit_l*tgt  (accumulates);
+ * d_attn_ext (nullable) = extra gradient arriving on the attention weights themselves. */
+int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* lengths,
+                     const float* attn, const float* d_weighted, const float* d_attn_ext,
+                     float* d_tgt, float* d_context, int B, int L, int H, void* stream);
+
+/* nn.LSTMCell pointwise half (policy.py:53,159,238): gates [B,4H] (i,f,g,o pre-activations,
+ * biases already added) + c0 -> h1, c1; acts [B,4H] keeps the activated gates for backward. */
+int vln_lstm_pointwise_fwd(const float* gates, const float* c0, float* h1, float* c1, float* acts,
+                           int B, int H, void* stream);
+int vln_lstm_pointwise_bwd(const float* acts, const float* c0, const float* c1, const float* d_h1,
+                           const float* d_c1, float* d_gates, float* d_c0, int B, int H, void* stream);
+
+/* Action head (envdrop.py:166-195, follower.py:107-135, monitor.py:143-176): masked
+ * log-softmax, CE(ignore_index=-1), argmax / Philox-sampled / teacher action, log-prob and
+ * entropy of the chosen action.  logits [B,16] with -inf beyond the valid slots.
+ *   feedback: 0 teacher, 1 argmax, 2 sample.  Outputs per episode: ce, action (int32),
+ *   logp (of action), entropy, probs[B,16] (saved for backward). */
+int vln_policy_fwd(const float* logits, const int32_t* target, int feedback, uint64_t seed,
+                   uint64_t offset, float* ce, int32_t* action, float* logp, float* entropy,
+                   float* probs, int B, void* stream);
+/* dlogits[b,j] = g_ce[b]*(p - onehot(target)) + g_logp[b]*(onehot(action) - p)
+ *               - g_ent[b]*p*(log p + H)   (each g_* nullable) */
+int vln_policy_bwd(const float* probs, const int32_t* target, const int32_t* action,
+                   const float* entropy, const float* g_ce, const float* g_logp, const float* g_ent,
+                   float* dlogits, int B, void* stream);
+
+/* nn.Dropout on a dense fp32 tensor with the library's Philox stream (fwd and bwd are the same
+ * op: y = x * keep / (1-p)). */
+int vln_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
+                void* stream);
+/* keep-mask bytes (1 = kept) for elements [0,n) of the stream (seed, offset). */
+int vln_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* Stub-simulator transition + observation on index tables (EnvBatch.makeActions
+ * common_env.py:91-110, R2RBatch.observe :299-330, _teacher_action base.py:159-178, reward
+ * shaping envdrop.py:207-219).  state = (vp, view, ended) per episode, updated in place.
+ *   action[b] in 0..n_cand (n_cand = STOP) or -1.  Outputs: teacher[b] for the NEW state
+ *   (-1 if ended), dist[b], reward[b] (EnvDrop shaping), mask[b] = !ended before the step. */
+int vln_env_step(int32_t* vp, int32_t* view, uint8_t* ended, const int32_t* goal,
+                 const int32_t* action, const int32_t* cand_vp, const int32_t* cand_view,
+                 const int32_t* n_cand, const int32_t* next_hop, const float* dist_tbl,
+                 const int64_t* sq_off, const int32_t* vp_local, float* last_dist,
+                 int32_t* teacher, float* reward, float* mask, int B, void* stream);
+/* teacher/dist for the current state without moving (reset). */
+int vln_env_observe(const int32_t* vp, const uint8_t* ended, const int32_t* goal,
+                    const int32_t* cand_vp, const int32_t* n_cand, const int32_t* next_hop,
+                    const float* dist_tbl, const int64_t* sq_off, const int32_t* vp_local,
+                    int32_t* teacher, float* dist, int B, void* stream);
+
+/* Gradient clip + optimiser in one pass over flat fp32 buffers (trainer.py:423-427:
+ * clip_grad_norm_(encoder,40), clip_grad_norm_(decoder,40), critic unclipped, RMSprop/Adam).
+ * The flat buffer is laid out as n_groups (<=4) contiguous groups, group k = [group_off[k],
+ * group_off[k+1]) (host array of n_groups+1 offsets); max_norm[k] <= 0 means "not clipped"
+ * (host array).  sqnorm [n_groups] is device scratch holding each group's squared L2 norm of
+ * grad*grad_scale.  kind 0 = RMSprop(alpha=.99, eps=1e-8), 1 = Adam(.9,.999,1e-8), torch semantics;
+ * step is the 1-based Adam step count. */
+int vln_grad_sqnorm(const float* grad, const int64_t* group_off, int n_groups, float* sqnorm,
+                    float grad_scale, void* stream);
+int vln_optim_step(float* param, const float* grad, float* state1, float* state2,
+                   const int64_t* group_off, const float* max_norm, int n_groups,
+                   const float* sqnorm, float grad_scale, int kind, float lr, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLN_B200_H_ */

@@ -1,0 +1,287 @@
+"""GPU parity tests of the C-ABI kernels against the oracle (plain PyTorch fp32 / numpy).
+
+Tolerances (stated per the north star): gathers / indexing / env transitions are BIT-EXACT;
+floating-point kernels must match the fp32 oracle to max-relative error <= 1e-4 here
+(the system-level bar is 1e-3 on logits and loss)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import clvln_b200
+    from clvln_b200 import ops
+    from clvln_b200.environ import make_world
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda:0")
+    world = make_world(n_scans=4, seed=3)
+    store = ops.FeatureStore.from_world(world, dev)
+    return world, store, ops, dev
+
+
+def relerr(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+def rand_state(world, B, dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    vp = torch.randint(0, world.n_vp, (B,), generator=g, dtype=torch.int32)
+    view = torch.randint(0, 36, (B,), generator=g, dtype=torch.int32)
+    return vp.to(dev), view.to(dev)
+
+
+def expected_pano(world, vp, view):
+    from clvln_b200.environ.world import static_loc4
+    loc4 = torch.from_numpy(static_loc4())
+    img = world.table[vp.cpu().long()].float()
+    ang = loc4[view.cpu().long()].repeat_interleave(32, dim=2)
+    return torch.cat((img, ang), 2)
+
+
+def expected_cand(world, vp, view, C):
+    B = vp.shape[0]
+    out = torch.zeros(B, C, 2176)
+    for b in range(B):
+        g, v = int(vp[b]), int(view[b])
+        for j in range(int(world.n_cand[g])):
+            out[b, j, :2048] = world.table[g, int(world.cand_view[g, j])].float()
+            out[b, j, 2048:] = torch.from_numpy(world.cand_ang4[g, j, v % 12]).repeat_interleave(32)
+    return out
+
+
+def test_gather_pano_bit_exact(setup):
+    world, store, ops, dev = setup
+    vp, view = rand_state(world, 19, dev)
+    out = ops.gather_pano(store, vp, view)
+    assert torch.equal(out.cpu(), expected_pano(world, vp, view))
+
+
+def test_gather_cand_bit_exact(setup):
+    world, store, ops, dev = setup
+    vp, view = rand_state(world, 23, dev, 1)
+    out, lens = ops.gather_cand(store, vp, view)
+    assert torch.equal(out.cpu(), expected_cand(world, vp, view, 16))
+    assert torch.equal(lens.cpu().long(), torch.from_numpy(world.n_cand[vp.cpu().long().numpy()]).long() + 1)
+
+
+@pytest.mark.parametrize("split", [1, 2, 4, 8])
+@pytest.mark.parametrize("drop_p", [0.0, 0.3])
+def test_pano_attn_fwd_bwd(setup, split, drop_p):
+    world, store, ops, dev = setup
+    B = 13
+    vp, view = rand_state(world, B, dev, 2)
+    torch.manual_seed(split)
+    q = (torch.randn(B, 2176, device=dev) * 0.05).requires_grad_(True)
+    seed, off = 77, 5
+    out, attn = ops.pano_attn(store, vp, view, q, drop_p, seed, off, split)
+    g_out = torch.randn_like(out)
+    (dq,) = torch.autograd.grad(out, q, g_out)
+    # oracle: SoftDotAttention maths (units.py:107-118) on the materialised, masked tensor
+    img = expected_pano(world, vp, view).to(dev)
+    if drop_p > 0:
+        keep = ops.dropout_mask((B, 36, 2048), drop_p, seed, off, dev).float()
+        assert abs(keep.mean().item() - (1 - drop_p)) < 0.01
+        img = torch.cat((img[..., :2048] * keep * (1.0 / (1.0 - drop_p)), img[..., 2048:]), -1)
+    q2 = q.detach().clone().requires_grad_(True)
+    logit = torch.einsum("bvf,bf->bv", img, q2)
+    a = torch.softmax(logit, 1)
+    ref = torch.einsum("bv,bvf->bf", a, img)
+    (dq_ref,) = torch.autograd.grad(ref, q2, g_out)
+    assert relerr(attn, a) < 1e-4
+    assert relerr(out, ref) < 1e-4
+    assert relerr(dq, dq_ref) < 1e-4
+
+
+@pytest.mark.parametrize("drop_p", [0.0, 0.3])
+def test_cand_logits_fwd_bwd(setup, drop_p):
+    world, store, ops, dev = setup
+    B = 21
+    vp, view = rand_state(world, B, dev, 4)
+    tgt = (torch.randn(B, 2176, device=dev) * 0.05).requires_grad_(True)
+    bias = torch.randn(B, device=dev).requires_grad_(True)
+    seed, off = 9, 11
+    logits = ops.cand_logits(store, vp, view, tgt, bias, drop_p, seed, off)
+    cand = expected_cand(world, vp, view, 16).to(dev)
+    if drop_p > 0:
+        keep = ops.dropout_mask((B, 16, 2048), drop_p, seed, off, dev).float()
+        cand = torch.cat((cand[..., :2048] * keep * (1.0 / (1.0 - drop_p)), cand[..., 2048:]), -1)
+    n = torch.from_numpy(world.n_cand[vp.cpu().long().numpy()]).to(dev)
+    t2, b2 = tgt.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    ref = torch.einsum("bcf,bf->bc", cand, t2) + b2.unsqueeze(1)
+    invalid = torch.arange(16, device=dev).unsqueeze(0) > n.unsqueeze(1)
+    ref = ref.masked_fill(invalid, -math.inf)
+    assert torch.equal(torch.isinf(logits), invalid)
+    fin = ~invalid
+    assert relerr(logits[fin], ref[fin]) < 1e-4
+    g = torch.randn(B, 16, device=dev).masked_fill(invalid, 0.0)
+    dt, db = torch.autograd.grad(logits, (tgt, bias), g)
+    dt_ref, db_ref = torch.autograd.grad(ref.masked_fill(invalid, 0.0), (t2, b2), g)
+    assert relerr(dt, dt_ref) < 1e-4 and relerr(db, db_ref) < 1e-4
+
+
+@pytest.mark.parametrize("L,H", [(80, 512), (37, 256), (80, 1024)])
+def test_ctx_attn_fwd_bwd(setup, L, H):
+    from oracle import port_modules as P
+    _, _, ops, dev = setup
+    B = 9
+    torch.manual_seed(L)
+    ctx = torch.randn(B, L, H, device=dev).requires_grad_(True)
+    tgt = (torch.randn(B, H, device=dev) * 0.1).requires_grad_(True)
+    lengths = torch.randint(1, L + 1, (B,), device=dev, dtype=torch.int32)
+    lengths[0] = L
+    weighted, attn = ops.ctx_attn(ctx, tgt, lengths)
+    mask = torch.arange(L, device=dev).unsqueeze(0) >= lengths.unsqueeze(1)
+    c2, t2 = ctx.detach().clone().requires_grad_(True), tgt.detach().clone().requires_grad_(True)
+    eye = torch.eye(H, device=dev)
+    w_ref, a_ref = P.soft_dot_attention(t2, c2, eye, None, mask)     # linear_in = identity
+    assert relerr(attn, a_ref) < 1e-4 and relerr(weighted, w_ref) < 1e-4
+    gw, ga = torch.randn_like(weighted), torch.randn_like(attn)
+    dc, dt = torch.autograd.grad((weighted, attn), (ctx, tgt), (gw, ga))
+    dc_ref, dt_ref = torch.autograd.grad((w_ref, a_ref), (c2, t2), (gw, ga))
+    assert relerr(dc, dc_ref) < 1e-4 and relerr(dt, dt_ref) < 1e-4
+
+
+def test_lstm_pointwise(setup):
+    _, _, ops, dev = setup
+    B, H = 7, 512
+    gates = torch.randn(B, 4 * H, device=dev, requires_grad=True)
+    c0 = torch.randn(B, H, device=dev, requires_grad=True)
+    h1, c1 = ops.lstm_pointwise(gates, c0)
+    g2, c02 = gates.detach().clone().requires_grad_(True), c0.detach().clone().requires_grad_(True)
+    i, f, g, o = g2.chunk(4, 1)
+    c1r = torch.sigmoid(f) * c02 + torch.sigmoid(i) * torch.tanh(g)
+    h1r = torch.sigmoid(o) * torch.tanh(c1r)
+    assert relerr(h1, h1r) < 1e-5 and relerr(c1, c1r) < 1e-5
+    gh, gc = torch.randn_like(h1), torch.randn_like(c1)
+    dg, dc = torch.autograd.grad((h1, c1), (gates, c0), (gh, gc))
+    dgr, dcr = torch.autograd.grad((h1r, c1r), (g2, c02), (gh, gc))
+    assert relerr(dg, dgr) < 1e-4 and relerr(dc, dcr) < 1e-4
+
+
+def test_policy_head(setup):
+    import torch.nn.functional as F
+    _, _, ops, dev = setup
+    B = 33
+    torch.manual_seed(0)
+    logits = torch.randn(B, 16, device=dev) * 2
+    nvalid = torch.randint(2, 17, (B,), device=dev)
+    invalid = torch.arange(16, device=dev).unsqueeze(0) >= nvalid.unsqueeze(1)
+    logits = logits.masked_fill(invalid, -math.inf).requires_grad_(True)
+    target = (torch.rand(B, device=dev) * nvalid).long()
+    target[::5] = -1
+    # teacher + CE
+    ce, logp, ent, act = ops.policy_head(logits, target, "teacher")
+    l2 = logits.detach().clone().requires_grad_(True)
+    ce_ref = F.cross_entropy(l2, target, ignore_index=-1, reduction="none")
+    assert torch.equal(act.long(), target) and relerr(ce, ce_ref) < 1e-5
+    cat = torch.distributions.Categorical(F.softmax(l2, 1))
+    assert relerr(ent, cat.entropy()) < 1e-4
+    w = torch.rand(B, device=dev)
+    (d,) = torch.autograd.grad((ce * w).sum(), logits)
+    (d_ref,) = torch.autograd.grad((ce_ref * w).sum(), l2)
+    assert relerr(d, d_ref) < 1e-4
+    # argmax
+    _, _, _, a = ops.policy_head(logits, target, "argmax")
+    assert torch.equal(a.long(), logits.max(1)[1])
+    # sample: deterministic in (seed, offset), valid, log-prob/entropy gradients match autograd
+    ce, logp, ent, a = ops.policy_head(logits, target, "sample", 5, 9)
+    _, _, _, a_again = ops.policy_head(logits, target, "sample", 5, 9)
+    assert torch.equal(a, a_again)
+    assert bool((a.long() < nvalid).all()) and bool((a >= 0).all())
+    lp_ref = cat.log_prob(a.long())
+    assert relerr(logp, lp_ref) < 1e-4
+    g1, g2 = torch.randn(B, device=dev), torch.randn(B, device=dev)
+    (d,) = torch.autograd.grad((logp * g1).sum() + (ent * g2).sum(), logits)
+    (d_ref,) = torch.autograd.grad((lp_ref * g1).sum() + (cat.entropy() * g2).sum(), l2)
+    assert relerr(d, d_ref) < 1e-4
+    # sampling frequencies follow the softmax
+    big = torch.tensor([[0.0, 1.0, 2.0, -1.0] + [-math.inf] * 12], device=dev).repeat(20000, 1)
+    _, _, _, s = ops.policy_head(big, None, "sample", 1, 2)
+    freq = torch.bincount(s.long(), minlength=16).float() / 20000
+    assert (freq - F.softmax(big[0], 0)).abs().max() < 0.015
+
+
+def test_dropout(setup):
+    _, _, ops, dev = setup
+    x = torch.randn(1000, 37, device=dev, requires_grad=True)
+    y = ops.dropout(x, 0.5, 3, 4)
+    keep = ops.dropout_mask(x.shape, 0.5, 3, 4, dev).float()
+    assert torch.equal(y, x * keep * 2.0)
+    assert abs(keep.mean().item() - 0.5) < 0.01
+    (g,) = torch.autograd.grad(y.sum(), x)
+    assert torch.equal(g, keep * 2.0)
+
+
+def test_env_step_matches_world(setup):
+    world, store, ops, dev = setup
+    from clvln_b200.environ import make_items
+    items = make_items(world, 24, seed=5)
+    B = len(items)
+    vp = torch.tensor([it["path_g"][0] for it in items], dtype=torch.int32, device=dev)
+    goal = torch.tensor([it["path_g"][-1] for it in items], dtype=torch.int32, device=dev)
+    view = torch.full((B,), 12, dtype=torch.int32, device=dev)
+    ended = torch.zeros(B, dtype=torch.uint8, device=dev)
+    teacher, dist = ops.env_observe(store, vp, ended, goal)
+    cur = [it["path_g"][0] for it in items]
+    for b in range(B):
+        assert int(teacher[b]) == world.teacher_action(cur[b], int(goal[b]))
+        assert float(dist[b]) == float(world.distance(cur[b], int(goal[b])))
+    last = dist.clone()
+    done = [False] * B
+    for step in range(9):
+        act = teacher.clone()
+        teacher, reward, mask = ops.env_step(store, vp, view, ended, goal, act, last)
+        for b in range(B):
+            a = int(act[b])
+            stop = done[b] or a < 0 or a >= int(world.n_cand[cur[b]])
+            if not stop:
+                exp_view = int(world.cand_view[cur[b], a])
+                cur[b] = int(world.cand_vp[cur[b], a])
+                assert int(view[b]) == exp_view
+            assert int(vp[b]) == cur[b]
+            assert float(mask[b]) == (0.0 if done[b] else 1.0)
+            if not done[b] and stop:
+                assert float(reward[b]) == 2.0                     # teacher path stops at the goal
+            done[b] = done[b] or stop
+            assert int(ended[b]) == int(done[b])
+            exp_t = -1 if done[b] else world.teacher_action(cur[b], int(goal[b]))
+            assert int(teacher[b]) == exp_t
+    assert all(done)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_fused_clip_optimizer(setup, kind):
+    import ctypes as C
+    from clvln_b200 import _lib
+    from clvln_b200.ops import _ptr, _stream
+    _, _, ops, dev = setup
+    torch.manual_seed(kind)
+    sizes = [5000, 12000, 700]
+    params = [torch.randn(n, device=dev) for n in sizes]
+    ref = [p.clone().requires_grad_(True) for p in params]
+    flat = torch.cat(params).contiguous()
+    s1, s2 = torch.zeros_like(flat), torch.zeros_like(flat)
+    opt = (torch.optim.RMSprop if kind == 0 else torch.optim.Adam)(ref, lr=1e-2)
+    off = (C.c_int64 * 4)(0, sizes[0], sizes[0] + sizes[1], sum(sizes))
+    mx = (C.c_float * 3)(40.0, 1.5, 0.0)
+    sq = torch.zeros(3, device=dev)
+    for step in range(1, 4):
+        grads = [torch.randn(n, device=dev) * (3.0 if i == 1 else 0.2) for i, n in enumerate(sizes)]
+        for r, g in zip(ref, grads):
+            r.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref[0]], 40.0)
+        torch.nn.utils.clip_grad_norm_([ref[1]], 1.5)
+        opt.step()
+        gflat = torch.cat(grads).contiguous()
+        _lib.check(_lib.lib().vln_grad_sqnorm(_ptr(gflat), off, 3, _ptr(sq), 1.0, _stream()))
+        _lib.check(_lib.lib().vln_optim_step(_ptr(flat), _ptr(gflat), _ptr(s1), _ptr(s2), off, mx, 3, _ptr(sq), 1.0,
+                                             kind, 1e-2, step, _stream()))
+        assert relerr(flat, torch.cat([r.detach() for r in ref])) < 2e-5
