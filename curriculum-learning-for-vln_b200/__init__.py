@@ -6,5 +6,13 @@ binding), ops.py (autograd wrappers), model/ agent/ engine/ environ/ utils/ (hos
 of the reference's tasks/R2R-judy/src interface for this path).
 """
 from . import environ  # noqa: F401
+from . import utils  # noqa: F401
 
-__all__ = ["environ"]
+__all__ = ["environ", "utils", "ops", "model", "agent", "engine"]
+
+
+def __getattr__(name):
+    if name in ("ops", "model", "agent", "engine"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

@@ -46,18 +46,22 @@ _SIGS = {
     "vln_ctx_destroy": ([_p], None),
     "vln_gather_pano": ([_p, _p, _p, _p, _p, _i, _p], _i),
     "vln_gather_cand": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
-    "vln_pano_attn": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _u64, _u64, _i, _p], _i),
-    "vln_cand_logits_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _u64, _u64, _p], _i),
-    "vln_cand_logits_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _u64, _u64, _p], _i),
+    "vln_gather_action_feat": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p], _i),
+    "vln_pano_attn": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _i, _p], _i),
+    "vln_cand_logits_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),
+    "vln_cand_logits_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),
     "vln_ctx_attn_fwd": ([_p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
     "vln_ctx_attn_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
     "vln_lstm_pointwise_fwd": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_pointwise_bwd": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
-    "vln_policy_fwd": ([_p, _p, _i, _u64, _u64, _p, _p, _p, _p, _p, _i, _p], _i),
+    "vln_policy_fwd": ([_p, _p, _i, _p, _u64, _p, _p, _p, _p, _p, _i, _p], _i),
     "vln_policy_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _p], _i),
-    "vln_dropout": ([_p, _p, _i64, _f, _u64, _u64, _p], _i),
-    "vln_dropout_mask": ([_p, _i64, _f, _u64, _u64, _p], _i),
-    "vln_env_step": ([_p] * 16 + [_i, _p], _i),
+    "vln_dropout": ([_p, _p, _i64, _f, _p, _u64, _p], _i),
+    "vln_dropout_mask": ([_p, _i64, _f, _p, _u64, _p], _i),
+    "vln_rng_advance": ([_p, _u64, _p], _i),
+    "vln_env_step": ([_p] * 21 + [_i, _p], _i),
+    "vln_a2c_fwd": ([_p] * 7 + [_f, _f] + [_p] * 4 + [_i, _i, _p], _i),
+    "vln_a2c_bwd": ([_p] * 4 + [_f] + [_p] * 3 + [_i, _i, _p], _i),
     "vln_env_observe": ([_p] * 11 + [_i, _p], _i),
     "vln_grad_sqnorm": ([_p, C.POINTER(_i64), _i, _p, _f, _p], _i),
     "vln_optim_step": ([_p, _p, _p, _p, C.POINTER(_i64), C.POINTER(_f), _i, _p, _f, _i, _f, _i, _p], _i),

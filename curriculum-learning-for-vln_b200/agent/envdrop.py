@@ -1,0 +1,116 @@
+"""EnvDrop agent (Tan et al., NAACL 2019): imitation (CE) + A2C, on the device-resident rollout.
+
+Mirrors src/agent/envdrop.py (ctor :27-73, rollout :86-278, save/load :298-313) — same
+arguments, same ``self.loss`` / ``self.ml_loss`` / ``self.rl_loss`` / ``self.logs`` outputs —
+with the per-step host work (numpy feature assembly :75-84, H2D copies, `.cpu()` of the actions
+:198, numpy reward shaping :207-219, the per-step critic calls of the A2C loop :240-264) replaced
+by kernels and one batched critic call.  Dead reference paths (speaker back-translation :104-120,
+avoid_cyclic :167-172) are not carried over.
+"""
+from collections import defaultdict
+
+import torch
+
+from .. import ops
+from ..model import EncoderLSTM, EnvDropDecoder, Critic
+from ..model.units import LengthMask
+from .base import BaseAgent, RolloutState
+
+
+class EnvDropAgent(BaseAgent):
+    def __init__(self, model_cfg, max_enc_len, results_dir, device, env, tokenizer, episode_len=20):
+        super().__init__(results_dir, device, env, tokenizer, episode_len=episode_len)
+        self.cfg = model_cfg
+        self.action_emb_size = model_cfg.ACT_EMB_SIZE
+        self.max_enc_len = max_enc_len
+        self.encoder = EncoderLSTM(tokenizer.vocab_size(), model_cfg.WORD_EMB_SIZE, model_cfg.HIDDEN_SIZE,
+                                   padding_idx=0, drop_ratio=model_cfg.DROP_RATE,
+                                   bidirectional=model_cfg.ENC_BIDIRECTION, num_layers=model_cfg.ENC_LAYERS)
+        self.decoder = EnvDropDecoder(hidden_size=model_cfg.HIDDEN_SIZE, drop_ratio=model_cfg.DROP_RATE,
+                                      feat_drop_ratio=model_cfg.FEAT_DROP_RATE, action_embed_size=self.action_emb_size,
+                                      angle_feat_size=self.angle_feat_size, feature_size=self.feature_size)
+        self.critic = Critic(hidden_size=model_cfg.HIDDEN_SIZE, drop_ratio=model_cfg.DROP_RATE)
+        self.logs = defaultdict(list)
+        self.loss = {}
+        self._finish_init()
+
+    def _modules(self):
+        return [self.encoder, self.decoder, self.critic]
+
+    def _ckpt_names(self):
+        return ["encoder", "decoder", "critic"]
+
+    def reset_loss(self):
+        self.losses = []
+        self.logs = defaultdict(list)
+
+    def _decode(self, st, t, h_tilde, h_t, c_t, ctx, ctx_mask):
+        pano, cands = st.pano(t), st.cands(t)
+        pano.split = self.pano_split
+        pose = ops.pose_feature(st.store, st.view[t])
+        logit, (h_t, c_t), h_tilde = self.decoder(pose, pano, cands, h_tilde, h_t, c_t, ctx, ctx_mask)
+        return logit, h_t, c_t, h_tilde
+
+    def rollout(self, train_ml=True, train_rl=False, train_cl=False, reset=True, restart=False, speaker=None,
+                avoid_cyclic=False, feedback="sample", return_traj=None):
+        assert speaker is None and not avoid_cyclic, "speaker / avoid_cyclic paths are not part of this build"
+        if feedback != "sample":
+            train_rl = False
+        ib = self.env.reset_index(restart=restart)
+        store = self.store_of(self.env)
+        B = ib.vp.shape[0]
+        T, poll = self._horizon(ib, feedback)
+        ctx, h_t, c_t = self.encoder(ib.tokens, ib.lengths)
+        ctx_mask = LengthMask(ib.lengths, ctx.shape[1])
+        st = RolloutState(store, ib, T + (1 if train_rl else 0))
+        training = self.encoder.training
+
+        ml = torch.zeros(B, device=self.device) if train_cl else torch.zeros((), device=self.device)
+        rewards, masks, hiddens, logps, ents = [], [], [], [], []
+        h_tilde = h_t
+        for t in range(T):
+            logit, h_t, c_t, h_tilde = self._decode(st, t, h_tilde, h_t, c_t, ctx, ctx_mask)
+            hiddens.append(h_t)
+            off = self.rng.next() if feedback == "sample" else 0
+            ce, logp, ent, action = ops.policy_head(logit, st.teacher, feedback, self.rng, off)
+            ml = ml + (ce if train_cl else ce.sum())
+            if self.trace is not None:
+                self.trace.append(dict(logits=logit.detach(), target=st.teacher, action=action))
+            reward, mask = st.step(t, action)
+            rewards.append(reward), masks.append(mask), logps.append(logp), ents.append(ent)
+            if feedback == "sample":
+                self.logs["entropy"].append(ent.sum().detach())
+            if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
+                break
+        n = st.steps
+        self.ml_loss = ml
+
+        rl = 0.0
+        if train_rl:
+            with torch.no_grad():                                   # envdrop.py:225-237: bootstrap value
+                _, last_h, _, _ = self._decode(st, n, h_tilde, h_t, c_t, ctx, ctx_mask)
+                last_value = self.critic(last_h)
+            values = self.critic(torch.stack(hiddens).view(n * B, -1)).view(n, B)
+            loss_b, stats = ops.a2c_loss(torch.stack(logps), torch.stack(ents), values, torch.stack(rewards),
+                                         torch.stack(masks), last_value, st.ended[n], self.cfg.GAMMA, 0.01)
+            rl = loss_b if train_cl else loss_b.sum()
+            self.logs["total"].append(stats[0])
+            self.logs["critic_loss"].append(stats[1])
+            if self.cfg.RL_NORMALIZE == "total":
+                rl = rl / stats[0]
+            elif self.cfg.RL_NORMALIZE == "batch":
+                rl = rl / B
+            else:
+                assert self.cfg.RL_NORMALIZE == "none"
+        self.rl_loss = rl
+
+        self.loss = {"ml_loss": ml * self.cfg.ML_WEIGHT / B if train_ml else 0.0,
+                     "rl_loss": rl if train_rl else 0.0}
+        if train_cl and not restart:
+            val = self.loss["ml_loss"] + self.loss["rl_loss"]
+            self.losses.append(0.0 if isinstance(val, float) else val.sum().detach())
+        self.last_state = st
+        self.last_batch = ib
+        if return_traj if return_traj is not None else not training:
+            return self._trajectories(st)
+        return []

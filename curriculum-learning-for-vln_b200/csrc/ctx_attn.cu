@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) ctx_attn_kernel(
       d_tgt[(size_t)b * H + col0 + c] = acc;
     }
     float* db = d_context + (size_t)b * L * H;
-    for (int i = tid; i < len * hv; i += kThreads) {
+    for (int i = tid; d_context != nullptr && i < len * hv; i += kThreads) {
       const int l = i / hv, c = i - l * hv;
       float4* p = reinterpret_cast<float4*>(db + (size_t)l * H + col0) + c;
       float4 cur = *p;
@@ -179,7 +179,7 @@ extern "C" int vln_ctx_attn_fwd(const float* context, const float* tgt, const in
 extern "C" int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* lengths, const float* attn,
                                 const float* d_weighted, const float* d_attn_ext, float* d_tgt, float* d_context,
                                 int B, int L, int H, void* stream) {
-  VLN_REQUIRE(context && tgt && lengths && attn && d_weighted && d_tgt && d_context && B > 0, "bad arguments");
+  VLN_REQUIRE(context && tgt && lengths && attn && d_weighted && d_tgt && B > 0, "bad arguments");
   return launch(context, tgt, lengths, const_cast<float*>(attn), nullptr, d_weighted, d_attn_ext, d_tgt, d_context,
                 1, B, L, H, (cudaStream_t)stream);
 }

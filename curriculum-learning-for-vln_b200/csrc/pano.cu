@@ -71,6 +71,30 @@ __global__ void __launch_bounds__(kThreads) gather_cand_kernel(
   }
 }
 
+// a_t_prev = cands[b, max(action,0)] (follower.py:164): one candidate row per episode.
+__global__ void __launch_bounds__(kThreads) gather_action_kernel(
+    const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ vp, const int32_t* __restrict__ view,
+    const int32_t* __restrict__ action, const uint8_t* __restrict__ ended, const int32_t* __restrict__ cand_view,
+    const float* __restrict__ cand_ang4, const int32_t* __restrict__ n_cand, float* __restrict__ out) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int g = vp[b];
+  const int a = action[b];
+  const int j = ((ended && ended[b]) || a < 0 || a >= n_cand[g]) ? 0 : a;
+  float* dst = out + (size_t)b * VLN_F;
+  if (j < n_cand[g]) {
+    const int cv = cand_view[(size_t)g * VLN_CMAX + j];
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(table + ((size_t)g * VLN_V + cv) * VLN_IMG) + t);
+    reinterpret_cast<float4*>(dst)[2 * t] = make_float4(bf16lo(x.x), bf16hi(x.x), bf16lo(x.y), bf16hi(x.y));
+    reinterpret_cast<float4*>(dst)[2 * t + 1] = make_float4(bf16lo(x.z), bf16hi(x.z), bf16lo(x.w), bf16hi(x.w));
+    if (t < VLN_ANG)
+      dst[VLN_IMG + t] = cand_ang4[(((size_t)g * VLN_CMAX + j) * 12 + (view[b] % 12)) * 4 + (t >> 5)];
+  } else {
+    reinterpret_cast<float4*>(dst)[2 * t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(dst)[2 * t + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < VLN_ANG) dst[VLN_IMG + t] = 0.f;
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // K3: fused gather + soft-dot attention over the panorama, forward (mode 0) / backward (mode 1).
 //
@@ -87,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) pano_attn_kernel(const __grid_consta
                                                              const float* __restrict__ loc4,
                                                              const float* __restrict__ vec,
                                                              float* __restrict__ attn_io, float* __restrict__ out,
-                                                             int mode, float drop_p, uint64_t seed, uint64_t offset,
+                                                             int mode, float drop_p, const uint64_t* __restrict__ rng, uint64_t call_off,
                                                              int FS) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -133,6 +157,7 @@ __global__ void __launch_bounds__(kThreads) pano_attn_kernel(const __grid_consta
   float scale = 1.0f;
   if (drop_p > 0.f) {   // policy.py:226-231 — feature dropout on the 2048 image dims only
     scale = 1.0f / (1.0f - drop_p);
+    const uint64_t seed = rng[0], offset = rng[1] + call_off;
     const uint32_t thr = drop_threshold(drop_p);
     const int nvec = nbox * VLN_V * 32;
     uint4* t4 = reinterpret_cast<uint4*>(tile);
@@ -226,7 +251,7 @@ __global__ void __launch_bounds__(512) cand_logits_fwd_kernel(
     const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ vp, const int32_t* __restrict__ view,
     const int32_t* __restrict__ cand_view, const float* __restrict__ cand_ang4, const int32_t* __restrict__ n_cand,
     const float* __restrict__ tgt, const float* __restrict__ bias, float* __restrict__ logits, float drop_p,
-    uint64_t seed, uint64_t offset) {
+    const uint64_t* __restrict__ rng, uint64_t call_off) {
   __shared__ __align__(16) float ts[VLN_F];
   __shared__ float ta[4];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
@@ -245,6 +270,8 @@ __global__ void __launch_bounds__(512) cand_logits_fwd_kernel(
     const int cv = cand_view[(size_t)g * VLN_CMAX + j];
     const uint4* src = reinterpret_cast<const uint4*>(table + ((size_t)g * VLN_V + cv) * VLN_IMG);
     const uint32_t thr = drop_threshold(drop_p);
+    uint64_t seed = 0, offset = 0;
+    if (drop_p > 0.f) { seed = rng[0]; offset = rng[1] + call_off; }
     float acc = 0.f;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -275,7 +302,7 @@ __global__ void __launch_bounds__(kThreads) cand_logits_bwd_kernel(
     const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ vp, const int32_t* __restrict__ view,
     const int32_t* __restrict__ cand_view, const float* __restrict__ cand_ang4, const int32_t* __restrict__ n_cand,
     const float* __restrict__ dlogits, float* __restrict__ d_tgt, float* __restrict__ d_bias, float drop_p,
-    uint64_t seed, uint64_t offset) {
+    const uint64_t* __restrict__ rng, uint64_t call_off) {
   __shared__ float dl[VLN_NSLOT];
   __shared__ int cvs[VLN_NSLOT];
   const int b = blockIdx.x, t = threadIdx.x;
@@ -287,6 +314,8 @@ __global__ void __launch_bounds__(kThreads) cand_logits_bwd_kernel(
   }
   __syncthreads();
   const uint32_t thr = drop_threshold(drop_p);
+  uint64_t seed = 0, offset = 0;
+  if (drop_p > 0.f) { seed = rng[0]; offset = rng[1] + call_off; }
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int j = 0; j < n; ++j) {
     uint4 x = __ldg(reinterpret_cast<const uint4*>(table + ((size_t)g * VLN_V + cvs[j]) * VLN_IMG) + t);
@@ -337,13 +366,25 @@ extern "C" int vln_gather_cand(const vln_ctx* ctx, const int32_t* vp, const int3
   return 0;
 }
 
+extern "C" int vln_gather_action_feat(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                                      const int32_t* action, const uint8_t* ended, const int32_t* cand_view,
+                                      const float* cand_ang4, const int32_t* n_cand, float* out, int B,
+                                      void* stream) {
+  VLN_REQUIRE(ctx && vp && view && action && cand_view && cand_ang4 && n_cand && out && B > 0, "bad arguments");
+  gather_action_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(ctx->table, vp, view, action, ended, cand_view,
+                                                                cand_ang4, n_cand, out);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
                              const float* vec, float* attn_io, float* out, int B, int mode, float drop_p,
-                             uint64_t seed, uint64_t offset, int split, void* stream) {
+                             const uint64_t* rng, uint64_t call_off, int split, void* stream) {
   VLN_REQUIRE(ctx && vp && view && loc4 && vec && attn_io && out && B > 0, "bad arguments");
   VLN_REQUIRE(split == 1 || split == 2 || split == 4 || split == 8, "split must be 1, 2, 4 or 8");
   VLN_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (forward) or 1 (backward)");
   VLN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");
+  VLN_REQUIRE(drop_p == 0.f || rng, "dropout needs an rng state");
   const int FS = VLN_IMG / split;
   const size_t smem = pano_smem_bytes(FS);
   static size_t configured = 0;
@@ -364,17 +405,17 @@ extern "C" int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pano_attn_kernel, ctx->tmap_tile, vp, view, loc4, vec, attn_io, out, mode,
-                                    drop_p, seed, offset, FS));
+                                    drop_p, rng, call_off, FS));
   return 0;
 }
 
 extern "C" int vln_cand_logits_fwd(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
                                    const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
                                    const float* tgt, const float* bias, float* logits, int B, float drop_p,
-                                   uint64_t seed, uint64_t offset, void* stream) {
+                                   const uint64_t* rng, uint64_t call_off, void* stream) {
   VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && tgt && logits && B > 0, "bad arguments");
   cand_logits_fwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(ctx->table, vp, view, cand_view, cand_ang4, n_cand, tgt,
-                                                             bias, logits, drop_p, seed, offset);
+                                                             bias, logits, drop_p, rng, call_off);
   VLN_LAUNCH_OK();
   return 0;
 }
@@ -382,10 +423,10 @@ extern "C" int vln_cand_logits_fwd(const vln_ctx* ctx, const int32_t* vp, const 
 extern "C" int vln_cand_logits_bwd(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
                                    const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
                                    const float* dlogits, float* d_tgt, float* d_bias, int B, float drop_p,
-                                   uint64_t seed, uint64_t offset, void* stream) {
+                                   const uint64_t* rng, uint64_t call_off, void* stream) {
   VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && dlogits && d_tgt && B > 0, "bad arguments");
   cand_logits_bwd_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(ctx->table, vp, view, cand_view, cand_ang4, n_cand,
-                                                                  dlogits, d_tgt, d_bias, drop_p, seed, offset);
+                                                                  dlogits, d_tgt, d_bias, drop_p, rng, call_off);
   VLN_LAUNCH_OK();
   return 0;
 }

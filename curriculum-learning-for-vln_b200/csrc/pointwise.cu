@@ -48,7 +48,7 @@ __global__ void lstm_pw_bwd_kernel(const float* __restrict__ acts, const float* 
 
 // ---- action head: one warp per episode, 16 slots -------------------------------------------------
 __global__ void policy_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ target, int feedback,
-                                  uint64_t seed, uint64_t offset, float* __restrict__ ce, int32_t* __restrict__ action,
+                                  const uint64_t* __restrict__ rng, uint64_t call_off, float* __restrict__ ce, int32_t* __restrict__ action,
                                   float* __restrict__ logp, float* __restrict__ entropy, float* __restrict__ probs,
                                   int B) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -68,7 +68,7 @@ __global__ void policy_fwd_kernel(const float* __restrict__ logits, const int32_
     const unsigned hit = __ballot_sync(0xffffffffu, x == m);
     act = __ffs(hit) - 1;
   } else {                                                // inverse-CDF sample, u ~ Philox(seed, offset, b)
-    const float u = philox_uniform(philox8(seed, offset, (uint64_t)b), 0);
+    const float u = philox_uniform(philox8(rng[0], rng[1] + call_off, (uint64_t)b), 0);
     float cdf = p;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -106,12 +106,12 @@ __global__ void policy_bwd_kernel(const float* __restrict__ probs, const int32_t
 }
 
 // ---- dropout ----------------------------------------------------------------------------------
-__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p, uint64_t seed,
-                               uint64_t offset) {
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
+                               const uint64_t* __restrict__ rng, uint64_t call_off) {
   const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t e0 = blk * 8;
   if (e0 >= n) return;
-  const Philox8 r = philox8(seed, offset, (uint64_t)blk);
+  const Philox8 r = philox8(rng[0], rng[1] + call_off, (uint64_t)blk);
   const uint32_t thr = drop_threshold(p);
   const float sc = 1.0f / (1.0f - p);
 #pragma unroll
@@ -119,11 +119,14 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
     if (e0 + j < n) y[e0 + j] = philox_keep(r, j, thr) ? x[e0 + j] * sc : 0.f;
 }
 
-__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, uint64_t seed, uint64_t offset) {
+__global__ void rng_advance_kernel(uint64_t* rng, uint64_t delta) { rng[1] += delta; }
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float p, const uint64_t* __restrict__ rng,
+                                    uint64_t call_off) {
   const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t e0 = blk * 8;
   if (e0 >= n) return;
-  const Philox8 r = philox8(seed, offset, (uint64_t)blk);
+  const Philox8 r = philox8(rng[0], rng[1] + call_off, (uint64_t)blk);
   const uint32_t thr = drop_threshold(p);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -154,40 +157,102 @@ __global__ void env_observe_kernel(const int32_t* __restrict__ vp, const uint8_t
   if (dist) dist[b] = dist_tbl[sq_off[cur] + vp_local[g]];
 }
 
-__global__ void env_step_kernel(int32_t* __restrict__ vp, int32_t* __restrict__ view, uint8_t* __restrict__ ended,
+__global__ void env_step_kernel(const int32_t* __restrict__ vp_in, const int32_t* __restrict__ view_in,
+                                const uint8_t* __restrict__ ended_in, const float* __restrict__ dist_in,
                                 const int32_t* __restrict__ goal, const int32_t* __restrict__ action,
                                 const int32_t* __restrict__ cand_vp, const int32_t* __restrict__ cand_view,
                                 const int32_t* __restrict__ n_cand, const int32_t* __restrict__ next_hop,
                                 const float* __restrict__ dist_tbl, const int64_t* __restrict__ sq_off,
-                                const int32_t* __restrict__ vp_local, float* __restrict__ last_dist,
-                                int32_t* __restrict__ teacher, float* __restrict__ reward, float* __restrict__ mask,
+                                const int32_t* __restrict__ vp_local, int32_t* __restrict__ vp_out,
+                                int32_t* __restrict__ view_out, uint8_t* __restrict__ ended_out,
+                                float* __restrict__ dist_out, int32_t* __restrict__ teacher,
+                                float* __restrict__ reward, float* __restrict__ mask, int32_t* __restrict__ n_active,
                                 int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  int cur = vp[b];
-  const int g = goal[b];
-  const bool was_ended = ended[b] != 0;
-  const int a = action[b];
-  const bool stop = was_ended || a < 0 || a >= n_cand[cur];       // envdrop.py:198-203
-  if (!stop) {
-    view[b] = cand_view[(size_t)cur * VLN_CMAX + a];              // agent turns to the view, then steps (misc.py:366-390)
-    cur = cand_vp[(size_t)cur * VLN_CMAX + a];
-    vp[b] = cur;
-  }
-  const float d = dist_tbl[sq_off[cur] + vp_local[g]];
-  if (reward) {                                                   // envdrop.py:207-213
-    float r = 0.f;
-    if (!was_ended) {
-      if (stop) r = d < 3.0f ? 2.f : -2.f;
-      else { const float dd = last_dist[b] - d; r = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f); }
+  bool running = false;
+  if (b < B) {
+    int cur = vp_in[b], vw = view_in[b];
+    const int g = goal[b];
+    const bool was_ended = ended_in[b] != 0;
+    const int a = action[b];
+    const bool stop = was_ended || a < 0 || a >= n_cand[cur];       // envdrop.py:198-203
+    if (!stop) {
+      vw = cand_view[(size_t)cur * VLN_CMAX + a];                   // agent turns to the view, then steps (misc.py:366-390)
+      cur = cand_vp[(size_t)cur * VLN_CMAX + a];
     }
-    reward[b] = r;
+    vp_out[b] = cur;
+    view_out[b] = vw;
+    const float d = dist_tbl[sq_off[cur] + vp_local[g]];
+    if (reward) {                                                   // envdrop.py:207-213
+      float r = 0.f;
+      if (!was_ended) {
+        if (stop) r = d < 3.0f ? 2.f : -2.f;
+        else { const float dd = dist_in[b] - d; r = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f); }
+      }
+      reward[b] = r;
+    }
+    if (mask) mask[b] = was_ended ? 0.f : 1.f;
+    dist_out[b] = d;
+    const bool now_ended = was_ended || stop;
+    ended_out[b] = now_ended ? 1 : 0;
+    running = !now_ended;
+    if (teacher) teacher[b] = now_ended ? -1 : teacher_slot(cur, g, cand_vp, n_cand, next_hop, sq_off, vp_local);
   }
-  if (mask) mask[b] = was_ended ? 0.f : 1.f;
-  last_dist[b] = d;
-  const bool now_ended = was_ended || stop;
-  ended[b] = now_ended ? 1 : 0;
-  if (teacher) teacher[b] = now_ended ? -1 : teacher_slot(cur, g, cand_vp, n_cand, next_hop, sq_off, vp_local);
+  if (n_active) {
+    const unsigned m = __ballot_sync(0xffffffffu, running);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_active, __popc(m));
+  }
+}
+
+// ---- A2C loss assembly (envdrop.py:240-264): one thread per episode, backwards in time ---------------
+__global__ void a2c_fwd_kernel(const float* __restrict__ reward, const float* __restrict__ mask,
+                               const float* __restrict__ logp, const float* __restrict__ entropy,
+                               const float* __restrict__ value, const float* __restrict__ last_value,
+                               const uint8_t* __restrict__ ended, float gamma, float ent_coef,
+                               float* __restrict__ loss_b, float* __restrict__ ret, float* __restrict__ total,
+                               float* __restrict__ critic_sq, int T, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float tot = 0.f, csq = 0.f;
+  if (b < B) {
+    const float lv = ended[b] ? 0.f : last_value[b];               // (~ended) * last_value, float32
+    double R = 0.0;
+    float acc = 0.f;
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t i = (size_t)t * B + b;
+      // numpy promotion: the first product is float32 * python float, every later one float64
+      R = (t == T - 1 ? (double)(lv * gamma) : R * (double)gamma) + (double)reward[i];
+      const double m = mask[i];
+      const double adv = R - (double)value[i];
+      float cur = (float)(-(double)logp[i] * adv * m);
+      cur = (float)((double)cur + adv * adv * m * 0.5);
+      if (ent_coef != 0.f) cur = (float)((double)cur + (double)(-ent_coef * entropy[i]) * m);
+      acc += cur;
+      ret[i] = (float)R;
+      tot += mask[i];
+      csq += (float)(adv * adv * m);
+    }
+    loss_b[b] = acc;
+  }
+  tot = warp_sum(tot);
+  csq = warp_sum(csq);
+  if ((threadIdx.x & 31) == 0) {
+    if (total) atomicAdd(total, tot);
+    if (critic_sq) atomicAdd(critic_sq, csq);
+  }
+}
+
+__global__ void a2c_bwd_kernel(const float* __restrict__ g_b, const float* __restrict__ mask,
+                               const float* __restrict__ value, const float* __restrict__ ret, float ent_coef,
+                               float* __restrict__ d_logp, float* __restrict__ d_value,
+                               float* __restrict__ d_entropy, int T, int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * B) return;
+  const int b = idx % B;
+  const float g = g_b[b] * mask[idx];
+  const float adv = ret[idx] - value[idx];
+  d_logp[idx] = -g * adv;
+  d_value[idx] = -g * adv;
+  if (d_entropy) d_entropy[idx] = -g * ent_coef;
 }
 
 // ---- gradient clip + optimiser ----------------------------------------------------------------------
@@ -270,12 +335,13 @@ extern "C" int vln_lstm_pointwise_bwd(const float* acts, const float* c0, const 
   return 0;
 }
 
-extern "C" int vln_policy_fwd(const float* logits, const int32_t* target, int feedback, uint64_t seed,
-                              uint64_t offset, float* ce, int32_t* action, float* logp, float* entropy, float* probs,
+extern "C" int vln_policy_fwd(const float* logits, const int32_t* target, int feedback, const uint64_t* rng,
+                              uint64_t call_off, float* ce, int32_t* action, float* logp, float* entropy, float* probs,
                               int B, void* stream) {
   VLN_REQUIRE(logits && B > 0 && feedback >= 0 && feedback <= 2, "bad arguments");
   VLN_REQUIRE(feedback != 0 || target, "teacher feedback needs targets");
-  policy_fwd_kernel<<<(B + 3) / 4, 128, 0, STREAM>>>(logits, target, feedback, seed, offset, ce, action, logp, entropy,
+  VLN_REQUIRE(feedback != 2 || rng, "sampling needs an rng state");
+  policy_fwd_kernel<<<(B + 3) / 4, 128, 0, STREAM>>>(logits, target, feedback, rng, call_off, ce, action, logp, entropy,
                                                      probs, B);
   VLN_LAUNCH_OK();
   return 0;
@@ -294,19 +360,27 @@ extern "C" int vln_policy_bwd(const float* probs, const int32_t* target, const i
   return 0;
 }
 
-extern "C" int vln_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
-                           void* stream) {
-  VLN_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
-  const int64_t blks = (n + 7) / 8;
-  dropout_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(x, y, n, p, seed, offset);
+extern "C" int vln_rng_advance(uint64_t* rng, uint64_t delta, void* stream) {
+  VLN_REQUIRE(rng, "bad arguments");
+  rng_advance_kernel<<<1, 1, 0, STREAM>>>(rng, delta);
   VLN_LAUNCH_OK();
   return 0;
 }
 
-extern "C" int vln_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
-  VLN_REQUIRE(mask && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
+extern "C" int vln_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* rng, uint64_t call_off,
+                           void* stream) {
+  VLN_REQUIRE(x && y && rng && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
   const int64_t blks = (n + 7) / 8;
-  dropout_mask_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(mask, n, p, seed, offset);
+  dropout_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(x, y, n, p, rng, call_off);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_dropout_mask(uint8_t* mask, int64_t n, float p, const uint64_t* rng, uint64_t call_off,
+                                void* stream) {
+  VLN_REQUIRE(mask && rng && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
+  const int64_t blks = (n + 7) / 8;
+  dropout_mask_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(mask, n, p, rng, call_off);
   VLN_LAUNCH_OK();
   return 0;
 }
@@ -322,17 +396,43 @@ extern "C" int vln_env_observe(const int32_t* vp, const uint8_t* ended, const in
   return 0;
 }
 
-extern "C" int vln_env_step(int32_t* vp, int32_t* view, uint8_t* ended, const int32_t* goal, const int32_t* action,
+extern "C" int vln_env_step(const int32_t* vp_in, const int32_t* view_in, const uint8_t* ended_in,
+                            const float* dist_in, const int32_t* goal, const int32_t* action,
                             const int32_t* cand_vp, const int32_t* cand_view, const int32_t* n_cand,
                             const int32_t* next_hop, const float* dist_tbl, const int64_t* sq_off,
-                            const int32_t* vp_local, float* last_dist, int32_t* teacher, float* reward, float* mask,
-                            int B, void* stream) {
-  VLN_REQUIRE(vp && view && ended && goal && action && cand_vp && cand_view && n_cand && next_hop && dist_tbl &&
-                  sq_off && vp_local && last_dist && B > 0,
+                            const int32_t* vp_local, int32_t* vp_out, int32_t* view_out, uint8_t* ended_out,
+                            float* dist_out, int32_t* teacher, float* reward, float* mask, int32_t* n_active, int B,
+                            void* stream) {
+  VLN_REQUIRE(vp_in && view_in && ended_in && dist_in && goal && action && cand_vp && cand_view && n_cand &&
+                  next_hop && dist_tbl && sq_off && vp_local && vp_out && view_out && ended_out && dist_out && B > 0,
               "bad arguments");
-  env_step_kernel<<<(B + 127) / 128, 128, 0, STREAM>>>(vp, view, ended, goal, action, cand_vp, cand_view, n_cand,
-                                                       next_hop, dist_tbl, sq_off, vp_local, last_dist, teacher, reward,
-                                                       mask, B);
+  env_step_kernel<<<(B + 127) / 128, 128, 0, STREAM>>>(vp_in, view_in, ended_in, dist_in, goal, action, cand_vp,
+                                                       cand_view, n_cand, next_hop, dist_tbl, sq_off, vp_local, vp_out,
+                                                       view_out, ended_out, dist_out, teacher, reward, mask, n_active,
+                                                       B);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_a2c_fwd(const float* reward, const float* mask, const float* logp, const float* entropy,
+                           const float* value, const float* last_value, const uint8_t* ended, float gamma,
+                           float ent_coef, float* loss_b, float* ret, float* total, float* critic_sq, int T, int B,
+                           void* stream) {
+  VLN_REQUIRE(reward && mask && logp && value && last_value && ended && loss_b && ret && T > 0 && B > 0,
+              "bad arguments");
+  VLN_REQUIRE(ent_coef == 0.f || entropy, "entropy term needs the entropies");
+  a2c_fwd_kernel<<<(B + 127) / 128, 128, 0, STREAM>>>(reward, mask, logp, entropy, value, last_value, ended, gamma,
+                                                      ent_coef, loss_b, ret, total, critic_sq, T, B);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_a2c_bwd(const float* g_b, const float* mask, const float* value, const float* ret,
+                           float ent_coef, float* d_logp, float* d_value, float* d_entropy, int T, int B,
+                           void* stream) {
+  VLN_REQUIRE(g_b && mask && value && ret && d_logp && d_value && T > 0 && B > 0, "bad arguments");
+  a2c_bwd_kernel<<<(T * B + 255) / 256, 256, 0, STREAM>>>(g_b, mask, value, ret, ent_coef, d_logp, d_value,
+                                                          d_entropy, T, B);
   VLN_LAUNCH_OK();
   return 0;
 }

@@ -1,0 +1,109 @@
+"""Flat-buffer optimiser: one fp32 parameter buffer, one gradient buffer, one NCCL all-reduce,
+one fused clip + update kernel.
+
+Replaces the reference's per-tensor sequence  zero_grad -> backward -> clip_grad_norm(encoder, 40)
+-> clip_grad_norm(decoder, 40) -> RMSprop/Adam.step  (trainer.py:102-113, 265-270, 423-427;
+curriculum.py:91-95, 303-308).  Parameters of each module group are laid out contiguously so
+"clip the encoder" is a range of the flat buffer; every parameter tensor becomes a view of the
+buffer (state_dict keys and shapes are untouched) and every ``.grad`` a view of the gradient
+buffer, so autograd accumulates straight into the buffer that NCCL reduces.
+
+Data parallel: gradients are summed over ranks by ONE all-reduce of the flat buffer
+and scaled by 1/world inside the update kernel — the result equals the mean of the per-rank
+gradients, each rank having run a reference-sized batch.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+
+KIND = {"rmsprop": 0, "adam": 1}
+
+
+class FlatOptimizer:
+    def __init__(self, groups, lr, kind="adam", max_norms=None, process_group=None):
+        """groups: list of parameter lists (e.g. [encoder params, decoder params, critic params]);
+        max_norms: per-group clip threshold (None / 0 = unclipped)."""
+        assert 1 <= len(groups) <= 4
+        self.kind = KIND[kind] if isinstance(kind, str) else int(kind)
+        self.lr = float(lr)
+        self.pg = process_group
+        params = [p for g in groups for p in g]
+        dev = params[0].device
+        assert dev.type == "cuda", "FlatOptimizer runs the fused CUDA update; parameters must be on the GPU"
+        sizes = [sum(p.numel() for p in g) for g in groups]
+        # pad each group to a multiple of 4 floats so views stay 16-byte aligned
+        offs, total = [0], 0
+        for s in sizes:
+            total += (s + 3) // 4 * 4
+            offs.append(total)
+        self.flat = torch.zeros(total, device=dev)
+        self.grad = torch.zeros(total, device=dev)
+        self.s1 = torch.zeros(total, device=dev)
+        self.s2 = torch.zeros(total, device=dev) if self.kind == 1 else None
+        self.sqnorm = torch.zeros(len(groups), device=dev)
+        self.params = params
+        for gi, g in enumerate(groups):
+            o = offs[gi]
+            for p in g:
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+                o += n
+        self._off = (C.c_int64 * (len(groups) + 1))(*offs)
+        mn = [float(m or 0.0) for m in (max_norms or [0.0] * len(groups))]
+        self._max = (C.c_float * len(groups))(*mn)
+        self.n_groups = len(groups)
+        self.step_count = 0
+        self.world = dist.get_world_size(self.pg) if dist.is_available() and dist.is_initialized() else 1
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+        for p in self.params:               # autograd may have replaced .grad; re-point it at the flat buffer
+            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr() or \
+                    p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
+                self._rebind()
+                break
+
+    def _rebind(self):
+        o_by_ptr = self.flat.data_ptr()
+        for p in self.params:
+            o = (p.data.data_ptr() - o_by_ptr) // 4
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def step(self):
+        scale = 1.0
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            scale = 1.0 / self.world
+        self.step_count += 1
+        ops._call("vln_grad_sqnorm", ops._ptr(self.grad), self._off, self.n_groups, ops._ptr(self.sqnorm), scale,
+                  ops._stream())
+        ops._call("vln_optim_step", ops._ptr(self.flat), ops._ptr(self.grad), ops._ptr(self.s1), ops._ptr(self.s2),
+                  self._off, self._max, self.n_groups, ops._ptr(self.sqnorm), scale, self.kind, self.lr,
+                  self.step_count, ops._stream())
+
+    def state_dict(self):
+        return {"s1": self.s1, "s2": self.s2, "step": self.step_count, "lr": self.lr, "kind": self.kind}
+
+    def load_state_dict(self, sd):
+        self.s1.copy_(sd["s1"])
+        if self.s2 is not None and sd.get("s2") is not None:
+            self.s2.copy_(sd["s2"])
+        self.step_count = int(sd["step"])
+
+
+def build_optimizer(cfg, agent, process_group=None):
+    """The reference's optimiser choice per agent: EnvDrop — one optimiser over encoder + decoder +
+    critic with the encoder and decoder clipped to 40 separately (trainer.py:380-381, 423-427);
+    Follower / Self-Monitor — Adam/RMSprop without clipping (trainer.py:66-67, 220)."""
+    kind = cfg.TRAIN.OPTIM if cfg.TRAIN.OPTIM in KIND else "adam"
+    groups = [[p for p in m.parameters() if p.requires_grad] for m in agent._modules()]
+    if cfg.MODEL.NAME == "ENVDROP":
+        max_norms = [40.0, 40.0, 0.0]
+    else:
+        max_norms = [0.0] * len(groups)
+    return FlatOptimizer(groups, cfg.TRAIN.LR, kind, max_norms, process_group)

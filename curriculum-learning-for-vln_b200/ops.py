@@ -1,10 +1,12 @@
-"""Torch-facing wrappers of the C-ABI kernels: a FeatureStore (HBM tables + TMA context) and
-torch.autograd.Function adapters.  PyTorch is plumbing here (memory, streams, autograd tape);
-the arithmetic runs in csrc/.
+"""Torch-facing wrappers of the C-ABI kernels: a FeatureStore (HBM tables + TMA context), lazy
+feature views, and torch.autograd.Function adapters.  PyTorch is plumbing here (memory, streams,
+autograd tape); the arithmetic runs in csrc/.  There is no CPU path: every op needs CUDA tensors
+and the built library.
 """
 import ctypes as C
 
 import torch
+import torch.nn.functional as F
 
 from . import _lib
 
@@ -30,19 +32,45 @@ def _f32c(t):
 
 def _i32c(t):
     assert t.is_cuda, "expected a CUDA tensor"
-    return t.to(torch.int32).contiguous()
+    return t if (t.dtype == torch.int32 and t.is_contiguous()) else t.to(torch.int32).contiguous()
+
+
+def _call(name, *args):
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
 
 
 class Rng:
-    """Philox stream bookkeeping: one seed, a fresh offset per dropout / sampling call site."""
+    """Philox stream bookkeeping.  ``state`` is a device int64[2] = {seed, base}; every dropout /
+    sampling call site takes the next ``call_off`` and its kernel draws from stream
+    (seed, base + call_off).  ``advance()`` moves the base on the device, so a captured CUDA graph
+    gets fresh masks on every replay.  ``log`` (when a list) records (tag, shape, p, call_off) of
+    every dropout site so tests can regenerate the very same masks for the oracle."""
 
-    def __init__(self, seed=2020):
-        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self.offset = 0
+    def __init__(self, seed=2020, device="cuda"):
+        self.state = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        self.off = 0
+        self.log = None
 
-    def next(self):
-        self.offset += 1
-        return self.seed, self.offset
+    def next(self, tag=None, shape=None, p=None):
+        self.off += 1
+        if self.log is not None and tag is not None:
+            self.log.append((tag, tuple(shape), float(p), self.off))
+        return self.off
+
+    def advance(self):
+        """Consume the offsets handed out since the last advance (device-side base += n)."""
+        n, self.off = self.off, 0
+        if n:
+            _call("vln_rng_advance", _ptr(self.state), n, _stream())
+
+    def begin_iteration(self):
+        """Restart call-site numbering (the same sites get the same call_off every iteration — a
+        requirement for graph replay) after moving the base past the previous iteration."""
+        self.advance()
+
+    @property
+    def ptr(self):
+        return _ptr(self.state)
 
 
 class FeatureStore:
@@ -59,11 +87,12 @@ class FeatureStore:
         self.n_vp = self.table.shape[0]
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _lib.check(_lib.lib().vln_ctx_create(C.byref(h), _ptr(self.table), self.n_vp, idx), "vln_ctx_create")
+        _call("vln_ctx_create", C.byref(h), _ptr(self.table), self.n_vp, idx)
         self.handle = h
         for k in ("loc4", "pose4", "cand_vp", "cand_view", "cand_ang4", "n_cand", "next_hop", "dist", "sq_off",
                   "vp_local"):
             setattr(self, k, tables[k])
+        self.pose128 = self.pose4.repeat_interleave(32, dim=1).contiguous()      # [36,128]
 
     @classmethod
     def from_world(cls, world, device):
@@ -78,13 +107,45 @@ class FeatureStore:
             pass
 
 
+class PanoView:
+    """Stands for the reference's ``img_feature`` tensor [B,36,2176] (base.py:141-147) without
+    materialising it: the rows live in the HBM table, keyed by (viewpoint, current view)."""
+
+    def __init__(self, store, vp, view):
+        self.store, self.vp, self.view = store, _i32c(vp), _i32c(view)
+        self.shape = (self.vp.shape[0], N_VIEWS, F_DIM)
+
+    def dense(self):
+        return gather_pano(self.store, self.vp, self.view)
+
+
+class CandView:
+    """Stands for ``candidate_feat`` [B,C,2176] + ``candidate_leng`` (base.py:149-157)."""
+
+    def __init__(self, store, vp, view):
+        self.store, self.vp, self.view = store, _i32c(vp), _i32c(view)
+        self.shape = (self.vp.shape[0], NSLOT, F_DIM)
+
+    def dense(self):
+        return gather_cand(self.store, self.vp, self.view)[0]
+
+    def lengths(self):
+        return self.store.n_cand[self.vp.long()] + 1
+
+
+# ---- GEMM-shaped pieces ---------------------------------------------------------------------------
+def linear(x, w, b=None):
+    """y = x W^T + b.  Plain library GEMM (cuBLAS through torch) until the tcgen05 path replaces it
+    for the LSTM gates."""
+    return F.linear(x, w, b)
+
+
 # ---- bit-exact gathers ---------------------------------------------------------------------------
 def gather_pano(store, vp, view):
     vp, view = _i32c(vp), _i32c(view)
     B = vp.shape[0]
     out = torch.empty((B, N_VIEWS, F_DIM), device=vp.device, dtype=torch.float32)
-    _lib.check(_lib.lib().vln_gather_pano(store.handle, _ptr(vp), _ptr(view), _ptr(store.loc4), _ptr(out), B,
-                                          _stream()), "vln_gather_pano")
+    _call("vln_gather_pano", store.handle, _ptr(vp), _ptr(view), _ptr(store.loc4), _ptr(out), B, _stream())
     return out
 
 
@@ -93,34 +154,42 @@ def gather_cand(store, vp, view, C_slots=NSLOT):
     B = vp.shape[0]
     out = torch.empty((B, C_slots, F_DIM), device=vp.device, dtype=torch.float32)
     lens = torch.empty((B,), device=vp.device, dtype=torch.int32)
-    _lib.check(_lib.lib().vln_gather_cand(store.handle, _ptr(vp), _ptr(view), _ptr(store.cand_view),
-                                          _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(out), _ptr(lens), B,
-                                          C_slots, _stream()), "vln_gather_cand")
+    _call("vln_gather_cand", store.handle, _ptr(vp), _ptr(view), _ptr(store.cand_view), _ptr(store.cand_ang4),
+          _ptr(store.n_cand), _ptr(out), _ptr(lens), B, C_slots, _stream())
     return out, lens
+
+
+def gather_action_feat(store, vp, view, action, ended=None):
+    """a_t_prev = cands[b, max(cpu_a_t,0)] (follower.py:141-164, monitor.py:177-191): [B,2176]."""
+    vp, view, action = _i32c(vp), _i32c(view), _i32c(action)
+    B = vp.shape[0]
+    out = torch.empty((B, F_DIM), device=vp.device, dtype=torch.float32)
+    _call("vln_gather_action_feat", store.handle, _ptr(vp), _ptr(view), _ptr(action), _ptr(ended), _ptr(store.cand_view),
+          _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(out), B, _stream())
+    return out
 
 
 def pose_feature(store, view):
     """make_angle_feat(heading, elevation) of the agent's pose (envdrop.py:76-78): [B,128]."""
-    return store.pose4[view.long()].repeat_interleave(32, dim=1)
+    return store.pose128[view.long()]
 
 
 # ---- fused gather + panorama attention ---------------------------------------------------------
-def pano_attn_raw(store, vp, view, vec, attn, mode, drop_p=0.0, seed=0, offset=0, split=4):
+def pano_attn_raw(store, vp, view, vec, attn, mode, drop_p=0.0, rng=None, call_off=0, split=4, aux=None):
     B = vp.shape[0]
     out = torch.empty((B, F_DIM), device=vec.device, dtype=torch.float32)
-    _lib.check(_lib.lib().vln_pano_attn(store.handle, _ptr(vp), _ptr(view), _ptr(store.loc4), _ptr(vec), _ptr(attn),
-                                        _ptr(out), B, mode, float(drop_p), seed, offset, split, _stream()),
-               "vln_pano_attn")
+    _call("vln_pano_attn", store.handle, _ptr(vp), _ptr(view), _ptr(store.loc4), _ptr(vec), _ptr(attn),
+          _ptr(out), B, mode, float(drop_p), rng.ptr if rng is not None else None, call_off, split, _stream())
     return out
 
 
 class _PanoAttn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, store, vp, view, drop_p, seed, offset, split):
+    def forward(ctx, q, store, vp, view, drop_p, rng, call_off, split):
         q = _f32c(q)
         attn = torch.empty((q.shape[0], N_VIEWS), device=q.device, dtype=torch.float32)
-        out = pano_attn_raw(store, vp, view, q, attn, 0, drop_p, seed, offset, split)
-        ctx.store, ctx.cfg = store, (drop_p, seed, offset, split)
+        out = pano_attn_raw(store, vp, view, q, attn, 0, drop_p, rng, call_off, split)
+        ctx.store, ctx.cfg = store, (drop_p, rng, call_off, split)
         ctx.save_for_backward(vp, view, attn)
         ctx.mark_non_differentiable(attn)
         return out, attn
@@ -128,54 +197,52 @@ class _PanoAttn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, _d_attn):
         vp, view, attn = ctx.saved_tensors
-        drop_p, seed, offset, split = ctx.cfg
-        dq = pano_attn_raw(ctx.store, vp, view, _f32c(d_out), attn, 1, drop_p, seed, offset, split)
+        drop_p, rng, call_off, split = ctx.cfg
+        dq = pano_attn_raw(ctx.store, vp, view, _f32c(d_out), attn, 1, drop_p, rng, call_off, split)
         return dq, None, None, None, None, None, None, None
 
 
-def pano_attn(store, vp, view, q, drop_p=0.0, seed=0, offset=0, split=4):
+def pano_attn(store, vp, view, q, drop_p=0.0, rng=None, call_off=0, split=4):
     """(weighted [B,2176], attn [B,36]) = softmax_v(x~_v . q) over the episode's panorama."""
-    return _PanoAttn.apply(q, store, _i32c(vp), _i32c(view), drop_p, seed, offset, split)
+    return _PanoAttn.apply(q, store, _i32c(vp), _i32c(view), drop_p, rng, call_off, split)
 
 
 # ---- candidate logits -----------------------------------------------------------------------------
 class _CandLogits(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tgt, bias, store, vp, view, drop_p, seed, offset):
+    def forward(ctx, tgt, bias, store, vp, view, drop_p, rng, call_off):
         tgt = _f32c(tgt)
         bias = _f32c(bias) if bias is not None else None
         B = tgt.shape[0]
         logits = torch.empty((B, NSLOT), device=tgt.device, dtype=torch.float32)
-        _lib.check(_lib.lib().vln_cand_logits_fwd(store.handle, _ptr(vp), _ptr(view), _ptr(store.cand_view),
-                                                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(tgt), _ptr(bias),
-                                                  _ptr(logits), B, float(drop_p), seed, offset, _stream()),
-                   "vln_cand_logits_fwd")
-        ctx.store, ctx.cfg, ctx.has_bias = store, (drop_p, seed, offset), bias is not None
+        _call("vln_cand_logits_fwd", store.handle, _ptr(vp), _ptr(view), _ptr(store.cand_view),
+              _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(tgt), _ptr(bias), _ptr(logits), B, float(drop_p),
+              rng.ptr if rng is not None else None, call_off, _stream())
+        ctx.store, ctx.cfg, ctx.has_bias = store, (drop_p, rng, call_off), bias is not None
         ctx.save_for_backward(vp, view)
         return logits
 
     @staticmethod
     def backward(ctx, d_logits):
         vp, view = ctx.saved_tensors
-        drop_p, seed, offset = ctx.cfg
+        drop_p, rng, call_off = ctx.cfg
         store = ctx.store
         d_logits = _f32c(d_logits)
         B = d_logits.shape[0]
         d_tgt = torch.empty((B, F_DIM), device=d_logits.device, dtype=torch.float32)
         d_bias = torch.empty((B,), device=d_logits.device, dtype=torch.float32) if ctx.has_bias else None
-        _lib.check(_lib.lib().vln_cand_logits_bwd(store.handle, _ptr(vp), _ptr(view), _ptr(store.cand_view),
-                                                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(d_logits),
-                                                  _ptr(d_tgt), _ptr(d_bias), B, float(drop_p), seed, offset,
-                                                  _stream()), "vln_cand_logits_bwd")
+        _call("vln_cand_logits_bwd", store.handle, _ptr(vp), _ptr(view), _ptr(store.cand_view),
+              _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(d_logits), _ptr(d_tgt), _ptr(d_bias), B,
+              float(drop_p), rng.ptr if rng is not None else None, call_off, _stream())
         return d_tgt, d_bias, None, None, None, None, None, None
 
 
-def cand_logits(store, vp, view, tgt, bias=None, drop_p=0.0, seed=0, offset=0):
+def cand_logits(store, vp, view, tgt, bias=None, drop_p=0.0, rng=None, call_off=0):
     """[B,16] masked candidate logits straight from the table (no [B,C,2176] tensor)."""
-    return _CandLogits.apply(tgt, bias, store, _i32c(vp), _i32c(view), drop_p, seed, offset)
+    return _CandLogits.apply(tgt, bias, store, _i32c(vp), _i32c(view), drop_p, rng, call_off)
 
 
-# ---- instruction-context attention ------------------------------------------------------------------
+# ---- soft-dot attention over a dense context (instruction ctx, or a materialised feature tensor) ----
 class _CtxAttn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, context, tgt, lengths):
@@ -183,8 +250,8 @@ class _CtxAttn(torch.autograd.Function):
         B, L, H = context.shape
         attn = torch.empty((B, L), device=tgt.device, dtype=torch.float32)
         weighted = torch.empty((B, H), device=tgt.device, dtype=torch.float32)
-        _lib.check(_lib.lib().vln_ctx_attn_fwd(_ptr(context), _ptr(tgt), _ptr(lengths), _ptr(attn), _ptr(weighted),
-                                               B, L, H, _stream()), "vln_ctx_attn_fwd")
+        _call("vln_ctx_attn_fwd", _ptr(context), _ptr(tgt), _ptr(lengths), _ptr(attn), _ptr(weighted), B, L, H,
+              _stream())
         ctx.save_for_backward(context, tgt, lengths, attn)
         return weighted, attn
 
@@ -193,18 +260,25 @@ class _CtxAttn(torch.autograd.Function):
         context, tgt, lengths, attn = ctx.saved_tensors
         B, L, H = context.shape
         d_tgt = torch.empty_like(tgt)
-        d_context = torch.zeros_like(context)
+        d_context = torch.zeros_like(context) if ctx.needs_input_grad[0] else None
         d_weighted = _f32c(d_weighted) if d_weighted is not None else torch.zeros_like(tgt)
         d_attn = _f32c(d_attn) if d_attn is not None else None
-        _lib.check(_lib.lib().vln_ctx_attn_bwd(_ptr(context), _ptr(tgt), _ptr(lengths), _ptr(attn), _ptr(d_weighted),
-                                               _ptr(d_attn), _ptr(d_tgt), _ptr(d_context), B, L, H, _stream()),
-                   "vln_ctx_attn_bwd")
+        _call("vln_ctx_attn_bwd", _ptr(context), _ptr(tgt), _ptr(lengths), _ptr(attn), _ptr(d_weighted),
+              _ptr(d_attn), _ptr(d_tgt), _ptr(d_context), B, L, H, _stream())
         return d_context, d_tgt, None
 
 
 def ctx_attn(context, tgt, lengths):
     """(weighted [B,H], attn [B,L]): softmax over the first lengths[b] rows of context[b]."""
     return _CtxAttn.apply(context, tgt, _i32c(lengths))
+
+
+def mask_to_lengths(mask, L):
+    """The reference passes boolean pad masks (True = masked, always a suffix: base.py:128,
+    misc.py:481-486); the kernels take the number of valid rows."""
+    if mask is None:
+        return None
+    return (L - mask.sum(1)).to(torch.int32)
 
 
 # ---- LSTM pointwise ----------------------------------------------------------------------------------
@@ -214,8 +288,7 @@ class _LstmPointwise(torch.autograd.Function):
         gates, c0 = _f32c(gates), _f32c(c0)
         B, H = c0.shape
         h1, c1, acts = torch.empty_like(c0), torch.empty_like(c0), torch.empty_like(gates)
-        _lib.check(_lib.lib().vln_lstm_pointwise_fwd(_ptr(gates), _ptr(c0), _ptr(h1), _ptr(c1), _ptr(acts), B, H,
-                                                     _stream()), "vln_lstm_pointwise_fwd")
+        _call("vln_lstm_pointwise_fwd", _ptr(gates), _ptr(c0), _ptr(h1), _ptr(c1), _ptr(acts), B, H, _stream())
         ctx.save_for_backward(acts, c0, c1)
         return h1, c1
 
@@ -226,14 +299,41 @@ class _LstmPointwise(torch.autograd.Function):
         d_gates, d_c0 = torch.empty_like(acts), torch.empty_like(c0)
         d_h1 = _f32c(d_h1) if d_h1 is not None else None
         d_c1 = _f32c(d_c1) if d_c1 is not None else None
-        _lib.check(_lib.lib().vln_lstm_pointwise_bwd(_ptr(acts), _ptr(c0), _ptr(c1), _ptr(d_h1), _ptr(d_c1),
-                                                     _ptr(d_gates), _ptr(d_c0), B, H, _stream()),
-                   "vln_lstm_pointwise_bwd")
+        _call("vln_lstm_pointwise_bwd", _ptr(acts), _ptr(c0), _ptr(c1), _ptr(d_h1), _ptr(d_c1), _ptr(d_gates),
+              _ptr(d_c0), B, H, _stream())
         return d_gates, d_c0
 
 
 def lstm_pointwise(gates, c0):
     return _LstmPointwise.apply(gates, c0)
+
+
+def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
+    """nn.LSTMCell (policy.py:53,159,238): gate GEMMs + fused pointwise kernel."""
+    gates = linear(torch.cat((x, h), 1), torch.cat((w_ih, w_hh), 1), b_ih + b_hh)
+    return lstm_pointwise(gates, c)
+
+
+def lstm_sequence(xproj, lengths, w_hh, reverse):
+    """One direction of a packed-sequence LSTM (units.py:58-71) with length masking instead of
+    packing: rows stop at their own length (reverse rows start there), outputs past the length are
+    zero, final (h, c) are the states at each row's last valid step.  ``xproj`` [B,L,4H] already
+    holds x W_ih^T + b_ih + b_hh."""
+    B, L, H4 = xproj.shape
+    H = H4 // 4
+    h = xproj.new_zeros(B, H)
+    c = xproj.new_zeros(B, H)
+    outs = [None] * L
+    order = range(L - 1, -1, -1) if reverse else range(L)
+    live_all = (torch.arange(L, device=xproj.device).unsqueeze(0) < lengths.unsqueeze(1))    # [B,L]
+    for t in order:
+        live = live_all[:, t:t + 1]
+        gates = xproj[:, t] + linear(h, w_hh)
+        h_new, c_new = lstm_pointwise(gates, c)
+        h = torch.where(live, h_new, h)
+        c = torch.where(live, c_new, c)
+        outs[t] = h_new * live
+    return torch.stack(outs, 1), h, c
 
 
 # ---- action head ---------------------------------------------------------------------------------------
@@ -242,7 +342,7 @@ FEEDBACK = {"teacher": 0, "argmax": 1, "sample": 2}
 
 class _Policy(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target, feedback, seed, offset):
+    def forward(ctx, logits, target, feedback, rng, call_off):
         logits = _f32c(logits)
         B = logits.shape[0]
         dev = logits.device
@@ -250,9 +350,8 @@ class _Policy(torch.autograd.Function):
         logp, ent = torch.empty_like(ce), torch.empty_like(ce)
         action = torch.empty((B,), device=dev, dtype=torch.int32)
         probs = torch.empty((B, NSLOT), device=dev, dtype=torch.float32)
-        _lib.check(_lib.lib().vln_policy_fwd(_ptr(logits), _ptr(target), feedback, seed, offset, _ptr(ce),
-                                             _ptr(action), _ptr(logp), _ptr(ent), _ptr(probs), B, _stream()),
-                   "vln_policy_fwd")
+        _call("vln_policy_fwd", _ptr(logits), _ptr(target), feedback, rng.ptr if rng is not None else None,
+              call_off, _ptr(ce), _ptr(action), _ptr(logp), _ptr(ent), _ptr(probs), B, _stream())
         ctx.save_for_backward(probs, target, action, ent)
         ctx.mark_non_differentiable(action)
         return ce, logp, ent, action
@@ -263,52 +362,52 @@ class _Policy(torch.autograd.Function):
         B = probs.shape[0]
         d = torch.empty_like(probs)
         g = [_f32c(x) if x is not None else None for x in (g_ce, g_logp, g_ent)]
-        _lib.check(_lib.lib().vln_policy_bwd(_ptr(probs), _ptr(target), _ptr(action), _ptr(ent), _ptr(g[0]),
-                                             _ptr(g[1]), _ptr(g[2]), _ptr(d), B, _stream()), "vln_policy_bwd")
+        if target is None:
+            g[0] = None
+        _call("vln_policy_bwd", _ptr(probs), _ptr(target), _ptr(action), _ptr(ent), _ptr(g[0]), _ptr(g[1]),
+              _ptr(g[2]), _ptr(d), B, _stream())
         return d, None, None, None, None
 
 
-def policy_head(logits, target, feedback, seed=0, offset=0):
+def policy_head(logits, target, feedback, rng=None, call_off=0):
     """logits [B,16] (-inf = masked) -> (ce [B], logp [B], entropy [B], action int32 [B])."""
     if logits.shape[1] != NSLOT:
         pad = logits.new_full((logits.shape[0], NSLOT - logits.shape[1]), float("-inf"))
         logits = torch.cat((logits, pad), 1)
     fb = FEEDBACK[feedback] if isinstance(feedback, str) else int(feedback)
-    return _Policy.apply(logits, _i32c(target) if target is not None else None, fb, seed, offset)
+    return _Policy.apply(logits, _i32c(target) if target is not None else None, fb, rng, call_off)
 
 
 # ---- dropout ----------------------------------------------------------------------------------------------
 class _Dropout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, p, seed, offset):
+    def forward(ctx, x, p, rng, call_off):
         x = _f32c(x)
         y = torch.empty_like(x)
-        _lib.check(_lib.lib().vln_dropout(_ptr(x), _ptr(y), x.numel(), float(p), seed, offset, _stream()),
-                   "vln_dropout")
-        ctx.cfg = (p, seed, offset)
+        _call("vln_dropout", _ptr(x), _ptr(y), x.numel(), float(p), rng.ptr, call_off, _stream())
+        ctx.cfg = (p, rng, call_off)
         return y
 
     @staticmethod
     def backward(ctx, g):
-        p, seed, offset = ctx.cfg
+        p, rng, call_off = ctx.cfg
         g = _f32c(g)
         y = torch.empty_like(g)
-        _lib.check(_lib.lib().vln_dropout(_ptr(g), _ptr(y), g.numel(), float(p), seed, offset, _stream()),
-                   "vln_dropout")
+        _call("vln_dropout", _ptr(g), _ptr(y), g.numel(), float(p), rng.ptr, call_off, _stream())
         return y, None, None, None
 
 
-def dropout(x, p, seed, offset):
+def dropout(x, p, rng, tag="drop"):
+    """nn.Dropout on the library's Philox stream; identity when p == 0 (eval)."""
     if p <= 0.0:
         return x
-    return _Dropout.apply(x, p, seed, offset)
+    return _Dropout.apply(x, p, rng, rng.next(tag, x.shape, p))
 
 
-def dropout_mask(shape, p, seed, offset, device):
-    """The keep-mask (uint8) the kernels use for a tensor of this shape under (seed, offset)."""
-    m = torch.empty(shape, device=device, dtype=torch.uint8)
-    _lib.check(_lib.lib().vln_dropout_mask(_ptr(m), m.numel(), float(p), seed, offset, _stream()),
-               "vln_dropout_mask")
+def dropout_mask(shape, p, rng, call_off, device=None):
+    """The keep-mask (uint8) the kernels use for a tensor of this shape under (rng, call_off)."""
+    m = torch.empty(shape, device=device or rng.state.device, dtype=torch.uint8)
+    _call("vln_dropout_mask", _ptr(m), m.numel(), float(p), rng.ptr, call_off, _stream())
     return m
 
 
@@ -317,22 +416,63 @@ def env_observe(store, vp, ended, goal):
     B = vp.shape[0]
     teacher = torch.empty((B,), device=vp.device, dtype=torch.int32)
     dist = torch.empty((B,), device=vp.device, dtype=torch.float32)
-    _lib.check(_lib.lib().vln_env_observe(_ptr(vp), _ptr(ended), _ptr(goal), _ptr(store.cand_vp), _ptr(store.n_cand),
-                                          _ptr(store.next_hop), _ptr(store.dist), _ptr(store.sq_off),
-                                          _ptr(store.vp_local), _ptr(teacher), _ptr(dist), B, _stream()),
-               "vln_env_observe")
+    _call("vln_env_observe", _ptr(vp), _ptr(ended), _ptr(goal), _ptr(store.cand_vp), _ptr(store.n_cand),
+          _ptr(store.next_hop), _ptr(store.dist), _ptr(store.sq_off), _ptr(store.vp_local), _ptr(teacher),
+          _ptr(dist), B, _stream())
     return teacher, dist
 
 
-def env_step(store, vp, view, ended, goal, action, last_dist):
-    """In-place transition of (vp, view, ended, last_dist); returns (teacher, reward, mask)."""
+def env_step(store, vp, view, ended, dist, goal, action, out=None, n_active=None):
+    """(vp', view', ended', dist', teacher', reward, mask) for one transition; inputs untouched.
+    ``out`` may supply preallocated (vp', view', ended', dist') rows of a trajectory buffer."""
     B = vp.shape[0]
-    teacher = torch.empty((B,), device=vp.device, dtype=torch.int32)
-    reward = torch.empty((B,), device=vp.device, dtype=torch.float32)
-    mask = torch.empty((B,), device=vp.device, dtype=torch.float32)
-    _lib.check(_lib.lib().vln_env_step(_ptr(vp), _ptr(view), _ptr(ended), _ptr(goal), _ptr(action),
-                                       _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand),
-                                       _ptr(store.next_hop), _ptr(store.dist), _ptr(store.sq_off),
-                                       _ptr(store.vp_local), _ptr(last_dist), _ptr(teacher), _ptr(reward),
-                                       _ptr(mask), B, _stream()), "vln_env_step")
-    return teacher, reward, mask
+    dev = vp.device
+    if out is None:
+        out = (torch.empty_like(vp), torch.empty_like(view), torch.empty_like(ended), torch.empty_like(dist))
+    vp2, view2, ended2, dist2 = out
+    teacher = torch.empty((B,), device=dev, dtype=torch.int32)
+    reward = torch.empty((B,), device=dev, dtype=torch.float32)
+    mask = torch.empty((B,), device=dev, dtype=torch.float32)
+    _call("vln_env_step", _ptr(vp), _ptr(view), _ptr(ended), _ptr(dist), _ptr(goal), _ptr(_i32c(action)),
+          _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand), _ptr(store.next_hop), _ptr(store.dist),
+          _ptr(store.sq_off), _ptr(store.vp_local), _ptr(vp2), _ptr(view2), _ptr(ended2), _ptr(dist2),
+          _ptr(teacher), _ptr(reward), _ptr(mask), _ptr(n_active), B, _stream())
+    return vp2, view2, ended2, dist2, teacher, reward, mask
+
+
+# ---- A2C ---------------------------------------------------------------------------------------------------------
+class _A2C(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logp, entropy, value, reward, mask, last_value, ended, gamma, ent_coef):
+        T, B = reward.shape
+        dev = reward.device
+        logp, value = _f32c(logp), _f32c(value)
+        entropy = _f32c(entropy) if entropy is not None else None
+        loss_b = torch.empty((B,), device=dev, dtype=torch.float32)
+        ret = torch.empty((T, B), device=dev, dtype=torch.float32)
+        stats = torch.zeros((2,), device=dev, dtype=torch.float32)
+        _call("vln_a2c_fwd", _ptr(reward), _ptr(mask), _ptr(logp), _ptr(entropy), _ptr(value), _ptr(last_value),
+              _ptr(ended), float(gamma), float(ent_coef), _ptr(loss_b), _ptr(ret), _ptr(stats),
+              C.c_void_p(stats.data_ptr() + 4), T, B, _stream())
+        ctx.save_for_backward(mask, value, ret)
+        ctx.ent_coef = float(ent_coef)
+        ctx.has_ent = entropy is not None
+        ctx.mark_non_differentiable(stats)
+        return loss_b, stats
+
+    @staticmethod
+    def backward(ctx, g_b, _g_stats):
+        mask, value, ret = ctx.saved_tensors
+        T, B = mask.shape
+        d_logp, d_value = torch.empty_like(value), torch.empty_like(value)
+        d_ent = torch.empty_like(value) if ctx.has_ent else None
+        _call("vln_a2c_bwd", _ptr(_f32c(g_b)), _ptr(mask), _ptr(value), _ptr(ret), ctx.ent_coef, _ptr(d_logp),
+              _ptr(d_value), _ptr(d_ent), T, B, _stream())
+        return d_logp, d_ent, d_value, None, None, None, None, None, None
+
+
+def a2c_loss(logp, entropy, value, reward, mask, last_value, ended, gamma, ent_coef=0.01):
+    """Per-episode A2C loss [B] and stats [2] = (sum of masks, sum of masked critic errors^2)
+    (envdrop.py:240-264); all step tensors are time-major [T,B]."""
+    return _A2C.apply(logp, entropy, value, _f32c(reward), _f32c(mask), _f32c(last_value), ended.contiguous(),
+                      gamma, ent_coef if entropy is not None else 0.0)

@@ -15,6 +15,9 @@
  *     (thread-local);  nothing throws or exits;
  *   - layouts are row-major, innermost dimension last.  F = 2176 = 2048 image + 128 angle,
  *     V = 36 views, CMAX = 15 neighbours (+1 END slot => 16 action slots).
+ *   - randomness: `rng` is a DEVICE pointer to two uint64 {seed, base}; a call site passes its
+ *     own `call_off` and the kernel uses the stream (seed, base + call_off).  Keeping the base in
+ *     device memory lets a captured CUDA graph draw fresh masks on every replay (vln_rng_advance).
  *   - dropout: keep-mask bit for element e of a tensor = Philox4x32-10(seed, offset, e/8)
  *     16-bit lane (e%8) >= round(p*65536); kept values are scaled by 1/(1-p) (nn.Dropout).
  *     vln_dropout_mask() exposes the very same mask so the oracle can be fed identical masks.
@@ -69,7 +72,7 @@ int vln_gather_cand(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
  * x~ = dropout(table row) (+) angle embedding.  split in {1,2,4,8}: CTAs per episode (cluster). */
 int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
                   const float* vec, float* attn_io, float* out, int B, int mode, float drop_p,
-                  uint64_t seed, uint64_t offset, int split, void* stream);
+                  const uint64_t* rng, uint64_t call_off, int split, void* stream);
 
 /* Candidate logits (EnvDropDecoder.candidate_attn policy.py:199-206; also ActionScoring
  * units.py:173-185 after folding its Linear layers into tgt/bias on the host side):
@@ -79,12 +82,12 @@ int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, co
 int vln_cand_logits_fwd(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
                         const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
                         const float* tgt, const float* bias, float* logits, int B, float drop_p,
-                        uint64_t seed, uint64_t offset, void* stream);
+                        const uint64_t* rng, uint64_t call_off, void* stream);
 /* d_tgt[b] = sum_j dlogits[b,j] x~c[b,j];  d_bias[b] = sum_{j<=n_cand} dlogits[b,j] (may be NULL). */
 int vln_cand_logits_bwd(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
                         const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
                         const float* dlogits, float* d_tgt, float* d_bias, int B, float drop_p,
-                        uint64_t seed, uint64_t offset, void* stream);
+                        const uint64_t* rng, uint64_t call_off, void* stream);
 
 /* Soft-dot attention over the instruction context (SoftDotAttention.forward units.py:107-118,
  * the bmm/softmax/bmm part; linear_in/linear_out are GEMMs outside).  context fp32 [B,L,H],
@@ -92,7 +95,8 @@ int vln_cand_logits_bwd(const vln_ctx* ctx, const int32_t* vp, const int32_t* vi
 int vln_ctx_attn_fwd(const float* context, const float* tgt, const int32_t* lengths, float* attn,
                      float* weighted, int B, int L, int H, void* stream);
 /* d_tgt <- sum_l dlogit_l ctx_l ; d_context += attn_l*d_weighted + dlogit_l*tgt  (accumulates);
- * d_attn_ext (nullable) = extra gradient arriving on the attention weights themselves. */
+ * d_attn_ext (nullable) = extra gradient arriving on the attention weights themselves;
+ * d_context may be NULL when the context needs no gradient (a materialised feature tensor). */
 int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* lengths,
                      const float* attn, const float* d_weighted, const float* d_attn_ext,
                      float* d_tgt, float* d_context, int B, int L, int H, void* stream);
@@ -109,8 +113,8 @@ int vln_lstm_pointwise_bwd(const float* acts, const float* c0, const float* c1, 
  * entropy of the chosen action.  logits [B,16] with -inf beyond the valid slots.
  *   feedback: 0 teacher, 1 argmax, 2 sample.  Outputs per episode: ce, action (int32),
  *   logp (of action), entropy, probs[B,16] (saved for backward). */
-int vln_policy_fwd(const float* logits, const int32_t* target, int feedback, uint64_t seed,
-                   uint64_t offset, float* ce, int32_t* action, float* logp, float* entropy,
+int vln_policy_fwd(const float* logits, const int32_t* target, int feedback, const uint64_t* rng,
+                   uint64_t call_off, float* ce, int32_t* action, float* logp, float* entropy,
                    float* probs, int B, void* stream);
 /* dlogits[b,j] = g_ce[b]*(p - onehot(target)) + g_logp[b]*(onehot(action) - p)
  *               - g_ent[b]*p*(log p + H)   (each g_* nullable) */
@@ -120,26 +124,57 @@ int vln_policy_bwd(const float* probs, const int32_t* target, const int32_t* act
 
 /* nn.Dropout on a dense fp32 tensor with the library's Philox stream (fwd and bwd are the same
  * op: y = x * keep / (1-p)). */
-int vln_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
+int vln_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* rng, uint64_t call_off,
                 void* stream);
 /* keep-mask bytes (1 = kept) for elements [0,n) of the stream (seed, offset). */
-int vln_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+int vln_dropout_mask(uint8_t* mask, int64_t n, float p, const uint64_t* rng, uint64_t call_off, void* stream);
+/* rng[1] += delta (one thread); lets graph replays move to fresh streams. */
+int vln_rng_advance(uint64_t* rng, uint64_t delta, void* stream);
 
 /* Stub-simulator transition + observation on index tables (EnvBatch.makeActions
  * common_env.py:91-110, R2RBatch.observe :299-330, _teacher_action base.py:159-178, reward
- * shaping envdrop.py:207-219).  state = (vp, view, ended) per episode, updated in place.
- *   action[b] in 0..n_cand (n_cand = STOP) or -1.  Outputs: teacher[b] for the NEW state
- *   (-1 if ended), dist[b], reward[b] (EnvDrop shaping), mask[b] = !ended before the step. */
-int vln_env_step(int32_t* vp, int32_t* view, uint8_t* ended, const int32_t* goal,
-                 const int32_t* action, const int32_t* cand_vp, const int32_t* cand_view,
-                 const int32_t* n_cand, const int32_t* next_hop, const float* dist_tbl,
-                 const int64_t* sq_off, const int32_t* vp_local, float* last_dist,
-                 int32_t* teacher, float* reward, float* mask, int B, void* stream);
+ * shaping envdrop.py:207-219).  Out of place: state row t -> state row t+1, so a rollout keeps
+ * its whole [T+1,B] trajectory on the device (backward kernels re-read vp/view of each step).
+ *   action[b] in 0..n_cand (n_cand = STOP) or -1.  Outputs for the NEW state: teacher[b]
+ *   (-1 if ended), dist[b]; for the transition: reward[b] (EnvDrop shaping), mask[b] = !ended
+ *   before the step.  n_active (nullable): atomically += number of episodes still running
+ *   after the step (the device-side `ended.all()` of envdrop.py:219). */
+int vln_env_step(const int32_t* vp_in, const int32_t* view_in, const uint8_t* ended_in,
+                 const float* dist_in, const int32_t* goal, const int32_t* action,
+                 const int32_t* cand_vp, const int32_t* cand_view, const int32_t* n_cand,
+                 const int32_t* next_hop, const float* dist_tbl, const int64_t* sq_off,
+                 const int32_t* vp_local, int32_t* vp_out, int32_t* view_out, uint8_t* ended_out,
+                 float* dist_out, int32_t* teacher, float* reward, float* mask, int32_t* n_active,
+                 int B, void* stream);
 /* teacher/dist for the current state without moving (reset). */
 int vln_env_observe(const int32_t* vp, const uint8_t* ended, const int32_t* goal,
                     const int32_t* cand_vp, const int32_t* n_cand, const int32_t* next_hop,
                     const float* dist_tbl, const int64_t* sq_off, const int32_t* vp_local,
                     int32_t* teacher, float* dist, int B, void* stream);
+
+/* Feature of the action just taken (follower.py:164, monitor.py:191: a_t_prev = cands[i, max(a,0)]):
+ * the agent first rewrites STOP / ignored / already-ended actions to -1 (follower.py:141-146), so
+ * slot = (ended[b] || action[b] < 0 || action[b] >= n_cand) ? 0 : action[b]; out[b] = candidate
+ * row `slot` of state (vp[b], view[b]), all-zero if the viewpoint has no candidate.  `ended`
+ * (state BEFORE the step) may be NULL.  fp32 [B,2176], bit-exact. */
+int vln_gather_action_feat(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                           const int32_t* action, const uint8_t* ended, const int32_t* cand_view, const float* cand_ang4,
+                           const int32_t* n_cand, float* out, int B, void* stream);
+
+/* A2C loss assembly (envdrop.py:240-264).  Inputs are time-major [T,B]: reward, mask (fp32),
+ * logp, entropy, value (critic(hidden_states[t])), plus last_value[B] (critic(last_h), no grad)
+ * and ended[B] after the last step.  Discounted returns run backwards in time in float64, the
+ * first multiply by gamma in float32 (numpy promotion at envdrop.py:238-243).  Outputs:
+ *   loss_b[B] = sum_t mask*( -logp*(R-v) + 0.5*(R-v)^2 - ent_coef*entropy )   (advantage detached)
+ *   ret[T,B]  = the returns R_t (saved for backward), total[1] += sum mask, critic_sq[1] += sum mask*(R-v)^2 */
+int vln_a2c_fwd(const float* reward, const float* mask, const float* logp, const float* entropy,
+                const float* value, const float* last_value, const uint8_t* ended, float gamma,
+                float ent_coef, float* loss_b, float* ret, float* total, float* critic_sq, int T, int B,
+                void* stream);
+/* g_b[B] = d(total loss)/d(loss_b).  d_logp = -g*mask*(R-v); d_value = -g*mask*(R-v); d_entropy = -g*mask*ent_coef. */
+int vln_a2c_bwd(const float* g_b, const float* mask, const float* value, const float* ret,
+                float ent_coef, float* d_logp, float* d_value, float* d_entropy, int T, int B,
+                void* stream);
 
 /* Gradient clip + optimiser in one pass over flat fp32 buffers (trainer.py:423-427:
  * clip_grad_norm_(encoder,40), clip_grad_norm_(decoder,40), critic unclipped, RMSprop/Adam).

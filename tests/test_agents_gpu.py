@@ -1,0 +1,246 @@
+"""Rollout-level parity on the GPU: the product agents (device-resident rollouts through the
+C-ABI kernels) against the oracle's restatement of the reference agents (oracle/port_rollout.py,
+itself pinned to the real reference by tests/test_oracle_vs_reference.py and tests/golden).
+
+Bars (north star): logits and loss max-relative error <= 1e-3, gradient cosine >= 0.9999,
+teacher-forced argmax agreement >= 99.9 %; trajectories (integer state) bit-exact.
+Train-mode runs feed the oracle the very keep-masks the kernels drew (Philox streams are
+regenerated from the recorded call sites), and sampled actions are replayed as forced actions.
+"""
+import copy
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+KINDS = {"ENVDROP": 12, "FOLLOWER": 10, "SELF-MONITOR": 10}
+
+
+def _setup(kind, B=8, n_items=40, seed=1, fixed_len=None):
+    import clvln_b200
+    from clvln_b200 import utils
+    from clvln_b200.agent import build_agent
+    from clvln_b200.environ import make_world, make_items, R2RBatch
+    from oracle import port_env as PE, port_rollout as PR
+    dev = torch.device("cuda:0")
+    world = make_world(n_scans=3, seed=seed)
+    items = make_items(world, n_items, seed=seed, fixed_len=fixed_len)
+    cfg = utils.agent_cfg(kind)
+    cfg.AGENT.MAX_EPISODE_LEN = KINDS[kind]
+    random.seed(2020)
+    env = R2RBatch(world, items, batch_size=B, device=dev)
+    torch.manual_seed(2020)
+    agent = build_agent(cfg, utils.StubTokenizer(), dev)            # re-seeds random to 1 (base.py:28)
+    agent.env = env
+    agent.sync_every = 1
+    random.seed(2020)
+    penv = PE.R2RBatchPort(PE.WorldView(world), items, batch_size=B)
+    random.seed(1)
+    assert [d["instr_id"] for d in penv.data] == [d["instr_id"] for d in env.data]
+    mods = agent._modules()
+    sds = [{k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k
+                                                       and k != "position.pe")
+            for k, v in m.state_dict().items()} for m in mods]
+    mc = {"ENVDROP": cfg.MODEL.ENVDROP, "FOLLOWER": cfg.MODEL.FOLLOWER, "SELF-MONITOR": cfg.MODEL.MONITOR}[kind]
+    pag = PR.Agent(kind, sds[0], sds[1], sds[2] if len(sds) > 2 else None, hidden=mc.HIDDEN_SIZE,
+                   bidirectional=mc.ENC_BIDIRECTION, enc_layers=mc.ENC_LAYERS, episode_len=KINDS[kind])
+    return agent, pag, env, penv, sds, cfg
+
+
+def _grads(params):
+    return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).detach().flatten().cpu().double()
+                      for p in params])
+
+
+def _cos(a, b):
+    return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def _compare_traces(mine, theirs):
+    """Per-step logits (finite slots), -inf pattern, targets; returns teacher-argmax agreement."""
+    agree = tot = 0
+    for m, o in zip(mine, theirs):
+        C = o["logits"].shape[1]
+        lm = m["logits"][:, :C].cpu()
+        assert torch.equal(torch.isinf(lm), torch.isinf(o["logits"]))
+        if lm.shape[1] < m["logits"].shape[1]:
+            assert bool(torch.isinf(m["logits"][:, C:]).all())
+        assert torch.equal(m["target"].cpu().long(), o["target"].long())
+        live = o["target"] >= 0
+        fin = ~torch.isinf(o["logits"])
+        if live.any():
+            sel = fin & live.unsqueeze(1)
+            assert _rel(lm[sel], o["logits"][sel]) < 1e-3
+            agree += int((lm[live].argmax(1) == o["logits"][live].argmax(1)).sum())
+            tot += int(live.sum())
+    return agree, tot
+
+
+def _mask_feed(agent, cand_widths=None):
+    """Regenerate the kernels' keep-masks from the recorded call sites, grouped by oracle tag."""
+    from clvln_b200 import ops
+    feed = {}
+    for tag, shape, p, off in agent.rng.log:
+        feed.setdefault(tag, []).append(ops.dropout_mask(shape, p, agent.rng, off).cpu())
+    return feed
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_envdrop_rollouts_match_oracle(mode):
+    from oracle import port_modules as P, port_rollout as PR
+    agent, pag, env, penv, sds, cfg = _setup("ENVDROP")
+    getattr(agent, mode)()
+    agent.rng.log = [] if mode == "train" else None
+    agent.rng.begin_iteration()
+    # ---- product: teacher rollout (IL) + sampled rollout (A2C) on the same batch, one backward
+    agent.trace = []
+    agent.rollout(train_ml=True, train_rl=False, feedback="teacher")
+    ml, tr1, st1 = agent.loss["ml_loss"], agent.trace, agent.last_state
+    agent.trace = []
+    agent.rollout(train_ml=False, train_rl=True, restart=True, feedback="sample")
+    rl, tr2, st2 = agent.loss["rl_loss"], agent.trace, agent.last_state
+    (ml + rl).backward()
+    g_mine = _grads(agent.trainable_params())
+    # ---- oracle: same batch, same masks, the sampled actions replayed
+    drop = None
+    if mode == "train":
+        feed = _mask_feed(agent)
+        # critic masks: the oracle calls critic(last_h) first, then hidden_states[t] for t = T-1..0
+        last, vals = feed["critic"][0], feed["critic"][1]
+        n = len(tr2)
+        vals = vals.view(n, -1, vals.shape[-1])
+        feed["critic"] = [last] + [vals[t] for t in range(n - 1, -1, -1)]
+        steps = iter(tr1 + tr2 + [None])
+        # candidate masks are drawn for 16 slots; the oracle's tensor is max(n_cand)+1 wide per step
+        feed["cand"] = [m for m in feed["cand"]]
+        drop = _WidthDrop(feed)
+    forced = [t["action"].cpu().numpy() for t in tr2]
+    _, l1 = PR.rollout_envdrop(pag, penv, train_ml=True, train_rl=False, feedback="teacher", drop=drop)
+    otr1 = pag.trace["steps"]
+    _, l2 = PR.rollout_envdrop(pag, penv, train_ml=False, train_rl=True, restart=True, feedback=forced, drop=drop)
+    otr2 = pag.trace["steps"]
+    (l1["ml_loss"] + l2["rl_loss"]).backward()
+    g_ref = _grads([v for sd in sds for v in sd.values() if v.requires_grad])
+    # ---- compare
+    assert len(tr1) == len(otr1) and len(tr2) >= len(otr2)
+    a1, n1 = _compare_traces(tr1, otr1)
+    _compare_traces(tr2[:len(otr2)], otr2)
+    assert a1 / n1 >= 0.999
+    assert _rel(ml, l1["ml_loss"]) < 1e-3 and _rel(rl, l2["rl_loss"]) < 1e-3
+    assert g_mine.shape == g_ref.shape
+    assert _cos(g_mine, g_ref) >= 0.9999
+    assert _rel(g_mine, g_ref) < 5e-3
+
+
+class _WidthDrop:
+    """oracle Drop that crops an injected mask to the tensor it is applied to (the kernels draw
+    candidate masks for all 16 slots; the oracle's candidate tensor is only max(n_cand)+1 wide)."""
+
+    def __init__(self, masks):
+        self.mode = "masks"
+        self.masks = {k: list(v) for k, v in masks.items()}
+
+    def __call__(self, x, p, tag):
+        if p <= 0.0:
+            return x
+        keep = self.masks[tag].pop(0)
+        if keep.shape != x.shape:
+            keep = keep[tuple(slice(0, s) for s in x.shape)]
+        return x * keep.to(x.dtype) * (1.0 / (1.0 - p))
+
+
+@pytest.mark.parametrize("kind", ["FOLLOWER", "SELF-MONITOR"])
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_follower_monitor_rollouts_match_oracle(kind, mode):
+    from oracle import port_rollout as PR
+    agent, pag, env, penv, sds, cfg = _setup(kind)
+    getattr(agent, mode)()
+    pag.training = mode == "train"
+    agent.rng.log = [] if mode == "train" else None
+    agent.rng.begin_iteration()
+    agent.trace = []
+    agent.rollout(feedback="teacher")
+    l_t, tr1 = agent.ml_loss, agent.trace
+    agent.trace = []
+    agent.rollout(feedback="sample", train_cl=True)
+    l_s, tr2 = agent.ml_loss, agent.trace
+    (l_t + l_s.sum()).backward()
+    g_mine = _grads(agent.trainable_params())
+    drop = None
+    if mode == "train":
+        feed = _mask_feed(agent)
+        if "mlp" in feed:           # MLPwithBN runs twice per step: previous action, then the candidates
+            feed["mlp_prev"], feed["mlp_cand"] = feed["mlp"][0::2], feed["mlp"][1::2]
+        drop = _WidthDrop(feed)
+    forced = [t["action"].cpu().numpy() for t in tr2]
+    roll = PR.rollout_follower if kind == "FOLLOWER" else PR.rollout_monitor
+    o1 = roll(pag, penv, feedback="teacher", drop=drop)
+    otr1 = pag.trace["steps"]
+    o2 = roll(pag, penv, feedback=forced, train_cl=True, drop=drop)
+    otr2 = pag.trace["steps"]
+    (o1[1] + o2[1].sum()).backward()
+    g_ref = _grads([v for sd in sds for v in sd.values() if v.requires_grad])
+    assert len(tr1) == len(otr1) and len(tr2) >= len(otr2)
+    a1, n1 = _compare_traces(tr1, otr1)
+    _compare_traces(tr2[:len(otr2)], otr2)
+    assert a1 / n1 >= 0.999
+    assert _rel(l_t, o1[1]) < 1e-3 and _rel(l_s, o2[1]) < 1e-3
+    assert _cos(g_mine, g_ref) >= 0.9999
+    if kind == "SELF-MONITOR" and mode == "train":                  # BatchNorm running statistics
+        dsd = agent.decoder.state_dict()
+        for k in ("proj_navigable_mlp.mlp.0.running_mean", "proj_navigable_mlp.mlp.2.running_var"):
+            assert _rel(dsd[k], sds[1][k]) < 1e-4
+
+
+def test_trajectories_match_obs_dict_face():
+    """Device rollouts (argmax) produce the trajectories the obs-dict face + oracle agent produce."""
+    from oracle import port_rollout as PR
+    agent, pag, env, penv, sds, cfg = _setup("ENVDROP")
+    agent.eval()
+    traj = agent.rollout(train_ml=False, feedback="argmax")
+    otraj, _ = PR.rollout_envdrop(pag, penv, train_ml=False, feedback="argmax")
+    assert [t["instr_id"] for t in traj] == [t["instr_id"] for t in otraj]
+    for a, b in zip(traj, otraj):
+        assert [p[0] for p in a["path"]] == [p[0] for p in b["path"]]
+        assert np.allclose([p[1:] for p in a["path"]], [p[1:] for p in b["path"]])
+
+
+def test_train_step_and_flat_optimizer():
+    """One EnvDrop TrainStep == reference recipe (clip encoder/decoder to 40, RMSprop) applied to the
+    same gradients; parameters stay views of the flat buffer; the loss goes down over a few steps."""
+    from clvln_b200.engine import TrainStep
+    agent, pag, env, penv, sds, cfg = _setup("ENVDROP", B=8)
+    agent.train()
+    step = TrainStep(cfg, agent)
+    ref = [p.detach().clone().requires_grad_(True) for p in agent.trainable_params()]
+    opt = torch.optim.RMSprop(ref, lr=cfg.TRAIN.LR)
+    n_enc = len(list(agent.encoder.parameters()))
+    n_dec = len(list(agent.decoder.parameters()))
+    losses = []
+    for it in range(3):
+        before = [p.detach().clone() for p in agent.trainable_params()]
+        losses.append(float(step()))
+        for r, p, b in zip(ref, agent.trainable_params(), before):
+            assert torch.equal(r.detach(), b) or _rel(r.detach(), b) < 1e-5
+            r.data.copy_(b)
+            r.grad = p.grad.detach().clone()
+        torch.nn.utils.clip_grad_norm_(ref[:n_enc], 40.0)
+        torch.nn.utils.clip_grad_norm_(ref[n_enc:n_enc + n_dec], 40.0)
+        opt.step()
+        for r, p in zip(ref, agent.trainable_params()):
+            assert _rel(p, r) < 1e-4
+    assert all(np.isfinite(losses))
+    flat = step.opt.flat
+    for p in agent.trainable_params():
+        assert flat.data_ptr() <= p.data_ptr() < flat.data_ptr() + flat.numel() * 4

@@ -80,14 +80,14 @@ def test_pano_attn_fwd_bwd(setup, split, drop_p):
     vp, view = rand_state(world, B, dev, 2)
     torch.manual_seed(split)
     q = (torch.randn(B, 2176, device=dev) * 0.05).requires_grad_(True)
-    seed, off = 77, 5
-    out, attn = ops.pano_attn(store, vp, view, q, drop_p, seed, off, split)
+    rng, off = ops.Rng(77, dev), 5
+    out, attn = ops.pano_attn(store, vp, view, q, drop_p, rng, off, split)
     g_out = torch.randn_like(out)
     (dq,) = torch.autograd.grad(out, q, g_out)
     # oracle: SoftDotAttention maths (units.py:107-118) on the materialised, masked tensor
     img = expected_pano(world, vp, view).to(dev)
     if drop_p > 0:
-        keep = ops.dropout_mask((B, 36, 2048), drop_p, seed, off, dev).float()
+        keep = ops.dropout_mask((B, 36, 2048), drop_p, rng, off).float()
         assert abs(keep.mean().item() - (1 - drop_p)) < 0.01
         img = torch.cat((img[..., :2048] * keep * (1.0 / (1.0 - drop_p)), img[..., 2048:]), -1)
     q2 = q.detach().clone().requires_grad_(True)
@@ -107,11 +107,11 @@ def test_cand_logits_fwd_bwd(setup, drop_p):
     vp, view = rand_state(world, B, dev, 4)
     tgt = (torch.randn(B, 2176, device=dev) * 0.05).requires_grad_(True)
     bias = torch.randn(B, device=dev).requires_grad_(True)
-    seed, off = 9, 11
-    logits = ops.cand_logits(store, vp, view, tgt, bias, drop_p, seed, off)
+    rng, off = ops.Rng(9, dev), 11
+    logits = ops.cand_logits(store, vp, view, tgt, bias, drop_p, rng, off)
     cand = expected_cand(world, vp, view, 16).to(dev)
     if drop_p > 0:
-        keep = ops.dropout_mask((B, 16, 2048), drop_p, seed, off, dev).float()
+        keep = ops.dropout_mask((B, 16, 2048), drop_p, rng, off).float()
         cand = torch.cat((cand[..., :2048] * keep * (1.0 / (1.0 - drop_p)), cand[..., 2048:]), -1)
     n = torch.from_numpy(world.n_cand[vp.cpu().long().numpy()]).to(dev)
     t2, b2 = tgt.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
@@ -192,8 +192,15 @@ def test_policy_head(setup):
     _, _, _, a = ops.policy_head(logits, target, "argmax")
     assert torch.equal(a.long(), logits.max(1)[1])
     # sample: deterministic in (seed, offset), valid, log-prob/entropy gradients match autograd
-    ce, logp, ent, a = ops.policy_head(logits, target, "sample", 5, 9)
-    _, _, _, a_again = ops.policy_head(logits, target, "sample", 5, 9)
+    rng = ops.Rng(5, dev)
+    ce, logp, ent, a = ops.policy_head(logits, target, "sample", rng, 9)
+    _, _, _, a_again = ops.policy_head(logits, target, "sample", rng, 9)
+    rng.off = 3
+    rng.advance()                                                   # base += 3: a different stream
+    _, _, _, a_other = ops.policy_head(logits, target, "sample", rng, 9)
+    _, _, _, a_same = ops.policy_head(logits, target, "sample", rng, 6)
+    assert not torch.equal(a, a_other) and torch.equal(a, a_same)
+    rng = ops.Rng(5, dev)
     assert torch.equal(a, a_again)
     assert bool((a.long() < nvalid).all()) and bool((a >= 0).all())
     lp_ref = cat.log_prob(a.long())
@@ -204,7 +211,7 @@ def test_policy_head(setup):
     assert relerr(d, d_ref) < 1e-4
     # sampling frequencies follow the softmax
     big = torch.tensor([[0.0, 1.0, 2.0, -1.0] + [-math.inf] * 12], device=dev).repeat(20000, 1)
-    _, _, _, s = ops.policy_head(big, None, "sample", 1, 2)
+    _, _, _, s = ops.policy_head(big, None, "sample", ops.Rng(1, dev), 2)
     freq = torch.bincount(s.long(), minlength=16).float() / 20000
     assert (freq - F.softmax(big[0], 0)).abs().max() < 0.015
 
@@ -212,8 +219,11 @@ def test_policy_head(setup):
 def test_dropout(setup):
     _, _, ops, dev = setup
     x = torch.randn(1000, 37, device=dev, requires_grad=True)
-    y = ops.dropout(x, 0.5, 3, 4)
-    keep = ops.dropout_mask(x.shape, 0.5, 3, 4, dev).float()
+    rng = ops.Rng(3, dev)
+    rng.log = []
+    y = ops.dropout(x, 0.5, rng, "t")
+    assert rng.log == [("t", tuple(x.shape), 0.5, 1)]
+    keep = ops.dropout_mask(x.shape, 0.5, rng, 1).float()
     assert torch.equal(y, x * keep * 2.0)
     assert abs(keep.mean().item() - 0.5) < 0.01
     (g,) = torch.autograd.grad(y.sum(), x)
@@ -234,27 +244,90 @@ def test_env_step_matches_world(setup):
     for b in range(B):
         assert int(teacher[b]) == world.teacher_action(cur[b], int(goal[b]))
         assert float(dist[b]) == float(world.distance(cur[b], int(goal[b])))
-    last = dist.clone()
     done = [False] * B
+    n_active = torch.zeros(9, dtype=torch.int32, device=dev)
     for step in range(9):
         act = teacher.clone()
-        teacher, reward, mask = ops.env_step(store, vp, view, ended, goal, act, last)
+        vp0, view0 = vp.clone(), view.clone()
+        vp2, view2, ended2, dist2, teacher, reward, mask = ops.env_step(store, vp, view, ended, dist, goal, act,
+                                                                        n_active=n_active[step:step + 1])
+        assert torch.equal(vp, vp0) and torch.equal(view, view0)       # inputs untouched
         for b in range(B):
             a = int(act[b])
             stop = done[b] or a < 0 or a >= int(world.n_cand[cur[b]])
             if not stop:
                 exp_view = int(world.cand_view[cur[b], a])
                 cur[b] = int(world.cand_vp[cur[b], a])
-                assert int(view[b]) == exp_view
-            assert int(vp[b]) == cur[b]
+                assert int(view2[b]) == exp_view
+            assert int(vp2[b]) == cur[b]
             assert float(mask[b]) == (0.0 if done[b] else 1.0)
             if not done[b] and stop:
                 assert float(reward[b]) == 2.0                     # teacher path stops at the goal
             done[b] = done[b] or stop
-            assert int(ended[b]) == int(done[b])
+            assert int(ended2[b]) == int(done[b])
+            assert float(dist2[b]) == float(world.distance(cur[b], int(goal[b])))
             exp_t = -1 if done[b] else world.teacher_action(cur[b], int(goal[b]))
             assert int(teacher[b]) == exp_t
+        assert int(n_active[step]) == sum(not d for d in done)
+        vp, view, ended, dist = vp2, view2, ended2, dist2
     assert all(done)
+
+
+def test_gather_action_feat(setup):
+    world, store, ops, dev = setup
+    B = 40
+    vp, view = rand_state(world, B, dev, 8)
+    g = torch.Generator().manual_seed(3)
+    action = torch.randint(-1, 17, (B,), generator=g, dtype=torch.int32).to(dev)
+    ended = (torch.rand(B, generator=g) < 0.2).to(torch.uint8).to(dev)
+    out = ops.gather_action_feat(store, vp, view, action, ended)
+    cands = expected_cand(world, vp, view, 16)
+    for b in range(B):
+        a, n = int(action[b]), int(world.n_cand[int(vp[b])])
+        j = 0 if (int(ended[b]) or a < 0 or a >= n) else a
+        assert torch.equal(out[b].cpu(), cands[b, j])
+
+
+def test_a2c_loss(setup):
+    """vln_a2c_fwd/bwd against the reference's numpy/torch recipe (envdrop.py:240-264)."""
+    _, _, ops, dev = setup
+    T, B, gamma = 9, 13, 0.9
+    torch.manual_seed(1)
+    reward = torch.randint(-2, 3, (T, B)).float().to(dev)
+    ended_t = torch.rand(B) < 0.6
+    stop_at = torch.randint(1, T + 1, (B,))
+    mask = (torch.arange(T).unsqueeze(1) < torch.where(ended_t, stop_at, torch.full((B,), T)).unsqueeze(0)).float().to(dev)
+    reward = reward * mask
+    logp = (-torch.rand(T, B, device=dev)).requires_grad_(True)
+    ent = torch.rand(T, B, device=dev).requires_grad_(True)
+    value = torch.randn(T, B, device=dev).requires_grad_(True)
+    last_value = torch.randn(B, device=dev)
+    ended = ended_t.to(torch.uint8).to(dev)
+    loss_b, stats = ops.a2c_loss(logp, ent, value, reward, mask, last_value, ended, gamma, 0.01)
+    g = torch.rand(B, device=dev)
+    d = torch.autograd.grad((loss_b * g).sum(), (logp, ent, value))
+    # reference recipe
+    l2, e2, v2 = (x.detach().clone().requires_grad_(True) for x in (logp, ent, value))
+    disc = (~ended_t.numpy()) * last_value.cpu().numpy()
+    ref = torch.zeros(B, device=dev)
+    total, csq = 0, 0.0
+    for t in range(T - 1, -1, -1):
+        disc = disc * gamma + reward[t].cpu().numpy().astype(np.float64)
+        m = mask[t].bool()
+        r = torch.from_numpy(disc).to(dev)
+        adv = (r - v2[t]).detach()
+        cur = torch.zeros(B, device=dev)
+        cur += (-l2[t] * adv * m)
+        cur += (((r - v2[t]) ** 2) * m) * 0.5
+        cur += (-0.01 * e2[t] * m)
+        ref = ref + cur
+        total += int(m.sum())
+        csq += float((((r - v2[t]) ** 2) * m).sum())
+    d_ref = torch.autograd.grad((ref * g).sum(), (l2, e2, v2))
+    assert relerr(loss_b, ref.detach()) < 1e-5
+    assert float(stats[0]) == total and abs(float(stats[1]) - csq) / csq < 1e-5
+    for a, b in zip(d, d_ref):
+        assert relerr(a, b) < 1e-5
 
 
 @pytest.mark.parametrize("kind", [0, 1])
