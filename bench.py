@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Headline benchmark: EnvDrop training iterations per second (episodes/s), B=64 per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # reference algorithm on host cores
+
+One "step" = one full EnvDrop training iteration of the reference (trainer.py:411-429): a
+teacher-forced rollout (imitation loss) + a sampled 35-step rollout on the same minibatch (A2C) +
+backward + clip(encoder, 40) + clip(decoder, 40) + RMSprop, on B=64 episodes per GPU with
+instruction length 80, 36 views x 2176 features, hidden 512 (BASELINE.json configs[1]).
+Synthetic data of the real shape: the full 10 567-viewpoint bf16 feature table (1.56 GB, HBM
+resident), 90 random connectivity graphs, 14 039 episodes; random-init weights.
+
+The line printed by rank 0 carries, besides the base contract:
+  value     episodes/s with the minibatch index tensors staged in HBM before the timed region;
+  e2e       the same through the public TrainStep API: per-step pinned host->device copies of the
+            minibatch (tokens, lengths, start pose, goal) and a device->host read of the loss;
+  roofline  the fused gather + 36-view attention kernel, timed alone with CUDA events (a CUDA graph
+            of launches over rotating random viewpoints), algorithmic bytes B*36*2048*2 per launch;
+  cpu_baseline  the oracle's CPU restatement of the reference iteration on this host's cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train episodes/sec (EnvDrop IL+A2C iteration, B=64/GPU, L=80)"
+UNIT = "episodes/s"
+B_PER_GPU = 64
+ALGO_BYTES_PER_EPISODE_STEP = 36 * 2048 * 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--small", action="store_true", help="tiny world (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=int(os.environ.get("VLN_BENCH_GRAPH", "1")),
+                    help="replay the iteration as CUDA graphs (1) or launch eagerly (0)")
+    return ap.parse_args()
+
+
+def build_world(small, device, with_table=True):
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items, full_world_sizes
+    if small:
+        world = make_world(n_scans=6, seed=2020, device=device, with_table=with_table)
+        items = make_items(world, 2000, seed=2020, fixed_len=80)
+    else:
+        world = make_world(sizes=full_world_sizes(), seed=2020, device=device, with_table=with_table)
+        items = make_items(world, 14039, seed=2020, fixed_len=80)
+    return world, items
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.p, self.rows = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def roofline_pano(store, ops, torch, B, split, peaks):
+    """Time the fused gather+attention kernel alone (CUDA-graph of 32 launches over rotating random
+    viewpoint sets so that every launch reads HBM, not L2), CUDA events on the launch stream."""
+    dev = store.device
+    g = torch.Generator(device=dev).manual_seed(7)
+    n_sets = 32
+    vps = [torch.randint(0, store.n_vp, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(n_sets)]
+    view = torch.randint(0, 36, (B,), device=dev, dtype=torch.int32, generator=g)
+    q = torch.randn(B, 2176, device=dev) * 0.05
+    attn = torch.empty(B, 36, device=dev)
+    rng = ops.Rng(1, dev)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for k in range(3):
+            ops.pano_attn_raw(store, vps[k], view, q, attn, 0, 0.3, rng, 1, split)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for k in range(n_sets):
+            ops.pano_attn_raw(store, vps[k], view, q, attn, 0, 0.3, rng, 1, split)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / (reps * n_sets)
+    achieved = B * ALGO_BYTES_PER_EPISODE_STEP / t / 1e9
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return {"bound": "hbm", "kernel": "pano_attn fwd (fused gather + dropout + 36-view soft-dot attention)",
+            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback",
+            "us_per_launch": round(t * 1e6, 2), "episodes_per_launch": B, "split": split, "traffic": None}
+
+
+def cpu_iteration_factory(world_small, items, B, threads):
+    """The oracle's CPU restatement of one reference EnvDrop training iteration (test infrastructure
+    used here only as the timed CPU baseline)."""
+    import random
+    import torch
+    from clvln_b200 import utils
+    from clvln_b200.model import EncoderLSTM, EnvDropDecoder, Critic
+    from oracle import port_env as PE, port_modules as P, port_rollout as PR
+    torch.set_num_threads(threads)
+    cfg = utils.agent_cfg("ENVDROP")
+    mc = cfg.MODEL.ENVDROP
+    torch.manual_seed(2020)
+    mods = [EncoderLSTM(992, mc.WORD_EMB_SIZE, mc.HIDDEN_SIZE, 0, mc.DROP_RATE, True, 1),
+            EnvDropDecoder(mc.HIDDEN_SIZE, mc.DROP_RATE, mc.FEAT_DROP_RATE, mc.ACT_EMB_SIZE),
+            Critic(mc.HIDDEN_SIZE, mc.DROP_RATE)]
+    sds = [{k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()} for m in mods]
+    params = [v for sd in sds for v in sd.values()]
+    opt = torch.optim.RMSprop(params, lr=cfg.TRAIN.LR)
+    random.seed(2020)
+    penv = PE.R2RBatchPort(PE.WorldView(world_small), items, batch_size=B)
+    ag = PR.Agent("ENVDROP", sds[0], sds[1], sds[2], hidden=512, bidirectional=True, enc_layers=1, episode_len=35)
+    drop = P.Drop("torch")
+    n_enc, n_dec = len(sds[0]), len(sds[1])
+
+    def iteration():
+        _, l1 = PR.rollout_envdrop(ag, penv, train_ml=True, train_rl=False, feedback="teacher", drop=drop)
+        _, l2 = PR.rollout_envdrop(ag, penv, train_ml=False, train_rl=True, restart=True, feedback="sample", drop=drop)
+        loss = l1["ml_loss"] + l2["rl_loss"]
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params[:n_enc], 40.0)
+        torch.nn.utils.clip_grad_norm_(params[n_enc:n_enc + n_dec], 40.0)
+        opt.step()
+        return float(loss)
+    return iteration
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python
+    reference itself cannot travel to the GPU box) on all host threads, same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = host_threads()
+    from clvln_b200.environ import make_world, make_items
+    world = make_world(n_scans=8, seed=2020)
+    B = args.batch
+    items = make_items(world, max(4 * B, 256), seed=2020, fixed_len=80)
+    it = cpu_iteration_factory(world, items, B, threads)
+    t0 = time.time()
+    it()                                                  # probe (also the first warm-up)
+    probe = time.time() - t0
+    budget = 200.0
+    n_total = args.steps + args.warmup
+    if probe * n_total > budget and B > 16:               # bound the run: smaller per-step sample
+        B = 16
+        items = make_items(world, 256, seed=2020, fixed_len=80)
+        it = cpu_iteration_factory(world, items, B, threads)
+        it()
+    for _ in range(max(0, args.warmup - 1)):
+        it()
+    t0 = time.time()
+    for _ in range(args.steps):
+        it()
+    dt = time.time() - t0
+    v = B * args.steps / dt
+    sample = f"{args.steps} full EnvDrop training iterations (teacher + 35-step sampled rollout + backward + clip + RMSprop) at B={B}, L=80, 8-scan synthetic world, fp32, {threads} torch threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "EnvDrop IL+A2C training iteration, B=%d/step, L=80, 36x2176 features, H=512, <=35 steps" % B,
+                   "device": "host CPU", "torch_threads": threads},
+        "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import clvln_b200  # noqa: F401
+    from clvln_b200 import ops, utils, _lib
+    from clvln_b200.agent import build_agent
+    from clvln_b200.engine import TrainStep
+    from clvln_b200.engine.graphs import GraphedTrainStep
+    from clvln_b200.environ import R2RBatch
+    import random
+    _lib.lib()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+
+    world, items = build_world(args.small, dev)
+    cfg = utils.agent_cfg("ENVDROP")
+    cfg.TRAIN.BATCH_SIZE = args.batch
+    random.seed(2020)
+    env = R2RBatch(world, items, batch_size=args.batch, device=dev, rank=rank, world_size=world_size)
+    torch.manual_seed(2020)
+    agent = build_agent(cfg, utils.StubTokenizer(), dev)
+    agent.env = env
+    agent.train()
+    agent.sync_every = 0                                  # fixed-length sampled rollouts: no host polls
+    step = GraphedTrainStep(cfg, agent) if args.graph else TrainStep(cfg, agent)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, staged, read_loss):
+        if staged:
+            env.prefetch(n)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = ops.CALLS[0]
+        e0.record()
+        for _ in range(n):
+            loss = step()
+            if read_loss:
+                loss.item()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), ops.CALLS[0] - c0
+
+    timed(max(3, args.warmup), False, False)              # warm-up (also captures the graphs)
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    t_dev, launches = timed(args.steps, True, False)      # inputs resident in HBM before the region
+    t_e2e, _ = timed(args.steps, False, True)             # public API: H2D per step + loss read-back
+    clocks = clk.stop() if rank == 0 else None
+    h2d = env._last_ib.h2d_bytes
+    n_ep = args.batch * world_size * args.steps
+    out = {
+        "metric": METRIC, "value": round(n_ep / t_dev, 2), "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": round(t_dev / args.steps * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16 feature table, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": "EnvDrop IL+A2C training iteration (teacher rollout + 35-step sampled rollout + backward + clip + RMSprop), B=%d/GPU, L=80, 36x2176 features, H=512" % args.batch,
+                   "global_batch": args.batch * world_size, "parallelism": f"dp{world_size}",
+                   "table": "%d viewpoints x 36 x 2048 bf16 = %.2f GB in HBM" % (world.n_vp, world.n_vp * 36 * 2048 * 2 / 1e9),
+                   "l2": "inputs larger than L2: every step gathers random viewpoints from the %.2f GB table" % (world.n_vp * 36 * 2048 * 2 / 1e9),
+                   "cuda_graph": bool(args.graph)},
+        "e2e": {"value": round(n_ep / t_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(t_e2e / args.steps * 1e3, 3)},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if rank == 0:
+        store = agent.store_of(env)
+        out["roofline"] = roofline_pano(store, ops, torch, args.batch, agent.pano_split, peaks)
+        if world_size == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            from clvln_b200.environ import make_world, make_items
+            w_small = make_world(n_scans=8, seed=2020)
+            B = args.batch
+            it = cpu_iteration_factory(w_small, make_items(w_small, 4 * B, seed=2020, fixed_len=80), B, threads)
+            it()
+            n, t0 = 0, time.time()
+            while n < 2 or (time.time() - t0 < 12.0 and n < 50):
+                it()
+                n += 1
+            dt = time.time() - t0
+            out["cpu_baseline"] = {"value": round(B * n / dt, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": f"{n} full EnvDrop training iterations at B={B}, L=80 on an 8-scan synthetic world (oracle CPU restatement of the reference, fp32, {threads} torch threads, {dt:.1f} s)"}
+        print(json.dumps(out), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

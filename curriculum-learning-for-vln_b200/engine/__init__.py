@@ -2,6 +2,7 @@
 from .optim import FlatOptimizer, build_optimizer
 from .trainer import ClassicTrainer, NaiveCurriculum, SelfPacedCurriculum, TrainStep, build_trainer
 from .evaluator import Evaluation, evaluate
+from .graphs import GraphedTrainStep
 
 __all__ = ["FlatOptimizer", "build_optimizer", "ClassicTrainer", "NaiveCurriculum", "SelfPacedCurriculum", "TrainStep",
-           "build_trainer", "Evaluation", "evaluate"]
+           "build_trainer", "Evaluation", "evaluate", "GraphedTrainStep"]

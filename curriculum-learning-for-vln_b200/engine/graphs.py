@@ -1,0 +1,95 @@
+"""CUDA-graph replay of a training iteration.
+
+The reference's iteration is host-driven (one `.cpu()` per decoder step, envdrop.py:198); on a
+B200 the ~2 000 small launches of an EnvDrop iteration (two rollouts + backward) are bound by the
+Python/launch path, not by the GPU.  ``GraphedTrainStep`` captures zero_grad -> rollouts ->
+backward once per teacher-rollout length into a CUDA graph and replays it: the minibatch's index
+tensors are copied into static buffers, the Philox base lives in device memory and is advanced
+inside the graph, so every replay sees new data and new dropout masks / samples.  The gradient
+all-reduce and the fused clip + update stay outside the graph (3 launches).
+"""
+import torch
+
+from .. import ops
+from .trainer import TrainStep
+
+
+class _StaticEnv:
+    """Stands in for agent.env while capturing/replaying: hands out the static IndexBatch."""
+
+    def __init__(self, env, ib):
+        self._env, self._ib = env, ib
+
+    def reset_index(self, **kw):
+        return self._ib
+
+    def __getattr__(self, k):
+        return getattr(self._env, k)
+
+
+class GraphedTrainStep(TrainStep):
+    def __init__(self, cfg, agent, optimizer=None, weights=None, warmup=2):
+        super().__init__(cfg, agent, optimizer, weights)
+        self.graphs = {}
+        self.static = None
+        self.warmup = warmup
+        self.full_length = cfg.MODEL.NAME == "SELF-MONITOR"
+
+    def _body(self):
+        self.opt.zero_grad()
+        loss, item = self.losses()
+        loss.backward()
+        self.agent.rng.advance()
+        return loss.detach(), item
+
+    def _load(self, ib):
+        import copy
+        if self.static is None:
+            L = self.agent.env.max_len
+            st = copy.copy(ib)
+            st.tokens = torch.zeros((ib.tokens.shape[0], L), dtype=torch.int64, device=ib.tokens.device)
+            for k in ("lengths", "vp", "view", "goal", "index"):
+                setattr(st, k, getattr(ib, k).clone())
+            self.static = st
+        st = self.static
+        st.tokens.zero_()
+        st.tokens[:, :ib.tokens.shape[1]].copy_(ib.tokens)
+        for k in ("lengths", "vp", "view", "goal", "index"):
+            getattr(st, k).copy_(getattr(ib, k))
+        st.teacher_steps = ib.teacher_steps
+        return st
+
+    def __call__(self):
+        ag = self.agent
+        env = ag.env
+        ib = env.reset_index(full_length=self.full_length)
+        st = self._load(ib)
+        key = (min(ag.episode_len, ib.teacher_steps), id(env.world))
+        ag.env = _StaticEnv(env, st)
+        saved = ag.sync_every
+        ag.sync_every = 0
+        try:
+            if key not in self.graphs:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for _ in range(self.warmup):
+                        ag.rng.off = 0
+                        self._body()
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                ag.rng.off = 0
+                c0 = ops.CALLS[0]
+                with torch.cuda.graph(g):
+                    loss, item = self._body()
+                self.graphs[key] = (g, loss, item, ops.CALLS[0] - c0)
+            g, loss, item, n_calls = self.graphs[key]
+            g.replay()
+            ops.CALLS[0] += n_calls
+        finally:
+            ag.env = env
+            ag.sync_every = saved
+        self.opt.step()
+        if item is not None:
+            self.weights.record(st.index, item)
+        return loss

