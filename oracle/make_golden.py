@@ -1,0 +1,154 @@
+"""Generate tests/golden/*.pt from the REAL reference (container only: needs /root/reference).
+
+TEST INFRASTRUCTURE.  The reference has no golden vectors for this path, so they are produced by
+running its unmodified code here (through oracle/ref_loader.py + oracle/ref_harness.py) on seeded
+inputs; the committed fixtures then pin oracle/port_*.py wherever /root/reference is absent
+(tests/test_golden.py).  Two kinds:
+
+  modules.pt   small-dimension instances of EncoderLSTM (3 layouts), EnvDropDecoder,
+               AttnDecoderLSTM, MonitorDecoder (eval and BN-training), Critic: state_dict, inputs,
+               outputs — a few hundred KB.
+  rollouts.pt  the three real agents (shipped model sizes) on a seeded synthetic world:
+               teacher + forced-action rollouts in eval mode: per-step logits/targets, losses,
+               per-parameter gradient norms, trajectories, and the minibatch order over a
+               wrap-around.  World and weights are regenerated from seeds by the test.
+
+usage: python -m oracle.make_golden
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def module_cases():
+    from oracle import ref_loader
+    U, Pol = ref_loader.load_ref_models()
+    out = {}
+    torch.manual_seed(1234)
+    B, L, C, H, IMG = 4, 9, 5, 32, 16
+    F_ = IMG + 128
+    lens = torch.tensor([9, 7, 4, 2])
+    toks = torch.randint(4, 60, (B, L))
+    for i, l in enumerate(lens):
+        toks[i, l:] = 0
+    for name, (E, Hh, bi, nl) in {"enc_bi1": (24, H, True, 1), "enc_bi2": (20, H, True, 2), "enc_uni": (24, H, False, 1)}.items():
+        enc = U.EncoderLSTM(60, E, Hh, 0, 0.5, bi, nl).eval()
+        ctx, h, c = enc(toks, lens)
+        out[name] = dict(sd={k: v.clone() for k, v in enc.state_dict().items()}, cfg=(E, Hh, bi, nl), toks=toks, lens=lens,
+                         ctx=ctx.detach(), h=h.detach(), c=c.detach())
+    img, cand = torch.randn(B, 36, F_), torch.randn(B, C, F_)
+    mask = torch.zeros(B, L, dtype=torch.bool)
+    mask[1, 7:] = True
+    mask[3, 2:] = True
+    ctx = torch.randn(B, L, H)
+    a128, ht, c0 = torch.randn(B, 128), torch.randn(B, H), torch.randn(B, H)
+    dec = Pol.EnvDropDecoder(H, 0.5, 0.3, action_embed_size=8, feature_size=F_).eval()
+    lo, (h1, c1), htl = dec(a128, img.clone(), cand.clone(), ht, ht, c0, ctx, mask)
+    out["envdrop"] = dict(sd=dec.state_dict(), a=a128, img=img, cand=cand, ht=ht, c0=c0, ctx=ctx, mask=mask,
+                          logit=lo.detach(), h1=h1.detach(), c1=c1.detach(), h_tilde=htl.detach())
+    dec = Pol.AttnDecoderLSTM(H, 0.5, action_embed_size=F_, feature_size=F_).eval()
+    ap = torch.randn(B, F_)
+    lo, (h1, c1), (ac, av) = dec(img, ap, cand, ht, c0, ctx, mask)
+    out["follower"] = dict(sd=dec.state_dict(), img=img, ap=ap, cand=cand, h0=ht, c0=c0, ctx=ctx, mask=mask,
+                           logit=lo.detach(), h1=h1.detach(), c1=c1.detach(), alpha_c=ac.detach(), alpha_v=av.detach())
+    for training in (False, True):
+        dec = Pol.MonitorDecoder(H, 0.5, 12, [40], action_embed_size=F_, feature_size=F_)
+        dec.train(training)
+        for m in dec.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        sd0 = {k: v.clone() for k, v in dec.state_dict().items()}
+        ctx12 = torch.randn(B, 12, H)
+        m12 = torch.zeros(B, 12, dtype=torch.bool)
+        m12[:, 8:] = True
+        cm = torch.zeros(B, C, dtype=torch.bool)
+        cm[0, 3:] = True
+        cm[2, 2:] = True
+        (lo, pr), (h1, c1), (ca, va) = dec(None, ap, cand, ht, c0, ctx12, m12, cm)
+        out[f"monitor_train{int(training)}"] = dict(
+            sd=sd0, ap=ap, cand=cand, h0=ht, c0=c0, ctx=ctx12, mask=m12, cmask=cm, logit=lo.detach(), prog=pr.detach(),
+            h1=h1.detach(), c1=c1.detach(), ctx_attn=ca.detach(), cand_attn=va.detach(),
+            rm=dec.state_dict()["proj_navigable_mlp.mlp.0.running_mean"].clone(),
+            rv=dec.state_dict()["proj_navigable_mlp.mlp.2.running_var"].clone())
+    cr = Pol.Critic(H, 0.5).eval()
+    out["critic"] = dict(sd=cr.state_dict(), x=ht, y=cr(ht).detach())
+    return out
+
+
+def rollout_cases():
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items
+    from oracle import ref_harness as H
+    w = make_world(n_scans=3, seed=1)
+    items = make_items(w, 40, seed=1)
+    src = H.install(w, {"train": items})
+    import src.environ as environ
+    import src.agent as agent_mod
+    tok = H.StubTokenizer(items)
+    fs = H.feature_store(w)
+    dev = torch.device("cpu")
+    out = {"world": dict(n_scans=3, seed=1, n_items=40, B=8)}
+    # minibatch order across two wrap-arounds
+    random.seed(2020)
+    env = environ.R2RBatch(fs, batch_size=16, splits=["train"], tokenizer=tok)
+    random.seed(1)
+    order = []
+    for _ in range(7):
+        env._next_minibatch()
+        order.append([it["instr_id"] for it in env.batch])
+    out["order"] = order
+    for kind in ("ENVDROP", "FOLLOWER", "MONITOR"):
+        random.seed(2020)
+        torch.manual_seed(2020)
+        renv = environ.R2RBatch(fs, batch_size=8, splits=["train"], tokenizer=tok)
+        H.warm_candidate_buffer(renv)
+        cfg = H.model_cfg(kind)
+        if kind == "ENVDROP":
+            ag = agent_mod.EnvDropAgent(cfg, 80, "/tmp", dev, renv, tok, episode_len=12)
+        elif kind == "FOLLOWER":
+            ag = agent_mod.FollowerAgent(cfg, "/tmp", dev, renv, tok, episode_len=10)
+        else:
+            ag = agent_mod.SelfMonitorAgent(cfg, 80, "/tmp", dev, renv, tok, episode_len=10)
+            ag.reset_loss()
+        ag.env = renv
+        ag.eval()
+        mods = [ag.encoder, ag.decoder] + ([ag.critic] if kind == "ENVDROP" else [])
+        torch.manual_seed(7)
+        if kind == "ENVDROP":
+            t1 = ag.rollout(train_ml=True, train_rl=False, feedback="teacher")
+            l1 = ag.loss["ml_loss"]
+            t2 = ag.rollout(train_ml=False, train_rl=True, restart=True, feedback="sample")
+            l2 = ag.loss["rl_loss"]
+            loss = l1 + l2
+        else:
+            t1 = ag.rollout(feedback="teacher")
+            l1 = ag.ml_loss
+            t2 = ag.rollout(feedback="sample", train_cl=True)
+            l2 = ag.ml_loss
+            loss = l1 + l2.sum()
+        loss.backward()
+        gn = [float(p.grad.norm()) if p.grad is not None else 0.0 for m in mods for p in m.parameters()]
+        out[kind] = dict(traj1=t1, traj2=t2, l1=l1.detach(), l2=l2.detach(), grad_norms=gn,
+                         w_checksum=[float(p.detach().double().sum()) for m in mods for p in m.parameters()])
+    return out
+
+
+def main():
+    from oracle import ref_loader
+    assert ref_loader.reference_available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    torch.save(module_cases(), os.path.join(OUT, "modules.pt"))
+    torch.save(rollout_cases(), os.path.join(OUT, "rollouts.pt"))
+    for f in os.listdir(OUT):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

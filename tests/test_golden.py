@@ -1,0 +1,130 @@
+"""Pin the oracle (oracle/port_*.py) against golden vectors produced by the REAL reference
+(oracle/make_golden.py, run in the build container; fixtures under tests/golden/).  Runs anywhere
+(CPU) — this is what carries the pin to machines without /root/reference."""
+import os
+import random
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = os.path.join(HERE, "golden")
+
+
+def close(a, b, tol=1e-5):
+    d = (a - b).abs().max().item()
+    assert d <= tol * max(1.0, b.abs().max().item()), d
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return torch.load(os.path.join(G, "modules.pt"), weights_only=False)
+
+
+def test_encoder_variants(mods):
+    from oracle import port_modules as P
+    for name in ("enc_bi1", "enc_bi2", "enc_uni"):
+        c = mods[name]
+        E, H, bi, nl = c["cfg"]
+        ctx, h, cc = P.encoder_lstm(c["sd"], c["toks"], c["lens"], bidirectional=bi, num_layers=nl, drop_ratio=0.5)
+        close(ctx, c["ctx"]), close(h, c["h"]), close(cc, c["c"])
+
+
+def test_decoders_and_critic(mods):
+    from oracle import port_modules as P
+    c = mods["envdrop"]
+    lo, (h1, c1), ht, _ = P.envdrop_decoder(c["sd"], c["a"], c["img"], c["cand"], c["ht"], c["c0"], c["ctx"], c["mask"])
+    close(lo, c["logit"], 1e-4), close(h1, c["h1"]), close(c1, c["c1"]), close(ht, c["h_tilde"])
+    c = mods["follower"]
+    lo, (h1, c1), (ac, av) = P.follower_decoder(c["sd"], c["img"], c["ap"], c["cand"], c["h0"], c["c0"], c["ctx"], c["mask"])
+    close(lo, c["logit"], 1e-4), close(h1, c["h1"]), close(ac, c["alpha_c"]), close(av, c["alpha_v"])
+    for training in (0, 1):
+        c = mods[f"monitor_train{training}"]
+        sd = {k: v.clone() for k, v in c["sd"].items()}
+        (lo, pr), (h1, c1), (ca, va) = P.monitor_decoder(sd, c["ap"], c["cand"], c["h0"], c["c0"], c["ctx"], c["mask"],
+                                                         c["cmask"], training=bool(training))
+        close(lo, c["logit"], 2e-4), close(pr, c["prog"], 1e-4), close(h1, c["h1"], 1e-4), close(va, c["cand_attn"], 1e-4)
+        close(sd["proj_navigable_mlp.mlp.0.running_mean"], c["rm"]), close(sd["proj_navigable_mlp.mlp.2.running_var"], c["rv"], 1e-4)
+    c = mods["critic"]
+    close(P.critic(c["sd"], c["x"]), c["y"])
+
+
+@pytest.fixture(scope="module")
+def roll():
+    return torch.load(os.path.join(G, "rollouts.pt"), weights_only=False)
+
+
+def _world(roll):
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items
+    w = roll["world"]
+    world = make_world(n_scans=w["n_scans"], seed=w["seed"])
+    return world, make_items(world, w["n_items"], seed=w["seed"])
+
+
+def test_minibatch_order_matches_reference(roll):
+    """Product env and oracle env draw the reference's minibatches (incl. wrap-around reshuffles)."""
+    from clvln_b200.environ import R2RBatch
+    from oracle import port_env as PE
+    world, items = _world(roll)
+    for make in (lambda: R2RBatch(world, items, batch_size=16),
+                 lambda: PE.R2RBatchPort(PE.WorldView(world), items, batch_size=16)):
+        random.seed(2020)
+        env = make()
+        random.seed(1)
+        got = []
+        for _ in range(7):
+            env._next_minibatch()
+            got.append([it["instr_id"] for it in env.batch])
+        assert got == roll["order"]
+
+
+@pytest.mark.parametrize("kind", ["ENVDROP", "FOLLOWER", "MONITOR"])
+def test_port_rollouts_match_reference_golden(roll, kind):
+    """Oracle rollouts on regenerated world + weights reproduce the real agents' losses,
+    gradient norms and trajectories (eval mode; sampling replays torch's RNG stream)."""
+    from clvln_b200 import utils
+    from clvln_b200.model import EncoderLSTM, EnvDropDecoder, AttnDecoderLSTM, MonitorDecoder, Critic
+    from oracle import port_env as PE, port_rollout as PR
+    world, items = _world(roll)
+    g = roll[kind]
+    random.seed(2020)
+    torch.manual_seed(2020)
+    penv = PE.R2RBatchPort(PE.WorldView(world), items, batch_size=8)
+    # the reference builds encoder, decoder(, critic) in this order under the same seed; the product
+    # modules have the same parameter containers and init order, so the weights come out identical
+    if kind == "ENVDROP":
+        mods = [EncoderLSTM(992, 256, 512, 0, 0.5, True, 1), EnvDropDecoder(512, 0.5, 0.3, 64, 128, 2176), Critic(512, 0.5)]
+        kw = dict(hidden=512, bidirectional=True, enc_layers=1, episode_len=12)
+    elif kind == "FOLLOWER":
+        mods = [EncoderLSTM(992, 300, 256, 0, 0.5, True, 2), AttnDecoderLSTM(256, 0.5, 2176, 2176)]
+        kw = dict(hidden=256, bidirectional=True, enc_layers=2, episode_len=10)
+    else:
+        mods = [EncoderLSTM(992, 256, 512, 0, 0.5, False, 1), MonitorDecoder(512, 0.5, 80, [1024], 2176, 2176)]
+        kw = dict(hidden=512, bidirectional=False, enc_layers=1, episode_len=10)
+    chk = [float(p.detach().double().sum()) for m in mods for p in m.parameters()]
+    assert len(chk) == len(g["w_checksum"]) and max(abs(a - b) for a, b in zip(chk, g["w_checksum"])) < 1e-6, \
+        "regenerated weights differ from the reference's (torch init order changed?)"
+    sds = [{k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "running" not in k and k != "position.pe")
+            for k, v in m.state_dict().items()} for m in mods]
+    ag = PR.Agent("X", sds[0], sds[1], sds[2] if len(sds) > 2 else None, **kw)
+    random.seed(1)
+    torch.manual_seed(7)
+    if kind == "ENVDROP":
+        t1, l1 = PR.rollout_envdrop(ag, penv, train_ml=True, train_rl=False, feedback="teacher")
+        t2, l2 = PR.rollout_envdrop(ag, penv, train_ml=False, train_rl=True, restart=True, feedback="sample")
+        l1, l2 = l1["ml_loss"], l2["rl_loss"]
+        loss = l1 + l2
+    else:
+        fn = PR.rollout_follower if kind == "FOLLOWER" else PR.rollout_monitor
+        r1 = fn(ag, penv, feedback="teacher")
+        r2 = fn(ag, penv, feedback="sample", train_cl=True)
+        t1, l1, t2, l2 = r1[0], r1[1], r2[0], r2[1]
+        loss = l1 + l2.sum()
+    loss.backward()
+    assert t1 == g["traj1"] and t2 == g["traj2"]
+    close(l1.detach(), g["l1"], 1e-5), close(l2.detach(), g["l2"], 1e-5)
+    gn = [float(v.grad.norm()) if v.grad is not None else 0.0 for sd in sds for v in sd.values() if v.requires_grad]
+    assert len(gn) == len(g["grad_norms"])
+    for a, b in zip(gn, g["grad_norms"]):
+        assert abs(a - b) <= 1e-4 * max(1e-3, abs(b)), (a, b)

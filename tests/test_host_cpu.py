@@ -1,0 +1,247 @@
+"""CPU tests of the host logic: the C-ABI library loads and exports every symbol the header
+declares; the index-table environment agrees with the oracle's dict-and-loop environment;
+curriculum bookkeeping (CLR2R index map, self-paced weights) follows the reference; the N>1 data
+path (minibatch sharding, SELF-PACE all-gather) works under world_size-2 gloo."""
+import os
+import random
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import __graft_entry__ as G
+    from clvln_b200 import _lib
+    G.build()
+    hdr = open(os.path.join(ROOT, "include", "vln_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vln_[a-z0-9_]+)\s*\(", hdr))
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    assert declared and declared <= exported, sorted(declared - exported)
+    assert declared == set(_lib.exported_symbols()), sorted(declared ^ set(_lib.exported_symbols()))
+    L = _lib.lib()                                   # loads without a GPU; no compute calls here
+    assert L.vln_version() >= 100
+
+
+def _world(n_items=60, seed=3):
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items
+    w = make_world(n_scans=3, seed=seed)
+    return w, make_items(w, n_items, seed=seed)
+
+
+def test_obs_dict_face_matches_oracle_env():
+    """reset / teacher-following steps: features, candidates, teacher, distance bit-exact vs the oracle env."""
+    from clvln_b200.environ import R2RBatch
+    from oracle import port_env as PE
+    world, items = _world()
+    random.seed(5)
+    env = R2RBatch(world, items, batch_size=6)
+    random.seed(5)
+    penv = PE.R2RBatchPort(PE.WorldView(world), items, batch_size=6)
+    obs, pobs = env.reset(), penv.reset()
+    for step in range(6):
+        assert len(obs) == len(pobs)
+        acts = []
+        for a, b in zip(obs, pobs):
+            for k in ("instr_id", "scan", "viewpointId", "viewIndex", "heading", "elevation", "teacher", "instr_length"):
+                assert a[k] == b[k], k
+            assert np.float32(a["distance"]) == np.float32(b["distance"])
+            assert np.array_equal(a["feature"], b["feature"])
+            assert len(a["candidates"]) == len(b["candidates"])
+            for ca, cb in zip(a["candidates"], b["candidates"]):
+                assert ca["nextViewpointId"] == cb["nextViewpointId"] and ca["absViewIndex"] == cb["absViewIndex"]
+                assert np.array_equal(ca["feature"], cb["feature"])
+            act = -1
+            for k, c in enumerate(a["candidates"]):
+                if c["nextViewpointId"] == a["teacher"]:
+                    act = k
+            acts.append(act)
+        obs, pobs = env.step(np.array(acts), obs), penv.step(np.array(acts), pobs)
+    assert all(o["teacher"] == o["viewpointId"] for o in obs)          # everyone reached the goal
+
+
+def test_index_face_matches_obs_face():
+    from clvln_b200.environ import R2RBatch
+    from clvln_b200.environ.world import heading_to_view
+    world, items = _world()
+    random.seed(9)
+    env = R2RBatch(world, items, batch_size=8)
+    ib = env.reset_index()
+    obs = env.reset(restart=True)
+    assert [int(x) for x in ib.vp] == [o["g"] for o in obs]
+    assert [int(x) for x in ib.view] == [o["viewIndex"] for o in obs]
+    assert [int(x) for x in ib.lengths] == [o["instr_length"] for o in obs]
+    assert ib.tokens.shape[1] == int(ib.lengths[0]) and sorted(ib.lengths.tolist(), reverse=True) == ib.lengths.tolist()
+    for i, o in enumerate(obs):
+        assert np.array_equal(ib.tokens[i].numpy(), np.asarray(o["instr_encoding"])[:ib.tokens.shape[1]])
+    hops = max(len(it["path"]) - 1 for it in env.batch)
+    assert ib.teacher_steps == hops + 1
+    ib2 = env.reset_index(restart=True)
+    assert ib2 is ib
+
+
+def test_sharding_reassembles_global_batch():
+    from clvln_b200.environ import R2RBatch
+    world, items = _world(100)
+    random.seed(11)
+    g = R2RBatch(world, items, batch_size=16)
+    shards = []
+    for r in range(4):
+        random.seed(11)
+        shards.append(R2RBatch(world, items, batch_size=4, rank=r, world_size=4))
+    for _ in range(9):                                             # crosses a wrap-around
+        st = random.getstate()
+        g._next_minibatch()
+        after = random.getstate()
+        ids = [it["instr_id"] for it in g.batch]
+        for r, e in enumerate(shards):
+            random.setstate(st)
+            e._next_minibatch()
+            assert random.getstate() == after                      # every rank consumes the same stream
+            assert [it["instr_id"] for it in e.batch] == ids[r::4]
+            assert [it["instr_id"] for it in e.global_batch] == ids
+
+
+def test_curriculum_env_matches_oracle():
+    from clvln_b200.environ import CLR2RBatch, split_rounds
+    from oracle import port_env as PE
+    world, items = _world(120)
+    rounds = split_rounds(items)
+    assert sum(len(v) for v in rounds.values()) == 120 and all(len(rounds[k]) for k in range(1, 6))
+    random.seed(4)
+    env = CLR2RBatch(world, rounds, batch_size=10, c_rate=0.8)
+    random.seed(4)
+    penv = PE.CLR2RBatchPort(PE.WorldView(world), rounds, batch_size=10, c_rate=0.8)
+    assert np.array_equal(env.a, penv.a) and env.c == penv.c and len(env) == len(penv) == 120
+    for _ in range(15):                                            # crosses the wrap-around reshuffle
+        st = random.getstate()
+        env._next_minibatch()
+        random.setstate(st)
+        penv._next_minibatch()
+        assert env.cur_batch_index == penv.cur_batch_index
+    ib = env.reset_index()
+    assert ib.index.tolist() == env.cur_batch_index
+
+
+class _FakeCLEnv:
+    def __init__(self, n, seed=0):
+        rs = np.random.RandomState(seed)
+        self.a = rs.randint(1, 6, n).astype(np.float32)
+        self.c = self.a.sum() * 0.8
+        self.data = [{"instr_id": str(i)} for i in range(n)]
+
+    def __len__(self):
+        return len(self.a)
+
+    def index(self, item):
+        return int(item["instr_id"])
+
+
+@pytest.mark.parametrize("func", ["linear", "log", "binary"])
+def test_self_paced_weights_follow_reference_formulas(func):
+    """curriculum.py:214-220, 428-448 restated independently in numpy float32."""
+    from clvln_b200.engine import SelfPacedCurriculum
+    env = _FakeCLEnv(500)
+    sp = SelfPacedCurriculum(env, "cpu", pace_func=func, init_lamb=0.7, init_weight_ctrl=0.5, miu=0.2, interval=1,
+                             strategy="epoch", burn_in=0)
+    w0 = np.where(env.a <= 2, 1.0, 0.5).astype(np.float32)
+    assert np.array_equal(sp.weight.numpy(), w0)
+    rs = np.random.RandomState(1)
+    loss = torch.from_numpy((rs.rand(500) * 1.5).astype(np.float32))
+    sp.loss_for_item = loss
+    sp.after_epoch(1, None)
+    lamb = np.float32(0.7) + np.float32(0.2)
+    assert abs(float(sp.lamb) - float(lamb)) < 1e-7
+    l = loss.numpy()
+    mask = l >= lamb
+    w = w0.copy()
+    w[mask] = 0.01
+    if func == "linear":
+        w[~mask] = 1 - l[~mask] / lamb
+    elif func == "log":
+        w[~mask] = np.log(l[~mask] + (1 - lamb)) / np.log(1 - lamb)
+    else:
+        w[~mask] = 1.0
+    w[w < 0.01] = 0.01
+    if np.dot(env.a, w) > env.c:
+        w = w + env.a * (env.c - np.dot(env.a, w)) / (np.linalg.norm(env.a) ** 2)
+        w[w <= 0] = 0.001
+    assert np.allclose(sp.weight.numpy(), w, rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.ref
+def test_self_paced_update_matches_real_reference():
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("no /root/reference")
+    src = ref_loader.load_ref_agents()
+    from src.engine.curriculum import SelfPacedCurriculum as RefSP
+    from clvln_b200.engine import SelfPacedCurriculum
+    env = _FakeCLEnv(400, 3)
+    for func in ("linear", "log", "binary"):
+        kw = dict(pace_func=func, init_lamb=0.3, init_weight_ctrl=0.4, miu=0.3, interval=1, strategy="epoch", burn_in=0)
+        ref, mine = RefSP(env, "cpu", **kw), SelfPacedCurriculum(env, "cpu", **kw)
+        assert torch.equal(ref.weight, mine.weight)
+        loss = torch.rand(400, generator=torch.Generator().manual_seed(2))       # log pacing needs lambda < 1
+        ref.lamb = ref.lamb + ref.stepsize
+        ref.update_weight(loss.clone())
+        mine.loss_for_item = loss.clone()
+        mine.after_epoch(1, None)
+        assert not torch.isnan(ref.weight).any()
+        assert torch.equal(ref.weight, mine.weight), func          # bit-reproducible given identical losses
+
+
+def _gloo_worker(rank, world_size, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    import sys
+    sys.path.insert(0, ROOT)
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items, CLR2RBatch, split_rounds
+    from clvln_b200.engine import SelfPacedCurriculum
+    world = make_world(n_scans=3, seed=3)
+    items = make_items(world, 120, seed=3)
+    random.seed(2020)
+    env = CLR2RBatch(world, split_rounds(items), batch_size=8, rank=rank, world_size=world_size)
+    sp = SelfPacedCurriculum(env, "cpu", pace_func="linear", init_lamb=2.0, init_weight_ctrl=0.5, miu=2.0, interval=1,
+                             burn_in=0)
+    seen = []
+    for it in range(3):
+        ib = env.reset_index()
+        seen.append(ib.index.tolist())
+        sp.record(ib.index, ib.index.float() * 0.01 + it)              # a per-item "loss" every rank can verify
+    g = torch.zeros(4) + rank + 1                                     # gradient averaging recipe of FlatOptimizer
+    dist.all_reduce(g)
+    q.put((rank, seen, sp.loss_for_item.clone(), (g / world_size).tolist(), [it["instr_id"] for it in env.global_batch]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_and_curriculum_allgather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + random.randint(0, 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, seen0, l0, g0, gb0), (r1, seen1, l1, g1, gb1) = res
+    assert gb0 == gb1                                                  # same global minibatch on both ranks
+    assert torch.equal(l0, l1) and float(l0.abs().sum()) > 0           # replicated per-item losses after all-gather
+    assert g0 == g1 == [1.5] * 4                                       # mean of per-rank gradients
+    for a, b in zip(seen0, seen1):
+        assert not set(a) & set(b) and len(a) == len(b) == 8           # disjoint shards of the global batch
+    idx = torch.tensor(seen0[-1] + seen1[-1])
+    assert torch.allclose(l0[idx], idx.float() * 0.01 + 2)
