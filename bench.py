@@ -311,7 +311,7 @@ def run_b200(args):
     }
     if rank == 0:
         store = agent.store_of(env)
-        out["roofline"] = roofline_pano(store, ops, torch, args.batch, agent.pano_split, peaks)
+        out["roofline"] = roofline_pano(store, ops, torch, args.batch, agent.split_for(args.batch), peaks)
         if world_size == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             from clvln_b200.environ import make_world, make_items

@@ -47,7 +47,7 @@ _SIGS = {
     "vln_gather_pano": ([_p, _p, _p, _p, _p, _i, _p], _i),
     "vln_gather_cand": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_gather_action_feat": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p], _i),
-    "vln_pano_attn": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _i, _p], _i),
+    "vln_pano_attn": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _i, _p], _i),
     "vln_cand_logits_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),
     "vln_cand_logits_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),
     "vln_ctx_attn_fwd": ([_p, _p, _p, _p, _p, _i, _i, _i, _p], _i),

@@ -77,7 +77,7 @@ class BaseAgent:
         self._stores = {}
         self.sync_every = 4            # poll `all ended` every k steps in student-forced rollouts (0 = never)
         self.fixed_steps = None        # run exactly this many steps (CUDA-graph capture), no polling
-        self.pano_split = 2
+        self.pano_split = None         # parts per episode in the panorama kernel; None = by batch size
         self.last_state = None
         self.trace = None              # set to a list to record per-step logits / targets / actions
 
@@ -99,6 +99,12 @@ class BaseAgent:
         if key not in self._stores:
             self._stores[key] = ops.FeatureStore.from_world(env.world, self.device)
         return self._stores[key]
+
+    def split_for(self, B):
+        """Parts per episode for vln_pano_attn: split small batches so the units still cover the SMs."""
+        if self.pano_split is not None:
+            return self.pano_split
+        return 1 if B >= 48 else (2 if B >= 24 else 4)
 
     def _horizon(self, ib, feedback):
         if self.fixed_steps is not None:

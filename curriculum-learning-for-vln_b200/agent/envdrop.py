@@ -46,7 +46,7 @@ class EnvDropAgent(BaseAgent):
 
     def _decode(self, st, t, h_tilde, h_t, c_t, ctx, ctx_mask):
         pano, cands = st.pano(t), st.cands(t)
-        pano.split = self.pano_split
+        pano.split = self.split_for(st.B)
         pose = ops.pose_feature(st.store, st.view[t])
         logit, (h_t, c_t), h_tilde = self.decoder(pose, pano, cands, h_tilde, h_t, c_t, ctx, ctx_mask)
         return logit, h_t, c_t, h_tilde

@@ -50,7 +50,7 @@ class FollowerAgent(BaseAgent):
         ml = torch.zeros(B, device=self.device) if train_cl else torch.zeros((), device=self.device)
         for t in range(T):
             pano = st.pano(t)
-            pano.split = self.pano_split
+            pano.split = self.split_for(st.B)
             logit, (h_t, c_t), _ = self.decoder(pano, a_prev, st.cands(t), h_t, c_t, ctx, ctx_mask)
             target = st.teacher
             off = self.rng.next() if feedback == "sample" else 0

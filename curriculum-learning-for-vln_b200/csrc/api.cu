@@ -70,8 +70,24 @@ extern "C" int vln_ctx_create(vln_ctx** out, const void* table_bf16, int n_vp, i
     delete c;
     return rc;
   }
+  c->scratch = nullptr;
+  c->tickets = nullptr;
+  if (cudaMalloc(&c->scratch, (size_t)VLN_SPLIT_MAX_B * 4 * 2056 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&c->tickets, (size_t)VLN_SPLIT_MAX_B * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(c->tickets, 0, (size_t)VLN_SPLIT_MAX_B * sizeof(unsigned int)) != cudaSuccess) {
+    vln_set_error("vln_ctx_create: cannot allocate the split-unit scratch: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(c->scratch);
+    cudaFree(c->tickets);
+    delete c;
+    return -2;
+  }
   *out = c;
   return 0;
 }
 
-extern "C" void vln_ctx_destroy(vln_ctx* ctx) { delete ctx; }
+extern "C" void vln_ctx_destroy(vln_ctx* ctx) {
+  if (!ctx) return;
+  cudaFree(ctx->scratch);
+  cudaFree(ctx->tickets);
+  delete ctx;
+}

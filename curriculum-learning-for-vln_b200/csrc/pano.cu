@@ -1,5 +1,5 @@
-// Feature-table kernels: bit-exact gathers, the fused TMA gather + 36-view soft-dot attention
-// (forward and backward share one kernel), candidate logits forward/backward.
+// Feature-table kernels: bit-exact gathers and candidate logits forward/backward (the fused
+// gather + 36-view attention lives in pano_attn.cu).
 //
 // Roofline class: HBM.  Algorithmic bytes per episode-step: 36*2048*2 = 147 456 B (pano tile),
 // n_cand*4096 B (candidate rows).  See DESIGN.md §Kernels.
@@ -93,155 +93,6 @@ __global__ void __launch_bounds__(kThreads) gather_action_kernel(
     reinterpret_cast<float4*>(dst)[2 * t + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < VLN_ANG) dst[VLN_IMG + t] = 0.f;
   }
-}
-
-// -------------------------------------------------------------------------------------------
-// K3: fused gather + soft-dot attention over the panorama, forward (mode 0) / backward (mode 1).
-//
-// grid = (S, B), cluster = (S,1,1).  CTA `rank` of episode b owns image features
-// [rank*FS, (rank+1)*FS), FS = 2048/S: one TMA box per 256 columns lands the [36 x FS] bf16 slice
-// in shared memory (the only HBM read of the tile).  Per-view partial dot products are summed
-// across the cluster through distributed shared memory (36 floats per CTA), every CTA then holds
-// the full softmax (or its Jacobian-vector product) and produces its own FS output columns.
-// rank 0 also carries the 128 angle dimensions, which are only 4 distinct values per view.
-// -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) pano_attn_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                             const int32_t* __restrict__ vp,
-                                                             const int32_t* __restrict__ view,
-                                                             const float* __restrict__ loc4,
-                                                             const float* __restrict__ vec,
-                                                             float* __restrict__ attn_io, float* __restrict__ out,
-                                                             int mode, float drop_p, const uint64_t* __restrict__ rng, uint64_t call_off,
-                                                             int FS) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rank = (int)cluster_ctarank();
-  const int S = (int)cluster_nctarank();
-  const int b = blockIdx.y;
-  const int nbox = FS / kBoxCols;
-
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem);
-  float* vsl = reinterpret_cast<float*>(smem + (size_t)nbox * kBoxBytes);   // [FS] slice of q / d(out)
-  float* part = vsl + FS;                                                   // [36] (+4 pad)
-  float* sm = part + 40;                                                    // [36] (+4 pad)
-  float* loc = sm + 40;                                                     // [36*4]
-  float* qa = loc + 144;                                                    // [4]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(qa + 4);
-
-  const int g = vp[b];
-  const int cur_view = view[b];
-  if (tid == 0) {
-    tma_prefetch_desc(&tmap);
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, (uint32_t)(nbox * kBoxBytes));
-    for (int i = 0; i < nbox; ++i)
-      tma_load_2d(tile + (size_t)i * VLN_V * kBoxCols, &tmap, bar, rank * FS + i * kBoxCols, g * VLN_V);
-  }
-  // overlap with the TMA: stage the vector slice, the angle table row and the angle-group sums
-  const float* vrow = vec + (size_t)b * VLN_F;
-  for (int i = tid; i < FS; i += kThreads) vsl[i] = vrow[rank * FS + i];
-  for (int i = tid; i < 144; i += kThreads) loc[i] = loc4[(size_t)cur_view * 144 + i];
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float s = warp_sum(vrow[VLN_IMG + 32 * k + lane]);
-      if (lane == 0) qa[k] = s;
-    }
-  }
-  mbar_wait(bar, 0);
-
-  float scale = 1.0f;
-  if (drop_p > 0.f) {   // policy.py:226-231 — feature dropout on the 2048 image dims only
-    scale = 1.0f / (1.0f - drop_p);
-    const uint64_t seed = rng[0], offset = rng[1] + call_off;
-    const uint32_t thr = drop_threshold(drop_p);
-    const int nvec = nbox * VLN_V * 32;
-    uint4* t4 = reinterpret_cast<uint4*>(tile);
-    for (int i = tid; i < nvec; i += kThreads) {
-      const int box = i / (VLN_V * 32), r = i - box * (VLN_V * 32), v = r >> 5, j = r & 31;
-      const uint64_t e = (((uint64_t)b * VLN_V + v) * VLN_IMG + (uint64_t)(rank * FS + box * kBoxCols + j * 8)) >> 3;
-      t4[i] = apply_keep(t4[i], philox8(seed, offset, e), thr);
-    }
-  }
-  __syncthreads();
-
-  // phase 1: partial dot products, one warp per view
-  for (int v = warp; v < VLN_V; v += kThreads / 32) {
-    float acc = 0.f;
-    for (int box = 0; box < nbox; ++box) {
-      const uint4 x = reinterpret_cast<const uint4*>(tile)[(box * VLN_V + v) * 32 + lane];
-      const float4 q0 = reinterpret_cast<const float4*>(vsl)[(box * kBoxCols + lane * 8) / 4];
-      const float4 q1 = reinterpret_cast<const float4*>(vsl)[(box * kBoxCols + lane * 8) / 4 + 1];
-      acc += bf16lo(x.x) * q0.x + bf16hi(x.x) * q0.y + bf16lo(x.y) * q0.z + bf16hi(x.y) * q0.w +
-             bf16lo(x.z) * q1.x + bf16hi(x.z) * q1.y + bf16lo(x.w) * q1.z + bf16hi(x.w) * q1.w;
-    }
-    acc = warp_sum(acc) * scale;
-    if (lane == 0) {
-      if (rank == 0)
-        acc += loc[v * 4] * qa[0] + loc[v * 4 + 1] * qa[1] + loc[v * 4 + 2] * qa[2] + loc[v * 4 + 3] * qa[3];
-      part[v] = acc;
-    }
-  }
-  cluster_arrive();
-  cluster_wait();
-  if (tid < VLN_V) {
-    float tot = 0.f;
-    for (int r = 0; r < S; ++r) tot += dsmem_ld_f32(part + tid, (uint32_t)r);
-    sm[tid] = tot;
-  }
-  cluster_arrive();          // peers may retire their `part` once everyone has read it (wait at exit)
-  __syncthreads();
-
-  if (warp == 0) {
-    const bool has1 = lane + 32 < VLN_V;
-    const float x0 = sm[lane], x1 = has1 ? sm[lane + 32] : -INFINITY;
-    float a0, a1;
-    if (mode == 0) {
-      const float m = warp_max(fmaxf(x0, x1));
-      const float e0 = expf(x0 - m), e1 = has1 ? expf(x1 - m) : 0.f;
-      const float inv = 1.0f / warp_sum(e0 + e1);
-      a0 = e0 * inv;
-      a1 = e1 * inv;
-      if (rank == 0) {
-        attn_io[(size_t)b * VLN_V + lane] = a0;
-        if (has1) attn_io[(size_t)b * VLN_V + lane + 32] = a1;
-      }
-    } else {
-      const float p0 = attn_io[(size_t)b * VLN_V + lane], p1 = has1 ? attn_io[(size_t)b * VLN_V + lane + 32] : 0.f;
-      const float dot = warp_sum(p0 * x0 + (has1 ? p1 * x1 : 0.f));
-      a0 = p0 * (x0 - dot);
-      a1 = has1 ? p1 * (x1 - dot) : 0.f;
-    }
-    sm[lane] = a0;
-    if (has1) sm[lane + 32] = a1;
-  }
-  __syncthreads();
-
-  // phase 2: this CTA's output columns, two features per thread
-  float* orow = out + (size_t)b * VLN_F;
-  for (int p = tid; p < FS / 2; p += kThreads) {
-    const int f = 2 * p, box = f / kBoxCols, col = f - box * kBoxCols;
-    const uint32_t* colp = reinterpret_cast<const uint32_t*>(tile + (size_t)box * VLN_V * kBoxCols + col);
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 6
-    for (int v = 0; v < VLN_V; ++v) {
-      const uint32_t w = colp[v * (kBoxCols / 2)];
-      acc0 += sm[v] * bf16lo(w);
-      acc1 += sm[v] * bf16hi(w);
-    }
-    reinterpret_cast<float2*>(orow + rank * FS)[p] = make_float2(acc0 * scale, acc1 * scale);
-  }
-  if (rank == 0 && tid < VLN_ANG) {
-    const int k = tid >> 5;
-    float acc = 0.f;
-    for (int v = 0; v < VLN_V; ++v) acc += sm[v] * loc[v * 4 + k];
-    orow[VLN_IMG + tid] = acc;
-  }
-  cluster_wait();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -344,8 +195,6 @@ __global__ void __launch_bounds__(kThreads) cand_logits_bwd_kernel(
   }
 }
 
-size_t pano_smem_bytes(int FS) { return (size_t)(FS / kBoxCols) * kBoxBytes + (size_t)FS * 4 + (40 + 40 + 144 + 4) * 4 + 16; }
-
 }  // namespace
 
 extern "C" int vln_gather_pano(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
@@ -374,38 +223,6 @@ extern "C" int vln_gather_action_feat(const vln_ctx* ctx, const int32_t* vp, con
   gather_action_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(ctx->table, vp, view, action, ended, cand_view,
                                                                 cand_ang4, n_cand, out);
   VLN_LAUNCH_OK();
-  return 0;
-}
-
-extern "C" int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
-                             const float* vec, float* attn_io, float* out, int B, int mode, float drop_p,
-                             const uint64_t* rng, uint64_t call_off, int split, void* stream) {
-  VLN_REQUIRE(ctx && vp && view && loc4 && vec && attn_io && out && B > 0, "bad arguments");
-  VLN_REQUIRE(split == 1 || split == 2 || split == 4 || split == 8, "split must be 1, 2, 4 or 8");
-  VLN_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (forward) or 1 (backward)");
-  VLN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");
-  VLN_REQUIRE(drop_p == 0.f || rng, "dropout needs an rng state");
-  const int FS = VLN_IMG / split;
-  const size_t smem = pano_smem_bytes(FS);
-  static size_t configured = 0;
-  if (smem > configured) {
-    VLN_CHECK_CUDA(cudaFuncSetAttribute(pano_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(split, B);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = split;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pano_attn_kernel, ctx->tmap_tile, vp, view, loc4, vec, attn_io, out, mode,
-                                    drop_p, rng, call_off, FS));
   return 0;
 }
 

@@ -179,11 +179,12 @@ def pose_feature(store, view):
 
 
 # ---- fused gather + panorama attention ---------------------------------------------------------
-def pano_attn_raw(store, vp, view, vec, attn, mode, drop_p=0.0, rng=None, call_off=0, split=4, aux=None):
+def pano_attn_raw(store, vp, view, vec, attn, mode, drop_p=0.0, rng=None, call_off=0, split=2, fwd_out=None):
     B = vp.shape[0]
     out = torch.empty((B, F_DIM), device=vec.device, dtype=torch.float32)
     _call("vln_pano_attn", store.handle, _ptr(vp), _ptr(view), _ptr(store.loc4), _ptr(vec), _ptr(attn),
-          _ptr(out), B, mode, float(drop_p), rng.ptr if rng is not None else None, call_off, split, _stream())
+          _ptr(fwd_out), _ptr(out), B, mode, float(drop_p), rng.ptr if rng is not None else None, call_off, split,
+          _stream())
     return out
 
 
@@ -194,19 +195,19 @@ class _PanoAttn(torch.autograd.Function):
         attn = torch.empty((q.shape[0], N_VIEWS), device=q.device, dtype=torch.float32)
         out = pano_attn_raw(store, vp, view, q, attn, 0, drop_p, rng, call_off, split)
         ctx.store, ctx.cfg = store, (drop_p, rng, call_off, split)
-        ctx.save_for_backward(vp, view, attn)
+        ctx.save_for_backward(vp, view, attn, out)
         ctx.mark_non_differentiable(attn)
         return out, attn
 
     @staticmethod
     def backward(ctx, d_out, _d_attn):
-        vp, view, attn = ctx.saved_tensors
+        vp, view, attn, out = ctx.saved_tensors
         drop_p, rng, call_off, split = ctx.cfg
-        dq = pano_attn_raw(ctx.store, vp, view, _f32c(d_out), attn, 1, drop_p, rng, call_off, split)
+        dq = pano_attn_raw(ctx.store, vp, view, _f32c(d_out), attn, 1, drop_p, rng, call_off, split, out)
         return dq, None, None, None, None, None, None, None
 
 
-def pano_attn(store, vp, view, q, drop_p=0.0, rng=None, call_off=0, split=4):
+def pano_attn(store, vp, view, q, drop_p=0.0, rng=None, call_off=0, split=2):
     """(weighted [B,2176], attn [B,36]) = softmax_v(x~_v . q) over the episode's panorama."""
     return _PanoAttn.apply(q, store, _i32c(vp), _i32c(view), drop_p, rng, call_off, split)
 

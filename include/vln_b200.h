@@ -64,15 +64,18 @@ int vln_gather_cand(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
 
 /* Fused gather + soft-dot attention over the 36-view panorama (SoftDotAttention.forward,
  * units.py:107-118, with EnvDropDecoder's in-place feature dropout policy.py:226-231 folded
- * into the load).  One TMA read of the episode's tile; never materialises [B,36,2176].
+ * into the load).  Each table row is read from HBM once; [B,36,2176] is never materialised.
  *   mode 0 (forward):  vec = query q[B,2176];  attn_io <- softmax_v(x~_v . q) [B,36];
- *                      out <- sum_v attn_v x~_v  [B,2176]
- *   mode 1 (backward): vec = d(out) [B,2176], attn_io = saved attn (read);
- *                      out <- dq = sum_v dlogit_v x~_v,  dlogit = attn*(r - attn.r), r_v = x~_v . vec
- * x~ = dropout(table row) (+) angle embedding.  split in {1,2,4,8}: CTAs per episode (cluster). */
+ *                      out <- sum_v attn_v x~_v  [B,2176];  fwd_out unused (may be NULL)
+ *   mode 1 (backward): vec = d(out) [B,2176], attn_io = saved attn (read), fwd_out = saved forward
+ *                      `out`;  out <- dq = sum_v dlogit_v x~_v,  dlogit = attn*(r - attn.r), r_v = x~_v . vec
+ * x~ = dropout(table row) (+) angle embedding.  split in {1,2,4}: parts per episode (36/split views
+ * each, merged through the context's scratch slab; split > 1 needs B <= VLN_SPLIT_MAX_B and calls
+ * on one context must not overlap in time). */
+#define VLN_SPLIT_MAX_B 1024
 int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
-                  const float* vec, float* attn_io, float* out, int B, int mode, float drop_p,
-                  const uint64_t* rng, uint64_t call_off, int split, void* stream);
+                  const float* vec, float* attn_io, const float* fwd_out, float* out, int B, int mode,
+                  float drop_p, const uint64_t* rng, uint64_t call_off, int split, void* stream);
 
 /* Candidate logits (EnvDropDecoder.candidate_attn policy.py:199-206; also ActionScoring
  * units.py:173-185 after folding its Linear layers into tgt/bias on the host side):

@@ -1,7 +1,9 @@
-"""Config-5 microbench: gather + panorama attention (and candidate logits) HBM sweep.
+"""Config-5 microbench: fused gather + panorama attention (and candidate logits) HBM sweep.
 
-Random viewpoints over the full-size table (1.56 GB >> 126 MB L2) so every launch reads from
-HBM.  Prints one JSON line per (B, split, mode): achieved algorithmic GB/s = B*147456 / time."""
+Random viewpoints over the full-size table (1.56 GB >> 126 MB L2).  Each measurement replays a
+CUDA graph of N_SETS launches over different random index sets (so launches read HBM, not L2, and
+the host launch path is out of the timed region), CUDA events around the replays.
+One JSON line per (B, split, mode, drop): achieved algorithmic GB/s = B*147456 / time per launch."""
 import argparse
 import json
 import os
@@ -10,32 +12,43 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import clvln_b200  # noqa: E402
+import clvln_b200  # noqa: E402,F401
 from clvln_b200 import ops  # noqa: E402
 from clvln_b200.environ import world as W  # noqa: E402
 
+N_SETS = 16
 
-def timeit(fn, iters, warm=5):
-    for _ in range(warm):
-        fn()
+
+def time_graph(launch, reps=10):
+    """launch(k) enqueues the k-th variant; returns seconds per launch."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for k in range(2):
+            launch(k)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(N_SETS):
+            launch(k)
+    for _ in range(3):
+        g.replay()
     torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for s, e in evs:
-        s.record()
-        fn()
-        e.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
     torch.cuda.synchronize()
-    ts = sorted(s.elapsed_time(e) for s, e in evs)
-    return ts[len(ts) // 2] * 1e-3, ts[0] * 1e-3
+    return e0.elapsed_time(e1) * 1e-3 / (reps * N_SETS)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-vp", type=int, default=10567)
-    ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--batches", type=int, nargs="*", default=[16, 64, 128, 256, 512, 1024, 2048])
-    ap.add_argument("--splits", type=int, nargs="*", default=[1, 2, 4, 8])
-    ap.add_argument("--drop", type=float, default=0.0)
+    ap.add_argument("--splits", type=int, nargs="*", default=[1, 2, 4])
+    ap.add_argument("--drops", type=float, nargs="*", default=[0.0, 0.3])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peaks = {}
@@ -43,7 +56,6 @@ def main():
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = peaks.get("hbm_gbs", 6650.0)
-    # tables: only what the kernels index (random candidate tables are enough for bandwidth)
     n_vp = args.n_vp
     g = torch.Generator(device=dev).manual_seed(1)
     tables = dict(
@@ -56,38 +68,35 @@ def main():
         sq_off=torch.zeros(n_vp, device=dev, dtype=torch.int64), vp_local=torch.zeros(n_vp, device=dev, dtype=torch.int32),
         loc4=torch.from_numpy(W.static_loc4()).to(dev), pose4=torch.from_numpy(W.pose4()).to(dev))
     store = ops.FeatureStore(tables, dev)
+    rng = ops.Rng(1, dev)
     for B in args.batches:
-        vp = torch.randint(0, n_vp, (B,), device=dev, dtype=torch.int32, generator=g)
+        vps = [torch.randint(0, n_vp, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(N_SETS)]
         view = torch.randint(0, 36, (B,), device=dev, dtype=torch.int32, generator=g)
         q = torch.randn(B, 2176, device=dev) * 0.05
         attn = torch.empty(B, 36, device=dev)
+        fwd = torch.randn(B, 2176, device=dev)
         for split in args.splits:
-            for mode in (0, 1):
-                def run():
-                    # fresh random viewpoints each launch would need a sync; the table is 12x L2 and B*147KB
-                    # of it is touched per launch, so re-launching on the same indices at B<=512 can hit L2:
-                    # rotate through 16 index sets.
-                    run.k = (run.k + 1) % 16
-                    ops.pano_attn_raw(store, vps[run.k], view, q, attn, mode, args.drop, 1, 2, split)
-                vps = [torch.randint(0, n_vp, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(16)]
-                run.k = 0
-                med, best = timeit(run, args.iters)
-                gbs = B * 147456 / med / 1e9
-                print(json.dumps(dict(kernel="pano_attn", mode="fwd" if mode == 0 else "bwd", B=B, split=split,
-                                      drop=args.drop, us=round(med * 1e6, 2), best_us=round(best * 1e6, 2),
-                                      algo_GBs=round(gbs, 1), frac_of_measured_peak=round(gbs / peak, 3))), flush=True)
+            if split > 1 and B > 1024:
+                continue
+            for drop in args.drops:
+                for mode in (0, 1):
+                    t = time_graph(lambda k: ops.pano_attn_raw(store, vps[k], view, q, attn, mode, drop, rng, 2, split,
+                                                               fwd if mode else None))
+                    gbs = B * 147456 / t / 1e9
+                    print(json.dumps(dict(kernel="pano_attn", mode="fwd" if mode == 0 else "bwd", B=B, split=split,
+                                          drop=drop, us=round(t * 1e6, 2), algo_GBs=round(gbs, 1),
+                                          frac_of_measured_peak=round(gbs / peak, 3))), flush=True)
         tgt = torch.randn(B, 2176, device=dev) * 0.05
         logits = torch.empty(B, 16, device=dev)
-        ncs = tables["n_cand"][vp.long()].sum().item()
+        ncs = sum(int(tables["n_cand"][v.long()].sum()) for v in vps) / N_SETS
 
-        def run_c():
-            ops._lib.check(ops._lib.lib().vln_cand_logits_fwd(
-                store.handle, ops._ptr(vp), ops._ptr(view), ops._ptr(store.cand_view), ops._ptr(store.cand_ang4),
-                ops._ptr(store.n_cand), ops._ptr(tgt), None, ops._ptr(logits), B, args.drop, 1, 2, ops._stream()))
-        med, best = timeit(run_c, args.iters)
-        print(json.dumps(dict(kernel="cand_logits_fwd", B=B, us=round(med * 1e6, 2),
-                              algo_GBs=round(ncs * 4096 / med / 1e9, 1), note="same indices every launch (L2-warm)")),
-              flush=True)
+        def run_c(k):
+            ops._call("vln_cand_logits_fwd", store.handle, ops._ptr(vps[k]), ops._ptr(view), ops._ptr(store.cand_view),
+                      ops._ptr(store.cand_ang4), ops._ptr(store.n_cand), ops._ptr(tgt), None, ops._ptr(logits), B, 0.0,
+                      None, 0, ops._stream())
+        t = time_graph(run_c)
+        print(json.dumps(dict(kernel="cand_logits_fwd", B=B, us=round(t * 1e6, 2),
+                              algo_GBs=round(ncs * 4096 / t / 1e9, 1))), flush=True)
 
 
 if __name__ == "__main__":
