@@ -114,17 +114,23 @@ class EncoderLSTM(KernelModule):
         B, L, _ = x.shape
         h_last = c_last = None
         for layer in range(self.num_layers):
-            outs, hs, cs = [], [], []
+            xprojs, whhs = [], []
             for d in range(self.num_directions):
                 sfx = f"_l{layer}" + ("_reverse" if d else "")
                 w_ih, w_hh = getattr(self.lstm, "weight_ih" + sfx), getattr(self.lstm, "weight_hh" + sfx)
                 bias = getattr(self.lstm, "bias_ih" + sfx) + getattr(self.lstm, "bias_hh" + sfx)
-                xproj = ops.linear(x.reshape(B * L, -1), w_ih, bias).view(B, L, -1)
-                o, h, c = ops.lstm_sequence(xproj, lengths, w_hh, reverse=bool(d))
-                outs.append(o), hs.append(h), cs.append(c)
-            x = torch.cat(outs, 2) if len(outs) > 1 else outs[0]
-            h_last = torch.cat(hs, 1) if len(hs) > 1 else hs[0]
-            c_last = torch.cat(cs, 1) if len(cs) > 1 else cs[0]
+                xprojs.append(ops.linear(x.reshape(B * L, -1), w_ih, bias).view(B, L, -1))
+                whhs.append(w_hh)
+            if self.hidden_size in ops.LSTM_KERNEL_H:
+                # persistent cluster kernel: W_hh resident in SMEM, both directions in one launch
+                x, h_last, c_last = ops.lstm_layer(xprojs, whhs, lengths)
+            else:
+                # TODO(kernel): hidden sizes other than 128/256 per direction (Self-Monitor's 512) still run
+                # the step-by-step recurrence (one pointwise kernel + one GEMM per timestep)
+                res = [ops.lstm_sequence(xp, lengths, w, reverse=bool(d)) for d, (xp, w) in enumerate(zip(xprojs, whhs))]
+                x = torch.cat([r[0] for r in res], 2) if len(res) > 1 else res[0][0]
+                h_last = torch.cat([r[1] for r in res], 1) if len(res) > 1 else res[0][1]
+                c_last = torch.cat([r[2] for r in res], 1) if len(res) > 1 else res[0][2]
             if layer + 1 < self.num_layers:
                 x = self._drop(x, self.drop_ratio, "enc_interlayer")
         decoder_init = torch.tanh(ops.linear(h_last, self.enc2dec.weight, self.enc2dec.bias))

@@ -341,6 +341,65 @@ def lstm_sequence(xproj, lengths, w_hh, reverse):
     return torch.stack(outs, 1), h, c
 
 
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _LstmLayer(torch.autograd.Function):
+    """One (bi)directional LSTM layer over padded sequences: the persistent cluster kernel forward,
+    its BPTT twin backward; the weight gradient of W_hh is ONE GEMM over all timesteps."""
+
+    @staticmethod
+    def forward(ctx, lengths, n_dir, *tensors):
+        xproj = [_f32c(t) for t in tensors[:n_dir]]
+        w_hh = [_f32c(t) for t in tensors[n_dir:2 * n_dir]]
+        B, L, H4 = xproj[0].shape
+        H = H4 // 4
+        dev = xproj[0].device
+        out = torch.zeros((B, L, n_dir * H), device=dev)
+        h_last, c_last = torch.empty((B, n_dir * H), device=dev), torch.empty((B, n_dir * H), device=dev)
+        acts = [torch.empty((B, L, H4), device=dev) for _ in range(n_dir)]
+        cs = [torch.empty((B, L, H), device=dev) for _ in range(n_dir)]
+        _call("vln_lstm_seq_fwd", _ptr_array(xproj), _ptr_array(w_hh), _ptr(lengths), _ptr(out), _ptr_array(acts),
+              _ptr_array(cs), _ptr(h_last), _ptr(c_last), B, L, H, n_dir, _stream())
+        ctx.n_dir = n_dir
+        ctx.save_for_backward(lengths, out, *w_hh, *acts, *cs)
+        return out, h_last, c_last
+
+    @staticmethod
+    def backward(ctx, d_out, d_h, d_c):
+        n = ctx.n_dir
+        sv = ctx.saved_tensors
+        lengths, out = sv[0], sv[1]
+        w_hh, acts, cs = sv[2:2 + n], sv[2 + n:2 + 2 * n], sv[2 + 2 * n:2 + 3 * n]
+        B, L, H4 = acts[0].shape
+        H = H4 // 4
+        d_x = [torch.zeros_like(a) for a in acts]
+        d_out = _f32c(d_out) if d_out is not None else None
+        d_h = _f32c(d_h) if d_h is not None else None
+        d_c = _f32c(d_c) if d_c is not None else None
+        _call("vln_lstm_seq_bwd", _ptr_array(w_hh), _ptr(lengths), _ptr_array(acts), _ptr_array(cs), _ptr(d_out),
+              _ptr(d_h), _ptr(d_c), _ptr_array(d_x), B, L, H, n, _stream())
+        d_w = []
+        for k in range(n):
+            hk = out[:, :, k * H:(k + 1) * H]
+            hprev = torch.zeros_like(hk)
+            if k == 0:
+                hprev[:, 1:] = hk[:, :-1]                       # h_{t-1}; zero initial state
+            else:
+                hprev[:, :-1] = hk[:, 1:]                       # reversed direction: the previous step is t+1
+            d_w.append(d_x[k].reshape(B * L, H4).t() @ hprev.reshape(B * L, H))
+        return (None, None, *d_x, *d_w)
+
+
+def lstm_layer(xproj, w_hh, lengths):
+    """xproj / w_hh: lists with one entry per direction.  -> (out [B,L,n_dir*H], h_last, c_last)."""
+    return _LstmLayer.apply(_i32c(lengths), len(xproj), *xproj, *w_hh)
+
+
+LSTM_KERNEL_H = (128, 256)
+
+
 # ---- action head ---------------------------------------------------------------------------------------
 FEEDBACK = {"teacher": 0, "argmax": 1, "sample": 2}
 

@@ -111,6 +111,23 @@ int vln_lstm_pointwise_fwd(const float* gates, const float* c0, float* h1, float
 int vln_lstm_pointwise_bwd(const float* acts, const float* c0, const float* c1, const float* d_h1,
                            const float* d_c1, float* d_gates, float* d_c0, int B, int H, void* stream);
 
+/* Persistent length-masked (Bi)LSTM recurrence: the packed-sequence nn.LSTM of EncoderLSTM
+ * (units.py:58-71) for one layer, both directions in one launch.  Host arrays of n_dir (1 or 2)
+ * device pointers: xproj[k] [B,L,4H] = x W_ih^T + b_ih + b_hh, w_hh[k] [4H,H] (gate order i,f,g,o),
+ * acts[k] [B,L,4H] and cs[k] [B,L,H] (saved activations / cell states for backward).  Direction k
+ * writes columns [kH,(k+1)H) of out [B,L,n_dir*H] (pre-zeroed; stays zero past each row's length)
+ * and of h_last / c_last [B,n_dir*H] (state at each row's last valid step); direction 1 runs
+ * reversed in time.  H per direction must be 128 or 256.  A cluster of H/32 CTAs owns 8 batch rows:
+ * W_hh slices stay in shared memory across timesteps, h_t is exchanged through DSMEM. */
+int vln_lstm_seq_fwd(const float* const* xproj, const float* const* w_hh, const int32_t* lengths, float* out,
+                     float* const* acts, float* const* cs, float* h_last, float* c_last, int B, int L, int H,
+                     int n_dir, void* stream);
+/* Backward through time: d_out [B,L,n_dir*H], d_hlast / d_clast [B,n_dir*H] (each nullable) ->
+ * d_xproj[k] [B,L,4H] (pre-zeroed; masked steps stay zero).  dW_hh, dW_ih, dx are GEMMs on d_xproj. */
+int vln_lstm_seq_bwd(const float* const* w_hh, const int32_t* lengths, const float* const* acts,
+                     const float* const* cs, const float* d_out, const float* d_hlast, const float* d_clast,
+                     float* const* d_xproj, int B, int L, int H, int n_dir, void* stream);
+
 /* Action head (envdrop.py:166-195, follower.py:107-135, monitor.py:143-176): masked
  * log-softmax, CE(ignore_index=-1), argmax / Philox-sampled / teacher action, log-prob and
  * entropy of the chosen action.  logits [B,16] with -inf beyond the valid slots.

@@ -359,3 +359,35 @@ def test_fused_clip_optimizer(setup, kind):
         _lib.check(_lib.lib().vln_optim_step(_ptr(flat), _ptr(gflat), _ptr(s1), _ptr(s2), off, mx, 3, _ptr(sq), 1.0,
                                              kind, 1e-2, step, _stream()))
         assert relerr(flat, torch.cat([r.detach() for r in ref])) < 2e-5
+
+
+@pytest.mark.parametrize("H,E,B,L,ndir", [(256, 256, 64, 80, 2), (128, 300, 19, 33, 2), (256, 64, 5, 12, 1)])
+def test_lstm_layer_matches_oracle(setup, H, E, B, L, ndir):
+    """Persistent cluster LSTM (fwd + BPTT) vs the oracle's masked recurrence (== packed nn.LSTM)."""
+    from oracle import port_modules as P
+    _, _, ops, dev = setup
+    torch.manual_seed(H + B)
+    x = torch.randn(B, L, E, device=dev)
+    lengths = torch.randint(1, L + 1, (B,), device=dev).sort(descending=True)[0].to(torch.int32)
+    lengths[0] = L
+    ws = [(torch.randn(4 * H, E, device=dev) * 0.05, torch.randn(4 * H, H, device=dev) * 0.05,
+           torch.randn(4 * H, device=dev) * 0.1) for _ in range(ndir)]
+    mine = [[t.clone().requires_grad_(True) for t in w] for w in ws]
+    ref = [[t.clone().requires_grad_(True) for t in w] for w in ws]
+    xm, xr = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    xproj = [ops.linear(xm.reshape(B * L, E), w[0], w[2]).view(B, L, 4 * H) for w in mine]
+    out, h, c = ops.lstm_layer(xproj, [w[1] for w in mine], lengths)
+    outs, hs, cs = [], [], []
+    for k, w in enumerate(ref):
+        o, hh, cc = P._lstm_direction(xr, lengths, w[0], w[1], w[2], torch.zeros_like(w[2]), reverse=bool(k))
+        outs.append(o.transpose(0, 1)), hs.append(hh), cs.append(cc)
+    out_r, h_r, c_r = torch.cat(outs, 2), torch.cat(hs, 1), torch.cat(cs, 1)
+    assert relerr(out, out_r) < 1e-4 and relerr(h, h_r) < 1e-4 and relerr(c, c_r) < 1e-4
+    assert bool((out[lengths.long().unsqueeze(1) <= torch.arange(L, device=dev).unsqueeze(0)] == 0).all())
+    go, gh, gc = torch.randn_like(out), torch.randn_like(h), torch.randn_like(c)
+    (out * go).sum().add((h * gh).sum()).add((c * gc).sum()).backward()
+    (out_r * go).sum().add((h_r * gh).sum()).add((c_r * gc).sum()).backward()
+    assert relerr(xm.grad, xr.grad) < 2e-4
+    for wm, wr in zip(mine, ref):
+        for a, b in zip(wm, wr):
+            assert relerr(a.grad, b.grad) < 2e-4
