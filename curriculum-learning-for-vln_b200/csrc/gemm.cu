@@ -1,0 +1,315 @@
+// Skinny linear layers on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+//   y[m, n] += sum_k x[m, k] * w[n, k]  (+ bias[n])        m < M <= 128 (a batch of episodes),
+//                                                           n < N (gate rows / projection outputs)
+// used for the decoder LSTMCell gates (policy.py:53,159,238), the 512<->2176 attention / candidate
+// projections (units.py:107, policy.py:199-206), linear_in/linear_out, and — with the transposed
+// weight copies — for their input gradients.
+//
+// Swap-AB: the WEIGHT rows sit on MMA-M (tiles of 128), the batch on MMA-N (64 or 128), so a 64-row
+// batch still fills the 128-lane datapath; split-K spreads a layer over ~all 148 SMs (partial sums
+// meet in y through red.global.add.f32 — y must be zero-initialised or hold a previous partial sum).
+//
+// Precision: bf16x3.  Weights are pre-split once per optimiser step into bf16 hi + lo
+// (vln_split_bf16), activations are split on the fly while they are staged; three MMAs
+// (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) reproduce the fp32 product to ~2^-16 relative,
+// which keeps the rollout inside the 1e-3 logit/loss bar that a plain bf16 or tf32 GEMM would miss.
+//
+// Warp roles (256 threads): warp 0 = TMA producer of the weight tiles (128B-swizzled boxes),
+// warp 1 = MMA issuer (one elected lane), warps 4-7 = activation stagers during the main loop
+// (fp32 -> bf16 hi/lo, written with the 128B swizzle by hand) and epilogue afterwards
+// (tcgen05.ld -> bias -> red.add).  4-stage mbarrier ring, accumulator in TMEM.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+int vln_make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                     uint32_t box_cols, uint32_t box_rows, int swizzle128);
+
+namespace {
+
+constexpr int kBK = 64;                 // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int kTileN = 128;             // weight rows per CTA (MMA M)
+constexpr int kThreads = 256;
+
+template <int MP>
+struct Cfg {
+  static constexpr int kStages = MP == 64 ? 4 : 3;
+  static constexpr int kABytes = kTileN * kBK * 2;   // 16 KB per hi / lo weight tile
+  static constexpr int kBBytes = MP * kBK * 2;       // 8 / 16 KB per hi / lo activation tile
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B: 8-row groups of 128-byte rows, SBO = 1024 B, LBO = 1 (unused), version 1 (sm_100)
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {   // round-to-nearest-even, a in the low half
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+template <int MP>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                     const float* __restrict__ x, int ldx, int M, int N, int K, const float* __restrict__ bias,
+                     float* __restrict__ y, int ldy, int splits) {
+  using C = Cfg<MP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + C::kStages * C::kStageBytes);
+  uint64_t* full_w = bars;                       // TMA bytes landed
+  uint64_t* full_x = bars + C::kStages;          // activation tile staged (4 warp arrivals)
+  uint64_t* empty = bars + 2 * C::kStages;       // MMAs that read the stage have completed
+  uint64_t* acc_done = bars + 3 * C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int nkb = K / kBK;
+  const int kb0 = (int)((long long)split * nkb / splits), kb1 = (int)((long long)(split + 1) * nkb / splits);
+  const int n_iter = kb1 - kb0;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&full_x[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {   // TMEM accumulator: MP fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(MP)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (n_iter > 0) {
+    if (warp == 0) {
+      // ---------------- TMA producer: weight tiles (hi, lo) ----------------
+      if (lane == 0) {
+        for (int it = 0; it < n_iter; ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          uint8_t* st = base + (size_t)s * C::kStageBytes;
+          mbar_expect_tx(&full_w[s], 2 * C::kABytes);
+          tma_load_2d(st, &tm_hi, &full_w[s], (kb0 + it) * kBK, tile * kTileN);
+          tma_load_2d(st + C::kABytes, &tm_lo, &full_w[s], (kb0 + it) * kBK, tile * kTileN);
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------- MMA issuer ----------------
+      if (lane == 0) {
+        // instruction descriptor: D = F32, A = B = BF16, both K-major, N = MP, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MP >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+        for (int it = 0; it < n_iter; ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1u;
+          mbar_wait(&full_w[s], ph);
+          mbar_wait(&full_x[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(base + (size_t)s * C::kStageBytes), a_lo = a_hi + C::kABytes;
+          const uint32_t b_hi = a_lo + C::kABytes, b_lo = b_hi + C::kBBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint32_t ko = k * 32;                      // 16 bf16 = 32 bytes along the swizzled row
+            umma_bf16(tmem_d, make_sdesc(a_hi + ko), make_sdesc(b_hi + ko), idesc, (it | k) != 0);
+            umma_bf16(tmem_d, make_sdesc(a_hi + ko), make_sdesc(b_lo + ko), idesc, 1u);
+            umma_bf16(tmem_d, make_sdesc(a_lo + ko), make_sdesc(b_hi + ko), idesc, 1u);
+          }
+          umma_commit(&empty[s]);                            // frees the stage when these MMAs retire
+        }
+        umma_commit(acc_done);
+      }
+    } else if (warp >= 4) {
+      // ---------------- activation stagers: fp32 -> bf16 hi/lo, 128B-swizzled rows ----------------
+      const int t = tid - 128;                               // 0..127
+      constexpr int TPR = 128 / MP;                          // threads per activation row (2 or 1)
+      constexpr int CPT = kBK / TPR;                         // columns per thread (32 or 64)
+      const int r = t / TPR, c0 = (t % TPR) * CPT;
+      const bool live = r < M;
+      const float* xr = x + (size_t)r * ldx + c0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* bh = base + (size_t)s * C::kStageBytes + 2 * C::kABytes;
+        uint8_t* bl = bh + C::kBBytes;
+        const float* src = xr + (size_t)(kb0 + it) * kBK;
+#pragma unroll
+        for (int ch = 0; ch < CPT / 8; ++ch) {               // 8 columns = one 16-byte chunk
+          float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+          if (live) {
+            f0 = __ldg(reinterpret_cast<const float4*>(src + ch * 8));
+            f1 = __ldg(reinterpret_cast<const float4*>(src + ch * 8 + 4));
+          }
+          const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float a = v[2 * p], b = v[2 * p + 1];
+            const float ah = __bfloat162float(__float2bfloat16_rn(a)), bhh = __bfloat162float(__float2bfloat16_rn(b));
+            hi[p] = pack_bf16(a, b);
+            lo[p] = pack_bf16(a - ah, b - bhh);
+          }
+          const int chunk = (c0 >> 3) + ch;                  // 16-byte chunk index within the 128-byte row
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(bh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(bl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();                                 // generic-proxy stores -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_x[s]);
+      }
+      // ---------------- epilogue: TMEM -> registers -> (bias) -> red.add into y ----------------
+      mbar_wait(acc_done, 0);
+      tc_fence_after();
+      const int wq = warp & 3;                               // TMEM lane quarter this warp may access
+      const int n = tile * kTileN + wq * 32 + lane;
+      const float bv = (bias != nullptr && split == 0 && n < N) ? bias[n] : 0.f;
+#pragma unroll
+      for (int cb = 0; cb < MP / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cb * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n < N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = cb * 32 + j;
+            if (m < M) atomicAdd(y + (size_t)m * ldy + n, __uint_as_float(v[j]) + bv);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && split == 0 && bias != nullptr) {
+    // degenerate split without k-blocks cannot happen for split 0 unless K == 0; nothing to do
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(MP) : "memory");
+  }
+}
+
+// fp32 [N,K] -> bf16 hi / lo [N,K] and (optionally) transposed hi / lo [K,N]
+__global__ void split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                  __nv_bfloat16* __restrict__ hi_t, __nv_bfloat16* __restrict__ lo_t, int N, int K) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;               // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int n = n0 + j, k = k0 + tx;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = w[(size_t)n * K + k];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[(size_t)n * K + k] = h;
+      lo[(size_t)n * K + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+    tile[j][tx] = v;
+  }
+  if (hi_t == nullptr) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int k = k0 + j, n = n0 + tx;
+    if (n < N && k < K) {
+      const float v = tile[tx][j];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi_t[(size_t)k * N + n] = h;
+      lo_t[(size_t)k * N + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+template <int MP>
+int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
+                  float* y, int ldy, int splits, cudaStream_t stream) {
+  CUtensorMap tm_hi, tm_lo;
+  int rc = vln_make_tmap_2d(&tm_hi, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
+  if (rc) return rc;
+  rc = vln_make_tmap_2d(&tm_lo, w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    VLN_CHECK_CUDA(cudaFuncSetAttribute(linear_bf16x3_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MP>::kSmem));
+    configured = true;
+  }
+  const int tiles = (N + kTileN - 1) / kTileN;
+  linear_bf16x3_kernel<MP><<<dim3(tiles, splits), kThreads, Cfg<MP>::kSmem, stream>>>(tm_hi, tm_lo, x, ldx, M, N, K, bias, y,
+                                                                                     ldy, splits);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
+                                 const float* bias, float* y, int ldy, int splits, void* stream) {
+  VLN_REQUIRE(w_hi && w_lo && x && y && N > 0 && M > 0, "bad arguments");
+  VLN_REQUIRE(K > 0 && K % kBK == 0, "K must be a positive multiple of 64");
+  VLN_REQUIRE(M <= 128, "at most 128 activation rows");
+  VLN_REQUIRE(((uintptr_t)x & 15) == 0 && ldx % 4 == 0, "x rows must be 16-byte aligned");
+  VLN_REQUIRE(((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)w_lo & 15) == 0, "weights must be 16-byte aligned");
+  const int nkb = K / kBK;
+  if (splits <= 0) {                                           // fill the machine: tiles x splits ~ #SMs
+    const int tiles = (N + kTileN - 1) / kTileN;
+    splits = (148 + tiles - 1) / tiles;
+  }
+  if (splits > nkb) splits = nkb;
+  if (splits < 1) splits = 1;
+  if (M <= 64) return launch_linear<64>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, splits, (cudaStream_t)stream);
+  return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, splits, (cudaStream_t)stream);
+}
+
+extern "C" int vln_split_bf16(const float* w, void* hi, void* lo, void* hi_t, void* lo_t, int N, int K, void* stream) {
+  VLN_REQUIRE(w && hi && lo && N > 0 && K > 0, "bad arguments");
+  VLN_REQUIRE((hi_t == nullptr) == (lo_t == nullptr), "transposed outputs come as a pair");
+  split_bf16_kernel<<<dim3((K + 31) / 32, (N + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, (__nv_bfloat16*)hi_t, (__nv_bfloat16*)lo_t, N, K);
+  VLN_LAUNCH_OK();
+  return 0;
+}

@@ -80,6 +80,7 @@ class FlatOptimizer:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
             scale = 1.0 / self.world
         self.step_count += 1
+        ops.WEIGHT_EPOCH[0] += 1          # parameters change under raw pointers: bf16 weight splits are stale
         ops._call("vln_grad_sqnorm", ops._ptr(self.grad), self._off, self.n_groups, ops._ptr(self.sqnorm), scale,
                   ops._stream())
         ops._call("vln_optim_step", ops._ptr(self.flat), ops._ptr(self.grad), ops._ptr(self.s1), ops._ptr(self.s2),

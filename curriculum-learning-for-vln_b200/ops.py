@@ -138,10 +138,97 @@ class CandView:
 
 
 # ---- GEMM-shaped pieces ---------------------------------------------------------------------------
-def linear(x, w, b=None):
-    """y = x W^T + b.  Plain library GEMM (cuBLAS through torch) until the tcgen05 path replaces it
-    for the LSTM gates."""
-    return F.linear(x, w, b)
+WEIGHT_EPOCH = [0]        # bumped by the fused optimiser (it updates parameters through raw pointers)
+USE_TC_LINEAR = [True]    # tcgen05 bf16x3 path for skinny linears; False = cuBLAS fp32 everywhere
+_split_cache = {}
+
+
+class _SplitWeight:
+    """bf16 hi/lo split of an fp32 weight [N,K] and of its transpose, refreshed lazily whenever the
+    parameter changed (autograd version counter, or the optimiser epoch)."""
+
+    def __init__(self, w):
+        N, K = w.shape
+        dev = w.device
+        self.hi = torch.empty((N, K), dtype=torch.bfloat16, device=dev)
+        self.lo = torch.empty_like(self.hi)
+        self.hi_t = torch.empty((K, N), dtype=torch.bfloat16, device=dev)
+        self.lo_t = torch.empty_like(self.hi_t)
+        self.stamp = None
+
+    def fresh(self, w):
+        stamp = (w._version, WEIGHT_EPOCH[0], w.data_ptr())
+        if stamp != self.stamp:
+            N, K = w.shape
+            _call("vln_split_bf16", _ptr(w), _ptr(self.hi), _ptr(self.lo), _ptr(self.hi_t), _ptr(self.lo_t), N, K,
+                  _stream())
+            self.stamp = stamp
+        return self
+
+
+def _split_of(w):
+    """The cached split of parameter ``w`` — keyed by the tensor OBJECT (validated through a weak
+    reference: ids and device addresses are recycled when an agent is rebuilt)."""
+    import weakref
+    key = id(w)
+    ent = _split_cache.get(key)
+    if ent is None or ent[0]() is not w:
+        if len(_split_cache) > 256:                         # drop entries whose parameter died
+            for k in [k for k, (r, _) in _split_cache.items() if r() is None]:
+                del _split_cache[k]
+        ent = _split_cache[key] = (weakref.ref(w), _SplitWeight(w))
+    return ent[1].fresh(w)
+
+
+def _tc_matmul(x, hi, lo, N, K, bias=None, out=None):
+    """out (+)= x @ W^T (+ bias) on the tcgen05 kernel; W given by its bf16 hi/lo split [N,K]."""
+    M = x.shape[0]
+    if out is None:
+        out = torch.zeros((M, N), device=x.device, dtype=torch.float32)
+    _call("vln_linear_bf16x3", _ptr(hi), _ptr(lo), N, K, _ptr(x), x.stride(0), M, _ptr(bias), _ptr(out), out.stride(0), 0,
+          _stream())
+    return out
+
+
+class _LinearTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, acc):
+        x = _f32c(x)
+        sw = _split_of(w)
+        N, K = w.shape
+        y = _tc_matmul(x, sw.hi, sw.lo, N, K, b.detach() if b is not None else None,
+                       acc.detach().clone() if acc is not None else None)
+        ctx.save_for_backward(x, w)
+        ctx.sw, ctx.has_b, ctx.has_acc = sw, b is not None, acc is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _f32c(dy)
+        N, K = w.shape
+        sw = ctx.sw
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if N % 64 == 0:
+                dx = _tc_matmul(dy, sw.hi_t, sw.lo_t, K, N)
+            else:
+                dx = dy @ w
+        if ctx.needs_input_grad[1]:
+            dw = dy.t() @ x
+        if ctx.has_b and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db, (dy if ctx.has_acc else None)
+
+
+def linear(x, w, b=None, acc=None):
+    """y = x W^T + b (+ acc).  Batches of at most 128 rows run on the tcgen05 bf16x3 kernel
+    (csrc/gemm.cu); larger ones (encoder input projection, batched critic) are plain library GEMMs."""
+    if (USE_TC_LINEAR[0] and x.is_cuda and x.dim() == 2 and x.shape[0] <= 128 and w.shape[1] % 64 == 0
+            and x.dtype == torch.float32):
+        return _LinearTC.apply(x, w, b, acc)
+    y = F.linear(x, w, b)
+    return y if acc is None else y + acc
 
 
 # ---- bit-exact gathers ---------------------------------------------------------------------------
@@ -315,7 +402,7 @@ def lstm_pointwise(gates, c0):
 
 def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
     """nn.LSTMCell (policy.py:53,159,238): gate GEMMs + fused pointwise kernel."""
-    gates = linear(torch.cat((x, h), 1), torch.cat((w_ih, w_hh), 1), b_ih + b_hh)
+    gates = linear(h, w_hh, None, acc=linear(x, w_ih, b_ih + b_hh))
     return lstm_pointwise(gates, c)
 
 

@@ -111,6 +111,18 @@ int vln_lstm_pointwise_fwd(const float* gates, const float* c0, float* h1, float
 int vln_lstm_pointwise_bwd(const float* acts, const float* c0, const float* c1, const float* d_h1,
                            const float* d_c1, float* d_gates, float* d_c0, int B, int H, void* stream);
 
+/* Skinny linear layer on tcgen05 tensor cores (nn.Linear / nn.LSTMCell gate GEMMs of policy.py and
+ * units.py at batch sizes <= 128):  y[m,n] += sum_k x[m,k] w[n,k] (+ bias[n]),  m < M <= 128.
+ * w_hi / w_lo: the weight [N,K] split into bf16 hi + lo (vln_split_bf16); x fp32 [M,K] row stride ldx;
+ * y fp32 row stride ldy, ACCUMULATED into (zero it first, or chain calls to sum several products —
+ * e.g. x W_ih^T + h W_hh^T).  K % 64 == 0.  splits <= 0 picks a split-K factor that fills the GPU.
+ * bf16x3 (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) ~ fp32 accuracy.  For input gradients pass
+ * the transposed split (w^T as a [K,N] weight) and x = dY. */
+int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
+                      const float* bias, float* y, int ldy, int splits, void* stream);
+/* fp32 w [N,K] -> bf16 hi, lo [N,K] and, if hi_t/lo_t are given, the transposed pair [K,N]. */
+int vln_split_bf16(const float* w, void* hi, void* lo, void* hi_t, void* lo_t, int N, int K, void* stream);
+
 /* Persistent length-masked (Bi)LSTM recurrence: the packed-sequence nn.LSTM of EncoderLSTM
  * (units.py:58-71) for one layer, both directions in one launch.  Host arrays of n_dir (1 or 2)
  * device pointers: xproj[k] [B,L,4H] = x W_ih^T + b_ih + b_hh, w_hh[k] [4H,H] (gate order i,f,g,o),

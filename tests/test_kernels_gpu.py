@@ -391,3 +391,31 @@ def test_lstm_layer_matches_oracle(setup, H, E, B, L, ndir):
     for wm, wr in zip(mine, ref):
         for a, b in zip(wm, wr):
             assert relerr(a.grad, b.grad) < 2e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 2048, 2240), (64, 2176, 512), (7, 512, 1024), (100, 2048, 512), (64, 64, 128),
+                                   (33, 1000, 192)])
+def test_linear_tcgen05_bf16x3(setup, M, N, K):
+    """tcgen05 bf16x3 skinny linear (fwd, input/weight/bias grads, accumulate) vs fp64 reference.
+    Tolerance 2e-5 max-rel: three bf16 products recover ~16 mantissa bits."""
+    _, _, ops, dev = setup
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=dev, requires_grad=True)
+    w = (torch.randn(N, K, device=dev) * 0.05).requires_grad_(True)
+    b = torch.randn(N, device=dev, requires_grad=True)
+    acc = torch.randn(M, N, device=dev, requires_grad=True)
+    assert ops.USE_TC_LINEAR[0]
+    y = ops.linear(x, w, b, acc)
+    ref = (x.double() @ w.double().t() + b.double() + acc.double())
+    assert relerr(y.double(), ref) < 2e-5
+    y2 = ops.linear(x, w)                                              # no bias, no accumulate
+    assert relerr(y2.double(), x.double() @ w.double().t()) < 2e-5
+    g = torch.randn_like(y)
+    dx, dw, db, dacc = torch.autograd.grad(y, (x, w, b, acc), g)
+    assert relerr(dx.double(), g.double() @ w.double()) < 2e-5
+    assert relerr(dw.double(), g.double().t() @ x.double()) < 1e-5
+    assert relerr(db, g.sum(0)) < 1e-5 and torch.equal(dacc, g)
+    # the split cache follows in-place weight updates (autograd version counter)
+    with torch.no_grad():
+        w.mul_(0.5)
+    assert relerr(ops.linear(x, w).double(), x.double() @ w.double().t()) < 2e-5
