@@ -15,6 +15,7 @@ from .. import ops
 from ..model import EncoderLSTM, EnvDropDecoder, Critic
 from ..model.units import LengthMask
 from .base import BaseAgent, RolloutState
+from .fused import FusedDecoder
 
 
 class EnvDropAgent(BaseAgent):
@@ -32,6 +33,8 @@ class EnvDropAgent(BaseAgent):
         self.critic = Critic(hidden_size=model_cfg.HIDDEN_SIZE, drop_ratio=model_cfg.DROP_RATE)
         self.logs = defaultdict(list)
         self.loss = {}
+        self.fused = True              # decoder rollout as one hand-differentiated node (agent/fused.py)
+        self._fused = FusedDecoder(self.decoder)
         self._finish_init()
 
     def _modules(self):
@@ -65,34 +68,50 @@ class EnvDropAgent(BaseAgent):
         st = RolloutState(store, ib, T + (1 if train_rl else 0))
         training = self.encoder.training
 
-        ml = torch.zeros(B, device=self.device) if train_cl else torch.zeros((), device=self.device)
-        rewards, masks, hiddens, logps, ents = [], [], [], [], []
-        h_tilde = h_t
-        for t in range(T):
-            logit, h_t, c_t, h_tilde = self._decode(st, t, h_tilde, h_t, c_t, ctx, ctx_mask)
-            hiddens.append(h_t)
-            off = self.rng.next() if feedback == "sample" else 0
-            ce, logp, ent, action = ops.policy_head(logit, st.teacher, feedback, self.rng, off)
-            ml = ml + (ce if train_cl else ce.sum())
+        if self.fused and self.device.type == "cuda":
+            (ce, logps, ents, hiddens, logits, actions, targets, rewards, masks, last_h) = self._fused.run(
+                self.rng, st, ctx, ctx_mask.lengths, h_t, c_t, T, feedback, train_rl, poll, self.split_for(B))
+            n = st.steps
+            ml = ce.sum(0) if train_cl else ce.sum()
             if self.trace is not None:
-                self.trace.append(dict(logits=logit.detach(), target=st.teacher, action=action))
-            reward, mask = st.step(t, action)
-            rewards.append(reward), masks.append(mask), logps.append(logp), ents.append(ent)
+                self.trace += [dict(logits=logits[t], target=targets[t], action=actions[t]) for t in range(n)]
             if feedback == "sample":
-                self.logs["entropy"].append(ent.sum().detach())
-            if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
-                break
-        n = st.steps
+                self.logs["entropy"].append(ents.sum().detach())
+            if train_rl:
+                with torch.no_grad():
+                    last_value = self.critic(last_h)
+                values = self.critic(hiddens.reshape(n * B, -1)).view(n, B)
+        else:
+            ml = torch.zeros(B, device=self.device) if train_cl else torch.zeros((), device=self.device)
+            rewards, masks, hiddens, logps, ents = [], [], [], [], []
+            h_tilde = h_t
+            for t in range(T):
+                logit, h_t, c_t, h_tilde = self._decode(st, t, h_tilde, h_t, c_t, ctx, ctx_mask)
+                hiddens.append(h_t)
+                off = self.rng.next() if feedback == "sample" else 0
+                ce, logp, ent, action = ops.policy_head(logit, st.teacher, feedback, self.rng, off)
+                ml = ml + (ce if train_cl else ce.sum())
+                if self.trace is not None:
+                    self.trace.append(dict(logits=logit.detach(), target=st.teacher, action=action))
+                reward, mask = st.step(t, action)
+                rewards.append(reward), masks.append(mask), logps.append(logp), ents.append(ent)
+                if feedback == "sample":
+                    self.logs["entropy"].append(ent.sum().detach())
+                if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
+                    break
+            n = st.steps
+            if train_rl:
+                with torch.no_grad():                               # envdrop.py:225-237: bootstrap value
+                    _, last_h, _, _ = self._decode(st, n, h_tilde, h_t, c_t, ctx, ctx_mask)
+                    last_value = self.critic(last_h)
+                values = self.critic(torch.stack(hiddens).view(n * B, -1)).view(n, B)
+                logps, ents, rewards, masks = (torch.stack(x) for x in (logps, ents, rewards, masks))
         self.ml_loss = ml
 
         rl = 0.0
         if train_rl:
-            with torch.no_grad():                                   # envdrop.py:225-237: bootstrap value
-                _, last_h, _, _ = self._decode(st, n, h_tilde, h_t, c_t, ctx, ctx_mask)
-                last_value = self.critic(last_h)
-            values = self.critic(torch.stack(hiddens).view(n * B, -1)).view(n, B)
-            loss_b, stats = ops.a2c_loss(torch.stack(logps), torch.stack(ents), values, torch.stack(rewards),
-                                         torch.stack(masks), last_value, st.ended[n], self.cfg.GAMMA, 0.01)
+            loss_b, stats = ops.a2c_loss(logps, ents, values, rewards, masks, last_value, st.ended[n],
+                                         self.cfg.GAMMA, 0.01)
             rl = loss_b if train_cl else loss_b.sum()
             self.logs["total"].append(stats[0])
             self.logs["critic_loss"].append(stats[1])

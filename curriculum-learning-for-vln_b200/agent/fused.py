@@ -1,0 +1,298 @@
+"""Fused EnvDrop decoder rollout: the T decoder steps of envdrop.py:134-221 as ~11 kernels per step
+forward and ~12 backward, with a hand-written backward through time instead of an autograd tape.
+
+The module-level path (model/policy.py: EnvDropDecoder.forward, one autograd node per op) stays the
+drop-in for callers that use the nn.Module directly; the agent's rollout goes through here.  Per
+step the chain is (reference lines in policy.py):
+
+    q      = W_vin  drop(h~_{t-1})                         :233 + units.py:107   tcgen05 GEMM
+    v      = pano_attn(table[vp_t], q)                      :234, units.py:108-118 fused gather+attention
+    gates  = [W_ih | W_hh] [act_emb | v | h~_{t-1}] + b     :236-238              ONE GEMM over the concatenation
+    h, c   = LSTM pointwise; WH = [. | drop(h)]             :238-240
+    tq     = W_tin drop(h)                                  units.py:107
+    WH[:H] = ctx_attn(ctx, tq)                              units.py:108-118
+    pre    = W_out WH                                       units.py:119-120
+    h~_t   = tanh(pre); hc = drop(h~_t)                     :243
+    tgt    = W_cand hc                                      :199-206
+    logit  = cand_logits(table, tgt)                        :205 + envdrop.py:166-173
+    action, ce, logp, entropy = policy head                 envdrop.py:177-195
+    state' = env step                                       envdrop.py:198-219
+    XH'[:64] = drop(tanh(W_a pose(view') + b_a))            :222-223
+
+The GEMM operands are row-strided buffers, so no torch.cat / elementwise kernel remains.  Backward
+walks the steps in reverse with the transposed weight splits; the five weight gradients are ONE
+[N x T*B] x [T*B x K] GEMM each at the end (dY and X of every step are kept stacked).
+"""
+import ctypes as C
+
+import torch
+
+from .. import ops
+from ..ops import _call, _ptr, _stream
+
+H_ACT = 64
+
+
+def _p(t, off=0):
+    """Device pointer of tensor `t` advanced by `off` fp32 elements."""
+    return C.c_void_p(t.data_ptr() + 4 * off)
+
+
+class _CatSplit:
+    """bf16 hi/lo split of [W_ih | W_hh] (and of its transpose), refreshed with the weight epoch."""
+
+    def __init__(self):
+        self.stamp = None
+        self.sw = None
+        self.cat = None
+
+    def fresh(self, w_ih, w_hh):
+        stamp = (w_ih._version, w_hh._version, ops.WEIGHT_EPOCH[0], w_ih.data_ptr(), w_hh.data_ptr())
+        if stamp != self.stamp:
+            self.cat = torch.cat((w_ih.detach(), w_hh.detach()), 1).contiguous()
+            if self.sw is None:
+                self.sw = ops._SplitWeight(self.cat)
+            self.sw.stamp = None
+            self.sw.fresh(self.cat)
+            self.stamp = stamp
+        return self.sw
+
+
+def _gemm(hi, lo, N, K, x, ldx, M, bias, y, ldy):
+    """y[M,N] (+)= x[M,K] W^T (+ bias) on the tcgen05 kernel, in row blocks of 128."""
+    for m0 in range(0, M, 128):
+        m = min(128, M - m0)
+        _call("vln_linear_bf16x3", _ptr(hi), _ptr(lo), N, K, C.c_void_p(x.value + 4 * m0 * ldx), ldx, m, bias,
+              C.c_void_p(y.value + 4 * m0 * ldy), ldy, 0, _stream())
+
+
+class FusedDecoder:
+    """The EnvDrop decoder rollout as one autograd node.  ``run`` returns per-step stacks
+    (ce, logp, entropy [n,B]; h_1 [n,B,H]) that carry gradients, plus detached logits / actions /
+    teacher targets / rewards / masks and the bootstrap hidden state."""
+
+    def __init__(self, decoder):
+        self.dec = decoder
+        self.cat = _CatSplit()
+
+    def params(self):
+        d = self.dec
+        return [d.act_embed[0].weight, d.act_embed[0].bias, d.lstm.weight_ih, d.lstm.weight_hh, d.lstm.bias_ih,
+                d.lstm.bias_hh, d.text_attn.linear_in.weight, d.text_attn.linear_out.weight,
+                d.visual_attn.linear_in.weight, d.cand_attn.weight]
+
+    def run(self, rng, st, ctx, lengths, h0, c0, T, feedback, bootstrap, poll, split):
+        return _Rollout.apply(self, rng, st, lengths, T, feedback, bootstrap, poll, split, ctx, h0, c0, *self.params())
+
+
+N_META = 9          # non-tensor arguments of _Rollout.apply before (ctx, h0, c0, *params)
+
+
+class _Rollout(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, fd, rng, st, lengths, T, feedback, bootstrap, poll, split, ctx, h0, c0, *params):
+        dec = fd.dec
+        w_act, b_act, w_ih, w_hh, b_ih, b_hh = [q.detach() for q in params[:6]]
+        ctx, h0, c0 = ops._f32c(ctx.detach()), ops._f32c(h0.detach()), ops._f32c(c0.detach())
+        store = st.store
+        dev = ctx.device
+        B, L, H = ctx.shape
+        F, G4, KX = ops.F_DIM, 4 * H, H_ACT + ops.F_DIM + H
+        p = dec.drop_ratio if dec.training else 0.0
+        pf = dec.feat_drop_ratio if dec.training else 0.0
+        fb = ops.FEEDBACK[feedback]
+        S = T + (1 if bootstrap else 0)                       # decoder passes (the bootstrap one only up to h_1)
+        rp = rng.ptr
+
+        # ---- weights: bf16 hi/lo splits, refreshed once per optimiser step ----
+        s_cat = fd.cat.fresh(w_ih, w_hh)
+        s_tin, s_out, s_vin, s_cand = (ops._split_of(w) for w in params[6:10])
+        bsum = (b_ih + b_hh).contiguous()
+
+        # ---- buffers: GEMM accumulators come out of one zero-filled slab ----
+        zero = torch.zeros(S * B * (F + G4) + T * B * (H + H + F), device=dev)
+        cur = [0]
+
+        def carve(*shape):
+            k = 1
+            for s_ in shape:
+                k *= s_
+            t_ = zero[cur[0]:cur[0] + k].view(*shape)
+            cur[0] += k
+            return t_
+        Q, GATES = carve(S, B, F), carve(S, B, G4)
+        TQ, PRE, TGT = carve(T, B, H), carve(T, B, H), carve(T, B, F)
+        XH = torch.empty((S + 1, B, KX), device=dev)
+        HQ = torch.empty((S + 1, B, H), device=dev)
+        HC = torch.empty((T, B, H), device=dev)
+        ACT = torch.empty((S + 1, B, H_ACT), device=dev)
+        ACTS = torch.empty((S, B, G4), device=dev)
+        CS = torch.empty((S + 1, B, H), device=dev)
+        H1 = torch.empty((S, B, H), device=dev)
+        WH = torch.empty((T, B, 2 * H), device=dev)
+        ATTV = torch.empty((S, B, ops.N_VIEWS), device=dev)
+        ATTC = torch.empty((T, B, L), device=dev)
+        LOGIT = torch.empty((T, B, ops.NSLOT), device=dev)
+        PROBS = torch.empty((T, B, ops.NSLOT), device=dev)
+        CE, LOGP, ENT = (torch.zeros((T, B), device=dev) for _ in range(3))
+        REWARD, MASK = torch.zeros((T, B), device=dev), torch.zeros((T, B), device=dev)
+        ACTION = torch.full((T, B), -1, dtype=torch.int32, device=dev)
+        TEACH = torch.empty((T + 1, B), dtype=torch.int32, device=dev)
+        TEACH[0].copy_(st.teacher)
+        CS[0].copy_(c0)
+
+        # ---- dropout / sampling stream offsets, in the call order of EnvDropDecoder.forward ----
+        offs = []
+
+        def alloc(t):
+            d = dict(act=0, img=0, cand=0, hprev=0, h1=0, ht=0, sample=0)
+            if p > 0.0:
+                d["act"] = rng.next("act", (B, H_ACT), p)
+            if pf > 0.0:
+                d["img"] = rng.next("img", (B, ops.N_VIEWS, ops.IMG_DIM), pf)
+                d["cand"] = rng.next("cand", (B, ops.NSLOT, ops.IMG_DIM), pf)
+            if p > 0.0:
+                d["hprev"] = rng.next("h_prev", (B, H), p)
+                d["h1"] = rng.next("h1", (B, H), p)
+                d["ht"] = rng.next("h_tilde", (B, H), p)
+            if fb == 2 and t < T:
+                d["sample"] = rng.next()
+            offs.append(d)
+
+        def act_embed(t):
+            _call("vln_envdrop_act_fwd", _ptr(st.view[t]), _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t]),
+                  _ptr(XH[t]), KX, B, H_ACT, p, rp, offs[t]["act"], _stream())
+
+        def visual_and_lstm(t, need_drop):
+            _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, B, None, _p(Q[t]), F)
+            _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4), _ptr(Q[t]), F,
+                  _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, B, 0, pf, rp, offs[t]["img"], split, _stream())
+            _gemm(s_cat.hi, s_cat.lo, G4, KX, _p(XH[t]), KX, B, _ptr(bsum), _p(GATES[t]), G4)
+            _call("vln_lstm_pointwise_drop_fwd", _ptr(GATES[t]), _ptr(CS[t]), _ptr(H1[t]), _ptr(CS[t + 1]),
+                  _ptr(ACTS[t]), _p(WH[t], H) if need_drop else None, 2 * H, B, H, p, rp, offs[t]["h1"], _stream())
+
+        alloc(0)
+        _call("vln_envdrop_state_fwd", _ptr(h0), 0, _p(XH[0], H_ACT + F), KX, _ptr(HQ[0]), None, B, H, p, rp,
+              offs[0]["hprev"], 0, _stream())
+        act_embed(0)
+        n = 0
+        for t in range(T):
+            visual_and_lstm(t, True)
+            _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, B, None, _p(TQ[t]), H)
+            _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, B, L,
+                  H, _stream())
+            _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, B, None, _p(PRE[t]), H)
+            more = t + 1 < S
+            if more:
+                alloc(t + 1)
+            _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
+                  _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), B, H, p, rp,
+                  offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _stream())
+            _gemm(s_cand.hi, s_cand.lo, F, H, _p(HC[t]), H, B, None, _p(TGT[t]), F)
+            _call("vln_cand_logits_fwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
+                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(TGT[t]), None, _ptr(LOGIT[t]), B, pf, rp,
+                  offs[t]["cand"], _stream())
+            _call("vln_policy_fwd", _ptr(LOGIT[t]), _ptr(TEACH[t]), fb, rp, offs[t]["sample"], _ptr(CE[t]),
+                  _ptr(ACTION[t]), _ptr(LOGP[t]), _ptr(ENT[t]), _ptr(PROBS[t]), B, _stream())
+            _call("vln_env_step", _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(st.ended[t]), _ptr(st.dist[t]), _ptr(st.goal),
+                  _ptr(ACTION[t]), _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand), _ptr(store.next_hop),
+                  _ptr(store.dist), _ptr(store.sq_off), _ptr(store.vp_local), _ptr(st.vp[t + 1]), _ptr(st.view[t + 1]),
+                  _ptr(st.ended[t + 1]), _ptr(st.dist[t + 1]), _ptr(TEACH[t + 1]), _ptr(REWARD[t]), _ptr(MASK[t]),
+                  _ptr(st.n_active[t:t + 1]), B, _stream())
+            st.steps = n = t + 1
+            if more:
+                act_embed(t + 1)
+            if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
+                break
+        if bootstrap:                                           # envdrop.py:225-237: h_1 of the state after the last step
+            visual_and_lstm(n, False)
+        st.teacher = TEACH[n]
+
+        fctx.fd, fctx.st, fctx.rp = fd, st, rp
+        fctx.cfg = (n, B, L, H, p, pf, split, offs)
+        fctx.splits = (s_cat, s_vin, s_tin, s_out, s_cand)
+        fctx.save_for_backward(ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH)
+        outs = (CE[:n], LOGP[:n], ENT[:n], H1[:n], LOGIT[:n], ACTION[:n], TEACH[:n], REWARD[:n], MASK[:n],
+                H1[n].clone() if bootstrap else H1[:0].clone())
+        fctx.mark_non_differentiable(*outs[4:])
+        return outs
+
+    @staticmethod
+    def backward(fctx, d_ce, d_logp, d_ent, d_h1, *_unused):
+        ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH = fctx.saved_tensors
+        n, B, L, H, p, pf, split, offs = fctx.cfg
+        s_cat, s_vin, s_tin, s_out, s_cand = fctx.splits
+        st, rp = fctx.st, fctx.rp
+        store = st.store
+        dev = ctx.device
+        F, G4, KX = ops.F_DIM, 4 * H, H_ACT + ops.F_DIM + H
+        OH = H_ACT + F                                          # column of h~ inside an XH row
+        d_ce, d_logp, d_ent, d_h1 = (ops._f32c(g) if g is not None else None for g in (d_ce, d_logp, d_ent, d_h1))
+
+        zero = torch.zeros(n * B * (H + 2 * H + KX + H), device=dev)
+        cur = [0]
+
+        def carve(*shape):
+            k = 1
+            for s_ in shape:
+                k *= s_
+            t_ = zero[cur[0]:cur[0] + k].view(*shape)
+            cur[0] += k
+            return t_
+        DHC, DWH, DXH, DHQ = carve(n, B, H), carve(n, B, 2 * H), carve(n, B, KX), carve(n, B, H)
+        DTGT = torch.empty((n, B, F), device=dev)
+        DPRE = torch.empty((n, B, H), device=dev)
+        DTQ = torch.empty((n, B, H), device=dev)
+        DGATES = torch.empty((n, B, G4), device=dev)
+        DQ = torch.empty((n, B, F), device=dev)
+        DACT = torch.empty((n, B, H_ACT), device=dev)
+        DLOG = torch.empty((B, ops.NSLOT), device=dev)
+        DC = torch.empty((2, B, H), device=dev)
+        d_ctx = torch.zeros_like(ctx)
+
+        for t in range(n - 1, -1, -1):
+            last = t == n - 1
+            _call("vln_policy_bwd", _ptr(PROBS[t]), _ptr(TEACH[t]), _ptr(ACTION[t]), _ptr(ENT[t]),
+                  _ptr(d_ce[t]) if d_ce is not None else None, _ptr(d_logp[t]) if d_logp is not None else None,
+                  _ptr(d_ent[t]) if d_ent is not None else None, _ptr(DLOG), B, _stream())
+            _call("vln_cand_logits_bwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
+                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(DLOG), _ptr(DTGT[t]), None, B, pf, rp,
+                  offs[t]["cand"], _stream())
+            _gemm(s_cand.hi_t, s_cand.lo_t, H, F, _p(DTGT[t]), F, B, None, _p(DHC[t]), H)
+            _call("vln_envdrop_state_bwd", _ptr(DHC[t]), None if last else _p(DXH[t + 1], OH), KX,
+                  None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), B, H, p, rp,
+                  0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
+            _gemm(s_out.hi_t, s_out.lo_t, 2 * H, H, _p(DPRE[t]), H, B, None, _p(DWH[t]), 2 * H)
+            _call("vln_ctx_attn_bwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H, None,
+                  _ptr(DTQ[t]), _ptr(d_ctx), B, L, H, _stream())
+            _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, B, None, _p(DWH[t], H), 2 * H)
+            _call("vln_lstm_pointwise_drop_bwd", _ptr(ACTS[t]), _ptr(CS[t]), _ptr(CS[t + 1]), _p(DWH[t], H), 2 * H,
+                  _ptr(d_h1[t]) if d_h1 is not None else None, None if last else _ptr(DC[(t + 1) & 1]),
+                  _ptr(DGATES[t]), _ptr(DC[t & 1]), B, H, p, rp, offs[t]["h1"], _stream())
+            _gemm(s_cat.hi_t, s_cat.lo_t, KX, G4, _p(DGATES[t]), G4, B, None, _p(DXH[t]), KX)
+            _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4),
+                  _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, B, 1, pf, rp,
+                  offs[t]["img"], split, _stream())
+            _gemm(s_vin.hi_t, s_vin.lo_t, H, F, _p(DQ[t]), F, B, None, _p(DHQ[t]), H)
+            _call("vln_envdrop_act_bwd", _ptr(DXH[t]), KX, _ptr(ACT[t]), _ptr(DACT[t]), B, H_ACT, p, rp,
+                  offs[t]["act"], _stream())
+        d_h0 = torch.empty((B, H), device=dev)
+        _call("vln_envdrop_state_bwd", None, _p(DXH[0], OH), KX, _ptr(DHQ[0]), None, 0, 0, _ptr(d_h0), B, H, p, rp,
+              offs[0]["hprev"], 0, _stream())
+        d_c0 = DC[0]
+
+        # ---- weight gradients: one GEMM per weight over all n*B rows ----
+        nb = n * B
+        dG = DGATES.view(nb, G4)
+        d_wcat = ops.wgrad(dG, XH[:n].reshape(nb, KX))
+        d_b = dG.sum(0)
+        d_w_tin = ops.wgrad(DTQ.view(nb, H), WH[:n, :, H:].reshape(nb, H))
+        d_w_out = ops.wgrad(DPRE.view(nb, H), WH[:n].reshape(nb, 2 * H))
+        d_w_vin = ops.wgrad(DQ.view(nb, F), HQ[:n].reshape(nb, H))
+        d_w_cand = ops.wgrad(DTGT.view(nb, F), HC[:n].reshape(nb, H))
+        pose = store.pose128[st.view[:n].reshape(-1).long()]
+        dA = DACT.view(nb, H_ACT)
+        d_w_act = ops.wgrad(dA, pose)
+        d_b_act = dA.sum(0)
+        return (None,) * N_META + (d_ctx, d_h0, d_c0, d_w_act, d_b_act, d_wcat[:, :OH], d_wcat[:, OH:], d_b, d_b,
+                                   d_w_tin, d_w_out, d_w_vin, d_w_cand)

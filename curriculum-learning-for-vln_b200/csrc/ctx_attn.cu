@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(kThreads) ctx_attn_kernel(
     float* __restrict__ attn, float* __restrict__ weighted,            // fwd outputs
     const float* __restrict__ d_weighted, const float* __restrict__ d_attn_ext, float* __restrict__ d_tgt,
     float* __restrict__ d_context,                                      // bwd
-    int mode, int L, int H, int HS) {
+    int mode, int L, int H, int HS, int ld_w) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* tile = reinterpret_cast<float*>(smem);          // [L][HS]
   float* vsl = tile + (size_t)L * HS;                    // [HS]  tgt slice (fwd) / d_weighted slice (bwd)
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kThreads) ctx_attn_kernel(
     const int l = i / hv, c = i - l * hv;
     reinterpret_cast<float4*>(tile)[l * hv + c] = __ldg(reinterpret_cast<const float4*>(cb + (size_t)l * H + col0) + c);
   }
-  const float* v_in = (mode == 0 ? tgt : d_weighted) + (size_t)b * H + col0;
+  const float* v_in = (mode == 0 ? tgt + (size_t)b * H : d_weighted + (size_t)b * ld_w) + col0;
   for (int i = tid; i < HS; i += kThreads) {
     vsl[i] = v_in[i];
     if (mode == 1) tsl[i] = tgt[(size_t)b * H + col0 + i];
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) ctx_attn_kernel(
     for (int c = tid; c < HS; c += kThreads) {
       float acc = 0.f;
       for (int l = 0; l < len; ++l) acc += sm[l] * tile[l * HS + c];
-      weighted[(size_t)b * H + col0 + c] = acc;
+      weighted[(size_t)b * ld_w + col0 + c] = acc;
     }
   } else {
     for (int c = tid; c < HS; c += kThreads) {
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(kThreads) ctx_attn_kernel(
 
 int launch(const float* context, const float* tgt, const int32_t* lengths, float* attn, float* weighted,
            const float* d_weighted, const float* d_attn_ext, float* d_tgt, float* d_context, int mode, int B, int L,
-           int H, cudaStream_t stream) {
+           int H, int ld_w, cudaStream_t stream) {
+  VLN_REQUIRE(ld_w >= H, "row stride of weighted / d_weighted must be >= H");
   VLN_REQUIRE(L > 0 && L <= kMaxL, "L must be in 1..96");
   VLN_REQUIRE(H % 16 == 0 && H >= 64, "H must be a multiple of 16");
   int S = 4;
@@ -163,23 +164,34 @@ int launch(const float* context, const float* tgt, const int32_t* lengths, float
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ctx_attn_kernel, context, tgt, lengths, attn, weighted, d_weighted,
-                                    d_attn_ext, d_tgt, d_context, mode, L, H, HS));
+                                    d_attn_ext, d_tgt, d_context, mode, L, H, HS, ld_w));
   return 0;
 }
 
 }  // namespace
 
+extern "C" int vln_ctx_attn_fwd_ld(const float* context, const float* tgt, const int32_t* lengths, float* attn,
+                                   float* weighted, int ld_weighted, int B, int L, int H, void* stream) {
+  VLN_REQUIRE(context && tgt && lengths && attn && weighted && B > 0, "bad arguments");
+  return launch(context, tgt, lengths, attn, weighted, nullptr, nullptr, nullptr, nullptr, 0, B, L, H, ld_weighted,
+                (cudaStream_t)stream);
+}
+
 extern "C" int vln_ctx_attn_fwd(const float* context, const float* tgt, const int32_t* lengths, float* attn,
                                 float* weighted, int B, int L, int H, void* stream) {
-  VLN_REQUIRE(context && tgt && lengths && attn && weighted && B > 0, "bad arguments");
-  return launch(context, tgt, lengths, attn, weighted, nullptr, nullptr, nullptr, nullptr, 0, B, L, H,
-                (cudaStream_t)stream);
+  return vln_ctx_attn_fwd_ld(context, tgt, lengths, attn, weighted, H, B, L, H, stream);
+}
+
+extern "C" int vln_ctx_attn_bwd_ld(const float* context, const float* tgt, const int32_t* lengths, const float* attn,
+                                   const float* d_weighted, int ld_d_weighted, const float* d_attn_ext, float* d_tgt,
+                                   float* d_context, int B, int L, int H, void* stream) {
+  VLN_REQUIRE(context && tgt && lengths && attn && d_weighted && d_tgt && B > 0, "bad arguments");
+  return launch(context, tgt, lengths, const_cast<float*>(attn), nullptr, d_weighted, d_attn_ext, d_tgt, d_context,
+                1, B, L, H, ld_d_weighted, (cudaStream_t)stream);
 }
 
 extern "C" int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* lengths, const float* attn,
                                 const float* d_weighted, const float* d_attn_ext, float* d_tgt, float* d_context,
                                 int B, int L, int H, void* stream) {
-  VLN_REQUIRE(context && tgt && lengths && attn && d_weighted && d_tgt && B > 0, "bad arguments");
-  return launch(context, tgt, lengths, const_cast<float*>(attn), nullptr, d_weighted, d_attn_ext, d_tgt, d_context,
-                1, B, L, H, (cudaStream_t)stream);
+  return vln_ctx_attn_bwd_ld(context, tgt, lengths, attn, d_weighted, H, d_attn_ext, d_tgt, d_context, B, L, H, stream);
 }

@@ -296,8 +296,8 @@ extern "C" int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int 
   VLN_REQUIRE(((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)w_lo & 15) == 0, "weights must be 16-byte aligned");
   const int nkb = K / kBK;
   if (splits <= 0) {                                           // fill the machine: tiles x splits ~ #SMs
-    const int tiles = (N + kTileN - 1) / kTileN;
-    splits = (148 + tiles - 1) / tiles;
+    const int tiles = (N + kTileN - 1) / kTileN;       // one CTA per SM (the ring takes the whole shared memory):
+    splits = 148 / tiles;                              // stay within ONE wave of 148 CTAs
   }
   if (splits > nkb) splits = nkb;
   if (splits < 1) splits = 1;

@@ -62,7 +62,8 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
                  const int32_t* __restrict__ view, const float* __restrict__ loc4, const float* __restrict__ vec,
                  float* __restrict__ attn_io, const float* __restrict__ fwd_out, float* __restrict__ out,
                  float* __restrict__ scratch, unsigned int* __restrict__ tickets, int B, int S, int mode,
-                 float drop_p, const uint64_t* __restrict__ rng, uint64_t call_off) {
+                 float drop_p, const uint64_t* __restrict__ rng, uint64_t call_off, int ld_vec, int ld_out,
+                 int ld_fwd) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,7 +119,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   auto prefetch_unit = [&](int uu, int buf) {
     if (uu < n_units) {
       const int e = uu / S;
-      const float* vr = vec + (size_t)e * VLN_F;
+      const float* vr = vec + (size_t)e * ld_vec;
       for (int c = tid; c < VLN_F / 4; c += kConsumers) cp_async16(&sm.qbuf[buf][c * 4], vr + c * 4);
       const float* lr = loc4 + (size_t)__ldg(view + e) * (VLN_V * 4);
       if (tid < VLN_V) cp_async16(&sm.locbuf[buf][tid * 4], lr + tid * 4);
@@ -262,8 +263,8 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
 #pragma unroll
       for (int w = 0; w < kConsumerWarps; ++w) oA += wsc[w] * sm.red[w * kRed + VLN_IMG + tid];
     }
-    float* orow = out + (size_t)ep * VLN_F;
-    const float* frow = mode == 1 ? fwd_out + (size_t)ep * VLN_F : nullptr;
+    float* orow = out + (size_t)ep * ld_out;
+    const float* frow = mode == 1 ? fwd_out + (size_t)ep * ld_fwd : nullptr;
     bool finalize = true;
     if (S == 1) {
       const float f1 = mode == 0 ? scale / L : scale;
@@ -381,15 +382,20 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
 
 }  // namespace
 
-extern "C" int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
-                             const float* vec, float* attn_io, const float* fwd_out, float* out, int B, int mode,
-                             float drop_p, const uint64_t* rng, uint64_t call_off, int split, void* stream) {
+extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
+                                const float* vec, int ld_vec, float* attn_io, const float* fwd_out, int ld_fwd,
+                                float* out, int ld_out, int B, int mode, float drop_p, const uint64_t* rng,
+                                uint64_t call_off, int split, void* stream) {
   VLN_REQUIRE(ctx && vp && view && loc4 && vec && attn_io && out && B > 0, "bad arguments");
   VLN_REQUIRE(split == 1 || split == 2 || split == 4, "split must be 1, 2 or 4");
   VLN_REQUIRE(mode == 0 || (mode == 1 && fwd_out), "mode must be 0 (forward) or 1 (backward, needs fwd_out)");
   VLN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");
   VLN_REQUIRE(drop_p == 0.f || rng, "dropout needs an rng state");
   VLN_REQUIRE(split == 1 || B <= VLN_SPLIT_MAX_B, "split > 1 supports at most VLN_SPLIT_MAX_B episodes per call");
+  VLN_REQUIRE(ld_vec >= VLN_F && ld_out >= VLN_F && (mode == 0 || ld_fwd >= VLN_F), "row strides must be >= 2176");
+  VLN_REQUIRE(ld_vec % 4 == 0 && ld_out % 4 == 0 && ld_fwd % 4 == 0 && ((uintptr_t)vec & 15) == 0 &&
+                  ((uintptr_t)out & 15) == 0 && ((uintptr_t)fwd_out & 15) == 0,
+              "rows must be 16-byte aligned");
   static bool configured = false;
   if (!configured) {
     VLN_CHECK_CUDA(cudaFuncSetAttribute(pano_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
@@ -399,7 +405,14 @@ extern "C" int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_
   const int grid = units < ctx->num_sms ? units : ctx->num_sms;
   pano_attn_kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(
       ctx->table, vp, view, loc4, vec, attn_io, fwd_out, out, ctx->scratch, ctx->tickets, B, split, mode, drop_p, rng,
-      call_off);
+      call_off, ld_vec, ld_out, ld_fwd);
   VLN_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
+                             const float* vec, float* attn_io, const float* fwd_out, float* out, int B, int mode,
+                             float drop_p, const uint64_t* rng, uint64_t call_off, int split, void* stream) {
+  return vln_pano_attn_ld(ctx, vp, view, loc4, vec, VLN_F, attn_io, fwd_out, VLN_F, out, VLN_F, B, mode, drop_p, rng,
+                          call_off, split, stream);
 }

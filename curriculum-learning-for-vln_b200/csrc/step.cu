@@ -1,0 +1,320 @@
+// Glue kernels of the fused EnvDrop decoder step (EnvDropDecoder.forward policy.py:208-246 inside
+// the rollout loop envdrop.py:134-221) and of its backward.
+//
+// The step is a chain of grid-wide dependencies (skinny GEMM -> gather/attention -> GEMM -> ...);
+// everything BETWEEN two such kernels — tanh, the four nn.Dropout sites, the concatenations
+// torch.cat((prev_act_emb, visual_feat)) / cat((weighted, h)), the action embedding, the LSTMCell
+// pointwise half, the action head + simulator transition — is folded into the handful of kernels
+// below, writing straight into the row-strided operand buffers of the next GEMM:
+//
+//   XH[t]  [B, 64 + 2176 + 512]  = [ drop(tanh(W_a pose + b_a)) | visual attention output | h~_{t-1} ]
+//   WH[t]  [B, 512 + 512]        = [ text-attention weighted context | drop(h_t) ]
+//
+// Dropout masks come from the same (seed, base + call_off, element/8) Philox blocks as
+// vln_dropout on a dense [B, n] tensor, so vln_dropout_mask reproduces them for the oracle.
+// All kernels here are latency-bound (a few thousand threads); the point is the launch count.
+#include "common.cuh"
+
+namespace {
+
+struct Drop {
+  uint64_t seed, offset;
+  uint32_t thr;
+  float scale;
+  bool on;
+};
+
+__device__ __forceinline__ Drop make_drop(float p, const uint64_t* rng, uint64_t call_off) {
+  Drop d;
+  d.on = p > 0.f;
+  d.thr = drop_threshold(p);
+  d.scale = d.on ? 1.0f / (1.0f - p) : 1.0f;
+  d.seed = d.on ? rng[0] : 0;
+  d.offset = d.on ? rng[1] + call_off : 0;
+  return d;
+}
+// keep-scale factors (0 or 1/(1-p)) of the 8 elements of Philox block `blk`
+__device__ __forceinline__ void keep8(const Drop& d, uint64_t blk, float (&k)[8]) {
+  if (!d.on) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k[j] = 1.f;
+    return;
+  }
+  const Philox8 r = philox8(d.seed, d.offset, blk);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k[j] = philox_keep(r, j, d.thr) ? d.scale : 0.f;
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---- h~ state: tanh + the two dropout sites that consume it -------------------------------------
+__global__ void state_fwd_kernel(const float* __restrict__ src, int apply_tanh, float* __restrict__ xh_next, int ld_xh,
+                                 float* __restrict__ hq_next, float* __restrict__ hc_cur, int B, int H, float p,
+                                 const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // 8-element block index
+  const int hb = H / 8;
+  if (i >= B * hb) return;
+  const int b = i / hb, h = (i - b * hb) * 8;
+  float v[8], k[8], o[8];
+  ld8(src + (size_t)b * H + h, v);
+  if (apply_tanh) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+  }
+  if (xh_next) st8(xh_next + (size_t)b * ld_xh + h, v);
+  if (hq_next) {
+    keep8(make_drop(p, rng, off_q), (uint64_t)i, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = v[j] * k[j];
+    st8(hq_next + (size_t)b * H + h, o);
+  }
+  if (hc_cur) {
+    keep8(make_drop(p, rng, off_c), (uint64_t)i, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = v[j] * k[j];
+    st8(hc_cur + (size_t)b * H + h, o);
+  }
+}
+
+// d_src = (drop_c'(d_hc) + d_xh_next + drop_q'(d_hq_next)) * (apply_tanh ? 1 - h~^2 : 1)
+__global__ void state_bwd_kernel(const float* __restrict__ d_hc, const float* __restrict__ d_xh_next, int ld_dxh,
+                                 const float* __restrict__ d_hq_next, const float* __restrict__ htilde, int ld_h,
+                                 int apply_tanh, float* __restrict__ d_src, int B, int H, float p,
+                                 const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hb = H / 8;
+  if (i >= B * hb) return;
+  const int b = i / hb, h = (i - b * hb) * 8;
+  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, v[8], k[8];
+  if (d_hc) {
+    ld8(d_hc + (size_t)b * H + h, v);
+    keep8(make_drop(p, rng, off_c), (uint64_t)i, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += v[j] * k[j];
+  }
+  if (d_xh_next) {
+    ld8(d_xh_next + (size_t)b * ld_dxh + h, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += v[j];
+  }
+  if (d_hq_next) {
+    ld8(d_hq_next + (size_t)b * H + h, v);
+    keep8(make_drop(p, rng, off_q), (uint64_t)i, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += v[j] * k[j];
+  }
+  if (apply_tanh) {
+    ld8(htilde + (size_t)b * ld_h + h, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= 1.f - v[j] * v[j];
+  }
+  st8(d_src + (size_t)b * H + h, g);
+}
+
+// ---- action embedding of the agent's pose: drop(tanh(W_a angle128(view) + b_a)) ------------------
+// angle128 = pose4[view] each value repeated x32 (misc.py:286-293), so the 128-wide dot product is
+// 4 values against 4 group sums of the weight row.
+__device__ __forceinline__ float act_embed_one(const float* __restrict__ w_row, const float* __restrict__ p4, float bias) {
+  float acc = bias;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; i += 4) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w_row + 32 * k + i));
+      s += (w.x + w.y) + (w.z + w.w);
+    }
+    acc = fmaf(p4[k], s, acc);
+  }
+  return tanhf(acc);
+}
+
+__global__ void act_fwd_kernel(const int32_t* __restrict__ view, const float* __restrict__ pose4,
+                               const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ act,
+                               float* __restrict__ xh, int ld_xh, int B, int E, float p,
+                               const uint64_t* __restrict__ rng, uint64_t call_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, j = i - b * E;
+  const float a = act_embed_one(w + (size_t)j * VLN_ANG, pose4 + (size_t)view[b] * 4, bias[j]);
+  act[i] = a;
+  float k[8];
+  keep8(make_drop(p, rng, call_off), (uint64_t)(i >> 3), k);
+  xh[(size_t)b * ld_xh + j] = a * k[i & 7];
+}
+
+// d_actpre[b,j] = drop'(d_xh[b,j]) * (1 - act^2)
+__global__ void act_bwd_kernel(const float* __restrict__ d_xh, int ld_dxh, const float* __restrict__ act,
+                               float* __restrict__ d_actpre, int B, int E, float p, const uint64_t* __restrict__ rng,
+                               uint64_t call_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * E) return;
+  const int b = i / E, j = i - b * E;
+  float k[8];
+  keep8(make_drop(p, rng, call_off), (uint64_t)(i >> 3), k);
+  const float a = act[i];
+  d_actpre[i] = d_xh[(size_t)b * ld_dxh + j] * k[i & 7] * (1.f - a * a);
+}
+
+// ---- nn.LSTMCell pointwise half + dropout of h_1 into the text-attention operand buffer -----------
+__global__ void lstm_pw_drop_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c0,
+                                        float* __restrict__ h1, float* __restrict__ c1, float* __restrict__ acts,
+                                        float* __restrict__ h1_drop, int ld_drop, int B, int H, float p,
+                                        const uint64_t* __restrict__ rng, uint64_t call_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hb = H / 8;
+  if (i >= B * hb) return;
+  const int b = i / hb, h = (i - b * hb) * 8;
+  const float* gr = gates + (size_t)b * 4 * H + h;
+  float gi[8], gf[8], gg[8], go[8], c[8], hh[8], k[8];
+  ld8(gr, gi); ld8(gr + H, gf); ld8(gr + 2 * H, gg); ld8(gr + 3 * H, go);
+  ld8(c0 + (size_t)b * H + h, c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gi[j] = sigmoidf_(gi[j]); gf[j] = sigmoidf_(gf[j]); gg[j] = tanhf(gg[j]); go[j] = sigmoidf_(go[j]);
+    c[j] = gf[j] * c[j] + gi[j] * gg[j];
+    hh[j] = go[j] * tanhf(c[j]);
+  }
+  st8(c1 + (size_t)b * H + h, c);
+  st8(h1 + (size_t)b * H + h, hh);
+  if (acts) {
+    float* ar = acts + (size_t)b * 4 * H + h;
+    st8(ar, gi); st8(ar + H, gf); st8(ar + 2 * H, gg); st8(ar + 3 * H, go);
+  }
+  if (h1_drop) {
+    keep8(make_drop(p, rng, call_off), (uint64_t)i, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hh[j] *= k[j];
+    st8(h1_drop + (size_t)b * ld_drop + h, hh);
+  }
+}
+
+// d_h1 = drop'(d_h1_drop) + d_h1_extra ; then the LSTMCell pointwise backward
+__global__ void lstm_pw_drop_bwd_kernel(const float* __restrict__ acts, const float* __restrict__ c0,
+                                        const float* __restrict__ c1, const float* __restrict__ d_h1_drop, int ld_drop,
+                                        const float* __restrict__ d_h1_extra, const float* __restrict__ d_c1,
+                                        float* __restrict__ d_gates, float* __restrict__ d_c0, int B, int H, float p,
+                                        const uint64_t* __restrict__ rng, uint64_t call_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hb = H / 8;
+  if (i >= B * hb) return;
+  const int b = i / hb, h = (i - b * hb) * 8;
+  const float* ar = acts + (size_t)b * 4 * H + h;
+  float gi[8], gf[8], gg[8], go[8], cp[8], cn[8], dh[8], dc[8], k[8], v[8];
+  ld8(ar, gi); ld8(ar + H, gf); ld8(ar + 2 * H, gg); ld8(ar + 3 * H, go);
+  ld8(c0 + (size_t)b * H + h, cp);
+  ld8(c1 + (size_t)b * H + h, cn);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dh[j] = 0.f;
+  if (d_h1_drop) {
+    ld8(d_h1_drop + (size_t)b * ld_drop + h, v);
+    keep8(make_drop(p, rng, call_off), (uint64_t)i, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dh[j] = v[j] * k[j];
+  }
+  if (d_h1_extra) {
+    ld8(d_h1_extra + (size_t)b * H + h, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dh[j] += v[j];
+  }
+  if (d_c1) ld8(d_c1 + (size_t)b * H + h, dc);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dc[j] = 0.f;
+  }
+  float di[8], df[8], dg[8], dgo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float tc = tanhf(cn[j]);
+    const float dcj = dc[j] + dh[j] * go[j] * (1.f - tc * tc);
+    di[j] = dcj * gg[j] * gi[j] * (1.f - gi[j]);
+    df[j] = dcj * cp[j] * gf[j] * (1.f - gf[j]);
+    dg[j] = dcj * gi[j] * (1.f - gg[j] * gg[j]);
+    dgo[j] = dh[j] * tc * go[j] * (1.f - go[j]);
+    dc[j] = dcj * gf[j];
+  }
+  float* dr = d_gates + (size_t)b * 4 * H + h;
+  st8(dr, di); st8(dr + H, df); st8(dr + 2 * H, dg); st8(dr + 3 * H, dgo);
+  st8(d_c0 + (size_t)b * H + h, dc);
+}
+
+}  // namespace
+
+#define STREAM ((cudaStream_t)stream)
+
+extern "C" int vln_envdrop_state_fwd(const float* src, int apply_tanh, float* xh_next, int ld_xh, float* hq_next,
+                                     float* hc_cur, int B, int H, float p, const uint64_t* rng, uint64_t off_q,
+                                     uint64_t off_c, void* stream) {
+  VLN_REQUIRE(src && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
+  VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
+  VLN_REQUIRE(!xh_next || ld_xh % 4 == 0, "xh rows must be 16-byte aligned");
+  const int n = B * (H / 8);
+  state_fwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(src, apply_tanh, xh_next, ld_xh, hq_next, hc_cur, B, H, p, rng,
+                                                        off_q, off_c);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_envdrop_state_bwd(const float* d_hc, const float* d_xh_next, int ld_dxh, const float* d_hq_next,
+                                     const float* htilde, int ld_h, int apply_tanh, float* d_src, int B, int H, float p,
+                                     const uint64_t* rng, uint64_t off_q, uint64_t off_c, void* stream) {
+  VLN_REQUIRE(d_src && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
+  VLN_REQUIRE(!apply_tanh || htilde, "tanh backward needs the saved h~");
+  VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
+  const int n = B * (H / 8);
+  state_bwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(d_hc, d_xh_next, ld_dxh, d_hq_next, htilde, ld_h, apply_tanh,
+                                                        d_src, B, H, p, rng, off_q, off_c);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_envdrop_act_fwd(const int32_t* view, const float* pose4, const float* w, const float* bias, float* act,
+                                   float* xh, int ld_xh, int B, int E, float p, const uint64_t* rng, uint64_t call_off,
+                                   void* stream) {
+  VLN_REQUIRE(view && pose4 && w && bias && act && xh && B > 0 && E > 0, "bad arguments");
+  VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
+  act_fwd_kernel<<<(B * E + 127) / 128, 128, 0, STREAM>>>(view, pose4, w, bias, act, xh, ld_xh, B, E, p, rng, call_off);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_envdrop_act_bwd(const float* d_xh, int ld_dxh, const float* act, float* d_actpre, int B, int E,
+                                   float p, const uint64_t* rng, uint64_t call_off, void* stream) {
+  VLN_REQUIRE(d_xh && act && d_actpre && B > 0 && E > 0, "bad arguments");
+  VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
+  act_bwd_kernel<<<(B * E + 127) / 128, 128, 0, STREAM>>>(d_xh, ld_dxh, act, d_actpre, B, E, p, rng, call_off);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_lstm_pointwise_drop_fwd(const float* gates, const float* c0, float* h1, float* c1, float* acts,
+                                           float* h1_drop, int ld_drop, int B, int H, float p, const uint64_t* rng,
+                                           uint64_t call_off, void* stream) {
+  VLN_REQUIRE(gates && c0 && h1 && c1 && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
+  VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng || !h1_drop), "dropout needs 0 <= p < 1 and an rng state");
+  const int n = B * (H / 8);
+  lstm_pw_drop_fwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(gates, c0, h1, c1, acts, h1_drop, ld_drop, B, H, p, rng,
+                                                               call_off);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_lstm_pointwise_drop_bwd(const float* acts, const float* c0, const float* c1, const float* d_h1_drop,
+                                           int ld_drop, const float* d_h1_extra, const float* d_c1, float* d_gates,
+                                           float* d_c0, int B, int H, float p, const uint64_t* rng, uint64_t call_off,
+                                           void* stream) {
+  VLN_REQUIRE(acts && c0 && c1 && d_gates && d_c0 && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
+  VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng || !d_h1_drop), "dropout needs 0 <= p < 1 and an rng state");
+  const int n = B * (H / 8);
+  lstm_pw_drop_bwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(acts, c0, c1, d_h1_drop, ld_drop, d_h1_extra, d_c1,
+                                                               d_gates, d_c0, B, H, p, rng, call_off);
+  VLN_LAUNCH_OK();
+  return 0;
+}

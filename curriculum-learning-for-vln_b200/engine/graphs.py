@@ -79,6 +79,9 @@ class GraphedTrainStep(TrainStep):
                 torch.cuda.current_stream().wait_stream(s)
                 g = torch.cuda.CUDAGraph()
                 ag.rng.off = 0
+                # the optimiser updates parameters through raw pointers between replays: make the capture
+                # re-derive every cached bf16 weight split, so the split kernels are part of the graph
+                ops.WEIGHT_EPOCH[0] += 1
                 c0 = ops.CALLS[0]
                 with torch.cuda.graph(g):
                     loss, item = self._body()

@@ -77,6 +77,14 @@ int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, co
                   const float* vec, float* attn_io, const float* fwd_out, float* out, int B, int mode,
                   float drop_p, const uint64_t* rng, uint64_t call_off, int split, void* stream);
 
+/* Same kernel with explicit row strides (in floats, multiples of 4, >= 2176) for vec, fwd_out and out, so the
+ * result can land inside a wider operand row (the LSTMCell input [act_emb | visual | h] of policy.py:236-238)
+ * and the backward can read its d(out) / saved forward output from there. */
+int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
+                     const float* vec, int ld_vec, float* attn_io, const float* fwd_out, int ld_fwd,
+                     float* out, int ld_out, int B, int mode, float drop_p, const uint64_t* rng,
+                     uint64_t call_off, int split, void* stream);
+
 /* Candidate logits (EnvDropDecoder.candidate_attn policy.py:199-206; also ActionScoring
  * units.py:173-185 after folding its Linear layers into tgt/bias on the host side):
  *   logits[b,j] = x~c[b,j] . tgt[b] + bias[b]   j <= n_cand (END row is all-zero features)
@@ -104,12 +112,54 @@ int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* leng
                      const float* attn, const float* d_weighted, const float* d_attn_ext,
                      float* d_tgt, float* d_context, int B, int L, int H, void* stream);
 
+/* Row-strided variants: `weighted` (forward) / `d_weighted` (backward) rows are ld floats apart, so the
+ * weighted context is written straight into cat((weighted, h)) (units.py:119) and its gradient read from there. */
+int vln_ctx_attn_fwd_ld(const float* context, const float* tgt, const int32_t* lengths, float* attn,
+                        float* weighted, int ld_weighted, int B, int L, int H, void* stream);
+int vln_ctx_attn_bwd_ld(const float* context, const float* tgt, const int32_t* lengths,
+                        const float* attn, const float* d_weighted, int ld_d_weighted, const float* d_attn_ext,
+                        float* d_tgt, float* d_context, int B, int L, int H, void* stream);
+
 /* nn.LSTMCell pointwise half (policy.py:53,159,238): gates [B,4H] (i,f,g,o pre-activations,
  * biases already added) + c0 -> h1, c1; acts [B,4H] keeps the activated gates for backward. */
 int vln_lstm_pointwise_fwd(const float* gates, const float* c0, float* h1, float* c1, float* acts,
                            int B, int H, void* stream);
 int vln_lstm_pointwise_bwd(const float* acts, const float* c0, const float* c1, const float* d_h1,
                            const float* d_c1, float* d_gates, float* d_c0, int B, int H, void* stream);
+
+/* LSTMCell pointwise half fused with the nn.Dropout of h_1 that follows it in EnvDropDecoder.forward
+ * (policy.py:238-240): h1_drop (nullable; rows ld_drop floats apart) = dropout(h1; p, call_off), written
+ * into the [weighted | h] operand of text_attn.linear_out.  Backward: d_h1 = dropout'(d_h1_drop) +
+ * d_h1_extra (nullable: the critic's gradient on the undropped h_1, envdrop.py:247) and d_c1 (nullable). */
+int vln_lstm_pointwise_drop_fwd(const float* gates, const float* c0, float* h1, float* c1, float* acts,
+                                float* h1_drop, int ld_drop, int B, int H, float p, const uint64_t* rng,
+                                uint64_t call_off, void* stream);
+int vln_lstm_pointwise_drop_bwd(const float* acts, const float* c0, const float* c1, const float* d_h1_drop,
+                                int ld_drop, const float* d_h1_extra, const float* d_c1, float* d_gates,
+                                float* d_c0, int B, int H, float p, const uint64_t* rng, uint64_t call_off,
+                                void* stream);
+
+/* Glue of the fused EnvDrop decoder step (EnvDropDecoder.forward policy.py:208-246): everything between
+ * two grid-wide kernels of the step, writing into the operand rows of the next GEMM.
+ * state_fwd: h~ = apply_tanh ? tanh(src) : src  (src = linear_out pre-activation, units.py:120, or the
+ *   encoder's decoder_init);  xh_next[b, 0:H) (rows ld_xh apart) = h~ (LSTM hidden input of the NEXT step,
+ *   policy.py:238);  hq_next [B,H] = dropout(h~; p, off_q) (next step's prev_h1_drop, policy.py:233);
+ *   hc_cur [B,H] = dropout(h~; p, off_c) (this step's h_tilde_drop, policy.py:243).  Outputs nullable.
+ * state_bwd: d_src = (dropout_c'(d_hc) + d_xh_next + dropout_q'(d_hq_next)) * (apply_tanh ? 1-h~^2 : 1);
+ *   each gradient input nullable; htilde rows ld_h apart.
+ * act_fwd: act [B,E] = tanh(W_a angle128(pose4[view]) + b_a) (policy.py:222, envdrop.py:76-78), and
+ *   xh[b, 0:E) = dropout(act; p, call_off).   act_bwd: d_actpre = dropout'(d_xh[:, 0:E)) * (1 - act^2). */
+int vln_envdrop_state_fwd(const float* src, int apply_tanh, float* xh_next, int ld_xh, float* hq_next,
+                          float* hc_cur, int B, int H, float p, const uint64_t* rng, uint64_t off_q,
+                          uint64_t off_c, void* stream);
+int vln_envdrop_state_bwd(const float* d_hc, const float* d_xh_next, int ld_dxh, const float* d_hq_next,
+                          const float* htilde, int ld_h, int apply_tanh, float* d_src, int B, int H, float p,
+                          const uint64_t* rng, uint64_t off_q, uint64_t off_c, void* stream);
+int vln_envdrop_act_fwd(const int32_t* view, const float* pose4, const float* w, const float* bias, float* act,
+                        float* xh, int ld_xh, int B, int E, float p, const uint64_t* rng, uint64_t call_off,
+                        void* stream);
+int vln_envdrop_act_bwd(const float* d_xh, int ld_dxh, const float* act, float* d_actpre, int B, int E,
+                        float p, const uint64_t* rng, uint64_t call_off, void* stream);
 
 /* Skinny linear layer on tcgen05 tensor cores (nn.Linear / nn.LSTMCell gate GEMMs of policy.py and
  * units.py at batch sizes <= 128):  y[m,n] += sum_k x[m,k] w[n,k] (+ bias[n]),  m < M <= 128.

@@ -96,10 +96,14 @@ def _mask_feed(agent, cand_widths=None):
     return feed
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "modules"])
 @pytest.mark.parametrize("mode", ["eval", "train"])
-def test_envdrop_rollouts_match_oracle(mode):
+def test_envdrop_rollouts_match_oracle(mode, fused):
+    """fused: the agent's hand-differentiated decoder rollout (agent/fused.py);
+    modules: the same rollout through the drop-in nn.Modules (one autograd node per op)."""
     from oracle import port_modules as P, port_rollout as PR
     agent, pag, env, penv, sds, cfg = _setup("ENVDROP")
+    agent.fused = fused
     getattr(agent, mode)()
     agent.rng.log = [] if mode == "train" else None
     agent.rng.begin_iteration()
@@ -244,3 +248,28 @@ def test_train_step_and_flat_optimizer():
     flat = step.opt.flat
     for p in agent.trainable_params():
         assert flat.data_ptr() <= p.data_ptr() < flat.data_ptr() + flat.numel() * 4
+
+
+def test_graph_replay_tracks_the_optimiser():
+    """CUDA-graph replays of the iteration must see the weights the fused optimiser wrote (the bf16
+    weight splits are re-derived inside the graph): graphed steps == eager steps.  Dropout off and
+    teacher forcing only, so both runs are deterministic functions of the weights."""
+    from clvln_b200.engine import TrainStep
+    from clvln_b200.engine.graphs import GraphedTrainStep
+    finals = []
+    for graphed in (False, True):
+        agent, pag, env, penv, sds, cfg = _setup("ENVDROP", B=8, fixed_len=20)
+        agent.train()
+        agent.encoder.drop_ratio = agent.decoder.drop_ratio = agent.decoder.feat_drop_ratio = 0.0
+        cfg.AGENT.FEEDBACK = "teacher"
+        cfg.TRAIN.LR = 1e-3
+        init = [p.detach().clone() for p in agent.trainable_params()]
+        step = (GraphedTrainStep if graphed else TrainStep)(cfg, agent)
+        losses = [float(step()) for _ in range(5)]
+        finals.append((losses, init, [p.detach().clone() for p in agent.trainable_params()]))
+    (l0, i0, p0), (l1, _, p1) = finals
+    assert np.allclose(l0, l1, rtol=2e-3, atol=1e-4), (l0, l1)
+    assert max(_rel(a, b) for a, b in zip(p0, i0)) > 1e-3           # the optimiser did move the weights
+    # RMSprop turns round-off in near-zero gradients into +-lr steps, so compare against the distance moved
+    for a, b, i in zip(p0, p1, i0):
+        assert float((a - b).norm()) <= 0.1 * float((a - i).norm()) + 1e-6
