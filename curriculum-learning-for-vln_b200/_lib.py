@@ -50,7 +50,7 @@ _SIGS = {
     "vln_pano_attn": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _i, _p], _i),
     "vln_pano_attn_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _f, _p, _u64, _i, _p], _i),
     "vln_ctx_attn_fwd_ld": ([_p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
-    "vln_ctx_attn_bwd_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p], _i),
+    "vln_ctx_attn_bwd_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p], _i),
     "vln_lstm_pointwise_drop_fwd": ([_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _u64, _p], _i),
     "vln_lstm_pointwise_drop_bwd": ([_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _p], _i),
     "vln_envdrop_state_fwd": ([_p, _i, _p, _i, _p, _p, _i, _i, _f, _p, _u64, _u64, _p], _i),
@@ -63,7 +63,7 @@ _SIGS = {
     "vln_ctx_attn_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p], _i),
     "vln_lstm_pointwise_fwd": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_pointwise_bwd": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
-    "vln_linear_bf16x3": ([_p, _p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _p], _i),
+    "vln_linear_bf16x3": ([_p, _p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _i, _p], _i),
     "vln_split_bf16": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_seq_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "vln_lstm_seq_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),

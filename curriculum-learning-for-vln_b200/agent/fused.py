@@ -58,12 +58,12 @@ class _CatSplit:
         return self.sw
 
 
-def _gemm(hi, lo, N, K, x, ldx, M, bias, y, ldy):
-    """y[M,N] (+)= x[M,K] W^T (+ bias) on the tcgen05 kernel, in row blocks of 128."""
+def _gemm(hi, lo, N, K, x, ldx, M, bias, y, ldy, accumulate=1):
+    """y[M,N] += x[M,K] W^T (+ bias) on the tcgen05 kernel, in row blocks of 128 (y starts zero-filled)."""
     for m0 in range(0, M, 128):
         m = min(128, M - m0)
         _call("vln_linear_bf16x3", _ptr(hi), _ptr(lo), N, K, C.c_void_p(x.value + 4 * m0 * ldx), ldx, m, bias,
-              C.c_void_p(y.value + 4 * m0 * ldy), ldy, 0, _stream())
+              C.c_void_p(y.value + 4 * m0 * ldy), ldy, accumulate, 0, _stream())
 
 
 class FusedDecoder:
@@ -109,15 +109,15 @@ class _Rollout(torch.autograd.Function):
         s_tin, s_out, s_vin, s_cand = (ops._split_of(w) for w in params[6:10])
         bsum = (b_ih + b_hh).contiguous()
 
-        # ---- buffers: GEMM accumulators come out of one zero-filled slab ----
-        zero = torch.zeros(S * B * (F + G4) + T * B * (H + H + F), device=dev)
+        # ---- buffers: the GEMM outputs (split-K partial sums meet there) come out of one zero-filled slab ----
+        slab = torch.zeros(S * B * (F + G4) + T * B * (H + H + F), device=dev)
         cur = [0]
 
         def carve(*shape):
             k = 1
             for s_ in shape:
                 k *= s_
-            t_ = zero[cur[0]:cur[0] + k].view(*shape)
+            t_ = slab[cur[0]:cur[0] + k].view(*shape)
             cur[0] += k
             return t_
         Q, GATES = carve(S, B, F), carve(S, B, G4)
@@ -229,14 +229,14 @@ class _Rollout(torch.autograd.Function):
         OH = H_ACT + F                                          # column of h~ inside an XH row
         d_ce, d_logp, d_ent, d_h1 = (ops._f32c(g) if g is not None else None for g in (d_ce, d_logp, d_ent, d_h1))
 
-        zero = torch.zeros(n * B * (H + 2 * H + KX + H), device=dev)
+        slab = torch.zeros(n * B * (H + 2 * H + KX + H), device=dev)
         cur = [0]
 
         def carve(*shape):
             k = 1
             for s_ in shape:
                 k *= s_
-            t_ = zero[cur[0]:cur[0] + k].view(*shape)
+            t_ = slab[cur[0]:cur[0] + k].view(*shape)
             cur[0] += k
             return t_
         DHC, DWH, DXH, DHQ = carve(n, B, H), carve(n, B, 2 * H), carve(n, B, KX), carve(n, B, H)
@@ -248,7 +248,7 @@ class _Rollout(torch.autograd.Function):
         DACT = torch.empty((n, B, H_ACT), device=dev)
         DLOG = torch.empty((B, ops.NSLOT), device=dev)
         DC = torch.empty((2, B, H), device=dev)
-        d_ctx = torch.zeros_like(ctx)
+        DLC = torch.empty((n, B, L), device=dev)                  # d(logit) of the text attention, per step
 
         for t in range(n - 1, -1, -1):
             last = t == n - 1
@@ -264,8 +264,8 @@ class _Rollout(torch.autograd.Function):
                   0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
             _gemm(s_out.hi_t, s_out.lo_t, 2 * H, H, _p(DPRE[t]), H, B, None, _p(DWH[t]), 2 * H)
             _call("vln_ctx_attn_bwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H, None,
-                  _ptr(DTQ[t]), _ptr(d_ctx), B, L, H, _stream())
-            _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, B, None, _p(DWH[t], H), 2 * H)
+                  _ptr(DTQ[t]), None, _ptr(DLC[t]), B, L, H, _stream())
+            _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, B, None, _p(DWH[t], H), 2 * H, accumulate=1)
             _call("vln_lstm_pointwise_drop_bwd", _ptr(ACTS[t]), _ptr(CS[t]), _ptr(CS[t + 1]), _p(DWH[t], H), 2 * H,
                   _ptr(d_h1[t]) if d_h1 is not None else None, None if last else _ptr(DC[(t + 1) & 1]),
                   _ptr(DGATES[t]), _ptr(DC[t & 1]), B, H, p, rp, offs[t]["h1"], _stream())
@@ -280,6 +280,10 @@ class _Rollout(torch.autograd.Function):
         _call("vln_envdrop_state_bwd", None, _p(DXH[0], OH), KX, _ptr(DHQ[0]), None, 0, 0, _ptr(d_h0), B, H, p, rp,
               offs[0]["hprev"], 0, _stream())
         d_c0 = DC[0]
+
+        # ---- d_ctx[b] = sum_t attn_t^T d_weighted_t + dlogit_t^T tq_t: one batched GEMM pair over all steps ----
+        d_ctx = torch.bmm(ATTC[:n].permute(1, 2, 0), DWH[:, :, :H].transpose(0, 1))
+        d_ctx.baddbmm_(DLC.permute(1, 2, 0), TQ[:n].transpose(0, 1))
 
         # ---- weight gradients: one GEMM per weight over all n*B rows ----
         nb = n * B

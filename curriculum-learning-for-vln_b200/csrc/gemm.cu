@@ -7,24 +7,47 @@
 // weight copies — for their input gradients.
 //
 // Swap-AB: the WEIGHT rows sit on MMA-M (tiles of 128), the batch on MMA-N (64 or 128), so a 64-row
-// batch still fills the 128-lane datapath; split-K spreads a layer over ~all 148 SMs (partial sums
-// meet in y through red.global.add.f32 — y must be zero-initialised or hold a previous partial sum).
+// batch still fills the 128-lane datapath; split-K spreads a layer over ~all 148 SMs.  Every CTA parks
+// its partial accumulator tile in shared memory (transposed, so a thread owns 4 consecutive outputs of
+// one batch row) and adds it to y with 16-byte vector reductions (REDG.ADD.F32x4); y is zero-filled
+// first unless the caller accumulates into it.  An alternative merge — the splits of a tile as a
+// thread-block cluster reducing through distributed shared memory, plain stores — is kept behind
+// VLN_GEMM_VARIANT=c8|c4|c2 for the record: on B200 it measured 1-7 us slower per launch (cluster
+// barrier + DSMEM reads cost ~3 us, and 17 clusters of 8 CTAs need two waves).
 //
 // Precision: bf16x3.  Weights are pre-split once per optimiser step into bf16 hi + lo
 // (vln_split_bf16), activations are split on the fly while they are staged; three MMAs
 // (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) reproduce the fp32 product to ~2^-16 relative,
 // which keeps the rollout inside the 1e-3 logit/loss bar that a plain bf16 or tf32 GEMM would miss.
 //
-// Warp roles (256 threads): warp 0 = TMA producer of the weight tiles (128B-swizzled boxes),
-// warp 1 = MMA issuer (one elected lane), warps 4-7 = activation stagers during the main loop
-// (fp32 -> bf16 hi/lo, written with the 128B swizzle by hand) and epilogue afterwards
-// (tcgen05.ld -> bias -> red.add).  4-stage mbarrier ring, accumulator in TMEM.
+// Warp roles (256 threads): warp 0 = TMA producer (weight tiles as 128B-swizzled bf16 boxes + the raw fp32
+// activation tile), warp 1 = MMA issuer (one elected lane), warps 4-7 = activation converters during the
+// main loop (shared fp32 -> bf16 hi/lo, written with the 128B swizzle by hand) and epilogue afterwards
+// (tcgen05.ld -> shared memory); all 8 warps then take part in the cluster reduction.  4-stage mbarrier
+// ring, accumulator in TMEM.
+#include <cstdlib>
+#include <cstring>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
 
 int vln_make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                      uint32_t box_cols, uint32_t box_rows, int swizzle128);
+int vln_make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                         uint32_t box_cols, uint32_t box_rows);
+
+// ---- optional phase stamps (VLN_GEMM_STAMPS=1): CTA (0,0) records clock64 at 9 phase boundaries + globaltimer ----
+__device__ unsigned long long g_stamps[64 * 12];
+__device__ unsigned int g_stamp_n;
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define STAMP(i)                                                                    \
+  do {                                                                              \
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[(slot % 64) * 12 + (i)] = (unsigned long long)clock64(); \
+  } while (0)
 
 namespace {
 
@@ -34,10 +57,11 @@ constexpr int kThreads = 256;
 
 template <int MP>
 struct Cfg {
-  static constexpr int kStages = MP == 64 ? 4 : 3;
+  static constexpr int kStages = MP == 64 ? 3 : 2;
   static constexpr int kABytes = kTileN * kBK * 2;   // 16 KB per hi / lo weight tile
   static constexpr int kBBytes = MP * kBK * 2;       // 8 / 16 KB per hi / lo activation tile
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kXBytes = MP * kBK * 4;       // 16 / 32 KB raw fp32 activation tile (TMA destination)
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes + kXBytes;
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -87,20 +111,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {   // round-to-
 template <int MP>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                     const float* __restrict__ x, int ldx, int M, int N, int K, const float* __restrict__ bias,
-                     float* __restrict__ y, int ldy, int splits) {
+                     const __grid_constant__ CUtensorMap tm_x, int M, int N, int K, const float* __restrict__ bias,
+                     float* __restrict__ y, int ldy, int splits, int accumulate, int mode, int dbg) {
   using C = Cfg<MP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + C::kStages * C::kStageBytes);
-  uint64_t* full_w = bars;                       // TMA bytes landed
-  uint64_t* full_x = bars + C::kStages;          // activation tile staged (4 warp arrivals)
+  uint64_t* full_w = bars;                       // TMA bytes landed (weight tiles + raw activation tile)
+  uint64_t* full_x = bars + C::kStages;          // activation tile converted (4 warp arrivals)
   uint64_t* empty = bars + 2 * C::kStages;       // MMAs that read the stage have completed
   uint64_t* acc_done = bars + 3 * C::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, split = blockIdx.y;
+  __shared__ unsigned int slot_s;
+  unsigned int slot = 0;
+  if (dbg && blockIdx.x == 0 && blockIdx.y == 0) {
+    if (tid == 0) {
+      slot_s = atomicAdd(&g_stamp_n, 1u);
+      g_stamps[(slot_s % 64) * 12 + 10] = gtimer();
+      g_stamps[(slot_s % 64) * 12 + 0] = (unsigned long long)clock64();
+    }
+    __syncthreads();
+    slot = slot_s;
+  }
+  const int tile = blockIdx.x, split = blockIdx.y;                   // cluster = the `splits` CTAs of one tile
   const int nkb = K / kBK;
   const int kb0 = (int)((long long)split * nkb / splits), kb1 = (int)((long long)(split + 1) * nkb / splits);
   const int n_iter = kb1 - kb0;
@@ -108,6 +143,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   if (tid == 0) {
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
+    tma_prefetch_desc(&tm_x);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_w[s], 1);
       mbar_init(&full_x[s], 4);
@@ -125,6 +161,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  if (tid == 0) STAMP(1);
 
   if (n_iter > 0) {
     if (warp == 0) {
@@ -135,9 +172,10 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
           const uint32_t ph = (it / C::kStages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           uint8_t* st = base + (size_t)s * C::kStageBytes;
-          mbar_expect_tx(&full_w[s], 2 * C::kABytes);
+          mbar_expect_tx(&full_w[s], 2 * C::kABytes + C::kXBytes);
           tma_load_2d(st, &tm_hi, &full_w[s], (kb0 + it) * kBK, tile * kTileN);
           tma_load_2d(st + C::kABytes, &tm_lo, &full_w[s], (kb0 + it) * kBK, tile * kTileN);
+          tma_load_2d(st + 2 * C::kABytes + 2 * C::kBBytes, &tm_x, &full_w[s], (kb0 + it) * kBK, 0);
         }
       }
     } else if (warp == 1) {
@@ -149,7 +187,9 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1u;
           mbar_wait(&full_w[s], ph);
+          if (it == 0) STAMP(2);
           mbar_wait(&full_x[s], ph);
+          if (it == 0) STAMP(3);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(base + (size_t)s * C::kStageBytes), a_lo = a_hi + C::kABytes;
           const uint32_t b_hi = a_lo + C::kABytes, b_lo = b_hi + C::kBBytes;
@@ -165,73 +205,128 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         umma_commit(acc_done);
       }
     } else if (warp >= 4) {
-      // ---------------- activation stagers: fp32 -> bf16 hi/lo, 128B-swizzled rows ----------------
+      // ---------------- activation converters: raw fp32 tile (TMA) -> bf16 hi/lo, 128B-swizzled rows ----------------
+      // A row of the raw tile is 64 floats = 16 float4; lane l of a warp takes float4 (l % 16) of row (l / 16),
+      // so shared-memory reads are conflict-free and nothing on this path waits for L2.
       const int t = tid - 128;                               // 0..127
-      constexpr int TPR = 128 / MP;                          // threads per activation row (2 or 1)
-      constexpr int CPT = kBK / TPR;                         // columns per thread (32 or 64)
-      const int r = t / TPR, c0 = (t % TPR) * CPT;
-      const bool live = r < M;
-      const float* xr = x + (size_t)r * ldx + c0;
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_wait(&full_w[s], ph);
         uint8_t* bh = base + (size_t)s * C::kStageBytes + 2 * C::kABytes;
         uint8_t* bl = bh + C::kBBytes;
-        const float* src = xr + (size_t)(kb0 + it) * kBK;
+        const float4* raw = reinterpret_cast<const float4*>(bl + C::kBBytes);
 #pragma unroll
-        for (int ch = 0; ch < CPT / 8; ++ch) {               // 8 columns = one 16-byte chunk
-          float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-          if (live) {
-            f0 = __ldg(reinterpret_cast<const float4*>(src + ch * 8));
-            f1 = __ldg(reinterpret_cast<const float4*>(src + ch * 8 + 4));
-          }
-          const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float a = v[2 * p], b = v[2 * p + 1];
-            const float ah = __bfloat162float(__float2bfloat16_rn(a)), bhh = __bfloat162float(__float2bfloat16_rn(b));
-            hi[p] = pack_bf16(a, b);
-            lo[p] = pack_bf16(a - ah, b - bhh);
-          }
-          const int chunk = (c0 >> 3) + ch;                  // 16-byte chunk index within the 128-byte row
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(bh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(bl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int i = 0; i < MP / 8; ++i) {
+          const int idx = i * 128 + t;                       // float4 index in the [MP][16] tile
+          const int r = idx >> 4, q = idx & 15;
+          const float4 f = raw[idx];
+          const float ax = __bfloat162float(__float2bfloat16_rn(f.x)), ay = __bfloat162float(__float2bfloat16_rn(f.y));
+          const float az = __bfloat162float(__float2bfloat16_rn(f.z)), aw = __bfloat162float(__float2bfloat16_rn(f.w));
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((((q >> 1) ^ (r & 7)) << 4) + ((q & 1) << 3));
+          *reinterpret_cast<uint2*>(bh + off) = make_uint2(pack_bf16(f.x, f.y), pack_bf16(f.z, f.w));
+          *reinterpret_cast<uint2*>(bl + off) = make_uint2(pack_bf16(f.x - ax, f.y - ay), pack_bf16(f.z - az, f.w - aw));
         }
         fence_proxy_async();                                 // generic-proxy stores -> visible to the MMA (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_x[s]);
       }
-      // ---------------- epilogue: TMEM -> registers -> (bias) -> red.add into y ----------------
+      // ---------------- epilogue, part 1: TMEM -> this CTA's partial tile red[m][n] in shared memory ----------------
+      // (the ring is free: acc_done fires after every MMA that read it has retired)
       mbar_wait(acc_done, 0);
+      if (tid == 128) STAMP(4);
       tc_fence_after();
       const int wq = warp & 3;                               // TMEM lane quarter this warp may access
-      const int n = tile * kTileN + wq * 32 + lane;
-      const float bv = (bias != nullptr && split == 0 && n < N) ? bias[n] : 0.f;
+      float* red = reinterpret_cast<float*>(base);
 #pragma unroll
       for (int cb = 0; cb < MP / 32; ++cb) {
         uint32_t v[32];
         tmem_ld32(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)(cb * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (n < N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int m = cb * 32 + j;
-            if (m < M) atomicAdd(y + (size_t)m * ldy + n, __uint_as_float(v[j]) + bv);
-          }
-        }
+        for (int j = 0; j < 32; ++j) red[(cb * 32 + j) * kTileN + wq * 32 + lane] = __uint_as_float(v[j]);
       }
     }
-  } else if (warp >= 4 && split == 0 && bias != nullptr) {
-    // degenerate split without k-blocks cannot happen for split 0 unless K == 0; nothing to do
   }
+  // ---------------- epilogue, part 2: cluster reduction through distributed shared memory ----------------
+  if (tid == 128) STAMP(5);
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) STAMP(6);
+  if (mode == 2) {
+    // experiment: no cluster; partial tiles meet in y through 16-byte vector reductions (REDG.ADD.F32x4)
+    const float* red = reinterpret_cast<const float*>(base);
+    for (int item = tid; item < MP * (kTileN / 4); item += kThreads) {
+      const int m = item / (kTileN / 4), c = (item - m * (kTileN / 4)) * 4;
+      const int n = tile * kTileN + c;
+      if (m >= M || n >= N) continue;
+      float4 acc = *reinterpret_cast<const float4*>(red + m * kTileN + c);
+      if (bias != nullptr && split == 0) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+        acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+      }
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(y + (size_t)m * ldy + n), "f"(acc.x), "f"(acc.y),
+                   "f"(acc.z), "f"(acc.w)
+                   : "memory");
+    }
+  } else {
+    if (splits > 1) {
+      cluster_arrive();
+      cluster_wait();
+    }
+    const float* red = reinterpret_cast<const float*>(base);
+    const uint32_t red_addr = smem_u32(red);
+    const int R = kTileN / splits;                           // weight rows reduced by this CTA
+    const int qpr = R / 4;                                   // float4 chunks per batch row
+    for (int item = tid; item < MP * qpr; item += kThreads) {
+      const int m = item / qpr, c = (item - m * qpr) * 4 + split * R;      // c: row offset inside the tile
+      const int n = tile * kTileN + c;
+      if (m >= M || n >= N) continue;
+      const uint32_t off = red_addr + (uint32_t)(m * kTileN + c) * 4u;
+      float4 p[8];
+#pragma unroll
+      for (int sidx = 0; sidx < 8; ++sidx) {                 // all remote loads in flight before the first add
+        p[sidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sidx < splits && (mode == 0 || sidx == split)) {
+          uint32_t ra;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(off), "r"(sidx));
+          asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(p[sidx].x), "=f"(p[sidx].y), "=f"(p[sidx].z), "=f"(p[sidx].w)
+                       : "r"(ra)
+                       : "memory");
+        }
+      }
+      float4 acc = p[0];
+#pragma unroll
+      for (int sidx = 1; sidx < 8; ++sidx) {
+        acc.x += p[sidx].x; acc.y += p[sidx].y; acc.z += p[sidx].z; acc.w += p[sidx].w;
+      }
+      if (bias != nullptr) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+        acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+      }
+      float4* dst = reinterpret_cast<float4*>(y + (size_t)m * ldy + n);
+      if (accumulate) {
+        const float4 o = *dst;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      *dst = acc;
+    }
+    if (splits > 1) {
+      cluster_arrive();                                      // nobody leaves while a peer may still read its tile
+      cluster_wait();
+    }
+  }
+  if (tid == 0) STAMP(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(MP) : "memory");
+  }
+  if (tid == 0) {
+    STAMP(8);
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[(slot % 64) * 12 + 11] = gtimer();
   }
 }
 
@@ -265,13 +360,35 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __
   }
 }
 
+// split-K merge strategy (read once): VLN_GEMM_VARIANT = red4 (default: vector reductions into y) |
+// c8 | c4 | c2 | c1 (splits of a tile form a cluster and reduce through DSMEM; measured slower)
+struct Variant {
+  int cap = 8, mode = 2, dbg = 0;
+  Variant() {
+    dbg = getenv("VLN_GEMM_STAMPS") != nullptr;
+    const char* e = getenv("VLN_GEMM_VARIANT");
+    if (!e) return;
+    if (!strcmp(e, "c8")) mode = 0;
+    else if (!strcmp(e, "c4")) mode = 0, cap = 4;
+    else if (!strcmp(e, "c2")) mode = 0, cap = 2;
+    else if (!strcmp(e, "c1")) mode = 0, cap = 1;
+  }
+};
+const Variant& variant() {
+  static Variant v;
+  return v;
+}
+
 template <int MP>
 int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
-                  float* y, int ldy, int splits, cudaStream_t stream) {
+                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream) {
   CUtensorMap tm_hi, tm_lo;
   int rc = vln_make_tmap_2d(&tm_hi, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
   if (rc) return rc;
   rc = vln_make_tmap_2d(&tm_lo, w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
+  if (rc) return rc;
+  CUtensorMap tm_x;                                         // rows >= M are out of bounds: the TMA unit zero-fills them
+  rc = vln_make_tmap_2d_f32(&tm_x, x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, kBK, MP);
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
@@ -279,30 +396,52 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
     configured = true;
   }
   const int tiles = (N + kTileN - 1) / kTileN;
-  linear_bf16x3_kernel<MP><<<dim3(tiles, splits), kThreads, Cfg<MP>::kSmem, stream>>>(tm_hi, tm_lo, x, ldx, M, N, K, bias, y,
-                                                                                     ldy, splits);
-  VLN_LAUNCH_OK();
+  const int mode = variant().mode;
+  if (mode == 2 && !accumulate) VLN_CHECK_CUDA(cudaMemset2DAsync(y, (size_t)ldy * 4, 0, (size_t)N * 4, M, stream));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles, splits);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<MP>::kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;        // the splits of one weight tile = one cluster
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = mode == 2 ? 1 : splits;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (mode == 2 || splits == 1) ? 0 : 1;
+  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP>, tm_hi, tm_lo, tm_x, M, N, K, bias, y, ldy, splits,
+                                    accumulate, mode, variant().dbg));
   return 0;
 }
 
 }  // namespace
 
 extern "C" int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
-                                 const float* bias, float* y, int ldy, int splits, void* stream) {
+                                 const float* bias, float* y, int ldy, int accumulate, int splits, void* stream) {
   VLN_REQUIRE(w_hi && w_lo && x && y && N > 0 && M > 0, "bad arguments");
   VLN_REQUIRE(K > 0 && K % kBK == 0, "K must be a positive multiple of 64");
   VLN_REQUIRE(M <= 128, "at most 128 activation rows");
   VLN_REQUIRE(((uintptr_t)x & 15) == 0 && ldx % 4 == 0, "x rows must be 16-byte aligned");
+  VLN_REQUIRE(N % 4 == 0 && ((uintptr_t)y & 15) == 0 && ldy % 4 == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
+              "N must be a multiple of 4 and y / bias 16-byte aligned");
   VLN_REQUIRE(((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)w_lo & 15) == 0, "weights must be 16-byte aligned");
   const int nkb = K / kBK;
-  if (splits <= 0) {                                           // fill the machine: tiles x splits ~ #SMs
-    const int tiles = (N + kTileN - 1) / kTileN;       // one CTA per SM (the ring takes the whole shared memory):
-    splits = 148 / tiles;                              // stay within ONE wave of 148 CTAs
-  }
+  const int tiles = (N + kTileN - 1) / kTileN;
+  if (splits <= 0) splits = 148 / tiles;                       // one CTA per SM, one wave
   if (splits > nkb) splits = nkb;
-  if (splits < 1) splits = 1;
-  if (M <= 64) return launch_linear<64>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, splits, (cudaStream_t)stream);
-  return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, splits, (cudaStream_t)stream);
+  int s = 1;                                                   // cluster size: power of two, at most 8 (portable limit)
+  while (s * 2 <= splits && s * 2 <= variant().cap) s *= 2;
+  if (variant().mode == 2) s = splits;
+  if (M <= 64) return launch_linear<64>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
+  return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int vln_debug_gemm_stamps(unsigned long long* out_host /*[64*12]*/, unsigned int* n) {
+  VLN_CHECK_CUDA(cudaDeviceSynchronize());
+  VLN_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_stamps, sizeof(unsigned long long) * 64 * 12));
+  VLN_CHECK_CUDA(cudaMemcpyFromSymbol(n, g_stamp_n, sizeof(unsigned int)));
+  return 0;
 }
 
 extern "C" int vln_split_bf16(const float* w, void* hi, void* lo, void* hi_t, void* lo_t, int N, int K, void* stream) {

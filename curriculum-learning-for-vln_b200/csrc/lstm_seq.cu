@@ -31,10 +31,29 @@ __device__ __forceinline__ void cluster_sync_all() {
   cluster_arrive();
   cluster_wait();
 }
-__device__ __forceinline__ void dsmem_st_f32(float* local_ptr, uint32_t rank, float v) {
-  uint32_t a = smem_u32(local_ptr), ra;
+// Asynchronous DSMEM store that signals the DESTINATION CTA's mbarrier (4 bytes of its transaction
+// count): the receiver waits on its own barrier for exactly the bytes it expects, so a timestep needs
+// no cluster-wide barrier (barrier.cluster also drains every outstanding global store of the step and
+// measured several microseconds per step on B200).
+__device__ __forceinline__ void dsmem_st_async_f32(float* local_ptr, uint64_t* local_bar, uint32_t rank, float v) {
+  uint32_t a = smem_u32(local_ptr), m = smem_u32(local_bar), ra, rm;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rm) : "r"(m), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra),
+               "r"(__float_as_uint(v)), "r"(rm)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
 }
 
 // one direction of a (bi)directional layer; both directions run in the same launch (grid.y)
@@ -65,6 +84,7 @@ struct SmemF {
   float w[kRows * (H + 8)];
   float h[2][kNB * H];
   float g[kNB * kRows];
+  uint64_t bar[2];                 // bar[k]: all kNB*H values of h buffer k have arrived
 };
 
 // xproj [B,L,4H] (x W_ih^T + b_ih + b_hh), w_hh [4H,H], lengths [B].
@@ -95,6 +115,11 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
     reinterpret_cast<float4*>(sm.w + lr * WS)[c4] = __ldg(reinterpret_cast<const float4*>(w_hh + (size_t)grow * H) + c4);
   }
   for (int i = tid; i < 2 * kNB * H; i += kThreads) (&sm.h[0][0])[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    fence_mbar_init();
+  }
 
   // pointwise role: thread = (batch pb, unit pu); c lives in a register for the whole sequence
   const int pb = tid >> 5, pu = tid & 31;
@@ -125,6 +150,7 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
   load_x(t);
   for (int s = 0; s < gmax; ++s, t += dt) {
     const int cur = s & 1, nxt = cur ^ 1;
+    if (tid == 0) mbar_expect_tx(&sm.bar[nxt], kNB * H * 4);       // this step's h_t: kNB*H floats from the C CTAs
     // ---- gates[b][row] partial sums over this thread's half of K ----
     float acc[kNB];
 #pragma unroll
@@ -166,13 +192,17 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
     // ---- all-gather h_t: my unit's value into every CTA's next buffer ----
     float* dst = sm.h[nxt] + pb * H + ug;
 #pragma unroll
-    for (int r = 0; r < C; ++r) dsmem_st_f32(dst, (uint32_t)r, h_new);
-    cluster_sync_all();
+    for (int r = 0; r < C; ++r) dsmem_st_async_f32(dst, &sm.bar[nxt], (uint32_t)r, h_new);
+    // Every CTA (this one included) has delivered its slice once the byte count is reached.  Buffer reuse is
+    // safe without a further barrier: a peer writes h[cur] again only in step s+1, which it enters after it
+    // received THIS CTA's slice of step s — sent after the matvec above finished reading h[cur].
+    mbar_wait_cluster(&sm.bar[nxt], (uint32_t)(s >> 1) & 1u);
   }
   if (valid) {
     d.h_last[(size_t)b * ld_last + ug] = h_reg;
     d.c_last[(size_t)b * ld_last + ug] = c_reg;
   }
+  cluster_sync_all();               // no CTA exits while a peer could still address its shared memory
 }
 
 // Backward through time.  d_out [B,L,H] (grad of `out`, may be NULL), d_hlast/d_clast [B,H] (may be NULL).
@@ -182,6 +212,7 @@ struct SmemB {
   float w[kRows * (H + 8)];
   float dg[kNB * kRows];                 // this CTA's dgates for the group
   float recv[2][(H / kHS) * kNB * kHS];  // partial dh for my units from every CTA (double buffered over steps)
+  uint64_t bar[2];                       // bar[k]: all C*kNB*32 partials of recv[k] have arrived
 };
 
 template <int H>
@@ -219,6 +250,11 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
   const int ug = rank * kHS + pu;
   float dh = (valid && d_hlast) ? d_hlast[(size_t)b * ld_last + ug] : 0.f;   // carried gradient wrt h_t, c_t of my unit
   float dc = (valid && d_clast) ? d_clast[(size_t)b * ld_last + ug] : 0.f;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    fence_mbar_init();
+  }
   cluster_sync_all();
 
   // forward visited t = 0..gmax-1 (or gmax-1..0 when reversed); walk it backwards
@@ -226,6 +262,7 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
   const int dt = reverse ? 1 : -1;
   for (int s = 0; s < gmax; ++s, t += dt) {
     const bool live = valid && t < len;
+    if (tid == 0) mbar_expect_tx(&sm.bar[s & 1], C * kNB * kHS * 4);
     float dgi = 0.f, dgf = 0.f, dgg = 0.f, dgo = 0.f;
     if (live) {
       const size_t o = (size_t)b * L + t;
@@ -262,9 +299,10 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
       // reduce-scatter: column k belongs to CTA k/32, slot [my rank][bb][k%32]
       const uint32_t owner = (uint32_t)(tid >> 5);
 #pragma unroll
-      for (int i = 0; i < kNB; ++i) dsmem_st_f32(sm.recv[s & 1] + (rank * kNB + i) * kHS + (tid & 31), owner, acc[i]);
+      for (int i = 0; i < kNB; ++i)
+        dsmem_st_async_f32(sm.recv[s & 1] + (rank * kNB + i) * kHS + (tid & 31), &sm.bar[s & 1], owner, acc[i]);
     }
-    cluster_sync_all();
+    mbar_wait_cluster(&sm.bar[s & 1], (uint32_t)(s >> 1) & 1u);
     // owner: dh_{t-1}[pb][my unit] = sum over the C partials (live rows); frozen rows pass dh through
     if (live) {
       float v = 0.f;
@@ -273,8 +311,10 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
       dh = v;
     }
     // recv is double buffered: a peer's stores of step s+1 go to the other half, and its stores of step
-    // s+2 come after it passed the barrier of step s+1, which this CTA reaches only after the reads above.
+    // s+2 come after it received this CTA's partials of step s+1, which are sent only after the reads above.
+    // sm.dg is rewritten in step s+1 only after this wait, i.e. after every local thread finished its matvec.
   }
+  cluster_sync_all();               // no CTA exits while a peer could still address its shared memory
 }
 
 template <typename K, typename D>

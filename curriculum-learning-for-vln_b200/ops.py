@@ -181,12 +181,13 @@ def _split_of(w):
 
 
 def _tc_matmul(x, hi, lo, N, K, bias=None, out=None):
-    """out (+)= x @ W^T (+ bias) on the tcgen05 kernel; W given by its bf16 hi/lo split [N,K]."""
+    """x @ W^T (+ bias) on the tcgen05 kernel, W given by its bf16 hi/lo split [N,K]; added to `out` if given."""
     M = x.shape[0]
+    acc = out is not None
     if out is None:
-        out = torch.zeros((M, N), device=x.device, dtype=torch.float32)
-    _call("vln_linear_bf16x3", _ptr(hi), _ptr(lo), N, K, _ptr(x), x.stride(0), M, _ptr(bias), _ptr(out), out.stride(0), 0,
-          _stream())
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    _call("vln_linear_bf16x3", _ptr(hi), _ptr(lo), N, K, _ptr(x), x.stride(0), M, _ptr(bias), _ptr(out), out.stride(0),
+          1 if acc else 0, 0, _stream())
     return out
 
 
@@ -259,7 +260,7 @@ def linear(x, w, b=None, acc=None):
     """y = x W^T + b (+ acc).  Batches of at most 128 rows run on the tcgen05 bf16x3 kernel
     (csrc/gemm.cu); larger ones (encoder input projection, batched critic) are plain library GEMMs."""
     if (USE_TC_LINEAR[0] and x.is_cuda and x.dim() == 2 and x.shape[0] <= 128 and w.shape[1] % 64 == 0
-            and x.dtype == torch.float32):
+            and w.shape[0] % 4 == 0 and x.dtype == torch.float32):
         return _LinearTC.apply(x, w, b, acc)
     y = _LinearLib.apply(x, w, b) if x.dim() == 2 else F.linear(x, w, b)
     return y if acc is None else y + acc

@@ -116,9 +116,12 @@ int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* leng
  * weighted context is written straight into cat((weighted, h)) (units.py:119) and its gradient read from there. */
 int vln_ctx_attn_fwd_ld(const float* context, const float* tgt, const int32_t* lengths, float* attn,
                         float* weighted, int ld_weighted, int B, int L, int H, void* stream);
+/* dlogit_out (nullable) [B,L] receives dlogit, so that d_context = sum over steps of
+ * attn^T d_weighted + dlogit^T tgt can be ONE batched GEMM at the end of a rollout instead of a
+ * read-modify-write of the whole context gradient per step (then pass d_context = NULL). */
 int vln_ctx_attn_bwd_ld(const float* context, const float* tgt, const int32_t* lengths,
                         const float* attn, const float* d_weighted, int ld_d_weighted, const float* d_attn_ext,
-                        float* d_tgt, float* d_context, int B, int L, int H, void* stream);
+                        float* d_tgt, float* d_context, float* dlogit_out, int B, int L, int H, void* stream);
 
 /* nn.LSTMCell pointwise half (policy.py:53,159,238): gates [B,4H] (i,f,g,o pre-activations,
  * biases already added) + c0 -> h1, c1; acts [B,4H] keeps the activated gates for backward. */
@@ -162,14 +165,15 @@ int vln_envdrop_act_bwd(const float* d_xh, int ld_dxh, const float* act, float* 
                         float p, const uint64_t* rng, uint64_t call_off, void* stream);
 
 /* Skinny linear layer on tcgen05 tensor cores (nn.Linear / nn.LSTMCell gate GEMMs of policy.py and
- * units.py at batch sizes <= 128):  y[m,n] += sum_k x[m,k] w[n,k] (+ bias[n]),  m < M <= 128.
+ * units.py at batch sizes <= 128):  y[m,n] (+)= sum_k x[m,k] w[n,k] (+ bias[n]),  m < M <= 128.
  * w_hi / w_lo: the weight [N,K] split into bf16 hi + lo (vln_split_bf16); x fp32 [M,K] row stride ldx;
- * y fp32 row stride ldy, ACCUMULATED into (zero it first, or chain calls to sum several products —
- * e.g. x W_ih^T + h W_hh^T).  K % 64 == 0.  splits <= 0 picks a split-K factor that fills the GPU.
- * bf16x3 (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) ~ fp32 accuracy.  For input gradients pass
- * the transposed split (w^T as a [K,N] weight) and x = dY. */
+ * y fp32 row stride ldy: overwritten (accumulate = 0) or added to (accumulate = 1, e.g. x W_ih^T + h W_hh^T).
+ * K % 64 == 0, N % 4 == 0.  splits <= 0 picks the split-K factor (a power of two <= 8: the splits of one
+ * 128-row weight tile are one thread-block cluster and reduce through distributed shared memory — no
+ * atomics, deterministic).  bf16x3 (hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) ~ fp32 accuracy.
+ * For input gradients pass the transposed split (w^T as a [K,N] weight) and x = dY. */
 int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
-                      const float* bias, float* y, int ldy, int splits, void* stream);
+                      const float* bias, float* y, int ldy, int accumulate, int splits, void* stream);
 /* fp32 w [N,K] -> bf16 hi, lo [N,K] and, if hi_t/lo_t are given, the transposed pair [K,N]. */
 int vln_split_bf16(const float* w, void* hi, void* lo, void* hi_t, void* lo_t, int N, int K, void* stream);
 
