@@ -102,8 +102,11 @@ class ClockSampler:
 
 
 def roofline_pano(store, ops, torch, B, split, peaks):
-    """Time the fused gather+attention kernel alone (CUDA-graph of 32 launches over rotating random
-    viewpoint sets so that every launch reads HBM, not L2), CUDA events on the launch stream."""
+    """Time the fused gather+attention kernel alone, configured exactly as the rollout launches it
+    (feature dropout 0.3 through pre-generated keep-bits, output into the strided LSTM operand row):
+    a CUDA graph of 32 launches over rotating random viewpoint sets so that every launch reads HBM,
+    not L2; CUDA events on the launch stream."""
+    import ctypes as C
     dev = store.device
     g = torch.Generator(device=dev).manual_seed(7)
     n_sets = 32
@@ -111,17 +114,25 @@ def roofline_pano(store, ops, torch, B, split, peaks):
     view = torch.randint(0, 36, (B,), device=dev, dtype=torch.int32, generator=g)
     q = torch.randn(B, 2176, device=dev) * 0.05
     attn = torch.empty(B, 36, device=dev)
+    out = torch.empty(B, 2752, device=dev)
     rng = ops.Rng(1, dev)
+    bits = torch.empty((n_sets, B * 36, 256), dtype=torch.uint8, device=dev)
+    ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, n_sets, 0.3, rng.ptr, 1, 7, ops._stream())
+
+    def launch(k):
+        ops._call("vln_pano_attn_ld", store.handle, ops._ptr(vps[k]), ops._ptr(view), ops._ptr(store.loc4), ops._ptr(q),
+                  2176, ops._ptr(attn), None, 2176, C.c_void_p(out.data_ptr() + 256), 2752, B, 0, 0.3, rng.ptr, 0,
+                  ops._ptr(bits[k]), split, ops._stream())
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
         for k in range(3):
-            ops.pano_attn_raw(store, vps[k], view, q, attn, 0, 0.3, rng, 1, split)
+            launch(k)
     torch.cuda.current_stream().wait_stream(s)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         for k in range(n_sets):
-            ops.pano_attn_raw(store, vps[k], view, q, attn, 0, 0.3, rng, 1, split)
+            launch(k)
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize()
@@ -135,10 +146,11 @@ def roofline_pano(store, ops, torch, B, split, peaks):
     t = e0.elapsed_time(e1) * 1e-3 / (reps * n_sets)
     achieved = B * ALGO_BYTES_PER_EPISODE_STEP / t / 1e9
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    return {"bound": "hbm", "kernel": "pano_attn fwd (fused gather + dropout + 36-view soft-dot attention)",
+    return {"bound": "hbm", "kernel": "pano_attn fwd (fused gather + feature dropout + 36-view soft-dot attention)",
             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback",
-            "us_per_launch": round(t * 1e6, 2), "episodes_per_launch": B, "split": split, "traffic": None}
+            "us_per_launch": round(t * 1e6, 2), "episodes_per_launch": B, "split": split, "traffic": None,
+            "note": "B=64 episodes per launch is the north-star shape: 9.4 MB per launch = 1.4 us at peak, so the launch is latency-bound; tools/microbench.py sweeps B up to 2048"}
 
 
 def cpu_iteration_factory(world_small, items, B, threads):

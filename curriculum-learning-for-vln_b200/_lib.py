@@ -48,7 +48,8 @@ _SIGS = {
     "vln_gather_cand": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_gather_action_feat": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p], _i),
     "vln_pano_attn": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _i, _p], _i),
-    "vln_pano_attn_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _f, _p, _u64, _i, _p], _i),
+    "vln_pano_attn_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _f, _p, _u64, _p, _i, _p], _i),
+    "vln_feature_mask_bits": ([_p, _i64, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_ctx_attn_fwd_ld": ([_p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "vln_ctx_attn_bwd_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p], _i),
     "vln_lstm_pointwise_drop_fwd": ([_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _u64, _p], _i),
@@ -56,7 +57,10 @@ _SIGS = {
     "vln_envdrop_state_fwd": ([_p, _i, _p, _i, _p, _p, _i, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_envdrop_state_bwd": ([_p, _p, _i, _p, _p, _i, _i, _p, _i, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_envdrop_act_fwd": ([_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _u64, _p], _i),
-    "vln_envdrop_act_bwd": ([_p, _i, _p, _p, _i, _i, _f, _p, _u64, _p], _i),
+    "vln_envdrop_act_bwd": ([_p, _i, _p, _p, _i, _i, _i, _f, _p, _u64, _u64, _p], _i),
+    "vln_policy_env_act_fwd": ([_p, _p, _i, _p, _u64] + [_p] * 5 + [_p] * 5 + [_p] * 7 + [_p] * 8 + [_p] * 5
+                               + [_i, _i, _f, _u64, _i, _p], _i),
+    "vln_cand_logits_bwd_policy": ([_p] * 14 + [_i, _f, _p, _u64, _p], _i),
     "vln_cand_logits_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),
     "vln_cand_logits_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),
     "vln_ctx_attn_fwd": ([_p, _p, _p, _p, _p, _i, _i, _i, _p], _i),

@@ -166,12 +166,19 @@ class _Rollout(torch.autograd.Function):
         def visual_and_lstm(t, need_drop):
             _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, B, None, _p(Q[t]), F)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4), _ptr(Q[t]), F,
-                  _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, B, 0, pf, rp, offs[t]["img"], split, _stream())
+                  _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, B, 0, pf, rp, offs[t]["img"],
+                  _ptr(MB[t]) if MB is not None else None, split, _stream())
             _gemm(s_cat.hi, s_cat.lo, G4, KX, _p(XH[t]), KX, B, _ptr(bsum), _p(GATES[t]), G4)
             _call("vln_lstm_pointwise_drop_fwd", _ptr(GATES[t]), _ptr(CS[t]), _ptr(H1[t]), _ptr(CS[t + 1]),
                   _ptr(ACTS[t]), _p(WH[t], H) if need_drop else None, 2 * H, B, H, p, rp, offs[t]["h1"], _stream())
 
-        alloc(0)
+        for t_ in range(S):                                     # all passes up front: the offsets are an arithmetic
+            alloc(t_)                                           # sequence, so ONE kernel draws every step's feature mask
+        MB = None
+        if pf > 0.0:
+            MB = torch.empty((S, B * ops.N_VIEWS, ops.IMG_DIM // 8), dtype=torch.uint8, device=dev)
+            stride = offs[1]["img"] - offs[0]["img"] if S > 1 else 0
+            _call("vln_feature_mask_bits", _ptr(MB), B * ops.N_VIEWS, S, pf, rp, offs[0]["img"], stride, _stream())
         _call("vln_envdrop_state_fwd", _ptr(h0), 0, _p(XH[0], H_ACT + F), KX, _ptr(HQ[0]), None, B, H, p, rp,
               offs[0]["hprev"], 0, _stream())
         act_embed(0)
@@ -183,8 +190,6 @@ class _Rollout(torch.autograd.Function):
                   H, _stream())
             _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, B, None, _p(PRE[t]), H)
             more = t + 1 < S
-            if more:
-                alloc(t + 1)
             _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
                   _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), B, H, p, rp,
                   offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _stream())
@@ -192,23 +197,24 @@ class _Rollout(torch.autograd.Function):
             _call("vln_cand_logits_fwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
                   _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(TGT[t]), None, _ptr(LOGIT[t]), B, pf, rp,
                   offs[t]["cand"], _stream())
-            _call("vln_policy_fwd", _ptr(LOGIT[t]), _ptr(TEACH[t]), fb, rp, offs[t]["sample"], _ptr(CE[t]),
-                  _ptr(ACTION[t]), _ptr(LOGP[t]), _ptr(ENT[t]), _ptr(PROBS[t]), B, _stream())
-            _call("vln_env_step", _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(st.ended[t]), _ptr(st.dist[t]), _ptr(st.goal),
-                  _ptr(ACTION[t]), _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand), _ptr(store.next_hop),
-                  _ptr(store.dist), _ptr(store.sq_off), _ptr(store.vp_local), _ptr(st.vp[t + 1]), _ptr(st.view[t + 1]),
-                  _ptr(st.ended[t + 1]), _ptr(st.dist[t + 1]), _ptr(TEACH[t + 1]), _ptr(REWARD[t]), _ptr(MASK[t]),
-                  _ptr(st.n_active[t:t + 1]), B, _stream())
+            # action head + simulator transition + the next pass's action embedding: one launch
+            _call("vln_policy_env_act_fwd", _ptr(LOGIT[t]), _ptr(TEACH[t]), fb, rp, offs[t]["sample"], _ptr(CE[t]),
+                  _ptr(ACTION[t]), _ptr(LOGP[t]), _ptr(ENT[t]), _ptr(PROBS[t]),
+                  _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(st.ended[t]), _ptr(st.dist[t]), _ptr(st.goal),
+                  _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand), _ptr(store.next_hop),
+                  _ptr(store.dist), _ptr(store.sq_off), _ptr(store.vp_local),
+                  _ptr(st.vp[t + 1]), _ptr(st.view[t + 1]), _ptr(st.ended[t + 1]), _ptr(st.dist[t + 1]),
+                  _ptr(TEACH[t + 1]), _ptr(REWARD[t]), _ptr(MASK[t]), _ptr(st.n_active[t:t + 1]),
+                  _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t + 1]) if more else None,
+                  _ptr(XH[t + 1]) if more else None, KX, H_ACT, p, offs[t + 1]["act"] if more else 0, B, _stream())
             st.steps = n = t + 1
-            if more:
-                act_embed(t + 1)
             if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
                 break
         if bootstrap:                                           # envdrop.py:225-237: h_1 of the state after the last step
             visual_and_lstm(n, False)
         st.teacher = TEACH[n]
 
-        fctx.fd, fctx.st, fctx.rp = fd, st, rp
+        fctx.fd, fctx.st, fctx.rp, fctx.MB = fd, st, rp, MB
         fctx.cfg = (n, B, L, H, p, pf, split, offs)
         fctx.splits = (s_cat, s_vin, s_tin, s_out, s_cand)
         fctx.save_for_backward(ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH)
@@ -222,7 +228,7 @@ class _Rollout(torch.autograd.Function):
         ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH = fctx.saved_tensors
         n, B, L, H, p, pf, split, offs = fctx.cfg
         s_cat, s_vin, s_tin, s_out, s_cand = fctx.splits
-        st, rp = fctx.st, fctx.rp
+        st, rp, MB = fctx.st, fctx.rp, fctx.MB
         store = st.store
         dev = ctx.device
         F, G4, KX = ops.F_DIM, 4 * H, H_ACT + ops.F_DIM + H
@@ -246,18 +252,15 @@ class _Rollout(torch.autograd.Function):
         DGATES = torch.empty((n, B, G4), device=dev)
         DQ = torch.empty((n, B, F), device=dev)
         DACT = torch.empty((n, B, H_ACT), device=dev)
-        DLOG = torch.empty((B, ops.NSLOT), device=dev)
         DC = torch.empty((2, B, H), device=dev)
         DLC = torch.empty((n, B, L), device=dev)                  # d(logit) of the text attention, per step
 
         for t in range(n - 1, -1, -1):
             last = t == n - 1
-            _call("vln_policy_bwd", _ptr(PROBS[t]), _ptr(TEACH[t]), _ptr(ACTION[t]), _ptr(ENT[t]),
+            _call("vln_cand_logits_bwd_policy", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
+                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(PROBS[t]), _ptr(TEACH[t]), _ptr(ACTION[t]), _ptr(ENT[t]),
                   _ptr(d_ce[t]) if d_ce is not None else None, _ptr(d_logp[t]) if d_logp is not None else None,
-                  _ptr(d_ent[t]) if d_ent is not None else None, _ptr(DLOG), B, _stream())
-            _call("vln_cand_logits_bwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
-                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(DLOG), _ptr(DTGT[t]), None, B, pf, rp,
-                  offs[t]["cand"], _stream())
+                  _ptr(d_ent[t]) if d_ent is not None else None, _ptr(DTGT[t]), B, pf, rp, offs[t]["cand"], _stream())
             _gemm(s_cand.hi_t, s_cand.lo_t, H, F, _p(DTGT[t]), F, B, None, _p(DHC[t]), H)
             _call("vln_envdrop_state_bwd", _ptr(DHC[t]), None if last else _p(DXH[t + 1], OH), KX,
                   None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), B, H, p, rp,
@@ -272,10 +275,10 @@ class _Rollout(torch.autograd.Function):
             _gemm(s_cat.hi_t, s_cat.lo_t, KX, G4, _p(DGATES[t]), G4, B, None, _p(DXH[t]), KX)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4),
                   _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, B, 1, pf, rp,
-                  offs[t]["img"], split, _stream())
+                  offs[t]["img"], _ptr(MB[t]) if MB is not None else None, split, _stream())
             _gemm(s_vin.hi_t, s_vin.lo_t, H, F, _p(DQ[t]), F, B, None, _p(DHQ[t]), H)
-            _call("vln_envdrop_act_bwd", _ptr(DXH[t]), KX, _ptr(ACT[t]), _ptr(DACT[t]), B, H_ACT, p, rp,
-                  offs[t]["act"], _stream())
+        _call("vln_envdrop_act_bwd", _ptr(DXH), KX, _ptr(ACT), _ptr(DACT), B, H_ACT, n, p, rp, offs[0]["act"],
+              (offs[1]["act"] - offs[0]["act"]) if len(offs) > 1 else 0, _stream())
         d_h0 = torch.empty((B, H), device=dev)
         _call("vln_envdrop_state_bwd", None, _p(DXH[0], OH), KX, _ptr(DHQ[0]), None, 0, 0, _ptr(d_h0), B, H, p, rp,
               offs[0]["hprev"], 0, _stream())

@@ -148,19 +148,33 @@ __global__ void __launch_bounds__(512) cand_logits_fwd_kernel(
   if (lane == 0) logits[(size_t)b * VLN_NSLOT + j] = res;
 }
 
+struct PolicyGrad {                                  // optional: compute dlogits in place of reading them
+  const float* probs; const int32_t* target; const int32_t* action; const float* entropy;
+  const float* g_ce; const float* g_logp; const float* g_ent;
+};
+
 // d_tgt[b, f] = sum_j dlogits[b, j] * x~c[b, j, f];  one 16-byte vector (8 features) per thread.
 __global__ void __launch_bounds__(kThreads) cand_logits_bwd_kernel(
     const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ vp, const int32_t* __restrict__ view,
     const int32_t* __restrict__ cand_view, const float* __restrict__ cand_ang4, const int32_t* __restrict__ n_cand,
     const float* __restrict__ dlogits, float* __restrict__ d_tgt, float* __restrict__ d_bias, float drop_p,
-    const uint64_t* __restrict__ rng, uint64_t call_off) {
+    const uint64_t* __restrict__ rng, uint64_t call_off, PolicyGrad pg) {
   __shared__ float dl[VLN_NSLOT];
   __shared__ int cvs[VLN_NSLOT];
   const int b = blockIdx.x, t = threadIdx.x;
   const int g = vp[b];
   const int n = n_cand[g];
   if (t < VLN_NSLOT) {
-    dl[t] = (t <= n) ? dlogits[(size_t)b * VLN_NSLOT + t] : 0.f;
+    float d = 0.f;
+    if (pg.probs) {                                  // dlogits from the action head's saved state (vln_policy_bwd)
+      const float p = pg.probs[(size_t)b * VLN_NSLOT + t];
+      if (pg.g_ce && pg.target[b] >= 0) d += pg.g_ce[b] * (p - (t == pg.target[b] ? 1.f : 0.f));
+      if (pg.g_logp && pg.action[b] >= 0) d += pg.g_logp[b] * ((t == pg.action[b] ? 1.f : 0.f) - p);
+      if (pg.g_ent && p > 0.f) d -= pg.g_ent[b] * p * (logf(p) + pg.entropy[b]);
+    } else {
+      d = dlogits[(size_t)b * VLN_NSLOT + t];
+    }
+    dl[t] = (t <= n) ? d : 0.f;
     cvs[t] = (t < n) ? cand_view[(size_t)g * VLN_CMAX + t] : 0;
   }
   __syncthreads();
@@ -243,7 +257,23 @@ extern "C" int vln_cand_logits_bwd(const vln_ctx* ctx, const int32_t* vp, const 
                                    const uint64_t* rng, uint64_t call_off, void* stream) {
   VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && dlogits && d_tgt && B > 0, "bad arguments");
   cand_logits_bwd_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(ctx->table, vp, view, cand_view, cand_ang4, n_cand,
-                                                                  dlogits, d_tgt, d_bias, drop_p, rng, call_off);
+                                                                  dlogits, d_tgt, d_bias, drop_p, rng, call_off,
+                                                                  PolicyGrad{});
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_cand_logits_bwd_policy(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                                          const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
+                                          const float* probs, const int32_t* target, const int32_t* action,
+                                          const float* entropy, const float* g_ce, const float* g_logp,
+                                          const float* g_ent, float* d_tgt, int B, float drop_p, const uint64_t* rng,
+                                          uint64_t call_off, void* stream) {
+  VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && probs && d_tgt && B > 0, "bad arguments");
+  VLN_REQUIRE((!g_ce || target) && (!g_logp || action) && (!g_ent || entropy), "missing saved action-head state");
+  cand_logits_bwd_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(
+      ctx->table, vp, view, cand_view, cand_ang4, n_cand, nullptr, d_tgt, nullptr, drop_p, rng, call_off,
+      PolicyGrad{probs, target, action, entropy, g_ce, g_logp, g_ent});
   VLN_LAUNCH_OK();
   return 0;
 }

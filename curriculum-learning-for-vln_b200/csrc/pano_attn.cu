@@ -29,7 +29,9 @@ constexpr int kConsumerWarps = 6;                        // 36, 18 rows split ev
 constexpr int kConsumers = kConsumerWarps * 32;
 constexpr int kThreads = kConsumers + 32;                // + producer warp
 constexpr int kRowBytes = VLN_IMG * 2;                   // 4 096
-constexpr int kStages = 32;                              // 128 KB ring; stage s is fed by producer lane s
+constexpr int kMaskBytes = VLN_IMG / 8;                  // 256: packed keep-bits of one row (vln_feature_mask_bits)
+constexpr int kStageBytes = kRowBytes + kMaskBytes;
+constexpr int kStages = 32;                              // 136 KB ring; stage s is fed by producer lane s
 constexpr int kRed = VLN_IMG + 8;                        // acc[2048], accA[4], m, l (or dsum), pad
 constexpr int kSlab = VLN_IMG + 8;                       // floats per (episode, part) scratch slab
 constexpr int kChunks = VLN_IMG / 4;                     // float4 chunks of an output row
@@ -46,7 +48,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 
 struct Smem {
-  uint8_t ring[kStages * kRowBytes];
+  uint8_t ring[kStages * kStageBytes];
   float red[kConsumerWarps * kRed];
   float qbuf[2][VLN_F];            // query / d_out row of this and the next unit (cp.async double buffer)
   float locbuf[2][VLN_V * 4];      // loc4[cur_view] rows
@@ -63,7 +65,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
                  float* __restrict__ attn_io, const float* __restrict__ fwd_out, float* __restrict__ out,
                  float* __restrict__ scratch, unsigned int* __restrict__ tickets, int B, int S, int mode,
                  float drop_p, const uint64_t* __restrict__ rng, uint64_t call_off, int ld_vec, int ld_out,
-                 int ld_fwd) {
+                 int ld_fwd, const uint8_t* __restrict__ mask_bits) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -87,19 +89,22 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
     // use never holds back the others (a blocking wait would reconverge the warp on the slowest slot).
     uint32_t n = lane;
     const __nv_bfloat16* src = nullptr;
+    const uint8_t* msrc = nullptr;
     auto locate = [&]() -> bool {
       const uint32_t k = n / (uint32_t)R, i = n - k * (uint32_t)R;
       const int u = blockIdx.x + (int)k * (int)gridDim.x;
       if (u >= n_units) return false;
       const int ep = u / S, part = u - ep * S;
       src = table + ((size_t)__ldg(vp + ep) * VLN_V + (size_t)part * R + i) * VLN_IMG;
+      if (mask_bits) msrc = mask_bits + ((size_t)ep * VLN_V + (size_t)part * R + i) * kMaskBytes;
       return true;
     };
     bool work = locate();
     while (__any_sync(0xffffffffu, work)) {
       if (work && mbar_test_wait(&sm.empty[lane], ((n / kStages) & 1u) ^ 1u)) {
-        mbar_expect_tx(&sm.full[lane], kRowBytes);
-        bulk_g2s(sm.ring + (size_t)lane * kRowBytes, src, kRowBytes, &sm.full[lane]);
+        mbar_expect_tx(&sm.full[lane], mask_bits ? kStageBytes : kRowBytes);
+        bulk_g2s(sm.ring + (size_t)lane * kStageBytes, src, kRowBytes, &sm.full[lane]);
+        if (mask_bits) bulk_g2s(sm.ring + (size_t)lane * kStageBytes + kRowBytes, msrc, kMaskBytes, &sm.full[lane]);
         n += kStages;
         work = locate();
       }
@@ -111,7 +116,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   const uint32_t thr = drop_threshold(drop_p);
   uint64_t seed = 0, offset = 0;
-  if (drop_p > 0.f) {
+  if (drop_p > 0.f && !mask_bits) {
     seed = rng[0];
     offset = rng[1] + call_off;
   }
@@ -170,11 +175,22 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
       const uint32_t s = n % kStages, ph = (n / kStages) & 1u;
       const int v = part * R + i;
       mbar_wait(&sm.full[s], ph);
-      const uint4* rowp = reinterpret_cast<const uint4*>(sm.ring + (size_t)s * kRowBytes);
+      const uint4* rowp = reinterpret_cast<const uint4*>(sm.ring + (size_t)s * kStageBytes);
       uint4 x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = rowp[j * 32 + lane];
-      if (drop_p > 0.f) {
+      if (mask_bits) {
+        // pre-generated keep-bits: byte j of this lane's 8-byte group covers the 8 features of x[j]
+        const uint2 mb = *reinterpret_cast<const uint2*>(sm.ring + (size_t)s * kStageBytes + kRowBytes + lane * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t bits = ((j < 4 ? mb.x : mb.y) >> ((j & 3) * 8)) & 0xFFu;
+          uint32_t* w = reinterpret_cast<uint32_t*>(&x[j]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            w[k] &= (((bits >> (2 * k)) & 1u) * 0x0000FFFFu) | (((bits >> (2 * k + 1)) & 1u) * 0xFFFF0000u);
+        }
+      } else if (drop_p > 0.f) {
         const uint64_t e0 = (((uint64_t)ep * VLN_V + (uint64_t)v) * VLN_IMG) >> 3;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -385,12 +401,13 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
 extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
                                 const float* vec, int ld_vec, float* attn_io, const float* fwd_out, int ld_fwd,
                                 float* out, int ld_out, int B, int mode, float drop_p, const uint64_t* rng,
-                                uint64_t call_off, int split, void* stream) {
+                                uint64_t call_off, const uint8_t* mask_bits, int split, void* stream) {
   VLN_REQUIRE(ctx && vp && view && loc4 && vec && attn_io && out && B > 0, "bad arguments");
   VLN_REQUIRE(split == 1 || split == 2 || split == 4, "split must be 1, 2 or 4");
   VLN_REQUIRE(mode == 0 || (mode == 1 && fwd_out), "mode must be 0 (forward) or 1 (backward, needs fwd_out)");
   VLN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");
-  VLN_REQUIRE(drop_p == 0.f || rng, "dropout needs an rng state");
+  VLN_REQUIRE(drop_p == 0.f || rng || mask_bits, "dropout needs an rng state or pre-generated keep-bits");
+  VLN_REQUIRE(!mask_bits || (drop_p > 0.f && ((uintptr_t)mask_bits & 15) == 0), "mask_bits: 16-byte aligned, with drop_p > 0");
   VLN_REQUIRE(split == 1 || B <= VLN_SPLIT_MAX_B, "split > 1 supports at most VLN_SPLIT_MAX_B episodes per call");
   VLN_REQUIRE(ld_vec >= VLN_F && ld_out >= VLN_F && (mode == 0 || ld_fwd >= VLN_F), "row strides must be >= 2176");
   VLN_REQUIRE(ld_vec % 4 == 0 && ld_out % 4 == 0 && ld_fwd % 4 == 0 && ((uintptr_t)vec & 15) == 0 &&
@@ -405,7 +422,7 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
   const int grid = units < ctx->num_sms ? units : ctx->num_sms;
   pano_attn_kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(
       ctx->table, vp, view, loc4, vec, attn_io, fwd_out, out, ctx->scratch, ctx->tickets, B, split, mode, drop_p, rng,
-      call_off, ld_vec, ld_out, ld_fwd);
+      call_off, ld_vec, ld_out, ld_fwd, mask_bits);
   VLN_LAUNCH_OK();
   return 0;
 }
@@ -414,5 +431,5 @@ extern "C" int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_
                              const float* vec, float* attn_io, const float* fwd_out, float* out, int B, int mode,
                              float drop_p, const uint64_t* rng, uint64_t call_off, int split, void* stream) {
   return vln_pano_attn_ld(ctx, vp, view, loc4, vec, VLN_F, attn_io, fwd_out, VLN_F, out, VLN_F, B, mode, drop_p, rng,
-                          call_off, split, stream);
+                          call_off, nullptr, split, stream);
 }

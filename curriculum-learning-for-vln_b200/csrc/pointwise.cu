@@ -133,6 +133,29 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float
     if (e0 + j < n) mask[e0 + j] = philox_keep(r, j, thr) ? 1 : 0;
 }
 
+// Packed keep-bits of the feature dropout for a whole rollout (policy.py:226-231 draws a fresh
+// [B,36,2048] mask every decoder step).  Row r of step t is 2048 features = 256 Philox blocks of 8;
+// output byte (c % 32) * 8 + c / 32 of that row holds the 8 keep-bits of block c, which is the order
+// in which a warp of the panorama kernel consumes them (lane = c % 32 reads its 8 bytes at once).
+// Same bits as vln_dropout_mask on the dense [rows, 2048] tensor with call_off = off0 + t * off_stride.
+__global__ void feature_mask_bits_kernel(uint8_t* __restrict__ bits, int64_t rows, int n_steps, float p,
+                                         const uint64_t* __restrict__ rng, uint64_t off0, uint64_t off_stride) {
+  const int64_t total = rows * 256 * n_steps;
+  const uint32_t thr = drop_threshold(p);
+  const uint64_t seed = rng[0], base = rng[1];
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row_t = o >> 8;                                   // (t, row)
+    const int w = (int)(o & 255);                                   // byte position inside the row
+    const int c = (w & 7) * 32 + (w >> 3);                          // Philox block of the row stored there
+    const int64_t t = row_t / rows, row = row_t - t * rows;
+    const Philox8 r = philox8(seed, base + off0 + (uint64_t)t * off_stride, (uint64_t)(row * 256 + c));
+    uint32_t b = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b |= (philox_keep(r, j, thr) ? 1u : 0u) << j;
+    bits[o] = (uint8_t)b;
+  }
+}
+
 // ---- environment on index tables -----------------------------------------------------------------
 __device__ __forceinline__ int teacher_slot(int cur, int goal, const int32_t* cand_vp, const int32_t* n_cand,
                                             const int32_t* next_hop, const int64_t* sq_off, const int32_t* vp_local) {
@@ -381,6 +404,17 @@ extern "C" int vln_dropout_mask(uint8_t* mask, int64_t n, float p, const uint64_
   VLN_REQUIRE(mask && rng && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
   const int64_t blks = (n + 7) / 8;
   dropout_mask_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(mask, n, p, rng, call_off);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_feature_mask_bits(uint8_t* bits, int64_t rows, int n_steps, float p, const uint64_t* rng,
+                                     uint64_t off0, uint64_t off_stride, void* stream) {
+  VLN_REQUIRE(bits && rng && rows > 0 && n_steps > 0 && p > 0.f && p < 1.f, "bad arguments");
+  const int64_t total = rows * 256 * n_steps;
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  feature_mask_bits_kernel<<<grid, 256, 0, STREAM>>>(bits, rows, n_steps, p, rng, off0, off_stride);
   VLN_LAUNCH_OK();
   return 0;
 }

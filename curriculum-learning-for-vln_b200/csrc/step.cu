@@ -150,17 +150,124 @@ __global__ void act_fwd_kernel(const int32_t* __restrict__ view, const float* __
   xh[(size_t)b * ld_xh + j] = a * k[i & 7];
 }
 
-// d_actpre[b,j] = drop'(d_xh[b,j]) * (1 - act^2)
+// d_actpre[t,b,j] = drop'(d_xh[t,b,j]) * (1 - act^2) for n_steps steps at once (step t draws its mask from
+// stream call_off + t*off_stride; d_xh rows of step t start at d_xh + t*B*ld_dxh)
 __global__ void act_bwd_kernel(const float* __restrict__ d_xh, int ld_dxh, const float* __restrict__ act,
-                               float* __restrict__ d_actpre, int B, int E, float p, const uint64_t* __restrict__ rng,
-                               uint64_t call_off) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * E) return;
+                               float* __restrict__ d_actpre, int B, int E, int n_steps, float p,
+                               const uint64_t* __restrict__ rng, uint64_t call_off, uint64_t off_stride) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_steps * B * E) return;
+  const int t = g / (B * E), i = g - t * (B * E);
   const int b = i / E, j = i - b * E;
   float k[8];
-  keep8(make_drop(p, rng, call_off), (uint64_t)(i >> 3), k);
-  const float a = act[i];
-  d_actpre[i] = d_xh[(size_t)b * ld_dxh + j] * k[i & 7] * (1.f - a * a);
+  keep8(make_drop(p, rng, call_off + (uint64_t)t * off_stride), (uint64_t)(i >> 3), k);
+  const float a = act[g];
+  d_actpre[g] = d_xh[((size_t)t * B + b) * ld_dxh + j] * k[i & 7] * (1.f - a * a);
+}
+
+// ---- action head + simulator transition + next step's action embedding: one warp per episode ------
+// (vln_policy_fwd, vln_env_step and vln_envdrop_act_fwd back to back; same arithmetic, one launch)
+struct EnvTables {
+  const int32_t* cand_vp; const int32_t* cand_view; const int32_t* n_cand; const int32_t* next_hop;
+  const float* dist_tbl; const int64_t* sq_off; const int32_t* vp_local;
+};
+__device__ __forceinline__ int teacher_slot_(int cur, int goal, const EnvTables& e) {
+  const int n = e.n_cand[cur];
+  if (cur == goal) return n;
+  const int nh = e.next_hop[e.sq_off[cur] + e.vp_local[goal]];
+  for (int j = 0; j < n; ++j)
+    if (e.cand_vp[(size_t)cur * VLN_CMAX + j] == nh) return j;
+  return n;
+}
+
+__global__ void policy_env_act_kernel(const float* __restrict__ logits, const int32_t* __restrict__ target, int feedback,
+                                      const uint64_t* __restrict__ rng, uint64_t off_sample, float* __restrict__ ce,
+                                      int32_t* __restrict__ action, float* __restrict__ logp, float* __restrict__ entropy,
+                                      float* __restrict__ probs, const int32_t* __restrict__ vp_in,
+                                      const int32_t* __restrict__ view_in, const uint8_t* __restrict__ ended_in,
+                                      const float* __restrict__ dist_in, const int32_t* __restrict__ goal, EnvTables env,
+                                      int32_t* __restrict__ vp_out, int32_t* __restrict__ view_out,
+                                      uint8_t* __restrict__ ended_out, float* __restrict__ dist_out,
+                                      int32_t* __restrict__ teacher_out, float* __restrict__ reward,
+                                      float* __restrict__ mask, int32_t* __restrict__ n_active,
+                                      const float* __restrict__ pose4, const float* __restrict__ w_act,
+                                      const float* __restrict__ b_act, float* __restrict__ act, float* __restrict__ xh,
+                                      int ld_xh, int E, float p_act, uint64_t off_act, int B) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  // ---- action head (policy_fwd_kernel) ----
+  const float x = lane < VLN_NSLOT ? logits[(size_t)b * VLN_NSLOT + lane] : -INFINITY;
+  const float m = warp_max(x);
+  const float e = (x == -INFINITY) ? 0.f : expf(x - m);
+  const float s = warp_sum(e);
+  const float p = e / s;
+  const float lp = x - m - logf(s);
+  const float ent = -warp_sum(p > 0.f ? p * lp : 0.f);
+  const int tg = target ? target[b] : -1;
+  int act_id;
+  if (feedback == 0) {
+    act_id = tg;
+  } else if (feedback == 1) {
+    act_id = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
+  } else {
+    const float u = philox_uniform(philox8(rng[0], rng[1] + off_sample, (uint64_t)b), 0);
+    float cdf = p;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, cdf, o);
+      if (lane >= o) cdf += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, p > 0.f && cdf > u);
+    const unsigned valid = __ballot_sync(0xffffffffu, p > 0.f);
+    act_id = hit ? __ffs(hit) - 1 : 31 - __clz(valid);
+  }
+  const float lp_t = __shfl_sync(0xffffffffu, lp, tg >= 0 ? tg : 0);
+  const float lp_a = __shfl_sync(0xffffffffu, lp, act_id >= 0 ? act_id : 0);
+  if (lane < VLN_NSLOT) probs[(size_t)b * VLN_NSLOT + lane] = p;
+  // ---- simulator transition (env_step_kernel), lane 0 ----
+  int vw = 0;
+  if (lane == 0) {
+    ce[b] = tg >= 0 ? -lp_t : 0.f;
+    action[b] = act_id;
+    logp[b] = act_id >= 0 ? lp_a : 0.f;
+    entropy[b] = ent;
+    int cur = vp_in[b];
+    vw = view_in[b];
+    const int g = goal[b];
+    const bool was_ended = ended_in[b] != 0;
+    const bool stop = was_ended || act_id < 0 || act_id >= env.n_cand[cur];
+    if (!stop) {
+      vw = env.cand_view[(size_t)cur * VLN_CMAX + act_id];
+      cur = env.cand_vp[(size_t)cur * VLN_CMAX + act_id];
+    }
+    vp_out[b] = cur;
+    view_out[b] = vw;
+    const float d = env.dist_tbl[env.sq_off[cur] + env.vp_local[g]];
+    float r = 0.f;
+    if (!was_ended) {
+      if (stop) r = d < 3.0f ? 2.f : -2.f;
+      else { const float dd = dist_in[b] - d; r = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f); }
+    }
+    reward[b] = r;
+    mask[b] = was_ended ? 0.f : 1.f;
+    dist_out[b] = d;
+    const bool now_ended = was_ended || stop;
+    ended_out[b] = now_ended ? 1 : 0;
+    teacher_out[b] = now_ended ? -1 : teacher_slot_(cur, g, env);
+    if (n_active && !now_ended) atomicAdd(n_active, 1);
+  }
+  // ---- next step's action embedding (act_fwd_kernel) for the new view ----
+  if (xh == nullptr) return;
+  vw = __shfl_sync(0xffffffffu, vw, 0);
+  const Drop dr = make_drop(p_act, rng, off_act);
+  for (int j = lane; j < E; j += 32) {
+    const float a = act_embed_one(w_act + (size_t)j * VLN_ANG, pose4 + (size_t)vw * 4, b_act[j]);
+    const int i = b * E + j;
+    act[i] = a;
+    float k[8];
+    keep8(dr, (uint64_t)(i >> 3), k);
+    xh[(size_t)b * ld_xh + j] = a * k[i & 7];
+  }
 }
 
 // ---- nn.LSTMCell pointwise half + dropout of h_1 into the text-attention operand buffer -----------
@@ -286,10 +393,38 @@ extern "C" int vln_envdrop_act_fwd(const int32_t* view, const float* pose4, cons
 }
 
 extern "C" int vln_envdrop_act_bwd(const float* d_xh, int ld_dxh, const float* act, float* d_actpre, int B, int E,
-                                   float p, const uint64_t* rng, uint64_t call_off, void* stream) {
-  VLN_REQUIRE(d_xh && act && d_actpre && B > 0 && E > 0, "bad arguments");
+                                   int n_steps, float p, const uint64_t* rng, uint64_t call_off, uint64_t off_stride,
+                                   void* stream) {
+  VLN_REQUIRE(d_xh && act && d_actpre && B > 0 && E > 0 && n_steps > 0, "bad arguments");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
-  act_bwd_kernel<<<(B * E + 127) / 128, 128, 0, STREAM>>>(d_xh, ld_dxh, act, d_actpre, B, E, p, rng, call_off);
+  act_bwd_kernel<<<(n_steps * B * E + 255) / 256, 256, 0, STREAM>>>(d_xh, ld_dxh, act, d_actpre, B, E, n_steps, p, rng,
+                                                                    call_off, off_stride);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_policy_env_act_fwd(const float* logits, const int32_t* target, int feedback, const uint64_t* rng,
+                                      uint64_t off_sample, float* ce, int32_t* action, float* logp, float* entropy,
+                                      float* probs, const int32_t* vp_in, const int32_t* view_in, const uint8_t* ended_in,
+                                      const float* dist_in, const int32_t* goal, const int32_t* cand_vp,
+                                      const int32_t* cand_view, const int32_t* n_cand, const int32_t* next_hop,
+                                      const float* dist_tbl, const int64_t* sq_off, const int32_t* vp_local,
+                                      int32_t* vp_out, int32_t* view_out, uint8_t* ended_out, float* dist_out,
+                                      int32_t* teacher_out, float* reward, float* mask, int32_t* n_active,
+                                      const float* pose4, const float* w_act, const float* b_act, float* act, float* xh,
+                                      int ld_xh, int E, float p_act, uint64_t off_act, int B, void* stream) {
+  VLN_REQUIRE(logits && ce && action && logp && entropy && probs && vp_in && view_in && ended_in && dist_in && goal &&
+                  cand_vp && cand_view && n_cand && next_hop && dist_tbl && sq_off && vp_local && vp_out && view_out &&
+                  ended_out && dist_out && teacher_out && reward && mask && B > 0,
+              "bad arguments");
+  VLN_REQUIRE(feedback >= 0 && feedback <= 2 && (feedback != 0 || target) && (feedback != 2 || rng), "bad feedback mode");
+  VLN_REQUIRE(!xh || (pose4 && w_act && b_act && act && E > 0 && (p_act == 0.f || rng)), "action embedding needs its weights");
+  EnvTables env{cand_vp, cand_view, n_cand, next_hop, dist_tbl, sq_off, vp_local};
+  policy_env_act_kernel<<<(B + 3) / 4, 128, 0, STREAM>>>(logits, target, feedback, rng, off_sample, ce, action, logp,
+                                                         entropy, probs, vp_in, view_in, ended_in, dist_in, goal, env,
+                                                         vp_out, view_out, ended_out, dist_out, teacher_out, reward, mask,
+                                                         n_active, pose4, w_act, b_act, act, xh, ld_xh, E, p_act, off_act,
+                                                         B);
   VLN_LAUNCH_OK();
   return 0;
 }

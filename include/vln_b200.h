@@ -80,10 +80,19 @@ int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, co
 /* Same kernel with explicit row strides (in floats, multiples of 4, >= 2176) for vec, fwd_out and out, so the
  * result can land inside a wider operand row (the LSTMCell input [act_emb | visual | h] of policy.py:236-238)
  * and the backward can read its d(out) / saved forward output from there. */
+/* mask_bits (nullable): pre-generated keep-bits [B,36,256 bytes] of this step's feature dropout
+ * (vln_feature_mask_bits) — the kernel then streams 256 mask bytes next to each 4 096-byte row instead of
+ * running Philox inline (which made the kernel ALU-bound: 15.4 us vs 7.6 us per launch at B=64). */
 int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
                      const float* vec, int ld_vec, float* attn_io, const float* fwd_out, int ld_fwd,
                      float* out, int ld_out, int B, int mode, float drop_p, const uint64_t* rng,
-                     uint64_t call_off, int split, void* stream);
+                     uint64_t call_off, const uint8_t* mask_bits, int split, void* stream);
+/* Packed keep-bits of the feature dropout (policy.py:226-231) for n_steps decoder steps at once:
+ * bits [n_steps, rows, 256] bytes, rows = B*36 panorama rows of 2048 features; step t uses the stream
+ * (seed, base + off0 + t*off_stride); the bits equal vln_dropout_mask on the dense [rows,2048] tensor.
+ * Byte (c%32)*8 + c/32 of a row = keep-bits of features [8c, 8c+8). */
+int vln_feature_mask_bits(uint8_t* bits, int64_t rows, int n_steps, float p, const uint64_t* rng,
+                          uint64_t off0, uint64_t off_stride, void* stream);
 
 /* Candidate logits (EnvDropDecoder.candidate_attn policy.py:199-206; also ActionScoring
  * units.py:173-185 after folding its Linear layers into tgt/bias on the host side):
@@ -161,8 +170,32 @@ int vln_envdrop_state_bwd(const float* d_hc, const float* d_xh_next, int ld_dxh,
 int vln_envdrop_act_fwd(const int32_t* view, const float* pose4, const float* w, const float* bias, float* act,
                         float* xh, int ld_xh, int B, int E, float p, const uint64_t* rng, uint64_t call_off,
                         void* stream);
+/* act_bwd covers n_steps steps in one launch: d_xh [n_steps,B,ld_dxh], act / d_actpre [n_steps,B,E]; step t
+ * regenerates its mask from stream call_off + t*off_stride. */
 int vln_envdrop_act_bwd(const float* d_xh, int ld_dxh, const float* act, float* d_actpre, int B, int E,
-                        float p, const uint64_t* rng, uint64_t call_off, void* stream);
+                        int n_steps, float p, const uint64_t* rng, uint64_t call_off, uint64_t off_stride,
+                        void* stream);
+/* vln_policy_fwd + vln_env_step + vln_envdrop_act_fwd (for the NEW view) in one launch, one warp per
+ * episode: the tail of a rollout step (envdrop.py:177-219) and the head of the next (policy.py:222-223).
+ * xh may be NULL (no following decoder pass): then the action embedding is skipped. */
+int vln_policy_env_act_fwd(const float* logits, const int32_t* target, int feedback, const uint64_t* rng,
+                           uint64_t off_sample, float* ce, int32_t* action, float* logp, float* entropy,
+                           float* probs, const int32_t* vp_in, const int32_t* view_in, const uint8_t* ended_in,
+                           const float* dist_in, const int32_t* goal, const int32_t* cand_vp,
+                           const int32_t* cand_view, const int32_t* n_cand, const int32_t* next_hop,
+                           const float* dist_tbl, const int64_t* sq_off, const int32_t* vp_local,
+                           int32_t* vp_out, int32_t* view_out, uint8_t* ended_out, float* dist_out,
+                           int32_t* teacher_out, float* reward, float* mask, int32_t* n_active,
+                           const float* pose4, const float* w_act, const float* b_act, float* act, float* xh,
+                           int ld_xh, int E, float p_act, uint64_t off_act, int B, void* stream);
+/* vln_policy_bwd folded into vln_cand_logits_bwd: dlogits are computed from the action head's saved
+ * probs / target / action / entropy and the incoming g_ce / g_logp / g_ent (each nullable). */
+int vln_cand_logits_bwd_policy(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
+                               const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
+                               const float* probs, const int32_t* target, const int32_t* action,
+                               const float* entropy, const float* g_ce, const float* g_logp,
+                               const float* g_ent, float* d_tgt, int B, float drop_p, const uint64_t* rng,
+                               uint64_t call_off, void* stream);
 
 /* Skinny linear layer on tcgen05 tensor cores (nn.Linear / nn.LSTMCell gate GEMMs of policy.py and
  * units.py at batch sizes <= 128):  y[m,n] (+)= sum_k x[m,k] w[n,k] (+ bias[n]),  m < M <= 128.
