@@ -4,18 +4,21 @@
 // The reference packs the padded batch and calls cuDNN; here a THREAD-BLOCK CLUSTER owns a group
 // of kNB batch rows for the whole sequence:
 //   * CTA r of the cluster owns hidden units [32r, 32r+32): its 128 gate rows (i,f,g,o x 32) of
-//     W_hh stay resident in shared memory for all timesteps (128 x H fp32, padded rows);
-//   * every step each CTA computes its 128 gate pre-activations for the group's kNB rows from the
-//     full h_{t-1} (kept in shared memory), applies the LSTM pointwise update to its 32 units
-//     (c stays in registers), and broadcasts its slice of h_t into every peer's shared memory
-//     through DSMEM; one cluster barrier per step;
+//     W_hh stay resident for all timesteps — in REGISTERS, as the A fragments of mma.m16n8k16 (bf16 hi
+//     and lo halves of every weight: warp w holds rows 16w..16w+15, 128 registers per thread at H=256);
+//   * every step each CTA computes its 128 gate pre-activations for the group's kNB = 8 rows (the MMA's
+//     N) from the full h_{t-1}, kept in shared memory as bf16 hi/lo pairs: three tensor-core products
+//     hi.hi + hi.lo + lo.hi with fp32 accumulation reproduce the fp32 matvec to ~2^-16 (the fp32 FMA
+//     version of this loop was bound by LDS bandwidth at ~5 us per step); then the LSTM pointwise update
+//     of its 32 units (c stays in registers), and its slice of h_t goes to every peer's shared memory
+//     through asynchronous DSMEM stores that signal the receiver's mbarrier (no cluster barrier per step);
 //   * rows stop at their own length (reverse rows start there) exactly like a packed sequence:
 //     state frozen and output zero where t >= length;  steps past the group's longest row are skipped.
 // Backward runs the same structure in reverse time: the pointwise gradient for the CTA's units,
 // partial dh_{t-1} = dgates . W_hh over its 128 rows, reduce-scattered to the owning CTAs via DSMEM.
 // dgates (= d xproj) goes to global memory; dW_hh / dW_ih / dx are single large GEMMs outside.
 //
-// Roofline class: latency (80 serial steps); FMA work per step per CTA = kNB*128*H.
+// Roofline class: latency (80 serial steps); per step and CTA 3 x 16 x H/16 MMAs (m16n8k16).
 #include "common.cuh"
 
 namespace {
@@ -56,6 +59,28 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf16_val(uint32_t bits) { return __uint_as_float(bits << 16); }
+// pack two fp32 values into bf16 pairs (first value in the low half): hi and the residual lo
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ah = bf16_bits(a), bh = bf16_bits(b);
+  hi = ah | (bh << 16);
+  lo = bf16_bits(a - bf16_val(ah)) | (bf16_bits(b - bf16_val(bh)) << 16);
+}
+__device__ __forceinline__ void dsmem_st_async_u32(void* local_ptr, uint64_t* local_bar, uint32_t rank, uint32_t v) {
+  uint32_t a = smem_u32(local_ptr), m = smem_u32(local_bar), ra, rm;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rm) : "r"(m), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(v), "r"(rm)
+               : "memory");
+}
+
 // one direction of a (bi)directional layer; both directions run in the same launch (grid.y)
 struct DirF {
   const float* xproj;   // [B,L,4H]
@@ -78,13 +103,14 @@ struct DirB {
   int reverse;
 };
 
-// shared memory: W slice [128][H+8], h double buffer [2][kNB][H], gates [kNB][128]
+// shared memory: h_{t-1} as bf16 hi / lo [2 buffers][kNB][H+8] (row padding: the 8 batch rows of a B fragment
+// fall into distinct banks), gates [kNB][128]
 template <int H>
 struct SmemF {
-  float w[kRows * (H + 8)];
-  float h[2][kNB * H];
+  uint16_t h_hi[2][kNB * (H + 8)];
+  uint16_t h_lo[2][kNB * (H + 8)];
   float g[kNB * kRows];
-  uint64_t bar[2];                 // bar[k]: all kNB*H values of h buffer k have arrived
+  uint64_t bar[2];                 // bar[k]: all kNB*H (hi, lo) pairs of h buffer k have arrived
 };
 
 // xproj [B,L,4H] (x W_ih^T + b_ih + b_hh), w_hh [4H,H], lengths [B].
@@ -93,7 +119,8 @@ template <int H>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last) {
   constexpr int C = H / kHS;       // cluster size
-  constexpr int WS = H + 8;        // padded row stride (floats): rows 0..3 x k-phase 0/1 hit distinct 16 B slots
+  constexpr int HP = H + 8;        // padded bf16 row of the h buffers
+  constexpr int KS = H / 16;       // k-steps of 16
   const DirF d = blockIdx.y == 0 ? d0 : d1;
   const float* __restrict__ xproj = d.xproj;
   const float* __restrict__ w_hh = d.w_hh;
@@ -103,18 +130,29 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
   const int reverse = d.reverse;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SmemF<H>& sm = *reinterpret_cast<SmemF<H>*>(smem_raw);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_ctarank();
   const int group = blockIdx.x / C;
   const int b0 = group * kNB;
 
-  // resident weight slice: local row lr = gate*32 + unit  <->  global row gate*H + rank*32 + unit
-  for (int i = tid; i < kRows * (H / 4); i += kThreads) {
-    const int lr = i / (H / 4), c4 = i - lr * (H / 4);
-    const int grow = (lr >> 5) * H + rank * kHS + (lr & 31);
-    reinterpret_cast<float4*>(sm.w + lr * WS)[c4] = __ldg(reinterpret_cast<const float4*>(w_hh + (size_t)grow * H) + c4);
+  // resident weight fragments: local row lr = gate*32 + unit  <->  global row gate*H + rank*32 + unit;
+  // warp w owns local rows 16w..16w+15 (A operand, row-major 16x16 tiles: a0/a2 row r0, a1/a3 row r0+8)
+  const int r0 = lane >> 2, c0 = (lane & 3) * 2;
+  uint32_t a_hi[KS][4], a_lo[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int lr = 16 * warp + r0 + (q & 1) * 8, col = ks * 16 + c0 + (q >> 1) * 8;
+      const int grow = (lr >> 5) * H + rank * kHS + (lr & 31);
+      const float2 wv = __ldg(reinterpret_cast<const float2*>(w_hh + (size_t)grow * H + col));
+      split_pair(wv.x, wv.y, a_hi[ks][q], a_lo[ks][q]);
+    }
   }
-  for (int i = tid; i < 2 * kNB * H; i += kThreads) (&sm.h[0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * kNB * HP; i += kThreads) {
+    (&sm.h_hi[0][0])[i] = 0;
+    (&sm.h_lo[0][0])[i] = 0;
+  }
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
     mbar_init(&sm.bar[1], 1);
@@ -131,11 +169,8 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
     if (b0 + i < B) gmax = max(gmax, min(lengths[b0 + i], L));
   float c_reg = 0.f, h_reg = 0.f;
   const int ug = rank * kHS + pu;   // global hidden unit
-  // matvec role: thread = (row mr, k-half mk)
-  const int mr = tid >> 1, mk = tid & 1;                  // the two k-phases interleave in 16-byte steps
-  const float* wrow = sm.w + mr * WS + mk * 4;
 
-  cluster_sync_all();               // weights + zeroed h visible cluster-wide before any DSMEM traffic
+  cluster_sync_all();               // zeroed h + initialised barriers visible cluster-wide before any DSMEM traffic
 
   float xp[4] = {0.f, 0.f, 0.f, 0.f};
   auto load_x = [&](int t) {
@@ -150,25 +185,25 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
   load_x(t);
   for (int s = 0; s < gmax; ++s, t += dt) {
     const int cur = s & 1, nxt = cur ^ 1;
-    if (tid == 0) mbar_expect_tx(&sm.bar[nxt], kNB * H * 4);       // this step's h_t: kNB*H floats from the C CTAs
-    // ---- gates[b][row] partial sums over this thread's half of K ----
-    float acc[kNB];
+    if (tid == 0) mbar_expect_tx(&sm.bar[nxt], kNB * H * 4);       // this step's h_t: kNB*H (hi, lo) pairs from the C CTAs
+    // ---- gates[n][16w + r] = sum_k W[row][k] h[n][k] on the tensor cores (B operand: n = batch row) ----
+    {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint16_t* hh = sm.h_hi[cur] + r0 * HP + c0;            // B fragment: n = lane/4, k pair = (lane%4)*2
+      const uint16_t* hl = sm.h_lo[cur] + r0 * HP + c0;
 #pragma unroll
-    for (int i = 0; i < kNB; ++i) acc[i] = 0.f;
-    const float* hb = sm.h[cur] + mk * 4;
-#pragma unroll 4
-    for (int k = 0; k < H; k += 8) {
-      const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
-#pragma unroll
-      for (int i = 0; i < kNB; ++i) {
-        const float4 h4 = *reinterpret_cast<const float4*>(hb + i * H + k);
-        acc[i] = fmaf(w4.x, h4.x, fmaf(w4.y, h4.y, fmaf(w4.z, h4.z, fmaf(w4.w, h4.w, acc[i]))));
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(hh + ks * 16), bh1 = *reinterpret_cast<const uint32_t*>(hh + ks * 16 + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(hl + ks * 16), bl1 = *reinterpret_cast<const uint32_t*>(hl + ks * 16 + 8);
+        mma_bf16(acc, a_hi[ks], bh0, bh1);
+        mma_bf16(acc, a_hi[ks], bl0, bl1);
+        mma_bf16(acc, a_lo[ks], bh0, bh1);
       }
-    }
-#pragma unroll
-    for (int i = 0; i < kNB; ++i) {
-      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 1);
-      if (mk == 0) sm.g[i * kRows + mr] = acc[i];
+      // D fragment: acc[0..1] = row r0, batch c0 / c0+1; acc[2..3] = row r0+8
+      sm.g[c0 * kRows + 16 * warp + r0] = acc[0];
+      sm.g[(c0 + 1) * kRows + 16 * warp + r0] = acc[1];
+      sm.g[c0 * kRows + 16 * warp + r0 + 8] = acc[2];
+      sm.g[(c0 + 1) * kRows + 16 * warp + r0 + 8] = acc[3];
     }
     __syncthreads();
     // ---- pointwise for (pb, pu) ----
@@ -190,9 +225,16 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
       ap[0] = ig; ap[H] = fg; ap[2 * H] = gg; ap[3 * H] = og;
     }
     // ---- all-gather h_t: my unit's value into every CTA's next buffer ----
-    float* dst = sm.h[nxt] + pb * H + ug;
+    // (as bf16 hi/lo: even units send the packed hi pair (pu, pu+1), odd units the packed lo pair (pu-1, pu))
+    {
+      const uint32_t hi16 = bf16_bits(h_new), lo16 = bf16_bits(h_new - bf16_val(hi16));
+      const uint32_t o_hi = __shfl_xor_sync(0xffffffffu, hi16, 1), o_lo = __shfl_xor_sync(0xffffffffu, lo16, 1);
+      const bool even = (pu & 1) == 0;
+      const uint32_t word = even ? (hi16 | (o_hi << 16)) : (o_lo | (lo16 << 16));
+      uint16_t* dst = even ? sm.h_hi[nxt] + pb * HP + ug : sm.h_lo[nxt] + pb * HP + ug - 1;
 #pragma unroll
-    for (int r = 0; r < C; ++r) dsmem_st_async_f32(dst, &sm.bar[nxt], (uint32_t)r, h_new);
+      for (int r = 0; r < C; ++r) dsmem_st_async_u32(dst, &sm.bar[nxt], (uint32_t)r, word);
+    }
     // Every CTA (this one included) has delivered its slice once the byte count is reached.  Buffer reuse is
     // safe without a further barrier: a peer writes h[cur] again only in step s+1, which it enters after it
     // received THIS CTA's slice of step s — sent after the matvec above finished reading h[cur].
@@ -209,8 +251,8 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
 // d_xproj [B,L,4H] must be pre-zeroed (masked steps stay zero).
 template <int H>
 struct SmemB {
-  float w[kRows * (H + 8)];
-  float dg[kNB * kRows];                 // this CTA's dgates for the group
+  uint16_t dg_hi[kNB * (kRows + 8)];     // this CTA's dgates for the group as bf16 hi / lo (B operand, padded rows)
+  uint16_t dg_lo[kNB * (kRows + 8)];
   float recv[2][(H / kHS) * kNB * kHS];  // partial dh for my units from every CTA (double buffered over steps)
   uint64_t bar[2];                       // bar[k]: all C*kNB*32 partials of recv[k] have arrived
 };
@@ -219,7 +261,9 @@ template <int H>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last) {
   constexpr int C = H / kHS;
-  constexpr int WS = H + 8;
+  constexpr int RP = kRows + 8;    // padded bf16 row of the dgates buffers
+  constexpr int MT = H / 128;      // 16-column m-tiles of dh per warp (8 warps cover H columns)
+  constexpr int KS = kRows / 16;   // k-steps over this CTA's 128 gate rows
   const DirB d = blockIdx.y == 0 ? d0 : d1;
   const float* __restrict__ w_hh = d.w_hh;
   const float* __restrict__ acts = d.acts;
@@ -231,14 +275,25 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
   const int reverse = d.reverse;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SmemB<H>& sm = *reinterpret_cast<SmemB<H>*>(smem_raw);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_ctarank();
   const int group = blockIdx.x / C;
   const int b0 = group * kNB;
-  for (int i = tid; i < kRows * (H / 4); i += kThreads) {
-    const int lr = i / (H / 4), c4 = i - lr * (H / 4);
-    const int grow = (lr >> 5) * H + rank * kHS + (lr & 31);
-    reinterpret_cast<float4*>(sm.w + lr * WS)[c4] = __ldg(reinterpret_cast<const float4*>(w_hh + (size_t)grow * H) + c4);
+  // resident fragments of W^T restricted to this CTA's gate rows: dh[k][n] = sum_lr W[lr][k] dg[n][lr];
+  // A[m = column k][kk = local row lr]; warp w owns columns 16*(MT*w + mt) .. +15
+  const int r0 = lane >> 2, c0 = (lane & 3) * 2;
+  uint32_t a_hi[MT][KS][4], a_lo[MT][KS][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = 16 * (MT * warp + mt) + r0 + (q & 1) * 8, lr = ks * 16 + c0 + (q >> 1) * 8;
+        const int g0 = (lr >> 5) * H + rank * kHS + (lr & 31), g1 = ((lr + 1) >> 5) * H + rank * kHS + ((lr + 1) & 31);
+        split_pair(__ldg(w_hh + (size_t)g0 * H + k), __ldg(w_hh + (size_t)g1 * H + k), a_hi[mt][ks][q], a_lo[mt][ks][q]);
+      }
+    }
   }
   const int pb = tid >> 5, pu = tid & 31;
   const int b = b0 + pb;
@@ -282,25 +337,44 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
       float* dp = d_xproj + o * (4 * H) + ug;
       dp[0] = dgi; dp[H] = dgf; dp[2 * H] = dgg; dp[3 * H] = dgo;
     }
-    float* gp = sm.dg + pb * kRows + pu;
-    gp[0] = dgi; gp[32] = dgf; gp[64] = dgg; gp[96] = dgo;
-    __syncthreads();
-    // partial dh_prev[bb][k] over my 128 rows: thread tid owns column k = tid (H <= 256) for all kNB rows
-    if (tid < H) {
-      float acc[kNB];
+    {
+      const float dgv[4] = {dgi, dgf, dgg, dgo};
 #pragma unroll
-      for (int i = 0; i < kNB; ++i) acc[i] = 0.f;
-#pragma unroll 4
-      for (int lr = 0; lr < kRows; ++lr) {
-        const float w = sm.w[lr * WS + tid];
-#pragma unroll
-        for (int i = 0; i < kNB; ++i) acc[i] = fmaf(sm.dg[i * kRows + lr], w, acc[i]);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t hi = bf16_bits(dgv[k]);
+        sm.dg_hi[pb * RP + k * kHS + pu] = (uint16_t)hi;
+        sm.dg_lo[pb * RP + k * kHS + pu] = (uint16_t)bf16_bits(dgv[k] - bf16_val(hi));
       }
-      // reduce-scatter: column k belongs to CTA k/32, slot [my rank][bb][k%32]
-      const uint32_t owner = (uint32_t)(tid >> 5);
+    }
+    __syncthreads();
+    // partial dh_prev[n][k] over my 128 rows on the tensor cores (B operand: n = batch row)
+    {
+      float acc[MT][4];
 #pragma unroll
-      for (int i = 0; i < kNB; ++i)
-        dsmem_st_async_f32(sm.recv[s & 1] + (rank * kNB + i) * kHS + (tid & 31), &sm.bar[s & 1], owner, acc[i]);
+      for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+      const uint16_t* gh = sm.dg_hi + r0 * RP + c0;
+      const uint16_t* gl = sm.dg_lo + r0 * RP + c0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(gh + ks * 16), bh1 = *reinterpret_cast<const uint32_t*>(gh + ks * 16 + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(gl + ks * 16), bl1 = *reinterpret_cast<const uint32_t*>(gl + ks * 16 + 8);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16(acc[mt], a_hi[mt][ks], bh0, bh1);
+          mma_bf16(acc[mt], a_hi[mt][ks], bl0, bl1);
+          mma_bf16(acc[mt], a_lo[mt][ks], bh0, bh1);
+        }
+      }
+      // reduce-scatter: column k belongs to CTA k/32, slot [my rank][n][k%32]
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = 16 * (MT * warp + mt) + r0 + (q >> 1) * 8, n = c0 + (q & 1);
+          dsmem_st_async_f32(sm.recv[s & 1] + (rank * kNB + n) * kHS + (k & 31), &sm.bar[s & 1], (uint32_t)(k >> 5),
+                             acc[mt][q]);
+        }
+      }
     }
     mbar_wait_cluster(&sm.bar[s & 1], (uint32_t)(s >> 1) & 1u);
     // owner: dh_{t-1}[pb][my unit] = sum over the C partials (live rows); frozen rows pass dh through
@@ -312,7 +386,7 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
     }
     // recv is double buffered: a peer's stores of step s+1 go to the other half, and its stores of step
     // s+2 come after it received this CTA's partials of step s+1, which are sent only after the reads above.
-    // sm.dg is rewritten in step s+1 only after this wait, i.e. after every local thread finished its matvec.
+    // sm.dg_* are rewritten in step s+1 only after this wait, i.e. after every local thread finished its MMAs.
   }
   cluster_sync_all();               // no CTA exits while a peer could still address its shared memory
 }
