@@ -108,6 +108,7 @@ class _Rollout(torch.autograd.Function):
         s_cat = fd.cat.fresh(w_ih, w_hh)
         s_tin, s_out, s_vin, s_cand = (ops._split_of(w) for w in params[6:10])
         bsum = (b_ih + b_hh).contiguous()
+        w_act = w_act.view(H_ACT, 4, 32).sum(2).contiguous()        # group sums: the angle feature is 4 values x32
 
         # ---- buffers: the GEMM outputs (split-K partial sums meet there) come out of one zero-filled slab ----
         slab = torch.zeros(S * B * (F + G4) + T * B * (H + H + F), device=dev)
@@ -255,13 +256,16 @@ class _Rollout(torch.autograd.Function):
         DC = torch.empty((2, B, H), device=dev)
         DLC = torch.empty((n, B, L), device=dev)                  # d(logit) of the text attention, per step
 
+        # ---- off the recursion: candidate-logit backward of ALL steps in one launch, then d(h~_drop) = dtgt W_cand
+        #      as a stack of 128-row GEMMs (none of it depends on the backward-in-time chain) ----
+        stride = (offs[1]["cand"] - offs[0]["cand"]) if len(offs) > 1 else 0
+        _call("vln_cand_logits_bwd_policy", store.handle, _ptr(st.vp), _ptr(st.view), _ptr(store.cand_view),
+              _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(PROBS), _ptr(TEACH), _ptr(ACTION), _ptr(ENT),
+              _ptr(d_ce) if d_ce is not None else None, _ptr(d_logp) if d_logp is not None else None,
+              _ptr(d_ent) if d_ent is not None else None, _ptr(DTGT), B, n, pf, rp, offs[0]["cand"], stride, _stream())
+        _gemm(s_cand.hi_t, s_cand.lo_t, H, F, _p(DTGT), F, n * B, None, _p(DHC), H)
         for t in range(n - 1, -1, -1):
             last = t == n - 1
-            _call("vln_cand_logits_bwd_policy", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
-                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(PROBS[t]), _ptr(TEACH[t]), _ptr(ACTION[t]), _ptr(ENT[t]),
-                  _ptr(d_ce[t]) if d_ce is not None else None, _ptr(d_logp[t]) if d_logp is not None else None,
-                  _ptr(d_ent[t]) if d_ent is not None else None, _ptr(DTGT[t]), B, pf, rp, offs[t]["cand"], _stream())
-            _gemm(s_cand.hi_t, s_cand.lo_t, H, F, _p(DTGT[t]), F, B, None, _p(DHC[t]), H)
             _call("vln_envdrop_state_bwd", _ptr(DHC[t]), None if last else _p(DXH[t + 1], OH), KX,
                   None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), B, H, p, rp,
                   0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())

@@ -1,6 +1,7 @@
 // C-ABI plumbing: errors, context (feature table + TMA descriptor).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -12,6 +13,15 @@ void vln_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool vln_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VLN_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 extern "C" const char* vln_last_error(void) { return g_err; }

@@ -34,6 +34,28 @@ void vln_set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The decoder step is a chain of ~20 short kernels, each a grid-wide dependency of the next.  Kernels of
+// the chain are launched with programmaticStreamSerialization: a kernel may start as soon as every CTA of
+// its predecessor has executed pdl_trigger() (first statement of each kernel), runs its prologue
+// (barrier init, TMEM allocation, weight-tile TMA) concurrently with the predecessor's tail and blocks in
+// pdl_wait() before it touches anything a predecessor writes.  VLN_PDL=0 turns the attribute off.
+bool vln_pdl_enabled();
+template <typename K, typename... Args>
+inline cudaError_t vln_launch_chain(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vln_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 struct vln_ctx {
   const __nv_bfloat16* table;
   int n_vp;
@@ -93,6 +115,8 @@ __host__ __device__ __forceinline__ float philox_uniform(const Philox8& r, int j
 }
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // ---- warp helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_attn_kernel(
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   const int len = max(0, min(lengths[b], L));
   const uint32_t bytes = (uint32_t)len * (uint32_t)H * 4u;
 
@@ -171,9 +173,8 @@ int launch(const float* context, const float* tgt, const int32_t* lengths, float
     VLN_CHECK_CUDA(cudaFuncSetAttribute(ctx_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  ctx_attn_kernel<<<B, kThreads, smem, stream>>>(context, tgt, lengths, attn, weighted, d_weighted, d_attn_ext, d_tgt,
-                                                 d_context, dlogit_out, mode, L, H, ld_w, staged);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(ctx_attn_kernel, dim3(B), dim3(kThreads), smem, stream, context, tgt, lengths, attn,
+                                  weighted, d_weighted, d_attn_ext, d_tgt, d_context, dlogit_out, mode, L, H, ld_w, staged));
   return 0;
 }
 

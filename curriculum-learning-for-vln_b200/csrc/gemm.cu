@@ -140,6 +140,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   const int kb0 = (int)((long long)split * nkb / splits), kb1 = (int)((long long)(split + 1) * nkb / splits);
   const int n_iter = kb1 - kb0;
 
+  pdl_trigger();
   if (tid == 0) {
     tma_prefetch_desc(&tm_hi);
     tma_prefetch_desc(&tm_lo);
@@ -175,6 +176,9 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
           mbar_expect_tx(&full_w[s], 2 * C::kABytes + C::kXBytes);
           tma_load_2d(st, &tm_hi, &full_w[s], (kb0 + it) * kBK, tile * kTileN);
           tma_load_2d(st + C::kABytes, &tm_lo, &full_w[s], (kb0 + it) * kBK, tile * kTileN);
+          // the weight tiles were written before this chain of kernels started; the activations come from the
+          // predecessor: everything downstream (conversion, MMA, epilogue) is ordered after this wait
+          if (it == 0) pdl_wait();
           tma_load_2d(st + 2 * C::kABytes + 2 * C::kBBytes, &tm_x, &full_w[s], (kb0 + it) * kBK, 0);
         }
       }
@@ -403,13 +407,22 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg<MP>::kSmem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;        // the splits of one weight tile = one cluster
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = mode == 2 ? 1 : splits;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (mode != 2 && splits > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;      // the splits of one weight tile = one cluster
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = splits;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (accumulate && vln_pdl_enabled()) {                    // part of a kernel chain (no memset node in front of it)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (mode == 2 || splits == 1) ? 0 : 1;
+  cfg.numAttrs = na;
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP>, tm_hi, tm_lo, tm_x, M, N, K, bias, y, ldy, splits,
                                     accumulate, mode, variant().dbg));
   return 0;

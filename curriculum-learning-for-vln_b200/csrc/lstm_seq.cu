@@ -188,17 +188,24 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
     if (tid == 0) mbar_expect_tx(&sm.bar[nxt], kNB * H * 4);       // this step's h_t: kNB*H (hi, lo) pairs from the C CTAs
     // ---- gates[n][16w + r] = sum_k W[row][k] h[n][k] on the tensor cores (B operand: n = batch row) ----
     {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      // six independent accumulator chains (3 products x even/odd k-step): a single chain would serialise
+      // 3*KS dependent MMAs (~25 cycles each) on the step's critical path
+      float ac[6][4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ac[i][0] = ac[i][1] = ac[i][2] = ac[i][3] = 0.f;
       const uint16_t* hh = sm.h_hi[cur] + r0 * HP + c0;            // B fragment: n = lane/4, k pair = (lane%4)*2
       const uint16_t* hl = sm.h_lo[cur] + r0 * HP + c0;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(hh + ks * 16), bh1 = *reinterpret_cast<const uint32_t*>(hh + ks * 16 + 8);
         const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(hl + ks * 16), bl1 = *reinterpret_cast<const uint32_t*>(hl + ks * 16 + 8);
-        mma_bf16(acc, a_hi[ks], bh0, bh1);
-        mma_bf16(acc, a_hi[ks], bl0, bl1);
-        mma_bf16(acc, a_lo[ks], bh0, bh1);
+        mma_bf16(ac[(ks & 1) * 3 + 0], a_hi[ks], bh0, bh1);
+        mma_bf16(ac[(ks & 1) * 3 + 1], a_hi[ks], bl0, bl1);
+        mma_bf16(ac[(ks & 1) * 3 + 2], a_lo[ks], bh0, bh1);
       }
+      float acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = ((ac[0][j] + ac[3][j]) + (ac[1][j] + ac[4][j])) + (ac[2][j] + ac[5][j]);
       // D fragment: acc[0..1] = row r0, batch c0 / c0+1; acc[2..3] = row r0+8
       sm.g[c0 * kRows + 16 * warp + r0] = acc[0];
       sm.g[(c0 + 1) * kRows + 16 * warp + r0] = acc[1];
@@ -349,9 +356,11 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
     __syncthreads();
     // partial dh_prev[n][k] over my 128 rows on the tensor cores (B operand: n = batch row)
     {
-      float acc[MT][4];
+      float ac[MT][3][4];                                      // independent chains per product (x MT tiles)
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ac[mt][i][0] = ac[mt][i][1] = ac[mt][i][2] = ac[mt][i][3] = 0.f;
       const uint16_t* gh = sm.dg_hi + r0 * RP + c0;
       const uint16_t* gl = sm.dg_lo + r0 * RP + c0;
 #pragma unroll
@@ -360,11 +369,16 @@ lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B
         const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(gl + ks * 16), bl1 = *reinterpret_cast<const uint32_t*>(gl + ks * 16 + 8);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          mma_bf16(acc[mt], a_hi[mt][ks], bh0, bh1);
-          mma_bf16(acc[mt], a_hi[mt][ks], bl0, bl1);
-          mma_bf16(acc[mt], a_lo[mt][ks], bh0, bh1);
+          mma_bf16(ac[mt][0], a_hi[mt][ks], bh0, bh1);
+          mma_bf16(ac[mt][1], a_hi[mt][ks], bl0, bl1);
+          mma_bf16(ac[mt][2], a_lo[mt][ks], bh0, bh1);
         }
       }
+      float acc[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mt][j] = (ac[mt][0][j] + ac[mt][1][j]) + ac[mt][2][j];
       // reduce-scatter: column k belongs to CTA k/32, slot [my rank][n][k%32]
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {

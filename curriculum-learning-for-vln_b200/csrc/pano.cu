@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(512) cand_logits_fwd_kernel(
   __shared__ __align__(16) float ts[VLN_F];
   __shared__ float ta[4];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
+  pdl_trigger();
+  pdl_wait();
   const int g = vp[b];
   const int n = n_cand[g];
   for (int i = tid; i < VLN_F; i += 512) ts[i] = tgt[(size_t)b * VLN_F + i];
@@ -158,10 +160,14 @@ __global__ void __launch_bounds__(kThreads) cand_logits_bwd_kernel(
     const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ vp, const int32_t* __restrict__ view,
     const int32_t* __restrict__ cand_view, const float* __restrict__ cand_ang4, const int32_t* __restrict__ n_cand,
     const float* __restrict__ dlogits, float* __restrict__ d_tgt, float* __restrict__ d_bias, float drop_p,
-    const uint64_t* __restrict__ rng, uint64_t call_off, PolicyGrad pg) {
+    const uint64_t* __restrict__ rng, uint64_t call_off, PolicyGrad pg, int B_step, uint64_t off_stride) {
   __shared__ float dl[VLN_NSLOT];
   __shared__ int cvs[VLN_NSLOT];
+  // rows may stack several decoder steps ([n_steps, B_step]): row b of step s draws its mask from stream
+  // call_off + s*off_stride with the element indices of a single [B_step,16,2048] tensor
   const int b = blockIdx.x, t = threadIdx.x;
+  const int bl = b % B_step;
+  call_off += (uint64_t)(b / B_step) * off_stride;
   const int g = vp[b];
   const int n = n_cand[g];
   if (t < VLN_NSLOT) {
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) cand_logits_bwd_kernel(
   for (int j = 0; j < n; ++j) {
     uint4 x = __ldg(reinterpret_cast<const uint4*>(table + ((size_t)g * VLN_V + cvs[j]) * VLN_IMG) + t);
     if (drop_p > 0.f) {
-      const uint64_t e = (((uint64_t)b * VLN_NSLOT + j) * VLN_IMG + (uint64_t)t * 8) >> 3;
+      const uint64_t e = (((uint64_t)bl * VLN_NSLOT + j) * VLN_IMG + (uint64_t)t * 8) >> 3;
       x = apply_keep(x, philox8(seed, offset, e), thr);
     }
     const float d = dl[j];
@@ -245,9 +251,8 @@ extern "C" int vln_cand_logits_fwd(const vln_ctx* ctx, const int32_t* vp, const 
                                    const float* tgt, const float* bias, float* logits, int B, float drop_p,
                                    const uint64_t* rng, uint64_t call_off, void* stream) {
   VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && tgt && logits && B > 0, "bad arguments");
-  cand_logits_fwd_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(ctx->table, vp, view, cand_view, cand_ang4, n_cand, tgt,
-                                                             bias, logits, drop_p, rng, call_off);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(cand_logits_fwd_kernel, dim3(B), dim3(512), 0, (cudaStream_t)stream, ctx->table, vp, view,
+                                  cand_view, cand_ang4, n_cand, tgt, bias, logits, drop_p, rng, call_off));
   return 0;
 }
 
@@ -258,7 +263,7 @@ extern "C" int vln_cand_logits_bwd(const vln_ctx* ctx, const int32_t* vp, const 
   VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && dlogits && d_tgt && B > 0, "bad arguments");
   cand_logits_bwd_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(ctx->table, vp, view, cand_view, cand_ang4, n_cand,
                                                                   dlogits, d_tgt, d_bias, drop_p, rng, call_off,
-                                                                  PolicyGrad{});
+                                                                  PolicyGrad{}, B, 0);
   VLN_LAUNCH_OK();
   return 0;
 }
@@ -267,13 +272,14 @@ extern "C" int vln_cand_logits_bwd_policy(const vln_ctx* ctx, const int32_t* vp,
                                           const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
                                           const float* probs, const int32_t* target, const int32_t* action,
                                           const float* entropy, const float* g_ce, const float* g_logp,
-                                          const float* g_ent, float* d_tgt, int B, float drop_p, const uint64_t* rng,
-                                          uint64_t call_off, void* stream) {
-  VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && probs && d_tgt && B > 0, "bad arguments");
+                                          const float* g_ent, float* d_tgt, int B, int n_steps, float drop_p,
+                                          const uint64_t* rng, uint64_t call_off, uint64_t off_stride, void* stream) {
+  VLN_REQUIRE(ctx && vp && view && cand_view && cand_ang4 && n_cand && probs && d_tgt && B > 0 && n_steps > 0,
+              "bad arguments");
   VLN_REQUIRE((!g_ce || target) && (!g_logp || action) && (!g_ent || entropy), "missing saved action-head state");
-  cand_logits_bwd_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(
+  cand_logits_bwd_kernel<<<B * n_steps, kThreads, 0, (cudaStream_t)stream>>>(
       ctx->table, vp, view, cand_view, cand_ang4, n_cand, nullptr, d_tgt, nullptr, drop_p, rng, call_off,
-      PolicyGrad{probs, target, action, entropy, g_ce, g_logp, g_ent});
+      PolicyGrad{probs, target, action, entropy, g_ce, g_logp, g_ent}, B, off_stride);
   VLN_LAUNCH_OK();
   return 0;
 }

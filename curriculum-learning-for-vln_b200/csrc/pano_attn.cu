@@ -77,11 +77,13 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
 
   int it = 0;
   PSTAMP(0);
+  pdl_trigger();
   if (tid == 0) {
     for (int r = 0; r < VLN_V; ++r) mbar_init(&sm.full[r], 1);
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();                                            // viewpoints, query and mask bits come from predecessors
   PSTAMP(1);
 
   // request row r of episode `ep` (and its keep-bits) into its slot
@@ -321,10 +323,9 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
     configured = true;
   }
   const int grid = B < ctx->num_sms ? B : ctx->num_sms;
-  pano_attn_kernel<<<grid, kThreads, sizeof(Smem), (cudaStream_t)stream>>>(ctx->table, vp, view, loc4, vec, attn_io, out, B,
-                                                                           mode, drop_p, rng, call_off, ld_vec, ld_out,
-                                                                           mask_bits, getenv("VLN_PANO_STAMPS") != nullptr);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(pano_attn_kernel, dim3(grid), dim3(kThreads), sizeof(Smem), (cudaStream_t)stream,
+                                  ctx->table, vp, view, loc4, vec, attn_io, out, B, mode, drop_p, rng, call_off, ld_vec,
+                                  ld_out, mask_bits, (int)(getenv("VLN_PANO_STAMPS") != nullptr)));
   return 0;
 }
 

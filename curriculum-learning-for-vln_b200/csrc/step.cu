@@ -58,6 +58,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __global__ void state_fwd_kernel(const float* __restrict__ src, int apply_tanh, float* __restrict__ xh_next, int ld_xh,
                                  float* __restrict__ hq_next, float* __restrict__ hc_cur, int B, int H, float p,
                                  const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;       // 8-element block index
   const int hb = H / 8;
   if (i >= B * hb) return;
@@ -88,6 +90,8 @@ __global__ void state_bwd_kernel(const float* __restrict__ d_hc, const float* __
                                  const float* __restrict__ d_hq_next, const float* __restrict__ htilde, int ld_h,
                                  int apply_tanh, float* __restrict__ d_src, int B, int H, float p,
                                  const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int hb = H / 8;
   if (i >= B * hb) return;
@@ -121,19 +125,11 @@ __global__ void state_bwd_kernel(const float* __restrict__ d_hc, const float* __
 // ---- action embedding of the agent's pose: drop(tanh(W_a angle128(view) + b_a)) ------------------
 // angle128 = pose4[view] each value repeated x32 (misc.py:286-293), so the 128-wide dot product is
 // 4 values against 4 group sums of the weight row.
-__device__ __forceinline__ float act_embed_one(const float* __restrict__ w_row, const float* __restrict__ p4, float bias) {
-  float acc = bias;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 32; i += 4) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(w_row + 32 * k + i));
-      s += (w.x + w.y) + (w.z + w.w);
-    }
-    acc = fmaf(p4[k], s, acc);
-  }
-  return tanhf(acc);
+// `wg` [E,4] holds the four group sums of every weight row (wg[j][k] = sum_i W[j][32k+i], computed once
+// per rollout on the host side of the C-ABI)
+__device__ __forceinline__ float act_embed_one(const float* __restrict__ wg_row, const float* __restrict__ p4, float bias) {
+  const float4 w = __ldg(reinterpret_cast<const float4*>(wg_row)), p = __ldg(reinterpret_cast<const float4*>(p4));
+  return tanhf(fmaf(p.w, w.w, fmaf(p.z, w.z, fmaf(p.y, w.y, fmaf(p.x, w.x, bias)))));
 }
 
 __global__ void act_fwd_kernel(const int32_t* __restrict__ view, const float* __restrict__ pose4,
@@ -143,7 +139,7 @@ __global__ void act_fwd_kernel(const int32_t* __restrict__ view, const float* __
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * E) return;
   const int b = i / E, j = i - b * E;
-  const float a = act_embed_one(w + (size_t)j * VLN_ANG, pose4 + (size_t)view[b] * 4, bias[j]);
+  const float a = act_embed_one(w + (size_t)j * 4, pose4 + (size_t)view[b] * 4, bias[j]);
   act[i] = a;
   float k[8];
   keep8(make_drop(p, rng, call_off), (uint64_t)(i >> 3), k);
@@ -193,6 +189,8 @@ __global__ void policy_env_act_kernel(const float* __restrict__ logits, const in
                                       const float* __restrict__ pose4, const float* __restrict__ w_act,
                                       const float* __restrict__ b_act, float* __restrict__ act, float* __restrict__ xh,
                                       int ld_xh, int E, float p_act, uint64_t off_act, int B) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   // ---- action head (policy_fwd_kernel) ----
@@ -261,7 +259,7 @@ __global__ void policy_env_act_kernel(const float* __restrict__ logits, const in
   vw = __shfl_sync(0xffffffffu, vw, 0);
   const Drop dr = make_drop(p_act, rng, off_act);
   for (int j = lane; j < E; j += 32) {
-    const float a = act_embed_one(w_act + (size_t)j * VLN_ANG, pose4 + (size_t)vw * 4, b_act[j]);
+    const float a = act_embed_one(w_act + (size_t)j * 4, pose4 + (size_t)vw * 4, b_act[j]);
     const int i = b * E + j;
     act[i] = a;
     float k[8];
@@ -275,6 +273,8 @@ __global__ void lstm_pw_drop_fwd_kernel(const float* __restrict__ gates, const f
                                         float* __restrict__ h1, float* __restrict__ c1, float* __restrict__ acts,
                                         float* __restrict__ h1_drop, int ld_drop, int B, int H, float p,
                                         const uint64_t* __restrict__ rng, uint64_t call_off) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int hb = H / 8;
   if (i >= B * hb) return;
@@ -309,6 +309,8 @@ __global__ void lstm_pw_drop_bwd_kernel(const float* __restrict__ acts, const fl
                                         const float* __restrict__ d_h1_extra, const float* __restrict__ d_c1,
                                         float* __restrict__ d_gates, float* __restrict__ d_c0, int B, int H, float p,
                                         const uint64_t* __restrict__ rng, uint64_t call_off) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int hb = H / 8;
   if (i >= B * hb) return;
@@ -363,9 +365,8 @@ extern "C" int vln_envdrop_state_fwd(const float* src, int apply_tanh, float* xh
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
   VLN_REQUIRE(!xh_next || ld_xh % 4 == 0, "xh rows must be 16-byte aligned");
   const int n = B * (H / 8);
-  state_fwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(src, apply_tanh, xh_next, ld_xh, hq_next, hc_cur, B, H, p, rng,
-                                                        off_q, off_c);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(state_fwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, src, apply_tanh, xh_next,
+                                  ld_xh, hq_next, hc_cur, B, H, p, rng, off_q, off_c));
   return 0;
 }
 
@@ -376,9 +377,8 @@ extern "C" int vln_envdrop_state_bwd(const float* d_hc, const float* d_xh_next, 
   VLN_REQUIRE(!apply_tanh || htilde, "tanh backward needs the saved h~");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
   const int n = B * (H / 8);
-  state_bwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(d_hc, d_xh_next, ld_dxh, d_hq_next, htilde, ld_h, apply_tanh,
-                                                        d_src, B, H, p, rng, off_q, off_c);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(state_bwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, d_hc, d_xh_next, ld_dxh,
+                                  d_hq_next, htilde, ld_h, apply_tanh, d_src, B, H, p, rng, off_q, off_c));
   return 0;
 }
 
@@ -420,12 +420,10 @@ extern "C" int vln_policy_env_act_fwd(const float* logits, const int32_t* target
   VLN_REQUIRE(feedback >= 0 && feedback <= 2 && (feedback != 0 || target) && (feedback != 2 || rng), "bad feedback mode");
   VLN_REQUIRE(!xh || (pose4 && w_act && b_act && act && E > 0 && (p_act == 0.f || rng)), "action embedding needs its weights");
   EnvTables env{cand_vp, cand_view, n_cand, next_hop, dist_tbl, sq_off, vp_local};
-  policy_env_act_kernel<<<(B + 3) / 4, 128, 0, STREAM>>>(logits, target, feedback, rng, off_sample, ce, action, logp,
-                                                         entropy, probs, vp_in, view_in, ended_in, dist_in, goal, env,
-                                                         vp_out, view_out, ended_out, dist_out, teacher_out, reward, mask,
-                                                         n_active, pose4, w_act, b_act, act, xh, ld_xh, E, p_act, off_act,
-                                                         B);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(policy_env_act_kernel, dim3((B + 3) / 4), dim3(128), 0, STREAM, logits, target, feedback,
+                                  rng, off_sample, ce, action, logp, entropy, probs, vp_in, view_in, ended_in, dist_in,
+                                  goal, env, vp_out, view_out, ended_out, dist_out, teacher_out, reward, mask, n_active,
+                                  pose4, w_act, b_act, act, xh, ld_xh, E, p_act, off_act, B));
   return 0;
 }
 
@@ -435,9 +433,8 @@ extern "C" int vln_lstm_pointwise_drop_fwd(const float* gates, const float* c0, 
   VLN_REQUIRE(gates && c0 && h1 && c1 && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng || !h1_drop), "dropout needs 0 <= p < 1 and an rng state");
   const int n = B * (H / 8);
-  lstm_pw_drop_fwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(gates, c0, h1, c1, acts, h1_drop, ld_drop, B, H, p, rng,
-                                                               call_off);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(lstm_pw_drop_fwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, gates, c0, h1, c1,
+                                  acts, h1_drop, ld_drop, B, H, p, rng, call_off));
   return 0;
 }
 
@@ -448,8 +445,7 @@ extern "C" int vln_lstm_pointwise_drop_bwd(const float* acts, const float* c0, c
   VLN_REQUIRE(acts && c0 && c1 && d_gates && d_c0 && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng || !d_h1_drop), "dropout needs 0 <= p < 1 and an rng state");
   const int n = B * (H / 8);
-  lstm_pw_drop_bwd_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(acts, c0, c1, d_h1_drop, ld_drop, d_h1_extra, d_c1,
-                                                               d_gates, d_c0, B, H, p, rng, call_off);
-  VLN_LAUNCH_OK();
+  VLN_CHECK_CUDA(vln_launch_chain(lstm_pw_drop_bwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, acts, c0, c1,
+                                  d_h1_drop, ld_drop, d_h1_extra, d_c1, d_gates, d_c0, B, H, p, rng, call_off));
   return 0;
 }

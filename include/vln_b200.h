@@ -159,7 +159,9 @@ int vln_lstm_pointwise_drop_bwd(const float* acts, const float* c0, const float*
  *   hc_cur [B,H] = dropout(h~; p, off_c) (this step's h_tilde_drop, policy.py:243).  Outputs nullable.
  * state_bwd: d_src = (dropout_c'(d_hc) + d_xh_next + dropout_q'(d_hq_next)) * (apply_tanh ? 1-h~^2 : 1);
  *   each gradient input nullable; htilde rows ld_h apart.
- * act_fwd: act [B,E] = tanh(W_a angle128(pose4[view]) + b_a) (policy.py:222, envdrop.py:76-78), and
+ * act_fwd: act [B,E] = tanh(W_a angle128(pose4[view]) + b_a) (policy.py:222, envdrop.py:76-78) — `w` is
+ *   W_a reduced to its four group sums [E,4] (w[j][k] = sum_i W_a[j][32k+i]: the angle feature repeats each of
+ *   its 4 values 32x, misc.py:286-293) — and
  *   xh[b, 0:E) = dropout(act; p, call_off).   act_bwd: d_actpre = dropout'(d_xh[:, 0:E)) * (1 - act^2). */
 int vln_envdrop_state_fwd(const float* src, int apply_tanh, float* xh_next, int ld_xh, float* hq_next,
                           float* hc_cur, int B, int H, float p, const uint64_t* rng, uint64_t off_q,
@@ -189,13 +191,15 @@ int vln_policy_env_act_fwd(const float* logits, const int32_t* target, int feedb
                            const float* pose4, const float* w_act, const float* b_act, float* act, float* xh,
                            int ld_xh, int E, float p_act, uint64_t off_act, int B, void* stream);
 /* vln_policy_bwd folded into vln_cand_logits_bwd: dlogits are computed from the action head's saved
- * probs / target / action / entropy and the incoming g_ce / g_logp / g_ent (each nullable). */
+ * probs / target / action / entropy and the incoming g_ce / g_logp / g_ent (each nullable).  Covers
+ * n_steps decoder steps in one launch (none of its inputs depends on the backward recursion): every array
+ * is [n_steps, B, ...]; step s regenerates its candidate mask from stream call_off + s*off_stride. */
 int vln_cand_logits_bwd_policy(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
                                const int32_t* cand_view, const float* cand_ang4, const int32_t* n_cand,
                                const float* probs, const int32_t* target, const int32_t* action,
                                const float* entropy, const float* g_ce, const float* g_logp,
-                               const float* g_ent, float* d_tgt, int B, float drop_p, const uint64_t* rng,
-                               uint64_t call_off, void* stream);
+                               const float* g_ent, float* d_tgt, int B, int n_steps, float drop_p,
+                               const uint64_t* rng, uint64_t call_off, uint64_t off_stride, void* stream);
 
 /* Skinny linear layer on tcgen05 tensor cores (nn.Linear / nn.LSTMCell gate GEMMs of policy.py and
  * units.py at batch sizes <= 128):  y[m,n] (+)= sum_k x[m,k] w[n,k] (+ bias[n]),  m < M <= 128.
