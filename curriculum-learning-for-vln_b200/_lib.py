@@ -68,6 +68,7 @@ _SIGS = {
     "vln_lstm_pointwise_fwd": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_pointwise_bwd": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_linear_bf16x3": ([_p, _p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _i, _p], _i),
+    "vln_linear_bf16x3_pair": ([_p] * 8 + [_i] * 5 + [_p], _i),
     "vln_split_bf16": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_seq_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "vln_lstm_seq_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),

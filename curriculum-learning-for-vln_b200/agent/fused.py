@@ -164,8 +164,9 @@ class _Rollout(torch.autograd.Function):
             _call("vln_envdrop_act_fwd", _ptr(st.view[t]), _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t]),
                   _ptr(XH[t]), KX, B, H_ACT, p, rp, offs[t]["act"], _stream())
 
-        def visual_and_lstm(t, need_drop):
-            _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, B, None, _p(Q[t]), F)
+        def visual_and_lstm(t, need_drop, q_done=False):
+            if not q_done:
+                _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, B, None, _p(Q[t]), F)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4), _ptr(Q[t]), F,
                   _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, B, 0, pf, rp, offs[t]["img"],
                   _ptr(MB[t]) if MB is not None else None, split, _stream())
@@ -184,8 +185,9 @@ class _Rollout(torch.autograd.Function):
               offs[0]["hprev"], 0, _stream())
         act_embed(0)
         n = 0
+        paired = B <= 128
         for t in range(T):
-            visual_and_lstm(t, True)
+            visual_and_lstm(t, True, q_done=paired and t > 0)
             _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, B, None, _p(TQ[t]), H)
             _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, B, L,
                   H, _stream())
@@ -194,7 +196,11 @@ class _Rollout(torch.autograd.Function):
             _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
                   _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), B, H, p, rp,
                   offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _stream())
-            _gemm(s_cand.hi, s_cand.lo, F, H, _p(HC[t]), H, B, None, _p(TGT[t]), F)
+            if paired and more:      # tgt_t = W_cand hc_t and q_{t+1} = W_vin hq_{t+1} both only wait for h~_t: one launch
+                _call("vln_linear_bf16x3_pair", _ptr(s_cand.hi), _ptr(s_cand.lo), _ptr(HC[t]), _ptr(TGT[t]), _ptr(s_vin.hi),
+                      _ptr(s_vin.lo), _ptr(HQ[t + 1]), _ptr(Q[t + 1]), F, H, H, B, F, _stream())
+            else:
+                _gemm(s_cand.hi, s_cand.lo, F, H, _p(HC[t]), H, B, None, _p(TGT[t]), F)
             _call("vln_cand_logits_fwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
                   _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(TGT[t]), None, _ptr(LOGIT[t]), B, pf, rp,
                   offs[t]["cand"], _stream())
@@ -212,7 +218,7 @@ class _Rollout(torch.autograd.Function):
             if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
                 break
         if bootstrap:                                           # envdrop.py:225-237: h_1 of the state after the last step
-            visual_and_lstm(n, False)
+            visual_and_lstm(n, False, q_done=paired and n > 0)
         st.teacher = TEACH[n]
 
         fctx.fd, fctx.st, fctx.rp, fctx.MB = fd, st, rp, MB

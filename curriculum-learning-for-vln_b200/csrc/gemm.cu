@@ -46,7 +46,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define STAMP(i)                                                                    \
   do {                                                                              \
-    if (dbg && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[(slot % 64) * 12 + (i)] = (unsigned long long)clock64(); \
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_stamps[(slot % 64) * 12 + (i)] = (unsigned long long)clock64(); \
   } while (0)
 
 namespace {
@@ -110,9 +110,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {   // round-to-
 
 template <int MP>
 __global__ void __launch_bounds__(kThreads, 1)
-linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                     const __grid_constant__ CUtensorMap tm_x, int M, int N, int K, const float* __restrict__ bias,
-                     float* __restrict__ y, int ldy, int splits, int accumulate, int mode, int dbg) {
+linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_constant__ CUtensorMap tm_lo0,
+                     const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_hi1,
+                     const __grid_constant__ CUtensorMap tm_lo1, const __grid_constant__ CUtensorMap tm_x1, int M, int N,
+                     int K, const float* __restrict__ bias, float* __restrict__ y0, float* __restrict__ y1, int ldy,
+                     int splits, int accumulate, int mode, int dbg) {
+  // blockIdx.z selects one of two independent problems of identical shape (e.g. the candidate projection of
+  // step t and the visual-attention query of step t+1, which both only wait for h~_t)
+  const CUtensorMap& tm_hi = blockIdx.z == 0 ? tm_hi0 : tm_hi1;
+  const CUtensorMap& tm_lo = blockIdx.z == 0 ? tm_lo0 : tm_lo1;
+  const CUtensorMap& tm_x = blockIdx.z == 0 ? tm_x0 : tm_x1;
+  float* __restrict__ y = blockIdx.z == 0 ? y0 : y1;
   using C = Cfg<MP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
@@ -383,9 +391,16 @@ const Variant& variant() {
   return v;
 }
 
+struct Second {                                            // second problem of a paired launch (same N, K, M, ld's)
+  const void* w_hi = nullptr;
+  const void* w_lo = nullptr;
+  const float* x = nullptr;
+  float* y = nullptr;
+};
+
 template <int MP>
 int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
-                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream) {
+                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec = Second()) {
   CUtensorMap tm_hi, tm_lo;
   int rc = vln_make_tmap_2d(&tm_hi, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
   if (rc) return rc;
@@ -394,6 +409,12 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   CUtensorMap tm_x;                                         // rows >= M are out of bounds: the TMA unit zero-fills them
   rc = vln_make_tmap_2d_f32(&tm_x, x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, kBK, MP);
   if (rc) return rc;
+  CUtensorMap tm_hi1 = tm_hi, tm_lo1 = tm_lo, tm_x1 = tm_x;
+  if (sec.y) {
+    if ((rc = vln_make_tmap_2d(&tm_hi1, sec.w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1))) return rc;
+    if ((rc = vln_make_tmap_2d(&tm_lo1, sec.w_lo, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1))) return rc;
+    if ((rc = vln_make_tmap_2d_f32(&tm_x1, sec.x, (uint64_t)M, (uint64_t)K, (uint64_t)ldx, kBK, MP))) return rc;
+  }
   static bool configured = false;
   if (!configured) {
     VLN_CHECK_CUDA(cudaFuncSetAttribute(linear_bf16x3_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MP>::kSmem));
@@ -403,7 +424,7 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   const int mode = variant().mode;
   if (mode == 2 && !accumulate) VLN_CHECK_CUDA(cudaMemset2DAsync(y, (size_t)ldy * 4, 0, (size_t)N * 4, M, stream));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles, splits);
+  cfg.gridDim = dim3(tiles, splits, sec.y ? 2 : 1);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg<MP>::kSmem;
   cfg.stream = stream;
@@ -423,7 +444,8 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP>, tm_hi, tm_lo, tm_x, M, N, K, bias, y, ldy, splits,
+  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP>, tm_hi, tm_lo, tm_x, tm_hi1, tm_lo1, tm_x1, M, N, K, bias, y,
+                                    sec.y ? sec.y : y, ldy, splits,
                                     accumulate, mode, variant().dbg));
   return 0;
 }
@@ -448,6 +470,26 @@ extern "C" int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int 
   if (variant().mode == 2) s = splits;
   if (M <= 64) return launch_linear<64>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
   return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
+}
+
+// Two independent products of identical shape in one launch: y0 += x0 W0^T, y1 += x1 W1^T (both accumulate).
+extern "C" int vln_linear_bf16x3_pair(const void* w0_hi, const void* w0_lo, const float* x0, float* y0, const void* w1_hi,
+                                      const void* w1_lo, const float* x1, float* y1, int N, int K, int ldx, int M, int ldy,
+                                      void* stream) {
+  VLN_REQUIRE(w0_hi && w0_lo && x0 && y0 && w1_hi && w1_lo && x1 && y1 && N > 0 && M > 0, "bad arguments");
+  VLN_REQUIRE(K > 0 && K % kBK == 0 && M <= 128 && N % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "bad shape");
+  VLN_REQUIRE(((uintptr_t)x0 & 15) == 0 && ((uintptr_t)x1 & 15) == 0 && ((uintptr_t)y0 & 15) == 0 && ((uintptr_t)y1 & 15) == 0,
+              "operands must be 16-byte aligned");
+  const int nkb = K / kBK;
+  const int tiles = (N + kTileN - 1) / kTileN;
+  int splits = 148 / (2 * tiles);                              // both problems together fill one wave
+  if (splits < 1) splits = 1;
+  if (splits > nkb) splits = nkb;
+  VLN_REQUIRE(variant().mode == 2, "paired launches need the vector-reduction split-K merge");
+  Second sec;
+  sec.w_hi = w1_hi; sec.w_lo = w1_lo; sec.x = x1; sec.y = y1;
+  if (M <= 64) return launch_linear<64>(w0_hi, w0_lo, N, K, x0, ldx, M, nullptr, y0, ldy, splits, 1, (cudaStream_t)stream, sec);
+  return launch_linear<128>(w0_hi, w0_lo, N, K, x0, ldx, M, nullptr, y0, ldy, splits, 1, (cudaStream_t)stream, sec);
 }
 
 extern "C" int vln_debug_gemm_stamps(unsigned long long* out_host /*[64*12]*/, unsigned int* n) {

@@ -19,7 +19,20 @@
 // dgates (= d xproj) goes to global memory; dW_hh / dW_ih / dx are single large GEMMs outside.
 //
 // Roofline class: latency (80 serial steps); per step and CTA 3 x 16 x H/16 MMAs (m16n8k16).
+#include <cstdlib>
+
 #include "common.cuh"
+
+// optional phase stamps of one timestep (VLN_LSTM_STAMPS=1): CTA (0,0), thread 0, step 10 of the forward kernel
+__device__ unsigned long long g_lstm_stamps[12];
+#define LSTAMP0(i)                                                                                      \
+  do {                                                                                                  \
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) g_lstm_stamps[i] = (unsigned long long)clock64(); \
+  } while (0)
+#define LSTAMP(i)                                                                                       \
+  do {                                                                                                  \
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && s == 10) g_lstm_stamps[i] = (unsigned long long)clock64(); \
+  } while (0)
 
 namespace {
 
@@ -46,12 +59,14 @@ __device__ __forceinline__ void dsmem_st_async_f32(float* local_ptr, uint64_t* l
                "r"(__float_as_uint(v)), "r"(rm)
                : "memory");
 }
+// (default .acquire.cta semantics: the data arrives in THIS CTA's shared memory through the async proxy and is
+// published by the barrier's transaction count, as with TMA; a cluster-scope acquire would add an L1 invalidate)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -117,7 +132,7 @@ struct SmemF {
 // out (pre-zeroed), acts [B,L,4H] (activated i,f,g,o), cs [B,L,H] (cell state), h_last/c_last.
 template <int H>
 __global__ void __launch_bounds__(kThreads, 1)
-lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last) {
+lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last, int dbg) {
   constexpr int C = H / kHS;       // cluster size
   constexpr int HP = H + 8;        // padded bf16 row of the h buffers
   constexpr int KS = H / 16;       // k-steps of 16
@@ -135,6 +150,7 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
   const int group = blockIdx.x / C;
   const int b0 = group * kNB;
 
+  LSTAMP0(6);
   // resident weight fragments: local row lr = gate*32 + unit  <->  global row gate*H + rank*32 + unit;
   // warp w owns local rows 16w..16w+15 (A operand, row-major 16x16 tiles: a0/a2 row r0, a1/a3 row r0+8)
   const int r0 = lane >> 2, c0 = (lane & 3) * 2;
@@ -183,8 +199,10 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
   int t = reverse ? gmax - 1 : 0;
   const int dt = reverse ? -1 : 1;
   load_x(t);
+  LSTAMP0(7);
   for (int s = 0; s < gmax; ++s, t += dt) {
     const int cur = s & 1, nxt = cur ^ 1;
+    LSTAMP(0);
     if (tid == 0) mbar_expect_tx(&sm.bar[nxt], kNB * H * 4);       // this step's h_t: kNB*H (hi, lo) pairs from the C CTAs
     // ---- gates[n][16w + r] = sum_k W[row][k] h[n][k] on the tensor cores (B operand: n = batch row) ----
     {
@@ -212,7 +230,9 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
       sm.g[c0 * kRows + 16 * warp + r0 + 8] = acc[2];
       sm.g[(c0 + 1) * kRows + 16 * warp + r0 + 8] = acc[3];
     }
+    LSTAMP(1);
     __syncthreads();
+    LSTAMP(2);
     // ---- pointwise for (pb, pu) ----
     const float x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
     load_x(t + dt);                                  // prefetch next step's input projection
@@ -231,6 +251,7 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
       float* ap = acts + o * (4 * H) + ug;
       ap[0] = ig; ap[H] = fg; ap[2 * H] = gg; ap[3 * H] = og;
     }
+    LSTAMP(3);
     // ---- all-gather h_t: my unit's value into every CTA's next buffer ----
     // (as bf16 hi/lo: even units send the packed hi pair (pu, pu+1), odd units the packed lo pair (pu-1, pu))
     {
@@ -245,13 +266,17 @@ lstm_seq_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B
     // Every CTA (this one included) has delivered its slice once the byte count is reached.  Buffer reuse is
     // safe without a further barrier: a peer writes h[cur] again only in step s+1, which it enters after it
     // received THIS CTA's slice of step s — sent after the matvec above finished reading h[cur].
+    LSTAMP(4);
     mbar_wait_cluster(&sm.bar[nxt], (uint32_t)(s >> 1) & 1u);
+    LSTAMP(5);
   }
+  LSTAMP0(8);
   if (valid) {
     d.h_last[(size_t)b * ld_last + ug] = h_reg;
     d.c_last[(size_t)b * ld_last + ug] = c_reg;
   }
   cluster_sync_all();               // no CTA exits while a peer could still address its shared memory
+  LSTAMP0(9);
 }
 
 // Backward through time.  d_out [B,L,H] (grad of `out`, may be NULL), d_hlast/d_clast [B,H] (may be NULL).
@@ -266,7 +291,7 @@ struct SmemB {
 
 template <int H>
 __global__ void __launch_bounds__(kThreads, 1)
-lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last) {
+lstm_seq_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last, int dbg) {
   constexpr int C = H / kHS;
   constexpr int RP = kRows + 8;    // padded bf16 row of the dgates buffers
   constexpr int MT = H / 128;      // 16-column m-tiles of dh per warp (8 warps cover H columns)
@@ -420,7 +445,7 @@ int launch_cluster(K kernel, size_t smem, int C, int n_dir, int B, cudaStream_t 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, d0, d1, lengths, B, L, ld_out, ld_last));
+  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, d0, d1, lengths, B, L, ld_out, ld_last, (int)(getenv("VLN_LSTM_STAMPS") != nullptr)));
   return 0;
 }
 
@@ -451,6 +476,12 @@ int launch_bwd(DirB d0, DirB d1, int n_dir, const int32_t* lengths, int B, int L
 }
 
 }  // namespace
+
+extern "C" int vln_debug_lstm_stamps(unsigned long long* out_host /*[8]*/) {
+  VLN_CHECK_CUDA(cudaDeviceSynchronize());
+  VLN_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_lstm_stamps, sizeof(unsigned long long) * 12));
+  return 0;
+}
 
 // n_dir = 1 or 2.  Direction k uses xproj[k], w_hh[k], acts[k], cs[k] and writes columns [k*H, (k+1)*H) of
 // out [B,L,n_dir*H] / h_last / c_last [B,n_dir*H]; direction 1 runs reversed in time.

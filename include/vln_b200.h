@@ -211,6 +211,12 @@ int vln_cand_logits_bwd_policy(const vln_ctx* ctx, const int32_t* vp, const int3
  * For input gradients pass the transposed split (w^T as a [K,N] weight) and x = dY. */
 int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
                       const float* bias, float* y, int ldy, int accumulate, int splits, void* stream);
+/* Two independent products of identical shape in ONE launch (y0 += x0 W0^T, y1 += x1 W1^T; both
+ * accumulate): the candidate projection of step t (policy.py:199-206) and the visual-attention query
+ * of step t+1 (units.py:107) both only wait for h~_t. */
+int vln_linear_bf16x3_pair(const void* w0_hi, const void* w0_lo, const float* x0, float* y0, const void* w1_hi,
+                           const void* w1_lo, const float* x1, float* y1, int N, int K, int ldx, int M, int ldy,
+                           void* stream);
 /* fp32 w [N,K] -> bf16 hi, lo [N,K] and, if hi_t/lo_t are given, the transposed pair [K,N]. */
 int vln_split_bf16(const float* w, void* hi, void* lo, void* hi_t, void* lo_t, int N, int K, void* stream);
 

@@ -442,3 +442,187 @@ def test_wgrad_tf32_tolerance(setup):
     cos = float((got * ref).sum() / (got.norm() * ref.norm()))
     assert cos > 1 - 1e-6
     assert relerr(ops.wgrad(dy, x).double(), ref) < 2e-5
+
+
+# ---- fused decoder-step kernels (agent/fused.py) against their unfused counterparts ------------------
+def test_feature_mask_bits_equal_dropout_mask(setup):
+    """Packed keep-bits of several steps == vln_dropout_mask of each step's dense [B*36, 2048] tensor
+    (bit-exact), in the byte order the panorama kernel consumes: byte (c%32)*8 + c//32 of a row = block c."""
+    _, _, ops, dev = setup
+    B, S, p = 5, 3, 0.3
+    rng = ops.Rng(11, dev)
+    bits = torch.empty((S, B * 36, 256), dtype=torch.uint8, device=dev)
+    ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, S, p, rng.ptr, 4, 7, ops._stream())
+    c = torch.arange(256, device=dev)
+    pos = (c % 32) * 8 + c // 32
+    w = (1 << torch.arange(8, device=dev)).to(torch.int32)
+    for s in range(S):
+        keep = ops.dropout_mask((B * 36, 256, 8), p, rng, 4 + 7 * s).to(torch.int32)      # [rows, block, lane]
+        want = (keep * w).sum(2).to(torch.uint8)                                          # byte of block c
+        assert torch.equal(bits[s][:, pos], want)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_pano_attn_mask_bits_equal_inline_philox(setup, mode):
+    """The kernel fed with pre-generated keep-bits computes exactly what it computes with inline Philox."""
+    world, store, ops, dev = setup
+    B, p = 21, 0.3
+    vp, view = rand_state(world, B, dev, 5)
+    rng = ops.Rng(3, dev)
+    vec = torch.randn(B, 2176, device=dev) * 0.05
+    attn = torch.softmax(torch.randn(B, 36, device=dev), 1)
+    bits = torch.empty((B * 36, 256), dtype=torch.uint8, device=dev)
+    ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, 1, p, rng.ptr, 9, 0, ops._stream())
+    outs = []
+    for mb in (None, bits):
+        a = attn.clone()
+        out = torch.empty(B, 2176, device=dev)
+        ops._call("vln_pano_attn_ld", store.handle, ops._ptr(vp), ops._ptr(view), ops._ptr(store.loc4), ops._ptr(vec), 2176,
+                  ops._ptr(a), None, 2176, ops._ptr(out), 2176, B, mode, p, rng.ptr, 9, ops._ptr(mb), 1, ops._stream())
+        outs.append((out, a))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_policy_env_act_equals_separate_kernels(setup):
+    """vln_policy_env_act_fwd == vln_policy_fwd + vln_env_step + vln_envdrop_act_fwd (bit-exact state, actions,
+    rewards; identical floating-point results)."""
+    world, store, ops, dev = setup
+    B, E, p = 37, 64, 0.5
+    torch.manual_seed(2)
+    vp, view = rand_state(world, B, dev, 9)
+    goal = torch.randint(0, world.n_vp, (B,), dtype=torch.int32).to(dev)
+    # goals must lie in the same scan as the viewpoint for the distance tables: reuse the viewpoint's own scan
+    goal = vp.clone()
+    ended = (torch.rand(B, device=dev) < 0.2).to(torch.uint8)
+    teacher, dist = ops.env_observe(store, vp, ended, goal)
+    n = store.n_cand[vp.long()]
+    logits = torch.randn(B, 16, device=dev)
+    logits[torch.arange(16, device=dev).unsqueeze(0) > n.unsqueeze(1)] = float("-inf")
+    rng = ops.Rng(5, dev)
+    w_act, b_act = torch.randn(E, 128, device=dev) * 0.1, torch.randn(E, device=dev) * 0.1
+    wg = w_act.view(E, 4, 32).sum(2).contiguous()
+    for fb in (0, 1, 2):
+        ce, logp, ent, action = ops.policy_head(logits, teacher, fb, rng, 3)
+        vp2, view2, ended2, dist2, teacher2, reward, mask = ops.env_step(store, vp, view, ended, dist, goal, action)
+        act = torch.empty(B, E, device=dev)
+        xh = torch.zeros(B, 96, device=dev)
+        ops._call("vln_envdrop_act_fwd", ops._ptr(view2), ops._ptr(store.pose4), ops._ptr(wg), ops._ptr(b_act), ops._ptr(act),
+                  ops._ptr(xh), 96, B, E, p, rng.ptr, 4, ops._stream())
+        o = dict(ce=torch.empty(B, device=dev), action=torch.empty(B, dtype=torch.int32, device=dev),
+                 logp=torch.empty(B, device=dev), ent=torch.empty(B, device=dev), probs=torch.empty(B, 16, device=dev),
+                 vp=torch.empty_like(vp), view=torch.empty_like(view), ended=torch.empty_like(ended),
+                 dist=torch.empty_like(dist), teacher=torch.empty_like(teacher), reward=torch.empty(B, device=dev),
+                 mask=torch.empty(B, device=dev), n_active=torch.zeros(1, dtype=torch.int32, device=dev),
+                 act=torch.empty(B, E, device=dev), xh=torch.zeros(B, 96, device=dev))
+        P = ops._ptr
+        ops._call("vln_policy_env_act_fwd", P(logits), P(teacher), fb, rng.ptr, 3, P(o["ce"]), P(o["action"]), P(o["logp"]),
+                  P(o["ent"]), P(o["probs"]), P(vp), P(view), P(ended), P(dist), P(goal), P(store.cand_vp), P(store.cand_view),
+                  P(store.n_cand), P(store.next_hop), P(store.dist), P(store.sq_off), P(store.vp_local), P(o["vp"]),
+                  P(o["view"]), P(o["ended"]), P(o["dist"]), P(o["teacher"]), P(o["reward"]), P(o["mask"]), P(o["n_active"]),
+                  P(store.pose4), P(wg), P(b_act), P(o["act"]), P(o["xh"]), 96, E, p, 4, B, ops._stream())
+        for a, b in ((ce, o["ce"]), (logp, o["logp"]), (ent, o["ent"]), (action, o["action"]), (vp2, o["vp"]),
+                     (view2, o["view"]), (ended2, o["ended"]), (dist2, o["dist"]), (teacher2, o["teacher"]),
+                     (reward, o["reward"]), (mask, o["mask"]), (act, o["act"]), (xh, o["xh"])):
+            assert torch.equal(a, b)
+        assert int(o["n_active"]) == int((ended2 == 0).sum())
+        # the action embedding itself: tanh(W_a angle128(view') + b_a), nn.Linear on the 128-wide feature
+        ref = torch.tanh(store.pose128[view2.long()] @ w_act.t() + b_act)
+        assert relerr(act, ref) < 1e-5
+
+
+def test_cand_bwd_policy_stacked_steps(setup):
+    """vln_cand_logits_bwd_policy over [n_steps, B] stacked rows == vln_policy_bwd + vln_cand_logits_bwd per step."""
+    world, store, ops, dev = setup
+    B, S, p = 11, 3, 0.3
+    rng = ops.Rng(8, dev)
+    g = torch.Generator().manual_seed(4)
+    vp = torch.randint(0, world.n_vp, (S, B), generator=g, dtype=torch.int32).to(dev)
+    view = torch.randint(0, 36, (S, B), generator=g, dtype=torch.int32).to(dev)
+    probs = torch.softmax(torch.randn(S, B, 16, device=dev), 2)
+    n = store.n_cand[vp.long()]
+    probs = probs * (torch.arange(16, device=dev).view(1, 1, 16) <= n.unsqueeze(2))
+    probs = probs / probs.sum(2, keepdim=True)
+    ent = -(probs * torch.log(probs.clamp_min(1e-30))).sum(2)
+    target = torch.randint(-1, 2, (S, B), dtype=torch.int32).to(dev).clamp_max(0) * 0 + torch.minimum(
+        torch.randint(0, 16, (S, B), dtype=torch.int32).to(dev), n)
+    action = torch.minimum(torch.randint(0, 16, (S, B), dtype=torch.int32).to(dev), n)
+    target[0, 0], action[1, 1] = -1, -1
+    g_ce, g_lp, g_en = (torch.randn(S, B, device=dev) for _ in range(3))
+    P = ops._ptr
+    d_all = torch.empty(S, B, 2176, device=dev)
+    ops._call("vln_cand_logits_bwd_policy", store.handle, P(vp), P(view), P(store.cand_view), P(store.cand_ang4), P(store.n_cand),
+              P(probs), P(target), P(action), P(ent), P(g_ce), P(g_lp), P(g_en), P(d_all), B, S, p, rng.ptr, 20, 5, ops._stream())
+    for s in range(S):
+        dl = torch.empty(B, 16, device=dev)
+        ops._call("vln_policy_bwd", P(probs[s]), P(target[s]), P(action[s]), P(ent[s]), P(g_ce[s]), P(g_lp[s]), P(g_en[s]),
+                  P(dl), B, ops._stream())
+        d = torch.empty(B, 2176, device=dev)
+        ops._call("vln_cand_logits_bwd", store.handle, P(vp[s]), P(view[s]), P(store.cand_view), P(store.cand_ang4),
+                  P(store.n_cand), P(dl), P(d), None, B, p, rng.ptr, 20 + 5 * s, ops._stream())
+        assert torch.equal(d, d_all[s])
+
+
+def test_step_glue_kernels(setup):
+    """state / LSTM-pointwise / action-embedding glue kernels against torch on the masks vln_dropout_mask yields."""
+    _, _, ops, dev = setup
+    B, H, p = 9, 512, 0.5
+    torch.manual_seed(6)
+    rng = ops.Rng(21, dev)
+    P = ops._ptr
+    sc = 1.0 / (1.0 - p)
+    keep = lambda shape, off: ops.dropout_mask(shape, p, rng, off).float() * sc
+    # state_fwd / state_bwd
+    src = torch.randn(B, H, device=dev)
+    xh = torch.zeros(B, H + 40, device=dev)
+    hq, hc = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev)
+    ops._call("vln_envdrop_state_fwd", P(src), 1, ops.C.c_void_p(xh.data_ptr() + 4 * 40), H + 40, P(hq), P(hc), B, H, p,
+              rng.ptr, 2, 3, ops._stream())
+    ht = torch.tanh(src)
+    assert relerr(xh[:, 40:], ht) < 1e-6 and bool((xh[:, :40] == 0).all())
+    assert relerr(hq, ht * keep((B, H), 2)) < 1e-6 and relerr(hc, ht * keep((B, H), 3)) < 1e-6
+    d_hc, d_hq, d_x = (torch.randn(B, H, device=dev) for _ in range(3))
+    d_src = torch.empty(B, H, device=dev)
+    ops._call("vln_envdrop_state_bwd", P(d_hc), P(d_x), H, P(d_hq), ops.C.c_void_p(xh.data_ptr() + 4 * 40), H + 40, 1, P(d_src),
+              B, H, p, rng.ptr, 2, 3, ops._stream())
+    ref = (d_hc * keep((B, H), 3) + d_x + d_hq * keep((B, H), 2)) * (1 - ht * ht)
+    assert relerr(d_src, ref) < 1e-5
+    # LSTM pointwise + dropout, forward and backward, against the unfused kernels
+    gates, c0 = torch.randn(B, 4 * H, device=dev), torch.randn(B, H, device=dev)
+    h1, c1 = ops.lstm_pointwise(gates, c0)
+    o = [torch.empty(B, H, device=dev) for _ in range(2)] + [torch.empty(B, 4 * H, device=dev), torch.zeros(B, 2 * H, device=dev)]
+    ops._call("vln_lstm_pointwise_drop_fwd", P(gates), P(c0), P(o[0]), P(o[1]), P(o[2]), ops.C.c_void_p(o[3].data_ptr() + 4 * H),
+              2 * H, B, H, p, rng.ptr, 6, ops._stream())
+    assert relerr(o[0], h1) < 1e-6 and relerr(o[1], c1) < 1e-6
+    assert relerr(o[3][:, H:], h1 * keep((B, H), 6)) < 1e-6 and bool((o[3][:, :H] == 0).all())
+    d_drop, d_extra, d_c1 = torch.randn(B, 2 * H, device=dev), torch.randn(B, H, device=dev), torch.randn(B, H, device=dev)
+    dg, dc0 = torch.empty(B, 4 * H, device=dev), torch.empty(B, H, device=dev)
+    ops._call("vln_lstm_pointwise_drop_bwd", P(o[2]), P(c0), P(o[1]), ops.C.c_void_p(d_drop.data_ptr() + 4 * H), 2 * H, P(d_extra),
+              P(d_c1), P(dg), P(dc0), B, H, p, rng.ptr, 6, ops._stream())
+    g2, c2 = gates.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+    hh, cc = ops.lstm_pointwise(g2, c2)
+    ((hh * (d_drop[:, H:] * keep((B, H), 6) + d_extra)).sum() + (cc * d_c1).sum()).backward()
+    assert relerr(dg, g2.grad) < 1e-5 and relerr(dc0, c2.grad) < 1e-5
+    # batched action-embedding backward
+    S, E = 3, 64
+    act = torch.tanh(torch.randn(S, B, E, device=dev))
+    d_xh = torch.randn(S, B, 96, device=dev)
+    d_pre = torch.empty(S, B, E, device=dev)
+    ops._call("vln_envdrop_act_bwd", P(d_xh), 96, P(act), P(d_pre), B, E, S, p, rng.ptr, 30, 4, ops._stream())
+    for s in range(S):
+        assert relerr(d_pre[s], d_xh[s, :, :E] * keep((B, E), 30 + 4 * s) * (1 - act[s] ** 2)) < 1e-5
+
+
+def test_linear_pair_equals_two_launches(setup):
+    _, _, ops, dev = setup
+    torch.manual_seed(9)
+    M, N, K = 64, 2176, 512
+    ws = [torch.randn(N, K, device=dev) * 0.05 for _ in range(2)]
+    xs = [torch.randn(M, K, device=dev) for _ in range(2)]
+    sw = [ops._SplitWeight(w).fresh(w) for w in ws]
+    ys = [torch.zeros(M, N, device=dev) for _ in range(2)]
+    P = ops._ptr
+    ops._call("vln_linear_bf16x3_pair", P(sw[0].hi), P(sw[0].lo), P(xs[0]), P(ys[0]), P(sw[1].hi), P(sw[1].lo), P(xs[1]), P(ys[1]),
+              N, K, K, M, N, ops._stream())
+    for w, x, y in zip(ws, xs, ys):
+        ref = x.double() @ w.double().t()
+        assert relerr(y.double(), ref) < 2e-5

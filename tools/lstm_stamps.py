@@ -1,0 +1,35 @@
+"""Phase timing of one encoder-LSTM timestep (VLN_LSTM_STAMPS=1): clock64 deltas inside step 10 of CTA (0,0)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+os.environ["VLN_LSTM_STAMPS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import clvln_b200  # noqa: E402,F401
+from clvln_b200 import ops, _lib  # noqa: E402
+
+dev = torch.device("cuda:0")
+B, L, H = 64, 80, 256
+xproj = [torch.randn(B, L, 4 * H, device=dev) * 0.1 for _ in range(2)]
+whh = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
+lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
+for _ in range(3):
+    ops.lstm_layer(xproj, whh, lengths)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ops.lstm_layer(xproj, whh, lengths)
+e1.record()
+torch.cuda.synchronize()
+print("fwd launch: %.1f us (%.2f us per timestep)" % (e0.elapsed_time(e1) * 100, e0.elapsed_time(e1) * 100 / L))
+L_ = _lib.lib()
+L_.vln_debug_lstm_stamps.argtypes = [C.c_void_p]
+buf = (C.c_ulonglong * 12)()
+L_.vln_debug_lstm_stamps(buf)
+names = ["mma + gate stores", "syncthreads", "pointwise + global stores", "st.async issue", "mbarrier wait"]
+print(", ".join(f"{n}={buf[i + 1] - buf[i]}" for i, n in enumerate(names)), "cycles; step total", buf[5] - buf[0])
+print("kernel: prologue (weight fragments, barrier init, cluster sync) = %d cycles, %d steps = %d cycles (%.0f per step), epilogue = %d"
+      % (buf[7] - buf[6], L, buf[8] - buf[7], (buf[8] - buf[7]) / L, buf[9] - buf[8]))
