@@ -63,14 +63,18 @@ class EnvDropAgent(BaseAgent):
         store = self.store_of(self.env)
         B = ib.vp.shape[0]
         T, poll = self._horizon(ib, feedback)
+        use_fused = self.fused and self.device.type == "cuda"
+        prep = None
+        if use_fused:            # decoder stream offsets + the rollout's feature-dropout bits (side stream, overlaps the encoder)
+            prep = self._fused.prepare(self.rng, B, T, feedback, train_rl, self.device)
         ctx, h_t, c_t = self.encoder(ib.tokens, ib.lengths)
         ctx_mask = LengthMask(ib.lengths, ctx.shape[1])
         st = RolloutState(store, ib, T + (1 if train_rl else 0))
         training = self.encoder.training
 
-        if self.fused and self.device.type == "cuda":
+        if use_fused:
             (ce, logps, ents, hiddens, logits, actions, targets, rewards, masks, last_h) = self._fused.run(
-                self.rng, st, ctx, ctx_mask.lengths, h_t, c_t, T, feedback, train_rl, poll, self.split_for(B))
+                self.rng, st, ctx, ctx_mask.lengths, h_t, c_t, T, feedback, train_rl, poll, self.split_for(B), prep)
             n = st.steps
             ml = ce.sum(0) if train_cl else ce.sum()
             if self.trace is not None:

@@ -74,6 +74,8 @@ class FusedDecoder:
     def __init__(self, decoder):
         self.dec = decoder
         self.cat = _CatSplit()
+        self._side = None
+        self._prep = None
 
     def params(self):
         d = self.dec
@@ -81,7 +83,51 @@ class FusedDecoder:
                 d.lstm.bias_hh, d.text_attn.linear_in.weight, d.text_attn.linear_out.weight,
                 d.visual_attn.linear_in.weight, d.cand_attn.weight]
 
-    def run(self, rng, st, ctx, lengths, h0, c0, T, feedback, bootstrap, poll, split):
+    def prepare(self, rng, B, T, feedback, bootstrap, device):
+        """Before the encoder runs: hand out the dropout / sampling stream offsets of every decoder pass (in
+        the call order of EnvDropDecoder.forward) and draw all feature-dropout keep-bits of the rollout with
+        ONE kernel on a side stream, so that it overlaps with the instruction encoder."""
+        dec = self.dec
+        H = dec.hidden_size
+        p = dec.drop_ratio if dec.training else 0.0
+        pf = dec.feat_drop_ratio if dec.training else 0.0
+        fb = ops.FEEDBACK[feedback]
+        S = T + (1 if bootstrap else 0)
+        offs = []
+        for t in range(S):
+            d = dict(act=0, img=0, cand=0, hprev=0, h1=0, ht=0, sample=0)
+            if p > 0.0:
+                d["act"] = rng.next("act", (B, H_ACT), p)
+            if pf > 0.0:
+                d["img"] = rng.next("img", (B, ops.N_VIEWS, ops.IMG_DIM), pf)
+                d["cand"] = rng.next("cand", (B, ops.NSLOT, ops.IMG_DIM), pf)
+            if p > 0.0:
+                d["hprev"] = rng.next("h_prev", (B, H), p)
+                d["h1"] = rng.next("h1", (B, H), p)
+                d["ht"] = rng.next("h_tilde", (B, H), p)
+            if fb == 2 and t < T:
+                d["sample"] = rng.next()
+            offs.append(d)
+        MB, side = None, None
+        if pf > 0.0:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            MB = torch.empty((S, B * ops.N_VIEWS, ops.IMG_DIM // 8), dtype=torch.uint8, device=device)   # owned by `main`
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                stride = offs[1]["img"] - offs[0]["img"] if S > 1 else 0
+                _call("vln_feature_mask_bits", _ptr(MB), B * ops.N_VIEWS, S, pf, rng.ptr, offs[0]["img"], stride, _stream())
+        return dict(offs=offs, MB=MB, side=side, p=p, pf=pf, S=S)
+
+    def run(self, rng, st, ctx, lengths, h0, c0, T, feedback, bootstrap, poll, split, prep=None):
+        if prep is None:
+            prep = self.prepare(rng, st.B, T, feedback, bootstrap, ctx.device)
+        if prep["side"] is not None:
+            torch.cuda.current_stream().wait_stream(prep["side"])
+            prep["side"] = None
+        self._prep = prep
         return _Rollout.apply(self, rng, st, lengths, T, feedback, bootstrap, poll, split, ctx, h0, c0, *self.params())
 
 
@@ -142,23 +188,9 @@ class _Rollout(torch.autograd.Function):
         TEACH[0].copy_(st.teacher)
         CS[0].copy_(c0)
 
-        # ---- dropout / sampling stream offsets, in the call order of EnvDropDecoder.forward ----
-        offs = []
-
-        def alloc(t):
-            d = dict(act=0, img=0, cand=0, hprev=0, h1=0, ht=0, sample=0)
-            if p > 0.0:
-                d["act"] = rng.next("act", (B, H_ACT), p)
-            if pf > 0.0:
-                d["img"] = rng.next("img", (B, ops.N_VIEWS, ops.IMG_DIM), pf)
-                d["cand"] = rng.next("cand", (B, ops.NSLOT, ops.IMG_DIM), pf)
-            if p > 0.0:
-                d["hprev"] = rng.next("h_prev", (B, H), p)
-                d["h1"] = rng.next("h1", (B, H), p)
-                d["ht"] = rng.next("h_tilde", (B, H), p)
-            if fb == 2 and t < T:
-                d["sample"] = rng.next()
-            offs.append(d)
+        prep = fd._prep
+        offs, MB = prep["offs"], prep["MB"]
+        assert prep["S"] == S and prep["p"] == p and prep["pf"] == pf
 
         def act_embed(t):
             _call("vln_envdrop_act_fwd", _ptr(st.view[t]), _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t]),
@@ -174,13 +206,6 @@ class _Rollout(torch.autograd.Function):
             _call("vln_lstm_pointwise_drop_fwd", _ptr(GATES[t]), _ptr(CS[t]), _ptr(H1[t]), _ptr(CS[t + 1]),
                   _ptr(ACTS[t]), _p(WH[t], H) if need_drop else None, 2 * H, B, H, p, rp, offs[t]["h1"], _stream())
 
-        for t_ in range(S):                                     # all passes up front: the offsets are an arithmetic
-            alloc(t_)                                           # sequence, so ONE kernel draws every step's feature mask
-        MB = None
-        if pf > 0.0:
-            MB = torch.empty((S, B * ops.N_VIEWS, ops.IMG_DIM // 8), dtype=torch.uint8, device=dev)
-            stride = offs[1]["img"] - offs[0]["img"] if S > 1 else 0
-            _call("vln_feature_mask_bits", _ptr(MB), B * ops.N_VIEWS, S, pf, rp, offs[0]["img"], stride, _stream())
         _call("vln_envdrop_state_fwd", _ptr(h0), 0, _p(XH[0], H_ACT + F), KX, _ptr(HQ[0]), None, B, H, p, rp,
               offs[0]["hprev"], 0, _stream())
         act_embed(0)

@@ -285,15 +285,24 @@ struct Groups {
   int n;
 };
 
+// Group offsets are multiples of 4 floats (FlatOptimizer pads every group), so a float4 never straddles groups.
+__device__ __forceinline__ int group_of(const Groups& gr, int64_t i) {
+  int k = 0;
+  while (k + 1 < gr.n && i >= gr.off[k + 1]) ++k;
+  return k;
+}
+
 __global__ void sqnorm_kernel(const float* __restrict__ grad, Groups gr, float scale, float* __restrict__ sqnorm) {
   __shared__ float red[4][32];
-  const int64_t n = gr.off[gr.n];
+  const int64_t n4 = gr.off[gr.n] >> 2;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float g = grad[i] * scale;
-    int k = 0;
-    while (k + 1 < gr.n && i >= gr.off[k + 1]) ++k;
-    acc[k] += g * g;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+    const float s = (g.x * scale) * (g.x * scale) + (g.y * scale) * (g.y * scale) + (g.z * scale) * (g.z * scale) +
+                    (g.w * scale) * (g.w * scale);
+    const int k = group_of(gr, i << 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += (j == k) ? s : 0.f;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -312,29 +321,48 @@ __global__ void sqnorm_kernel(const float* __restrict__ grad, Groups gr, float s
   }
 }
 
+__device__ __forceinline__ float rmsprop1(float& sq, float g, float p, float lr) {
+  sq = 0.99f * sq + 0.01f * g * g;
+  return p - lr * g / (sqrtf(sq) + 1e-8f);
+}
+__device__ __forceinline__ float adam1(float& m, float& v, float g, float p, float lr1, float rbc2) {
+  m = 0.9f * m + 0.1f * g;
+  v = 0.999f * v + 0.001f * g * g;
+  return p - lr1 * m / (sqrtf(v) * rbc2 + 1e-8f);
+}
+
 __global__ void optim_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ s1,
                              float* __restrict__ s2, Groups gr, const float* __restrict__ sqnorm, float scale,
                              int kind, float lr, float bc1, float bc2) {
-  const int64_t n = gr.off[gr.n];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int k = 0;
-    while (k + 1 < gr.n && i >= gr.off[k + 1]) ++k;
-    float g = grad[i] * scale;
-    if (gr.max_norm[k] > 0.f) {                                   // clip_grad_norm_: coef = max/(norm+1e-6), clamped to 1
-      const float coef = gr.max_norm[k] / (sqrtf(sqnorm[k]) + 1e-6f);
-      if (coef < 1.f) g *= coef;
+  const int64_t n4 = gr.off[gr.n] >> 2;
+  float coef[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                                   // clip_grad_norm_: coef = max/(norm+1e-6), clamped to 1
+    coef[k] = scale;
+    if (k < gr.n && gr.max_norm[k] > 0.f) {
+      const float c = gr.max_norm[k] / (sqrtf(sqnorm[k]) + 1e-6f);
+      if (c < 1.f) coef[k] = scale * c;
     }
+  }
+  const float lr1 = lr / bc1, rbc2 = 1.0f / sqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = group_of(gr, i << 2);
+    const float c = k == 0 ? coef[0] : (k == 1 ? coef[1] : (k == 2 ? coef[2] : coef[3]));
+    float4 g = __ldg(reinterpret_cast<const float4*>(grad) + i);
+    g.x *= c; g.y *= c; g.z *= c; g.w *= c;
+    float4 p = reinterpret_cast<float4*>(param)[i];
+    float4 a = reinterpret_cast<float4*>(s1)[i];
     if (kind == 0) {                                              // torch.optim.RMSprop defaults
-      const float sq = 0.99f * s1[i] + 0.01f * g * g;
-      s1[i] = sq;
-      param[i] -= lr * g / (sqrtf(sq) + 1e-8f);
+      p.x = rmsprop1(a.x, g.x, p.x, lr); p.y = rmsprop1(a.y, g.y, p.y, lr);
+      p.z = rmsprop1(a.z, g.z, p.z, lr); p.w = rmsprop1(a.w, g.w, p.w, lr);
     } else {                                                      // torch.optim.Adam defaults
-      const float m = 0.9f * s1[i] + 0.1f * g;
-      const float v = 0.999f * s2[i] + 0.001f * g * g;
-      s1[i] = m;
-      s2[i] = v;
-      param[i] -= (lr / bc1) * m / (sqrtf(v) / sqrtf(bc2) + 1e-8f);
+      float4 v = reinterpret_cast<float4*>(s2)[i];
+      p.x = adam1(a.x, v.x, g.x, p.x, lr1, rbc2); p.y = adam1(a.y, v.y, g.y, p.y, lr1, rbc2);
+      p.z = adam1(a.z, v.z, g.z, p.z, lr1, rbc2); p.w = adam1(a.w, v.w, g.w, p.w, lr1, rbc2);
+      reinterpret_cast<float4*>(s2)[i] = v;
     }
+    reinterpret_cast<float4*>(s1)[i] = a;
+    reinterpret_cast<float4*>(param)[i] = p;
   }
 }
 
@@ -484,6 +512,8 @@ extern "C" int vln_grad_sqnorm(const float* grad, const int64_t* group_off, int 
   VLN_REQUIRE(grad && group_off && sqnorm, "bad arguments");
   Groups g;
   VLN_REQUIRE(make_groups(&g, group_off, nullptr, n_groups) == 0, "1..4 groups supported");
+  for (int i = 0; i <= n_groups; ++i) VLN_REQUIRE(group_off[i] % 4 == 0, "group offsets must be multiples of 4 floats");
+  VLN_REQUIRE(((uintptr_t)grad & 15) == 0, "grad must be 16-byte aligned");
   VLN_CHECK_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(float) * n_groups, STREAM));
   sqnorm_kernel<<<296, 256, 0, STREAM>>>(grad, g, grad_scale, sqnorm);
   VLN_LAUNCH_OK();
@@ -496,6 +526,8 @@ extern "C" int vln_optim_step(float* param, const float* grad, float* state1, fl
   VLN_REQUIRE(param && grad && state1 && group_off && sqnorm && (kind == 0 || (kind == 1 && state2)), "bad arguments");
   Groups g;
   VLN_REQUIRE(make_groups(&g, group_off, max_norm, n_groups) == 0, "1..4 groups supported");
+  for (int i = 0; i <= n_groups; ++i) VLN_REQUIRE(group_off[i] % 4 == 0, "group offsets must be multiples of 4 floats");
+  VLN_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)state1 | (uintptr_t)state2) & 15) == 0, "buffers must be 16-byte aligned");
   const float bc1 = 1.0f - powf(0.9f, (float)step), bc2 = 1.0f - powf(0.999f, (float)step);
   optim_kernel<<<592, 256, 0, STREAM>>>(param, grad, state1, state2, g, sqnorm, grad_scale, kind, lr, bc1, bc2);
   VLN_LAUNCH_OK();

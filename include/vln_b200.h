@@ -309,7 +309,8 @@ int vln_a2c_bwd(const float* g_b, const float* mask, const float* value, const f
  * clip_grad_norm_(encoder,40), clip_grad_norm_(decoder,40), critic unclipped, RMSprop/Adam).
  * The flat buffer is laid out as n_groups (<=4) contiguous groups, group k = [group_off[k],
  * group_off[k+1]) (host array of n_groups+1 offsets); max_norm[k] <= 0 means "not clipped"
- * (host array).  sqnorm [n_groups] is device scratch holding each group's squared L2 norm of
+ * (host array).  Offsets must be multiples of 4 floats and the buffers 16-byte aligned (16-byte accesses).
+ * sqnorm [n_groups] is device scratch holding each group's squared L2 norm of
  * grad*grad_scale.  kind 0 = RMSprop(alpha=.99, eps=1e-8), 1 = Adam(.9,.999,1e-8), torch semantics;
  * step is the 1-based Adam step count. */
 int vln_grad_sqnorm(const float* grad, const int64_t* group_off, int n_groups, float* sqnorm,
