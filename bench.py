@@ -324,6 +324,10 @@ def run_b200(args):
     if rank == 0:
         store = agent.store_of(env)
         out["roofline"] = roofline_pano(store, ops, torch, args.batch, agent.split_for(args.batch), peaks)
+        # the same kernel at larger episode counts per launch (BASELINE config 5): where it leaves the latency regime
+        out["roofline"]["sweep"] = [
+            {k: r[k] for k in ("episodes_per_launch", "us_per_launch", "achieved", "frac")}
+            for r in (roofline_pano(store, ops, torch, b, 1, peaks) for b in (256, 1024, 2048))]
         if world_size == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             from clvln_b200.environ import make_world, make_items
