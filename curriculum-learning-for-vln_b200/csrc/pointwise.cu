@@ -135,8 +135,9 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float
 
 // Packed keep-bits of the feature dropout for a whole rollout (policy.py:226-231 draws a fresh
 // [B,36,2048] mask every decoder step).  Row r of step t is 2048 features = 256 Philox blocks of 8;
-// output byte (c % 32) * 8 + c / 32 of that row holds the 8 keep-bits of block c, which is the order
-// in which a warp of the panorama kernel consumes them (lane = c % 32 reads its 8 bytes at once).
+// output byte (c / 128) * 128 + (c % 32) * 4 + (c % 128) / 32 of that row holds the 8 keep-bits of block c:
+// each half of the row (one CTA of the panorama kernel's cluster) is 128 contiguous bytes, and lane c % 32
+// of a warp reads the four bytes of its four 16-byte column chunks at once.
 // Same bits as vln_dropout_mask on the dense [rows, 2048] tensor with call_off = off0 + t * off_stride.
 __global__ void feature_mask_bits_kernel(uint8_t* __restrict__ bits, int64_t rows, int n_steps, float p,
                                          const uint64_t* __restrict__ rng, uint64_t off0, uint64_t off_stride) {
@@ -146,7 +147,7 @@ __global__ void feature_mask_bits_kernel(uint8_t* __restrict__ bits, int64_t row
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row_t = o >> 8;                                   // (t, row)
     const int w = (int)(o & 255);                                   // byte position inside the row
-    const int c = (w & 7) * 32 + (w >> 3);                          // Philox block of the row stored there
+    const int c = (w >> 7) * 128 + (w & 3) * 32 + ((w & 127) >> 2);  // Philox block of the row stored there
     const int64_t t = row_t / rows, row = row_t - t * rows;
     const Philox8 r = philox8(seed, base + off0 + (uint64_t)t * off_stride, (uint64_t)(row * 256 + c));
     uint32_t b = 0;

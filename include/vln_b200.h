@@ -90,7 +90,7 @@ int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
 /* Packed keep-bits of the feature dropout (policy.py:226-231) for n_steps decoder steps at once:
  * bits [n_steps, rows, 256] bytes, rows = B*36 panorama rows of 2048 features; step t uses the stream
  * (seed, base + off0 + t*off_stride); the bits equal vln_dropout_mask on the dense [rows,2048] tensor.
- * Byte (c%32)*8 + c/32 of a row = keep-bits of features [8c, 8c+8). */
+ * Byte (c/128)*128 + (c%32)*4 + (c%128)/32 of a row = keep-bits of features [8c, 8c+8). */
 int vln_feature_mask_bits(uint8_t* bits, int64_t rows, int n_steps, float p, const uint64_t* rng,
                           uint64_t off0, uint64_t off_stride, void* stream);
 

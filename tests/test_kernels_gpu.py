@@ -447,14 +447,14 @@ def test_wgrad_tf32_tolerance(setup):
 # ---- fused decoder-step kernels (agent/fused.py) against their unfused counterparts ------------------
 def test_feature_mask_bits_equal_dropout_mask(setup):
     """Packed keep-bits of several steps == vln_dropout_mask of each step's dense [B*36, 2048] tensor
-    (bit-exact), in the byte order the panorama kernel consumes: byte (c%32)*8 + c//32 of a row = block c."""
+    (bit-exact), in the byte order the panorama kernel consumes: byte (c//128)*128 + (c%32)*4 + (c%128)//32 = block c."""
     _, _, ops, dev = setup
     B, S, p = 5, 3, 0.3
     rng = ops.Rng(11, dev)
     bits = torch.empty((S, B * 36, 256), dtype=torch.uint8, device=dev)
     ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, S, p, rng.ptr, 4, 7, ops._stream())
     c = torch.arange(256, device=dev)
-    pos = (c % 32) * 8 + c // 32
+    pos = (c // 128) * 128 + (c % 32) * 4 + (c % 128) // 32
     w = (1 << torch.arange(8, device=dev)).to(torch.int32)
     for s in range(S):
         keep = ops.dropout_mask((B * 36, 256, 8), p, rng, 4 + 7 * s).to(torch.int32)      # [rows, block, lane]

@@ -6,7 +6,7 @@ import sys
 
 import torch
 
-os.environ["VLN_PANO_STAMPS"] = "1"
+os.environ.setdefault("VLN_PANO_STAMPS", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import clvln_b200  # noqa: E402,F401
 from clvln_b200 import ops, _lib  # noqa: E402
@@ -43,4 +43,4 @@ for B in [int(a) for a in sys.argv[1:]] or [16, 64, 2048]:
         buf = (C.c_ulonglong * 16)()
         L.vln_debug_pano_stamps(buf)
         d = [buf[i] - buf[0] for i in range(1, 8)]
-        print(f"B={B} mask_bits={bits}: " + ", ".join(f"{n}={v}" for n, v in zip(names, d)))
+        print(f"B={B} mask_bits={bits}: " + ", ".join(f"{n}={v}" for n, v in zip(names, d)) + f" | unit starts at {buf[8] - buf[0]}")
