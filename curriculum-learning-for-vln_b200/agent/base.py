@@ -77,7 +77,7 @@ class BaseAgent:
         self._stores = {}
         self.sync_every = 4            # poll `all ended` every k steps in student-forced rollouts (0 = never)
         self.fixed_steps = None        # run exactly this many steps (CUDA-graph capture), no polling
-        self.pano_split = None         # parts per episode in the panorama kernel; None = by batch size
+        self.pano_split = None         # panorama kernel variant (vln_pano_attn `split`); None = automatic
         self.last_state = None
         self.trace = None              # set to a list to record per-step logits / targets / actions
 
@@ -101,10 +101,8 @@ class BaseAgent:
         return self._stores[key]
 
     def split_for(self, B):
-        """Parts per episode for vln_pano_attn: split small batches so the units still cover the SMs."""
-        if self.pano_split is not None:
-            return self.pano_split
-        return 1 if B >= 48 else (2 if B >= 24 else 4)
+        """Kernel variant of vln_pano_attn (1 = chosen by the library from B, 2 = cluster, 4 = streaming)."""
+        return 1 if self.pano_split is None else self.pano_split
 
     def _horizon(self, ib, feedback):
         if self.fixed_steps is not None:

@@ -66,6 +66,11 @@ struct vln_ctx {
   unsigned int* tickets;   // [VLN_SPLIT_MAX_B] arrival counters (return to 0 after every launch)
 };
 
+// streaming variant of the panorama attention (pano_stream.cu), selected by vln_pano_attn_ld
+cudaError_t vln_pano_stream_launch(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
+                                   const float* vec, int ld_vec, float* attn_io, float* out, int ld_out, int B, int mode,
+                                   float drop_p, const uint8_t* mask_bits, cudaStream_t stream);
+
 // ---- Philox4x32-10 ---------------------------------------------------------------------------
 struct Philox8 {
   uint32_t w[4];  // 8 x 16-bit lanes

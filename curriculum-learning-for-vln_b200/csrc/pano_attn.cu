@@ -119,12 +119,11 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
     seed = rng[0];
     offset = rng[1] + call_off;
   }
-  // stage the per-unit vectors (query half + angle part, angle table row, saved attention) of episode `e`.
-  // The last warp only requests rows, so neither job waits for the other.
+  // stage the per-unit vectors (query half + angle part, angle table row, saved attention) of episode `e`
   auto prefetch_unit = [&](int e, int vw, int ub) {          // vw = view[e], loaded one unit ahead
-    if (e < B && warp < kWarps - 1) {
+    if (e < B) {
       const float* vr = vec + (size_t)e * ld_vec;
-      for (int c = tid; c < kQ / 4; c += kThreads - 32) {
+      for (int c = tid; c < kQ / 4; c += kThreads) {
         const int src = c < kHalf / 4 ? col0 / 4 + c : VLN_IMG / 4 + (c - kHalf / 4);
         cp_async16(&sm.qbuf[ub][c * 4], vr + src * 4);
       }
@@ -144,9 +143,9 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
       g_next = __ldg(vp + cid + n_clusters);
       vw_next = __ldg(view + cid + n_clusters);
     }
-    if (cid < B && warp == kWarps - 1) {
-      for (int r = lane; r < VLN_V; r += 32) request_row(cid, g0, r, 0);
-    }
+    // every warp requests the three rows it will consume in phase 1 (one warp issuing all 36-72 bulk copies
+    // serialised ~30 cycles apiece: the first vectors were ready 1 us later with keep-bits than without)
+    if (cid < B && lane < VLN_V / kWarps) request_row(cid, g0, warp + lane * kWarps, 0);
     prefetch_unit(cid, vw0, 0);
   }
 
@@ -161,9 +160,9 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
       g_next = __ldg(vp + next_ep + n_clusters);
       vw_next = __ldg(view + next_ep + n_clusters);
     }
-    if (next_ep < B && warp == kWarps - 1) {
+    if (next_ep < B && lane < VLN_V / kWarps) {
       fence_proxy_async();                                 // order those generic-proxy accesses before the async writes
-      for (int r = lane; r < VLN_V; r += 32) request_row(next_ep, g_req, r, ub ^ 1);
+      request_row(next_ep, g_req, warp + lane * kWarps, ub ^ 1);
     }
     if (tid == 0) mbar_expect_tx(&sm.xbar[ub], VLN_V * 4); // the peer's 36 partial dot products of this unit
     cp_async_wait_all();
@@ -348,7 +347,7 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
                                 float* out, int ld_out, int B, int mode, float drop_p, const uint64_t* rng,
                                 uint64_t call_off, const uint8_t* mask_bits, int split, void* stream) {
   VLN_REQUIRE(ctx && vp && view && loc4 && vec && attn_io && out && B > 0, "bad arguments");
-  VLN_REQUIRE(split == 1 || split == 2 || split == 4, "split must be 1, 2 or 4 (kept for ABI stability; unused since v3)");
+  VLN_REQUIRE(split == 1 || split == 2 || split == 4, "split (kernel variant) must be 1 = automatic, 2 = cluster, 4 = streaming");
   VLN_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (forward) or 1 (backward)");
   VLN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");
   VLN_REQUIRE(drop_p == 0.f || rng || mask_bits, "dropout needs an rng state or pre-generated keep-bits");
@@ -358,6 +357,15 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
               "rows must be 16-byte aligned");
   (void)fwd_out;
   (void)ld_fwd;
+  // Two kernels serve this entry point: the 2-CTA-cluster kernel below minimises the latency of a launch with few
+  // episodes (the rollout's B = 64), the streaming kernel (pano_stream.cu) maximises bytes in flight for many.
+  static const int stream_min_b = getenv("VLN_PANO_STREAM_MIN_B") ? atoi(getenv("VLN_PANO_STREAM_MIN_B")) : 128;
+  const bool stream_ok = drop_p == 0.f || mask_bits;        // the streaming kernel has no inline Philox
+  if (stream_ok && (split == 4 || (split == 1 && B >= stream_min_b))) {
+    VLN_CHECK_CUDA(vln_pano_stream_launch(ctx, vp, view, loc4, vec, ld_vec, attn_io, out, ld_out, B, mode, drop_p, mask_bits,
+                                          (cudaStream_t)stream));
+    return 0;
+  }
   static bool configured = false;
   if (!configured) {
     VLN_CHECK_CUDA(cudaFuncSetAttribute(pano_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));

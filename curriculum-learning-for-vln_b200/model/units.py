@@ -143,7 +143,7 @@ def _attend(target, context, mask):
     if isinstance(context, ops.PanoView):
         return ops.pano_attn(context.store, context.vp, context.view, target, getattr(context, "drop_p", 0.0),
                              getattr(context, "rng", None), getattr(context, "call_off", 0),
-                             getattr(context, "split", 2))
+                             getattr(context, "split", 1))
     B, S, _ = context.shape
     return ops.ctx_attn(context, target, _lengths_of(mask, B, S, context.device))
 

@@ -301,7 +301,7 @@ def pose_feature(store, view):
 
 
 # ---- fused gather + panorama attention ---------------------------------------------------------
-def pano_attn_raw(store, vp, view, vec, attn, mode, drop_p=0.0, rng=None, call_off=0, split=2, fwd_out=None):
+def pano_attn_raw(store, vp, view, vec, attn, mode, drop_p=0.0, rng=None, call_off=0, split=1, fwd_out=None):
     B = vp.shape[0]
     out = torch.empty((B, F_DIM), device=vec.device, dtype=torch.float32)
     _call("vln_pano_attn", store.handle, _ptr(vp), _ptr(view), _ptr(store.loc4), _ptr(vec), _ptr(attn),
@@ -329,7 +329,7 @@ class _PanoAttn(torch.autograd.Function):
         return dq, None, None, None, None, None, None, None
 
 
-def pano_attn(store, vp, view, q, drop_p=0.0, rng=None, call_off=0, split=2):
+def pano_attn(store, vp, view, q, drop_p=0.0, rng=None, call_off=0, split=1):
     """(weighted [B,2176], attn [B,36]) = softmax_v(x~_v . q) over the episode's panorama."""
     return _PanoAttn.apply(q, store, _i32c(vp), _i32c(view), drop_p, rng, call_off, split)
 

@@ -69,9 +69,10 @@ int vln_gather_cand(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
  *                      out <- sum_v attn_v x~_v  [B,2176];  fwd_out unused (may be NULL)
  *   mode 1 (backward): vec = d(out) [B,2176], attn_io = saved attn (read), fwd_out = saved forward
  *                      `out`;  out <- dq = sum_v dlogit_v x~_v,  dlogit = attn*(r - attn.r), r_v = x~_v . vec
- * x~ = dropout(table row) (+) angle embedding.  split in {1,2,4}: parts per episode (36/split views
- * each, merged through the context's scratch slab; split > 1 needs B <= VLN_SPLIT_MAX_B and calls
- * on one context must not overlap in time). */
+ * x~ = dropout(table row) (+) angle embedding.  split (historical name) selects the kernel: 1 = automatic
+ * (by B), 2 = low-latency kernel (one episode per 2-CTA cluster, csrc/pano_attn.cu), 4 = streaming kernel
+ * (4-row chunks through a ring, single-pass online softmax, csrc/pano_stream.cu; needs drop_p == 0 or
+ * mask_bits, otherwise the call falls back to the cluster kernel). */
 #define VLN_SPLIT_MAX_B 1024
 int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
                   const float* vec, float* attn_io, const float* fwd_out, float* out, int B, int mode,

@@ -483,6 +483,40 @@ def test_pano_attn_mask_bits_equal_inline_philox(setup, mode):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("B", [21, 1500])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_pano_attn_streaming_kernel_matches_cluster_kernel(setup, mode, B, p, monkeypatch):
+    """The two kernels behind vln_pano_attn_ld (variant 2 = 2-CTA cluster, 4 = streaming, single-pass online
+    softmax) agree to fp32 rounding, with and without pre-generated keep-bits, into strided output rows.
+    B=1500 > resident CTAs: every CTA loops over several episodes (ring wrap-around across episodes)."""
+    world, store, ops, dev = setup
+    vp, view = rand_state(world, B, dev, 6)
+    rng = ops.Rng(5, dev)
+    torch.manual_seed(mode)
+    ld = 2176 + 64
+    vec = torch.randn(B, ld, device=dev) * 0.05
+    attn = torch.softmax(torch.randn(B, 36, device=dev) * 2, 1)
+    bits = None
+    if p > 0:
+        bits = torch.empty((B * 36, 256), dtype=torch.uint8, device=dev)
+        ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, 1, p, rng.ptr, 9, 0, ops._stream())
+    outs = []
+    for variant in (2, 4):
+        a = attn.clone()
+        out = torch.full((B, ld), 7.0, device=dev)
+        ops._call("vln_pano_attn_ld", store.handle, ops._ptr(vp), ops._ptr(view), ops._ptr(store.loc4), ops._ptr(vec), ld,
+                  ops._ptr(a), None, ld, ops._ptr(out), ld, B, mode, p, rng.ptr, 9, ops._ptr(bits), variant, ops._stream())
+        outs.append((out, a))
+    assert torch.equal(outs[1][0][:, 2176:], torch.full((B, 64), 7.0, device=dev))      # nothing past column 2176
+    assert relerr(outs[1][0][:, :2176], outs[0][0][:, :2176]) < 2e-5
+    assert relerr(outs[1][0][:, 2048:2176], outs[0][0][:, 2048:2176]) < 2e-5            # angle columns on their own scale
+    assert relerr(outs[1][1], outs[0][1]) < 2e-5
+    # per-episode scale as well: a wrong episode hides in a global max
+    num = (outs[1][0][:, :2176] - outs[0][0][:, :2176]).abs().amax(1)
+    assert (num / outs[0][0][:, :2176].abs().amax(1)).max().item() < 1e-4
+
+
 def test_policy_env_act_equals_separate_kernels(setup):
     """vln_policy_env_act_fwd == vln_policy_fwd + vln_env_step + vln_envdrop_act_fwd (bit-exact state, actions,
     rewards; identical floating-point results)."""

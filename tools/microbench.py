@@ -3,7 +3,7 @@
 Random viewpoints over the full-size table (1.56 GB >> 126 MB L2).  Each measurement replays a
 CUDA graph of N_SETS launches over different random index sets (so launches read HBM, not L2, and
 the host launch path is out of the timed region), CUDA events around the replays.
-One JSON line per (B, split, mode, drop): achieved algorithmic GB/s = B*147456 / time per launch."""
+One JSON line per (B, kernel variant, mode, drop): achieved algorithmic GB/s = B*147456 / time per launch."""
 import argparse
 import json
 import os
@@ -75,17 +75,27 @@ def main():
         q = torch.randn(B, 2176, device=dev) * 0.05
         attn = torch.empty(B, 36, device=dev)
         fwd = torch.randn(B, 2176, device=dev)
-        for split in args.splits:
-            if split > 1 and B > 1024:
-                continue
-            for drop in args.drops:
+        for drop in args.drops:
+            bits = None
+            if drop > 0:      # keep-bits as the rollout pre-generates them (vln_feature_mask_bits), one set per launch
+                bits = torch.empty((N_SETS, B * 36, 256), dtype=torch.uint8, device=dev)
+                ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, N_SETS, drop, rng.ptr, 1, 7, ops._stream())
+            for split in args.splits:      # kernel variant: 1 automatic, 2 cluster (low latency), 4 streaming
                 for mode in (0, 1):
-                    t = time_graph(lambda k: ops.pano_attn_raw(store, vps[k], view, q, attn, mode, drop, rng, 2, split,
-                                                               fwd if mode else None))
+                    out = torch.empty(B, 2176, device=dev)
+
+                    def run(k):
+                        ops._call("vln_pano_attn_ld", store.handle, ops._ptr(vps[k]), ops._ptr(view), ops._ptr(store.loc4),
+                                  ops._ptr(q), 2176, ops._ptr(attn), None, 2176, ops._ptr(out), 2176, B, mode, drop, rng.ptr, 0,
+                                  ops._ptr(bits[k]) if bits is not None else None, split, ops._stream())
+                    if mode == 1:
+                        attn.copy_(torch.softmax(torch.randn(B, 36, device=dev), 1))
+                    t = time_graph(run)
                     gbs = B * 147456 / t / 1e9
-                    print(json.dumps(dict(kernel="pano_attn", mode="fwd" if mode == 0 else "bwd", B=B, split=split,
+                    print(json.dumps(dict(kernel="pano_attn", mode="fwd" if mode == 0 else "bwd", B=B, variant=split,
                                           drop=drop, us=round(t * 1e6, 2), algo_GBs=round(gbs, 1),
                                           frac_of_measured_peak=round(gbs / peak, 3))), flush=True)
+            del bits
         tgt = torch.randn(B, 2176, device=dev) * 0.05
         logits = torch.empty(B, 16, device=dev)
         ncs = sum(int(tables["n_cand"][v.long()].sum()) for v in vps) / N_SETS
