@@ -153,6 +153,22 @@ def roofline_pano(store, ops, torch, B, split, peaks):
             "note": "B=64 episodes per launch is the north-star shape: 9.4 MB per launch = 1.4 us at peak, so the launch is latency-bound; tools/microbench.py sweeps B up to 2048"}
 
 
+def ncu_traffic(csv_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed `ncu --set full` capture
+    (profiles/, trimmed by tools/ncu_trim.py); None when the capture is not there."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for row in csv.reader(open(path)):
+        if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            vals = [float(v) for v in row[2:]]
+            tot += scale.get(row[1], 1.0) * sum(vals) / len(vals)
+    return int(tot) if tot else None
+
+
 def cpu_iteration_factory(world_small, items, B, threads):
     """The oracle's CPU restatement of one reference EnvDrop training iteration (test infrastructure
     used here only as the timed CPU baseline)."""
@@ -324,6 +340,9 @@ def run_b200(args):
     if rank == 0:
         store = agent.store_of(env)
         out["roofline"] = roofline_pano(store, ops, torch, args.batch, agent.split_for(args.batch), peaks)
+        if args.batch == 64:
+            out["roofline"]["traffic"] = ncu_traffic("r01_ncu_pano_cluster_B64.csv")
+            out["roofline"]["traffic_source"] = "profiles/r01_ncu_pano_cluster_B64.csv (ncu --set full, bytes per launch; algorithmic = 64 x 147456 = 9437184 + 589824 B of keep-bits)"
         # the same kernel at larger episode counts per launch (BASELINE config 5): where it leaves the latency regime
         out["roofline"]["sweep"] = [
             {k: r[k] for k in ("episodes_per_launch", "us_per_launch", "achieved", "frac")}

@@ -114,7 +114,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
                      const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_hi1,
                      const __grid_constant__ CUtensorMap tm_lo1, const __grid_constant__ CUtensorMap tm_x1, int M, int N,
                      int K, const float* __restrict__ bias, float* __restrict__ y0, float* __restrict__ y1, int ldy,
-                     int splits, int accumulate, int mode, int dbg) {
+                     int splits, int accumulate, int mode, int dbg, int m_tiles) {
   // blockIdx.z selects one of two independent problems of identical shape (e.g. the candidate projection of
   // step t and the visual-attention query of step t+1, which both only wait for h~_t)
   const CUtensorMap& tm_hi = blockIdx.z == 0 ? tm_hi0 : tm_hi1;
@@ -143,7 +143,10 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
     __syncthreads();
     slot = slot_s;
   }
-  const int tile = blockIdx.x, split = blockIdx.y;                   // cluster = the `splits` CTAs of one tile
+  // skinny launches: blockIdx.y = split-K slice of one weight tile (the `splits` CTAs of a tile may form a cluster);
+  // tall launches (m_tiles > 1, splits == 1): blockIdx.y = block of MP activation rows, plain stores into y
+  const int tile = blockIdx.x, split = m_tiles > 1 ? 0 : (int)blockIdx.y;
+  const int m0 = m_tiles > 1 ? (int)blockIdx.y * MP : 0;
   const int nkb = K / kBK;
   const int kb0 = (int)((long long)split * nkb / splits), kb1 = (int)((long long)(split + 1) * nkb / splits);
   const int n_iter = kb1 - kb0;
@@ -187,7 +190,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
           // the weight tiles were written before this chain of kernels started; the activations come from the
           // predecessor: everything downstream (conversion, MMA, epilogue) is ordered after this wait
           if (it == 0) pdl_wait();
-          tma_load_2d(st + 2 * C::kABytes + 2 * C::kBBytes, &tm_x, &full_w[s], (kb0 + it) * kBK, 0);
+          tma_load_2d(st + 2 * C::kABytes + 2 * C::kBBytes, &tm_x, &full_w[s], (kb0 + it) * kBK, m0);
         }
       }
     } else if (warp == 1) {
@@ -271,15 +274,19 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
     for (int item = tid; item < MP * (kTileN / 4); item += kThreads) {
       const int m = item / (kTileN / 4), c = (item - m * (kTileN / 4)) * 4;
       const int n = tile * kTileN + c;
-      if (m >= M || n >= N) continue;
+      if (m0 + m >= M || n >= N) continue;
       float4 acc = *reinterpret_cast<const float4*>(red + m * kTileN + c);
       if (bias != nullptr && split == 0) {
         const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
         acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
       }
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(y + (size_t)m * ldy + n), "f"(acc.x), "f"(acc.y),
-                   "f"(acc.z), "f"(acc.w)
-                   : "memory");
+      float* dst = y + (size_t)(m0 + m) * ldy + n;
+      if (m_tiles > 1 && !accumulate) {
+        *reinterpret_cast<float4*>(dst) = acc;              // the only writer of this element: no zero-fill, no reduction
+      } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w)
+                     : "memory");
+      }
     }
   } else {
     if (splits > 1) {
@@ -400,7 +407,7 @@ struct Second {                                            // second problem of 
 
 template <int MP>
 int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
-                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec = Second()) {
+                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec = Second(), int m_tiles = 1) {
   CUtensorMap tm_hi, tm_lo;
   int rc = vln_make_tmap_2d(&tm_hi, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
   if (rc) return rc;
@@ -422,9 +429,9 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   }
   const int tiles = (N + kTileN - 1) / kTileN;
   const int mode = variant().mode;
-  if (mode == 2 && !accumulate) VLN_CHECK_CUDA(cudaMemset2DAsync(y, (size_t)ldy * 4, 0, (size_t)N * 4, M, stream));
+  if (mode == 2 && !accumulate && m_tiles == 1) VLN_CHECK_CUDA(cudaMemset2DAsync(y, (size_t)ldy * 4, 0, (size_t)N * 4, M, stream));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(tiles, splits, sec.y ? 2 : 1);
+  cfg.gridDim = dim3(tiles, m_tiles > 1 ? m_tiles : splits, sec.y ? 2 : 1);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg<MP>::kSmem;
   cfg.stream = stream;
@@ -446,7 +453,7 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   cfg.numAttrs = na;
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP>, tm_hi, tm_lo, tm_x, tm_hi1, tm_lo1, tm_x1, M, N, K, bias, y,
                                     sec.y ? sec.y : y, ldy, splits,
-                                    accumulate, mode, variant().dbg));
+                                    accumulate, m_tiles > 1 ? 2 : mode, variant().dbg, m_tiles));
   return 0;
 }
 
@@ -470,6 +477,22 @@ extern "C" int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int 
   if (variant().mode == 2) s = splits;
   if (M <= 64) return launch_linear<64>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
   return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
+}
+
+// Tall activations (the encoder's input projection over all B*L token rows, units.py:58-63; the critic over all
+// T*B states, policy.py:263): blocks of 128 activation rows x 128 weight rows per CTA, whole K, plain stores.
+extern "C" int vln_linear_bf16x3_tall(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
+                                      const float* bias, float* y, int ldy, int accumulate, void* stream) {
+  VLN_REQUIRE(w_hi && w_lo && x && y && N > 0 && M > 0, "bad arguments");
+  VLN_REQUIRE(K > 0 && K % kBK == 0, "K must be a positive multiple of 64");
+  VLN_REQUIRE(((uintptr_t)x & 15) == 0 && ldx % 4 == 0, "x rows must be 16-byte aligned");
+  VLN_REQUIRE(N % 4 == 0 && ((uintptr_t)y & 15) == 0 && ldy % 4 == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
+              "N must be a multiple of 4 and y / bias 16-byte aligned");
+  VLN_REQUIRE(((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)w_lo & 15) == 0, "weights must be 16-byte aligned");
+  const int m_tiles = (M + 127) / 128;
+  VLN_REQUIRE(m_tiles <= 65535, "too many activation rows");
+  if (m_tiles == 1) return vln_linear_bf16x3(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, accumulate, 0, stream);
+  return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, 1, accumulate, (cudaStream_t)stream, Second(), m_tiles);
 }
 
 // Two independent products of identical shape in one launch: y0 += x0 W0^T, y1 += x1 W1^T (both accumulate).

@@ -49,6 +49,8 @@ def main():
     ap.add_argument("--batches", type=int, nargs="*", default=[16, 64, 128, 256, 512, 1024, 2048])
     ap.add_argument("--splits", type=int, nargs="*", default=[1, 2, 4])
     ap.add_argument("--drops", type=float, nargs="*", default=[0.0, 0.3])
+    ap.add_argument("--modes", type=int, nargs="*", default=[0, 1], help="0 forward, 1 backward")
+    ap.add_argument("--no-cand", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peaks = {}
@@ -81,7 +83,7 @@ def main():
                 bits = torch.empty((N_SETS, B * 36, 256), dtype=torch.uint8, device=dev)
                 ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, N_SETS, drop, rng.ptr, 1, 7, ops._stream())
             for split in args.splits:      # kernel variant: 1 automatic, 2 cluster (low latency), 4 streaming
-                for mode in (0, 1):
+                for mode in args.modes:
                     out = torch.empty(B, 2176, device=dev)
 
                     def run(k):
@@ -96,6 +98,8 @@ def main():
                                           drop=drop, us=round(t * 1e6, 2), algo_GBs=round(gbs, 1),
                                           frac_of_measured_peak=round(gbs / peak, 3))), flush=True)
             del bits
+        if args.no_cand:
+            continue
         tgt = torch.randn(B, 2176, device=dev) * 0.05
         logits = torch.empty(B, 16, device=dev)
         ncs = sum(int(tables["n_cand"][v.long()].sum()) for v in vps) / N_SETS
