@@ -68,6 +68,7 @@ _SIGS = {
     "vln_lstm_pointwise_fwd": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_pointwise_bwd": ([_p, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_linear_bf16x3": ([_p, _p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _i, _p], _i),
+    "vln_linear_bf16x3_tall": ([_p, _p, _i, _i, _p, _i, _i, _p, _p, _i, _i, _p], _i),
     "vln_linear_bf16x3_pair": ([_p] * 8 + [_i] * 5 + [_p], _i),
     "vln_split_bf16": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_seq_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
@@ -75,6 +76,8 @@ _SIGS = {
     "vln_policy_fwd": ([_p, _p, _i, _p, _u64, _p, _p, _p, _p, _p, _i, _p], _i),
     "vln_policy_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _p], _i),
     "vln_dropout": ([_p, _p, _i64, _f, _p, _u64, _p], _i),
+    "vln_embed_drop_fwd": ([_p, _p, _p, _i64, _i, _i, _f, _p, _u64, _p], _i),
+    "vln_embed_drop_bwd": ([_p, _p, _p, _i64, _i, _i, _i, _f, _p, _u64, _p], _i),
     "vln_dropout_mask": ([_p, _i64, _f, _p, _u64, _p], _i),
     "vln_rng_advance": ([_p, _u64, _p], _i),
     "vln_env_step": ([_p] * 21 + [_i, _p], _i),

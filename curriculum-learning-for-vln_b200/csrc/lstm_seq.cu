@@ -477,6 +477,39 @@ int launch_bwd(DirB d0, DirB d1, int n_dir, const int32_t* lengths, int B, int L
 
 }  // namespace
 
+// How many clusters of the recurrence kernels can be resident at once (cudaOccupancyMaxActiveClusters): a launch of
+// (B/8) * n_dir clusters beyond this runs in two waves, i.e. twice the 80-step latency chain.
+template <typename K>
+static int max_clusters(K kernel, size_t smem, int C, int* out) {
+  VLN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C * 64, 1);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VLN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(out, kernel, &cfg));
+  return 0;
+}
+extern "C" int vln_debug_lstm_occupancy(int H, int* fwd_clusters, int* bwd_clusters) {
+  VLN_REQUIRE(fwd_clusters && bwd_clusters, "bad arguments");
+  if (H == 256) {
+    if (int rc = max_clusters(lstm_seq_fwd_kernel<256>, sizeof(SmemF<256>), 8, fwd_clusters)) return rc;
+    return max_clusters(lstm_seq_bwd_kernel<256>, sizeof(SmemB<256>), 8, bwd_clusters);
+  }
+  if (H == 128) {
+    if (int rc = max_clusters(lstm_seq_fwd_kernel<128>, sizeof(SmemF<128>), 4, fwd_clusters)) return rc;
+    return max_clusters(lstm_seq_bwd_kernel<128>, sizeof(SmemB<128>), 4, bwd_clusters);
+  }
+  vln_set_error("vln_debug_lstm_occupancy: hidden size %d per direction is not supported (128 or 256)", H);
+  return -1;
+}
+
 extern "C" int vln_debug_lstm_stamps(unsigned long long* out_host /*[8]*/) {
   VLN_CHECK_CUDA(cudaDeviceSynchronize());
   VLN_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_lstm_stamps, sizeof(unsigned long long) * 12));

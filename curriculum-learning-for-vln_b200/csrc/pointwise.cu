@@ -107,16 +107,135 @@ __global__ void policy_bwd_kernel(const float* __restrict__ probs, const int32_t
 
 // ---- dropout ----------------------------------------------------------------------------------
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
-                               const uint64_t* __restrict__ rng, uint64_t call_off) {
+                               const uint64_t* __restrict__ rng, uint64_t call_off, int vec) {
   const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t e0 = blk * 8;
   if (e0 >= n) return;
   const Philox8 r = philox8(rng[0], rng[1] + call_off, (uint64_t)blk);
   const uint32_t thr = drop_threshold(p);
   const float sc = 1.0f / (1.0f - p);
+  if (vec && e0 + 8 <= n) {                                 // 16-byte aligned tensors: two float4 each way
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + e0)), b = __ldg(reinterpret_cast<const float4*>(x + e0) + 1);
+    float4 oa, ob;
+    oa.x = philox_keep(r, 0, thr) ? a.x * sc : 0.f; oa.y = philox_keep(r, 1, thr) ? a.y * sc : 0.f;
+    oa.z = philox_keep(r, 2, thr) ? a.z * sc : 0.f; oa.w = philox_keep(r, 3, thr) ? a.w * sc : 0.f;
+    ob.x = philox_keep(r, 4, thr) ? b.x * sc : 0.f; ob.y = philox_keep(r, 5, thr) ? b.y * sc : 0.f;
+    ob.z = philox_keep(r, 6, thr) ? b.z * sc : 0.f; ob.w = philox_keep(r, 7, thr) ? b.w * sc : 0.f;
+    reinterpret_cast<float4*>(y + e0)[0] = oa;
+    reinterpret_cast<float4*>(y + e0)[1] = ob;
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     if (e0 + j < n) y[e0 + j] = philox_keep(r, j, thr) ? x[e0 + j] * sc : 0.f;
+}
+
+// nn.Embedding + nn.Dropout of EncoderLSTM (units.py:48-52) in one pass: y[r, :] = drop(emb[tok[r], :]); the keep
+// mask is the one vln_dropout / vln_dropout_mask give for the dense [rows, E] tensor under (rng, call_off).
+__global__ void embed_drop_fwd_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb, float* __restrict__ y,
+                                      int64_t rows, int E, int V, float p, const uint64_t* __restrict__ rng, uint64_t call_off) {
+  const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = blk * 8, n = rows * E;
+  if (e0 >= n) return;
+  const Philox8 r = philox8(rng[0], rng[1] + call_off, (uint64_t)blk);
+  const uint32_t thr = drop_threshold(p);
+  const float sc = 1.0f / (1.0f - p);
+  if ((E & 7) == 0) {                                       // the 8 elements share a row; 32-byte aligned both sides
+    const int64_t row = e0 / E;
+    const int col = (int)(e0 - row * E);
+    int64_t t = tok[row];
+    t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+    const float4* src = reinterpret_cast<const float4*>(emb + t * E + col);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    float4 oa, ob;
+    oa.x = philox_keep(r, 0, thr) ? a.x * sc : 0.f; oa.y = philox_keep(r, 1, thr) ? a.y * sc : 0.f;
+    oa.z = philox_keep(r, 2, thr) ? a.z * sc : 0.f; oa.w = philox_keep(r, 3, thr) ? a.w * sc : 0.f;
+    ob.x = philox_keep(r, 4, thr) ? b.x * sc : 0.f; ob.y = philox_keep(r, 5, thr) ? b.y * sc : 0.f;
+    ob.z = philox_keep(r, 6, thr) ? b.z * sc : 0.f; ob.w = philox_keep(r, 7, thr) ? b.w * sc : 0.f;
+    reinterpret_cast<float4*>(y + e0)[0] = oa;
+    reinterpret_cast<float4*>(y + e0)[1] = ob;
+    return;
+  }
+  for (int j = 0; j < 8 && e0 + j < n; ++j) {
+    const int64_t row = (e0 + j) / E;
+    const int col = (int)(e0 + j - row * E);
+    int64_t t = tok[row];
+    t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+    y[e0 + j] = philox_keep(r, j, thr) ? __ldg(emb + t * E + col) * sc : 0.f;
+  }
+}
+
+// Its backward: d_emb[v, :] = sum over the rows r with tok[r] == v (in row order: deterministic, unlike an atomic
+// scatter; ATen's embedding_dense_backward sorts the indices instead) of mask(r, :) * d_y[r, :] / (1 - p); the
+// padding row gets zero (nn.Embedding(padding_idx=0), units.py:33).  One CTA per vocabulary entry, one thread per column.
+constexpr int kEmbChunk = 2048;
+__global__ void __launch_bounds__(256)
+embed_drop_bwd_kernel(const int64_t* __restrict__ tok, const float* __restrict__ dy, float* __restrict__ d_emb, int64_t rows,
+                      int E, int padding_idx, float p, const uint64_t* __restrict__ rng, uint64_t call_off) {
+  __shared__ int s_rows[kEmbChunk];
+  __shared__ int s_warp_cnt[8];
+  const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t thr = drop_threshold(p);
+  const float sc = 1.0f / (1.0f - p);
+  const uint64_t seed = rng[0], off = rng[1] + call_off;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};                      // columns tid, tid + 256, ... (E <= 1024)
+  if (v != padding_idx) {
+    for (int64_t base = 0; base < rows; base += kEmbChunk) {
+      // ordered compaction of the matching rows of this chunk (ballot + prefix over warps keeps row order);
+      // the chunk's tokens are fetched up front so the eight passes do not each wait for L2
+      int n_prev = 0;
+      bool hits[kEmbChunk / 256];
+#pragma unroll
+      for (int i = 0; i < kEmbChunk / 256; ++i) {
+        const int64_t r = base + i * 256 + tid;
+        hits[i] = r < rows && __ldg(tok + r) == (int64_t)v;
+      }
+#pragma unroll
+      for (int i = 0; i < kEmbChunk / 256; ++i) {
+        const unsigned m = __ballot_sync(0xffffffffu, hits[i]);
+        if (lane == 0) s_warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int before = n_prev;
+        for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
+        if (hits[i]) s_rows[before + __popc(m & ((1u << lane) - 1u))] = i * 256 + tid;
+        for (int w = 0; w < 8; ++w) n_prev += s_warp_cnt[w];
+        __syncthreads();
+      }
+      const int cnt = n_prev;                                 // identical in every thread
+      for (int k0 = 0; k0 < cnt; k0 += 4) {                   // four rows in flight, accumulated in row order
+        float val[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t r = base + s_rows[min(k0 + j, cnt - 1)];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = tid + c * 256;
+            val[j][c] = (k0 + j < cnt && col < E) ? __ldg(dy + r * E + col) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (k0 + j >= cnt) break;
+          const int64_t r = base + s_rows[k0 + j];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = tid + c * 256;
+            if (col < E) {
+              const int64_t idx = r * E + col;
+              const Philox8 ph = philox8(seed, off, (uint64_t)(idx >> 3));
+              if (philox_keep(ph, (int)(idx & 7), thr)) acc[c] += val[j][c] * sc;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int col = tid + c * 256;
+    if (col < E) d_emb[(size_t)v * E + col] = acc[c];
+  }
 }
 
 __global__ void rng_advance_kernel(uint64_t* rng, uint64_t delta) { rng[1] += delta; }
@@ -423,7 +542,27 @@ extern "C" int vln_dropout(const float* x, float* y, int64_t n, float p, const u
                            void* stream) {
   VLN_REQUIRE(x && y && rng && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
   const int64_t blks = (n + 7) / 8;
-  dropout_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(x, y, n, p, rng, call_off);
+  const int vec = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  dropout_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(x, y, n, p, rng, call_off, vec);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_embed_drop_fwd(const int64_t* tokens, const float* emb, float* y, int64_t rows, int E, int V, float p,
+                                  const uint64_t* rng, uint64_t call_off, void* stream) {
+  VLN_REQUIRE(tokens && emb && y && rng && rows > 0 && E > 0 && V > 0 && p >= 0.f && p < 1.f, "bad arguments");
+  VLN_REQUIRE((((uintptr_t)emb | (uintptr_t)y) & 15) == 0, "embedding table and output must be 16-byte aligned");
+  const int64_t blks = (rows * E + 7) / 8;
+  embed_drop_fwd_kernel<<<(unsigned)((blks + 255) / 256), 256, 0, STREAM>>>(tokens, emb, y, rows, E, V, p, rng, call_off);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vln_embed_drop_bwd(const int64_t* tokens, const float* d_y, float* d_emb, int64_t rows, int E, int V,
+                                  int padding_idx, float p, const uint64_t* rng, uint64_t call_off, void* stream) {
+  VLN_REQUIRE(tokens && d_y && d_emb && rng && rows > 0 && V > 0 && p >= 0.f && p < 1.f, "bad arguments");
+  VLN_REQUIRE(E > 0 && E <= 1024, "embedding width must be at most 1024");
+  embed_drop_bwd_kernel<<<V, 256, 0, STREAM>>>(tokens, d_y, d_emb, rows, E, padding_idx, p, rng, call_off);
   VLN_LAUNCH_OK();
   return 0;
 }

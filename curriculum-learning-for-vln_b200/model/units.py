@@ -108,9 +108,11 @@ class EncoderLSTM(KernelModule):
         dev = inputs.device
         if lengths.device != dev:
             lengths = lengths.to(dev)
-        x = self.embedding(inputs)
-        if not self.use_glove:
-            x = self._drop(x, self.drop_ratio, "enc_embed")
+        if self.use_glove:
+            x = self.embedding(inputs)                       # frozen GloVe rows, no dropout (units.py:49-52)
+        else:
+            p = self.drop_ratio if self.training else 0.0
+            x = ops.embed_dropout(inputs, self.embedding.weight, self.embedding.padding_idx, p, self._rng(inputs))
         B, L, _ = x.shape
         h_last = c_last = None
         for layer in range(self.num_layers):

@@ -237,9 +237,42 @@ def wgrad(dy, x):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def _tc_matmul_tall(x, hi, lo, N, K, bias=None):
+    """x @ W^T (+ bias) for M > 128 rows: 128x128 output blocks, plain stores (csrc/gemm.cu, tall mode)."""
+    M = x.shape[0]
+    out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    _call("vln_linear_bf16x3_tall", _ptr(hi), _ptr(lo), N, K, _ptr(x), x.stride(0), M, _ptr(bias), _ptr(out),
+          out.stride(0), 0, _stream())
+    return out
+
+
+class _LinearTall(torch.autograd.Function):
+    """Tall inputs (encoder input projection [B*L, E], batched critic [T*B, H]) on the same tcgen05 bf16x3
+    kernel, forward and input gradient; weight gradient through wgrad()."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _f32c(x)
+        sw = _split_of(w)
+        N, K = w.shape
+        ctx.save_for_backward(x, w)
+        ctx.sw, ctx.has_b = sw, b is not None
+        return _tc_matmul_tall(x, sw.hi, sw.lo, N, K, b.detach() if b is not None else None)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _f32c(dy)
+        N, K = w.shape
+        dx = _tc_matmul_tall(dy, ctx.sw.hi_t, ctx.sw.lo_t, K, N) if ctx.needs_input_grad[0] else None
+        dw = wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        db = dy.sum(0) if ctx.has_b and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
 class _LinearLib(torch.autograd.Function):
-    """Library GEMM for tall inputs (encoder input projection [B*L, E], batched critic): fp32 forward and
-    input gradient, weight gradient through wgrad()."""
+    """Library GEMM for shapes the tcgen05 kernel does not take (K not a multiple of 64, e.g. the Follower's
+    300-wide embeddings): fp32 forward and input gradient, weight gradient through wgrad()."""
 
     @staticmethod
     def forward(ctx, x, w, b):
@@ -257,11 +290,15 @@ class _LinearLib(torch.autograd.Function):
 
 
 def linear(x, w, b=None, acc=None):
-    """y = x W^T + b (+ acc).  Batches of at most 128 rows run on the tcgen05 bf16x3 kernel
-    (csrc/gemm.cu); larger ones (encoder input projection, batched critic) are plain library GEMMs."""
-    if (USE_TC_LINEAR[0] and x.is_cuda and x.dim() == 2 and x.shape[0] <= 128 and w.shape[1] % 64 == 0
-            and w.shape[0] % 4 == 0 and x.dtype == torch.float32):
+    """y = x W^T + b (+ acc) on the tcgen05 bf16x3 kernel (csrc/gemm.cu): split-K skinny launches for at
+    most 128 rows, 128x128 output blocks for taller inputs (encoder input projection, batched critic)."""
+    ok = (USE_TC_LINEAR[0] and x.is_cuda and x.dim() == 2 and w.shape[1] % 64 == 0 and w.shape[0] % 4 == 0
+          and x.dtype == torch.float32)
+    if ok and x.shape[0] <= 128:
         return _LinearTC.apply(x, w, b, acc)
+    if ok and w.shape[0] % 64 == 0:
+        y = _LinearTall.apply(x, w, b)
+        return y if acc is None else y + acc
     y = _LinearLib.apply(x, w, b) if x.dim() == 2 else F.linear(x, w, b)
     return y if acc is None else y + acc
 
@@ -588,6 +625,39 @@ def dropout(x, p, rng, tag="drop"):
     if p <= 0.0:
         return x
     return _Dropout.apply(x, p, rng, rng.next(tag, x.shape, p))
+
+
+class _EmbedDrop(torch.autograd.Function):
+    """nn.Embedding(padding_idx) -> nn.Dropout (units.py:48-52) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, tokens, weight, padding_idx, p, rng, call_off):
+        tokens = tokens.contiguous()
+        assert tokens.is_cuda and tokens.dtype == torch.int64
+        w = _f32c(weight)
+        V, E = w.shape
+        y = torch.empty(tokens.shape + (E,), device=w.device, dtype=torch.float32)
+        _call("vln_embed_drop_fwd", _ptr(tokens), _ptr(w), _ptr(y), tokens.numel(), E, V, float(p), rng.ptr, call_off,
+              _stream())
+        ctx.save_for_backward(tokens)
+        ctx.cfg = (V, E, -1 if padding_idx is None else int(padding_idx), float(p), rng, call_off)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        tokens, = ctx.saved_tensors
+        V, E, pad, p, rng, call_off = ctx.cfg
+        g = _f32c(g)
+        d_w = torch.empty((V, E), device=g.device, dtype=torch.float32)
+        _call("vln_embed_drop_bwd", _ptr(tokens), _ptr(g), _ptr(d_w), tokens.numel(), E, V, pad, p, rng.ptr, call_off,
+              _stream())
+        return None, d_w, None, None, None, None
+
+
+def embed_dropout(tokens, weight, padding_idx, p, rng, tag="enc_embed"):
+    """drop(embedding(tokens)); p == 0 (eval) is the plain lookup through the same kernel."""
+    off = rng.next(tag, tuple(tokens.shape) + (weight.shape[1],), p) if p > 0.0 else 0
+    return _EmbedDrop.apply(tokens, weight, padding_idx, p, rng, off)
 
 
 def dropout_mask(shape, p, rng, call_off, device=None):

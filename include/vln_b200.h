@@ -212,6 +212,12 @@ int vln_cand_logits_bwd_policy(const vln_ctx* ctx, const int32_t* vp, const int3
  * For input gradients pass the transposed split (w^T as a [K,N] weight) and x = dY. */
 int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
                       const float* bias, float* y, int ldy, int accumulate, int splits, void* stream);
+/* The same product for TALL activations (M > 128 rows): the encoder's input projection over all B*L token
+ * rows (nn.LSTM's x W_ih^T + b, units.py:58-63) and the critic over all T*B states (policy.py:263).
+ * One CTA per (128 weight rows x 128 activation rows) block over the whole K, plain stores (or += with
+ * accumulate = 1); same bf16x3 precision, same operand rules. */
+int vln_linear_bf16x3_tall(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M,
+                           const float* bias, float* y, int ldy, int accumulate, void* stream);
 /* Two independent products of identical shape in ONE launch (y0 += x0 W0^T, y1 += x1 W1^T; both
  * accumulate): the candidate projection of step t (policy.py:199-206) and the visual-attention query
  * of step t+1 (units.py:107) both only wait for h~_t. */
@@ -258,6 +264,14 @@ int vln_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* rn
                 void* stream);
 /* keep-mask bytes (1 = kept) for elements [0,n) of the stream (seed, offset). */
 int vln_dropout_mask(uint8_t* mask, int64_t n, float p, const uint64_t* rng, uint64_t call_off, void* stream);
+/* nn.Embedding(padding_idx) + nn.Dropout of EncoderLSTM.forward (units.py:48-52) in one pass over the
+ * [rows = B*L, E] token rows: y = drop(emb[tokens]) with the keep mask vln_dropout_mask gives for the dense
+ * [rows, E] tensor under (rng, call_off); p = 0 is a plain lookup.  The backward writes the whole d_emb [V,E]
+ * (rows of one vocabulary entry summed in row order: deterministic; the padding row is zero). */
+int vln_embed_drop_fwd(const int64_t* tokens, const float* emb, float* y, int64_t rows, int E, int V, float p,
+                       const uint64_t* rng, uint64_t call_off, void* stream);
+int vln_embed_drop_bwd(const int64_t* tokens, const float* d_y, float* d_emb, int64_t rows, int E, int V,
+                       int padding_idx, float p, const uint64_t* rng, uint64_t call_off, void* stream);
 /* rng[1] += delta (one thread); lets graph replays move to fresh streams. */
 int vln_rng_advance(uint64_t* rng, uint64_t delta, void* stream);
 

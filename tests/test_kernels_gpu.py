@@ -235,6 +235,52 @@ def test_dropout(setup):
     assert torch.equal(g, keep * 2.0)
 
 
+@pytest.mark.parametrize("E,p", [(256, 0.5), (300, 0.5), (256, 0.0)])
+def test_embed_dropout_fwd_bwd(setup, E, p):
+    """Embedding + dropout in one kernel (units.py:48-52): forward bit-equal to embedding * the Philox mask of
+    the dense tensor, backward equal to embedding_dense_backward of the masked gradient (padding row zero)."""
+    _, _, ops, dev = setup
+    torch.manual_seed(3)
+    B, L, V = 16, 37, 992
+    tok = torch.randint(0, V, (B, L), device=dev)
+    tok[:, -5:] = 0                                                      # padding
+    tok[0, :8] = 7                                                       # repeated entry
+    w = torch.randn(V, E, device=dev, requires_grad=True)
+    rng = ops.Rng(11, dev)
+    rng.log = []
+    y = ops.embed_dropout(tok, w, 0, p, rng)
+    if p > 0:
+        (tag, shape, pp, off), = rng.log
+        assert tag == "enc_embed" and shape == (B, L, E)
+        keep = ops.dropout_mask(shape, p, rng, off).float()
+    else:
+        assert rng.log == []
+        keep = torch.ones(B, L, E, device=dev)
+    w2 = w.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.embedding(tok, w2, padding_idx=0) * keep * (1.0 / (1.0 - p))
+    assert torch.equal(y, ref)
+    g = torch.randn_like(y)
+    dw, = torch.autograd.grad(y, w, g)
+    dref, = torch.autograd.grad(ref, w2, g)
+    assert float(dw[0].abs().max()) == 0.0
+    assert relerr(dw, dref) < 1e-5
+    dw_again, = torch.autograd.grad(ops.embed_dropout(tok, w, 0, 0.0, rng), w, g)    # deterministic summation order
+    dw_again2, = torch.autograd.grad(ops.embed_dropout(tok, w, 0, 0.0, rng), w, g)
+    assert torch.equal(dw_again, dw_again2)
+
+
+def test_dropout_unaligned_and_ragged(setup):
+    """The vectorised dropout path and the scalar tail / unaligned fallback draw the same mask."""
+    _, _, ops, dev = setup
+    rng = ops.Rng(5, dev)
+    base = torch.randn(4099, device=dev)
+    for x in (base, base[1:], base[:4096]):
+        y = ops._Dropout.apply(x.contiguous() if x.data_ptr() % 16 == 0 else x, 0.3, rng, 3)
+        keep = ops.dropout_mask(x.shape, 0.3, rng, 3).float()
+        sc = 1.0 / (1.0 - torch.tensor(0.3, dtype=torch.float32, device=dev))      # the kernel's fp32 1/(1-p)
+        assert torch.equal(y, x * keep * sc)
+
+
 def test_env_step_matches_world(setup):
     world, store, ops, dev = setup
     from clvln_b200.environ import make_items
@@ -423,6 +469,27 @@ def test_linear_tcgen05_bf16x3(setup, M, N, K):
     with torch.no_grad():
         w.mul_(0.5)
     assert relerr(ops.linear(x, w).double(), x.double() @ w.double().t()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(5120, 1024, 256), (2368, 512, 512), (129, 256, 64), (700, 192, 320)])
+def test_linear_tcgen05_tall(setup, M, N, K):
+    """Tall activations (encoder input projection over B*L rows, batched critic): 128x128 output blocks,
+    plain stores; forward + input gradient on the kernel vs fp64, ragged last row block included."""
+    _, _, ops, dev = setup
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=dev, requires_grad=True)
+    w = (torch.randn(N, K, device=dev) * 0.05).requires_grad_(True)
+    b = torch.randn(N, device=dev, requires_grad=True)
+    y = ops.linear(x, w, b)
+    assert y.shape == (M, N)
+    assert relerr(y.double(), x.double() @ w.double().t() + b.double()) < 2e-5
+    g = torch.randn_like(y)
+    dx, dw, db = torch.autograd.grad(y, (x, w, b), g)
+    assert relerr(dx.double(), g.double() @ w.double()) < 2e-5
+    assert relerr(dw.double(), g.double().t() @ x.double()) < 1e-5
+    assert relerr(db, g.sum(0)) < 1e-4
+    acc = torch.randn(M, N, device=dev)
+    assert relerr(ops.linear(x, w, None, acc).double(), x.double() @ w.double().t() + acc.double()) < 2e-5
 
 
 def test_wgrad_tf32_tolerance(setup):

@@ -33,3 +33,21 @@ names = ["mma + gate stores", "syncthreads", "pointwise + global stores", "st.as
 print(", ".join(f"{n}={buf[i + 1] - buf[i]}" for i, n in enumerate(names)), "cycles; step total", buf[5] - buf[0])
 print("kernel: prologue (weight fragments, barrier init, cluster sync) = %d cycles, %d steps = %d cycles (%.0f per step), epilogue = %d"
       % (buf[7] - buf[6], L, buf[8] - buf[7], (buf[8] - buf[7]) / L, buf[9] - buf[8]))
+L_.vln_debug_lstm_occupancy.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+f, b = C.c_int(0), C.c_int(0)
+for h in (256, 128):
+    if L_.vln_debug_lstm_occupancy(h, C.byref(f), C.byref(b)) == 0:
+        print(f"H={h}: max resident clusters fwd={f.value} bwd={b.value} (a B=64 bidirectional launch has 16)")
+# one wave or two?  time the launch at 8, 16, 24, 32 clusters (B = 32 .. 128, both directions)
+for Bx in (32, 56, 64, 96, 128):
+    xp = [torch.randn(Bx, L, 4 * H, device=dev) * 0.1 for _ in range(2)]
+    ln = torch.full((Bx,), L, dtype=torch.int32, device=dev)
+    for _ in range(2):
+        ops.lstm_layer(xp, whh, ln)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        ops.lstm_layer(xp, whh, ln)
+    e1.record()
+    torch.cuda.synchronize()
+    print("B=%d (%d clusters): fwd launch %.1f us" % (Bx, 2 * ((Bx + 7) // 8), e0.elapsed_time(e1) * 100))
