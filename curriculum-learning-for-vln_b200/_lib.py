@@ -73,6 +73,7 @@ _SIGS = {
     "vln_split_bf16": ([_p, _p, _p, _p, _p, _i, _i, _p], _i),
     "vln_lstm_seq_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "vln_lstm_seq_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
+    "vln_lstm_set_variant": ([_i], _i),
     "vln_policy_fwd": ([_p, _p, _i, _p, _u64, _p, _p, _p, _p, _p, _i, _p], _i),
     "vln_policy_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _i, _p], _i),
     "vln_dropout": ([_p, _p, _i64, _f, _p, _u64, _p], _i),

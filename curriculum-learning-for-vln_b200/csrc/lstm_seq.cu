@@ -20,6 +20,7 @@
 //
 // Roofline class: latency (80 serial steps); per step and CTA 3 x 16 x H/16 MMAs (m16n8k16).
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -516,6 +517,27 @@ extern "C" int vln_debug_lstm_stamps(unsigned long long* out_host /*[8]*/) {
   return 0;
 }
 
+// tcgen05 version of the two kernels (csrc/lstm_tc.cu): the default; VLN_LSTM_VARIANT=mma keeps the mma.sync kernels above.
+int vln_lstm_tc_fwd(const float* const* xproj, const float* const* w_hh, const int32_t* lengths, float* out,
+                    float* const* acts, float* const* cs, float* h_last, float* c_last, int B, int L, int H, int n_dir,
+                    cudaStream_t stream);
+int vln_lstm_tc_bwd(const float* const* w_hh, const int32_t* lengths, const float* const* acts, const float* const* cs,
+                    const float* d_out, const float* d_hlast, const float* d_clast, float* const* d_xproj, int B, int L,
+                    int H, int n_dir, cudaStream_t stream);
+static int g_variant = -1;                                // -1: read VLN_LSTM_VARIANT once; 0: mma.sync; 1: tcgen05
+static bool use_tc() {
+  if (g_variant < 0) {
+    const char* e = getenv("VLN_LSTM_VARIANT");
+    g_variant = (e && !strcmp(e, "mma")) ? 0 : 1;
+  }
+  return g_variant == 1;
+}
+extern "C" int vln_lstm_set_variant(int variant) {
+  VLN_REQUIRE(variant >= -1 && variant <= 1, "variant must be -1 (environment), 0 (mma.sync) or 1 (tcgen05)");
+  g_variant = variant;
+  return 0;
+}
+
 // n_dir = 1 or 2.  Direction k uses xproj[k], w_hh[k], acts[k], cs[k] and writes columns [k*H, (k+1)*H) of
 // out [B,L,n_dir*H] / h_last / c_last [B,n_dir*H]; direction 1 runs reversed in time.
 extern "C" int vln_lstm_seq_fwd(const float* const* xproj, const float* const* w_hh, const int32_t* lengths, float* out,
@@ -526,8 +548,11 @@ extern "C" int vln_lstm_seq_fwd(const float* const* xproj, const float* const* w
   DirF d[2] = {};
   for (int k = 0; k < n_dir; ++k) {
     VLN_REQUIRE(xproj[k] && w_hh[k] && acts[k] && cs[k], "null per-direction pointer");
+    VLN_REQUIRE(((uintptr_t)w_hh[k] & 15) == 0, "w_hh must be 16-byte aligned");
     d[k] = DirF{xproj[k], w_hh[k], out + k * H, acts[k], cs[k], h_last + k * H, c_last + k * H, k};
   }
+  if (use_tc() && (H == 256 || H == 128))
+    return vln_lstm_tc_fwd(xproj, w_hh, lengths, out, acts, cs, h_last, c_last, B, L, H, n_dir, (cudaStream_t)stream);
   if (H == 256) return launch_fwd<256>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);
   if (H == 128) return launch_fwd<128>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);
   vln_set_error("vln_lstm_seq_fwd: hidden size %d per direction is not supported (128 or 256)", H);
@@ -546,6 +571,8 @@ extern "C" int vln_lstm_seq_bwd(const float* const* w_hh, const int32_t* lengths
     d[k] = DirB{w_hh[k], acts[k], cs[k], d_out ? d_out + k * H : nullptr, d_hlast ? d_hlast + k * H : nullptr,
                 d_clast ? d_clast + k * H : nullptr, d_xproj[k], k};
   }
+  if (use_tc() && (H == 256 || H == 128))
+    return vln_lstm_tc_bwd(w_hh, lengths, acts, cs, d_out, d_hlast, d_clast, d_xproj, B, L, H, n_dir, (cudaStream_t)stream);
   if (H == 256) return launch_bwd<256>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);
   if (H == 128) return launch_bwd<128>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);
   vln_set_error("vln_lstm_seq_bwd: hidden size %d per direction is not supported (128 or 256)", H);

@@ -1,0 +1,699 @@
+// Persistent length-masked LSTM recurrence on the 5th-generation tensor cores (tcgen05), forward and
+// backward-through-time: the packed nn.LSTM of EncoderLSTM (units.py:58-71), one launch per layer for both
+// directions.  Same contract as csrc/lstm_seq.cu (the mma.sync version, kept behind VLN_LSTM_VARIANT=mma);
+// what changes is where the recurrent product runs:
+//
+//   * a thread-block CLUSTER of C = H/32 CTAs owns NB (16 or 32) batch rows for the whole sequence; CTA r owns
+//     hidden units [32r, 32r+32), i.e. 128 gate rows (i,f,g,o x 32) of W_hh;
+//   * those 128 x H weights stay resident in TENSOR MEMORY for all timesteps as the A operand of
+//     tcgen05.mma (bf16 hi and lo halves, two bf16 per 32-bit column: lane = gate row, H/2 + H/2 columns),
+//     written once with tcgen05.st.  A-from-TMEM matters at this shape: with A in shared memory every
+//     128xNBx16 MMA would re-read 4 KB of weights (32 cycles at 128 B/clk) against an 8-cycle MMA;
+//   * h_{t-1} is the B operand: bf16 hi / lo, K-major 128-byte-swizzled tiles in shared memory, double buffered.
+//     Every CTA computes gates[128 x NB] = W_r . h_{t-1} with 3 x H/16 MMAs (hi.hi + hi.lo + lo.hi, fp32
+//     accumulator in TMEM), four warps read the accumulator (tcgen05.ld), add the input projection, apply the
+//     gate non-linearity; all eight warps do the cell update for (unit, row) pairs and send the new h slice
+//     straight into every peer's NEXT B tile with 16-byte st.async stores that count on the receiver's mbarrier
+//     (no cluster barrier per step);
+//   * backward: A = W_hh^T restricted to the CTA's 128 gate rows (H x 128, H/128 M-tiles, resident in TMEM),
+//     B = this step's dgates (written locally), D = partial dh_{t-1}[H x NB], reduce-scattered to the owning
+//     CTAs with st.async and summed there in a fixed order (deterministic).
+//
+// NB = 16 keeps a B=64 bidirectional layer at 8 clusters: the mma.sync version (8 rows per cluster) needs 16
+// clusters of 8 CTAs where only 15 are resident on a B200 — two waves, i.e. twice the 80-step latency chain.
+// Roofline class: latency (L serial steps); tensor work per step and CTA is 3 x H/16 MMAs of 128 x NB x 16.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+// optional phase stamps (VLN_LSTM_STAMPS=1): CTA (0,0) of the forward kernel, step 10 and the kernel's prologue / end
+__device__ unsigned long long g_tc_stamps[16];
+#define TSTAMP(i, cond)                                                                              \
+  do {                                                                                               \
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && (cond)) g_tc_stamps[i] = (unsigned long long)clock64(); \
+  } while (0)
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kHS = 32;         // hidden units per CTA
+constexpr int kRows = 4 * kHS;  // gate rows per CTA
+constexpr int kGP = kRows + 4;  // padded row of the activated-gate buffer
+
+// Gate non-linearities on the SFU (ex2.approx + rcp.approx, ~2 ulp each): the precise expf / tanhf / IEEE division cost
+// ~2 900 cycles per step for the two rows a thread updates, more than the tensor-core product itself.  Absolute error
+// ~1e-7 per activation (tanh by 1 - 2 / (e^2x + 1): exact limits at +-inf, cancellation only below |x| ~ 1e-3).
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive();
+  cluster_wait();
+}
+// mbarrier wait that traps instead of spinning forever (a protocol bug then surfaces as a launch failure, not a hung GPU)
+__device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory operand: 8-row groups of 128-byte rows, SBO = 1024 B, descriptor version 1
+__device__ __forceinline__ uint64_t sdesc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D[tmem] (+)= A[tmem] . B[smem]   (A: lane = row, two bf16 per column; B: K-major swizzled tile).  Called by a whole
+// converged warp with warp-uniform operands; one elected lane issues.
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf16_val(uint32_t bits) { return __uint_as_float(bits << 16); }
+// two fp32 values -> packed bf16 pairs (first value in the low half): hi and the residual lo
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ah = bf16_bits(a), bh = bf16_bits(b);
+  hi = ah | (bh << 16);
+  lo = bf16_bits(a - bf16_val(ah)) | (bf16_bits(b - bf16_val(bh)) << 16);
+}
+// 16-byte asynchronous DSMEM store into CTA `rank`, counted (16 bytes) on that CTA's mbarrier
+__device__ __forceinline__ void dsmem_st_async_v4(void* local_ptr, uint64_t* local_bar, uint32_t rank, uint4 v) {
+  uint32_t a = smem_u32(local_ptr), m = smem_u32(local_bar), ra, rm;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rm) : "r"(m), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(ra),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rm)
+               : "memory");
+}
+
+struct DirF {
+  const float* xproj;   // [B,L,4H]
+  const float* w_hh;    // [4H,H]
+  float* out;           // [B,L,ld_out] + column offset of this direction
+  float* acts;          // [B,L,4H]
+  float* cs;            // [B,L,H]
+  float* h_last;        // [B,ld_last] + column offset
+  float* c_last;
+  int reverse;
+};
+struct DirB {
+  const float* w_hh;
+  const float* acts;
+  const float* cs;
+  const float* d_out;   // [B,L,ld_out] + column offset (may be NULL)
+  const float* d_hlast; // [B,ld_last] + column offset (may be NULL)
+  const float* d_clast;
+  float* d_xproj;       // [B,L,4H], pre-zeroed
+  int reverse;
+};
+
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = NB, M = 128
+template <int NB>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <int H, int NB>
+struct LayF {
+  static constexpr int KB = H / 64;                       // 64-wide k-blocks of the B operand (h_{t-1})
+  static constexpr int kTile = NB * 128;                  // bytes of one k-block tile: NB rows x 128 B
+  static constexpr int kHBytes = 2 * 2 * KB * kTile;      // [buffer][hi/lo][k-block]
+  static constexpr int kGOff = kHBytes;                   // float g[NB][kGP]: activated gates
+  static constexpr int kStageOff = kGOff + NB * kGP * 4;  // uint16 stage[hi/lo][NB][32]: this CTA's new h slice
+  static constexpr int kLenOff = kStageOff + 2 * NB * kHS * 2;
+  static constexpr int kBarOff = kLenOff + NB * 4;
+  static constexpr int kSmem = kBarOff + 64 + 1024;       // + barriers/TMEM slot + 1 KB alignment slack
+  static constexpr int kColD = 0, kColAhi = 32, kColAlo = 32 + H / 2;
+  static constexpr int kTmemCols = (32 + H) <= 256 ? 256 : 512;
+};
+
+template <int H, int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_tc_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last, int dbg) {
+  using S = LayF<H, NB>;
+  constexpr int C = H / kHS, KB = S::KB, KS = H / 16, RPT = NB / 8;
+  const DirF d = blockIdx.y == 0 ? d0 : d1;
+  const float* __restrict__ xproj = d.xproj;
+  const float* __restrict__ w_hh = d.w_hh;
+  float* __restrict__ out = d.out;
+  float* __restrict__ acts = d.acts;
+  float* __restrict__ cs = d.cs;
+  const int reverse = d.reverse;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* hb = base;
+  const uint32_t hb_addr = smem_u32(hb);
+  float* g = reinterpret_cast<float*>(base + S::kGOff);
+  uint16_t* stage = reinterpret_cast<uint16_t*>(base + S::kStageOff);
+  int* s_len = reinterpret_cast<int*>(base + S::kLenOff);
+  uint64_t* bar_h = reinterpret_cast<uint64_t*>(base + S::kBarOff);   // [2]: all hi/lo bytes of h buffer k have arrived
+  uint64_t* bar_acc = bar_h + 2;                                       // this step's MMAs have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_h + 3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction: lets ptxas keep MMA operands in uniform registers
+  const int rank = (int)cluster_ctarank();
+  const int b0 = (blockIdx.x / C) * NB;
+
+  TSTAMP(8, tid == 0);
+  for (int i = tid; i < S::kHBytes / 16; i += kThreads) reinterpret_cast<uint4*>(hb)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < NB) s_len[tid] = (b0 + tid < B) ? min(lengths[b0 + tid], L) : 0;
+  if (tid == 0) {
+    mbar_init(&bar_h[0], 1);
+    mbar_init(&bar_h[1], 1);
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(S::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  int gmax = 0;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) gmax = max(gmax, s_len[i]);
+  gmax = __shfl_sync(0xffffffffu, gmax, 0);
+
+  // resident weights: TMEM lane lr = gate*32 + unit  <->  global row gate*H + rank*32 + unit; K along the columns
+  if (warp < 4) {
+    const int lr = tid;
+    const float* wrow = w_hh + (size_t)((lr >> 5) * H + rank * kHS + (lr & 31)) * H;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 2
+    for (int j = 0; j < KS; ++j) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(wrow + j * 16) + qd);
+        split_pair(f.x, f.y, hi[2 * qd], lo[2 * qd]);
+        split_pair(f.z, f.w, hi[2 * qd + 1], lo[2 * qd + 1]);
+      }
+      tmem_st8(lane_base + S::kColAhi + 8 * j, hi);
+      tmem_st8(lane_base + S::kColAlo + 8 * j, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();              // the zero-filled h tiles are read by the tensor core (async proxy)
+  tc_fence_before();
+  TSTAMP(9, tid == 0);
+  cluster_sync_all();               // barriers initialised + buffers zeroed cluster-wide before any DSMEM traffic
+  tc_fence_after();
+  TSTAMP(10, tid == 0);
+
+  const int q = warp & 3;           // warps 4..7 move TMEM lane quarter q (= gate q) to shared memory
+  const int ug = rank * kHS + lane; // global hidden unit of the cell-update thread (rows warp, warp + 8, ...)
+  float xp[RPT][4];
+  auto load_x = [&](int t) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int n = warp + 8 * j;
+      const bool ok = t >= 0 && t < s_len[n];
+      const float* p = xproj + ((size_t)(b0 + n) * L + (ok ? t : 0)) * (4 * H) + ug;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xp[j][k] = ok ? __ldg(p + k * H) : 0.f;
+    }
+  };
+  float c_reg[RPT], h_reg[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) c_reg[j] = h_reg[j] = 0.f;
+
+  int t = reverse ? gmax - 1 : 0;
+  const int dt = reverse ? -1 : 1;
+  load_x(t);
+  constexpr uint32_t idesc = make_idesc<NB>();
+  for (int s = 0; s < gmax; ++s, t += dt) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    const bool send = s + 1 < gmax;                      // the last step's h has no consumer
+    TSTAMP(0, tid == 0 && s == 10);
+    if (tid == 0 && send) mbar_expect_tx(&bar_h[nxt], NB * H * 4);
+    if (warp == 0) {
+      if (s > 0) mbar_wait_g(&bar_h[cur], (uint32_t)((s - 1) >> 1) & 1u);
+      TSTAMP(1, tid == 0 && s == 10);
+      tc_fence_after();
+      const uint32_t bh = hb_addr + (uint32_t)((cur * 2 + 0) * KB * S::kTile);
+      const uint32_t bl = hb_addr + (uint32_t)((cur * 2 + 1) * KB * S::kTile);
+      const uint64_t dh0 = sdesc_sw128(bh), dl0 = sdesc_sw128(bl);
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint64_t inc = (uint64_t)(((ks >> 2) * S::kTile + (ks & 3) * 32) >> 4);   // address field is in 16-byte units
+        umma_ts(tmem + S::kColD, tmem + S::kColAhi + 8 * ks, dh0 + inc, idesc, ks != 0);
+        umma_ts(tmem + S::kColD, tmem + S::kColAhi + 8 * ks, dl0 + inc, idesc, 1u);
+        umma_ts(tmem + S::kColD, tmem + S::kColAlo + 8 * ks, dh0 + inc, idesc, 1u);
+      }
+      umma_commit(bar_acc);
+      __syncwarp();
+      TSTAMP(2, tid == 0 && s == 10);
+    } else if (warp >= 4) {
+      // W_r . h_{t-1} of my gate row (gate q, unit lane) for the NB batch rows: TMEM -> shared memory
+      mbar_wait_g(bar_acc, (uint32_t)s & 1u);
+      TSTAMP(3, tid == 128 && s == 10);
+      tc_fence_after();
+      uint32_t v[NB];
+#pragma unroll
+      for (int cg = 0; cg < NB / 16; ++cg) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + S::kColD + cg * 16, v + cg * 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int n = 0; n < NB; ++n) g[n * kGP + q * kHS + lane] = __uint_as_float(v[n]);
+      tc_fence_before();
+      TSTAMP(4, tid == 128 && s == 10);
+    }
+    __syncthreads();
+    TSTAMP(5, tid == 0 && s == 10);
+    // gates + cell update for (row n = warp + 8j, unit lane); new h as bf16 hi / lo into the staging tile
+    float xc[RPT][4];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xc[j][k] = xp[j][k];
+    load_x(t + dt);                                        // next step's input projection, in flight during the cell update
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int n = warp + 8 * j;
+      const float* gp = g + n * kGP + lane;
+      const float ig = sigmoidf_(gp[0] + xc[j][0]), fg = sigmoidf_(gp[32] + xc[j][1]), gg = tanhf_(gp[64] + xc[j][2]),
+                  og = sigmoidf_(gp[96] + xc[j][3]);
+      const float c_new = fg * c_reg[j] + ig * gg;
+      const float h_new = og * tanhf_(c_new);
+      if (t < s_len[n]) {                                  // rows past their length keep their state, outputs stay zero
+        c_reg[j] = c_new;
+        h_reg[j] = h_new;
+        const size_t o = (size_t)(b0 + n) * L + t;
+        out[o * ld_out + ug] = h_new;
+        cs[o * H + ug] = c_new;
+        float* ap = acts + o * (4 * H) + ug;
+        ap[0] = ig; ap[H] = fg; ap[2 * H] = gg; ap[3 * H] = og;
+      }
+      const uint32_t hi16 = bf16_bits(h_reg[j]);
+      stage[(0 * NB + n) * kHS + lane] = (uint16_t)hi16;
+      stage[(1 * NB + n) * kHS + lane] = (uint16_t)bf16_bits(h_reg[j] - bf16_val(hi16));
+      __syncwarp();
+      // all-gather: the 32 units of row n are 4 hi + 4 lo chunks of 16 bytes, each goes to all C CTAs' next B tile
+      // (issued per row, so the stores of one row travel while the next row is computed)
+      if (send) {
+#pragma unroll
+        for (int it = 0; it < C / 4; ++it) {
+          const int i = lane + 32 * it;
+          const int peer = i % C, ch = i / C;              // ch 0..7: hi chunks 0..3, lo chunks 0..3
+          const int hilo = ch >> 2, chunk = ch & 3;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + (hilo * NB + n) * kHS + chunk * 8);
+          const int k = rank * kHS + chunk * 8;            // first hidden unit of the chunk
+          uint8_t* dst = hb + (size_t)((nxt * 2 + hilo) * KB + (k >> 6)) * S::kTile + n * 128 +
+                         ((((k & 63) >> 3) ^ (n & 7)) << 4);
+          dsmem_st_async_v4(dst, &bar_h[nxt], (uint32_t)peer, val);
+        }
+      }
+    }
+    TSTAMP(6, tid == 0 && s == 10);
+    TSTAMP(7, tid == 0 && s == 10);
+    // Buffer reuse needs no further barrier: a peer writes h[cur] again only in step s+1, which it enters after
+    // it received THIS CTA's slice of step s — sent after this CTA's MMAs of step s (which read h[cur]) completed.
+  }
+  TSTAMP(11, tid == 0);
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int b = b0 + warp + 8 * j;
+    if (b < B) {
+      d.h_last[(size_t)b * ld_last + ug] = h_reg[j];
+      d.c_last[(size_t)b * ld_last + ug] = c_reg[j];
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();               // no CTA exits while a peer could still address its shared memory
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(S::kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward through time
+// ------------------------------------------------------------------------------------------------------------
+template <int H, int NB>
+struct LayB {
+  static constexpr int C = H / kHS;
+  static constexpr int MT = H / 128;                      // 128-column M-tiles of dh
+  static constexpr int kTile = NB * 128;                  // one 64-wide k-block of the dgates operand
+  static constexpr int kDgBytes = 2 * 2 * kTile;          // [hi/lo][k-block]
+  static constexpr int kRecvOff = kDgBytes;               // float recv[2][C][NB/4][32][4]: partial dh for my units
+  static constexpr int kRecvBytes = 2 * C * NB * kHS * 4;
+  static constexpr int kLenOff = kRecvOff + kRecvBytes;
+  static constexpr int kBarOff = kLenOff + NB * 4;
+  static constexpr int kSmem = kBarOff + 64 + 1024;
+  static constexpr int kColAhi = 64, kColAlo = 64 + MT * 64;    // D[mt] at column mt * 32
+  static constexpr int kTmemCols = (64 + 2 * MT * 64) <= 256 ? 256 : 512;
+};
+
+template <int H, int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B, int L, int ld_out, int ld_last, int dbg) {
+  using S = LayB<H, NB>;
+  constexpr int C = S::C, MT = S::MT, RPT = NB / 8, KS = kRows / 16;
+  const DirB d = blockIdx.y == 0 ? d0 : d1;
+  const float* __restrict__ w_hh = d.w_hh;
+  const float* __restrict__ acts = d.acts;
+  const float* __restrict__ cs = d.cs;
+  const float* __restrict__ d_out = d.d_out;
+  float* __restrict__ d_xproj = d.d_xproj;
+  const int reverse = d.reverse;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* dgb = base;
+  const uint32_t dg_addr = smem_u32(dgb);
+  float* recv = reinterpret_cast<float*>(base + S::kRecvOff);
+  int* s_len = reinterpret_cast<int*>(base + S::kLenOff);
+  uint64_t* bar_r = reinterpret_cast<uint64_t*>(base + S::kBarOff);   // [2]: all partials of recv[k] have arrived
+  uint64_t* bar_acc = bar_r + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_r + 3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction: lets ptxas keep MMA operands in uniform registers
+  const int rank = (int)cluster_ctarank();
+  const int b0 = (blockIdx.x / C) * NB;
+
+  if (tid < NB) s_len[tid] = (b0 + tid < B) ? min(lengths[b0 + tid], L) : 0;
+  if (tid == 0) {
+    mbar_init(&bar_r[0], 1);
+    mbar_init(&bar_r[1], 1);
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(S::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  int gmax = 0;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) gmax = max(gmax, s_len[i]);
+  gmax = __shfl_sync(0xffffffffu, gmax, 0);
+
+  // resident W^T restricted to this CTA's gate rows: dh[k][n] = sum_lr W[lr][k] dg[n][lr];  A[m = column k][kk = local row];
+  // M-tile mt is written by warps 4mt .. 4mt+3 (TMEM lane = k % 128)
+  if (warp < 4 * MT) {
+    const int mt = warp >> 2;
+    const int k = mt * 128 + (warp & 3) * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 2
+    for (int j = 0; j < KS; ++j) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int lr0 = 16 * j + 2 * p, lr1 = lr0 + 1;
+        const float w0 = __ldg(w_hh + (size_t)((lr0 >> 5) * H + rank * kHS + (lr0 & 31)) * H + k);
+        const float w1 = __ldg(w_hh + (size_t)((lr1 >> 5) * H + rank * kHS + (lr1 & 31)) * H + k);
+        split_pair(w0, w1, hi[p], lo[p]);
+      }
+      tmem_st8(lane_base + S::kColAhi + mt * 64 + 8 * j, hi);
+      tmem_st8(lane_base + S::kColAlo + mt * 64 + 8 * j, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  const int ug = rank * kHS + lane;
+  float dh[RPT], dc[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int b = b0 + warp + 8 * j;
+    dh[j] = (b < B && d.d_hlast) ? d.d_hlast[(size_t)b * ld_last + ug] : 0.f;
+    dc[j] = (b < B && d.d_clast) ? d.d_clast[(size_t)b * ld_last + ug] : 0.f;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+
+  // forward visited t = 0..gmax-1 (or gmax-1..0 when reversed); walk it backwards
+  int t = reverse ? 0 : gmax - 1;
+  const int dt = reverse ? 1 : -1;
+  constexpr uint32_t idesc = make_idesc<NB>();
+  for (int s = 0; s < gmax; ++s, t += dt) {
+    const int buf = s & 1;
+    const bool more = s + 1 < gmax;                      // dh of the step before the first one has no consumer
+    if (tid == 0 && more) mbar_expect_tx(&bar_r[buf], C * NB * kHS * 4);
+    // pointwise gradient for (row n = warp + 8j, unit lane); dgates -> d_xproj and, as bf16 hi / lo, the B tiles
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int n = warp + 8 * j;
+      const int len = s_len[n];
+      float dg[4] = {0.f, 0.f, 0.f, 0.f};
+      if (t < len) {
+        const size_t o = (size_t)(b0 + n) * L + t;
+        const float* ap = acts + o * (4 * H) + ug;
+        const float ig = ap[0], fg = ap[H], gg = ap[2 * H], og = ap[3 * H];
+        const float c1 = cs[o * H + ug];
+        const int tp = t - (reverse ? -1 : 1);                      // the step that produced c_{prev}
+        const float c0 = (tp >= 0 && tp < len) ? cs[((size_t)(b0 + n) * L + tp) * H + ug] : 0.f;
+        const float dht = dh[j] + (d_out ? d_out[o * ld_out + ug] : 0.f);
+        const float tc = tanhf_(c1);
+        const float dct = dc[j] + dht * og * (1.f - tc * tc);
+        dg[0] = dct * gg * ig * (1.f - ig);
+        dg[1] = dct * c0 * fg * (1.f - fg);
+        dg[2] = dct * ig * (1.f - gg * gg);
+        dg[3] = dht * tc * og * (1.f - og);
+        dc[j] = dct * fg;
+        float* dp = d_xproj + o * (4 * H) + ug;
+        dp[0] = dg[0]; dp[H] = dg[1]; dp[2 * H] = dg[2]; dp[3 * H] = dg[3];
+      }
+      if (more) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int lr = k * kHS + lane;                             // local gate row = K index of the MMA
+          const int kk = lr & 63;
+          const uint32_t off = (uint32_t)((lr >> 6) * S::kTile + n * 128 + (((kk >> 3) ^ (n & 7)) << 4) + (kk & 7) * 2);
+          const uint32_t hi = bf16_bits(dg[k]);
+          *reinterpret_cast<uint16_t*>(dgb + off) = (uint16_t)hi;
+          *reinterpret_cast<uint16_t*>(dgb + 2 * S::kTile + off) = (uint16_t)bf16_bits(dg[k] - bf16_val(hi));
+        }
+      }
+    }
+    if (!more) break;
+    fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      const uint64_t dh0 = sdesc_sw128(dg_addr), dl0 = sdesc_sw128(dg_addr + 2 * S::kTile);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint64_t inc = (uint64_t)(((ks >> 2) * S::kTile + (ks & 3) * 32) >> 4);
+          umma_ts(tmem + mt * 32, tmem + S::kColAhi + mt * 64 + 8 * ks, dh0 + inc, idesc, ks != 0);
+          umma_ts(tmem + mt * 32, tmem + S::kColAhi + mt * 64 + 8 * ks, dl0 + inc, idesc, 1u);
+          umma_ts(tmem + mt * 32, tmem + S::kColAlo + mt * 64 + 8 * ks, dh0 + inc, idesc, 1u);
+        }
+      }
+      umma_commit(bar_acc);
+    }
+    __syncwarp();
+    if (warp < 4 * MT) {
+      // reduce-scatter: TMEM lane = column k of M-tile mt -> owner CTA k / 32, slot [my rank][n / 4][k % 32][n % 4]
+      const int mt = warp >> 2, qq = warp & 3;
+      mbar_wait_g(bar_acc, (uint32_t)s & 1u);
+      tc_fence_after();
+      uint32_t v[NB];
+#pragma unroll
+      for (int cg = 0; cg < NB / 16; ++cg) tmem_ld16(tmem + ((uint32_t)(qq * 32) << 16) + mt * 32 + cg * 16, v + cg * 16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const uint32_t owner = (uint32_t)(mt * 4 + qq);
+#pragma unroll
+      for (int n4 = 0; n4 < NB / 4; ++n4) {
+        float* dst = recv + ((size_t)((buf * C + rank) * (NB / 4) + n4) * kHS + lane) * 4;
+        dsmem_st_async_v4(dst, &bar_r[buf], owner, make_uint4(v[4 * n4], v[4 * n4 + 1], v[4 * n4 + 2], v[4 * n4 + 3]));
+      }
+      tc_fence_before();
+    }
+    mbar_wait_g(&bar_r[buf], (uint32_t)(s >> 1) & 1u);
+    // owner: dh_{t-1}[n][my unit] = sum over the C partials in rank order (live rows); frozen rows pass dh through
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int n = warp + 8 * j;
+      if (t < s_len[n]) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < C; ++r) acc += recv[((size_t)((buf * C + r) * (NB / 4) + (n >> 2)) * kHS + lane) * 4 + (n & 3)];
+        dh[j] = acc;
+      }
+    }
+    // recv is double buffered: a peer's stores of step s+1 go to the other half, and its stores of step s+2 come
+    // after it received this CTA's partials of step s+1, which are sent only after the reads above.  The dgates
+    // tiles are rewritten in step s+1 only after this wait, i.e. after this CTA's MMAs of step s completed.
+  }
+  tc_fence_before();
+  cluster_sync_all();               // no CTA exits while a peer could still address its shared memory
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(S::kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <typename K>
+int max_active_clusters(K kernel, size_t smem, int C, int* out) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C * 64, 1);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VLN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(out, kernel, &cfg));
+  return 0;
+}
+
+template <typename K, typename D>
+int launch_tc(K kernel, size_t smem, int C, int NB, int n_dir, int B, cudaStream_t stream, D d0, D d1,
+              const int32_t* lengths, int L, int ld_out, int ld_last) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(((B + NB - 1) / NB) * C, n_dir);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, d0, d1, lengths, B, L, ld_out, ld_last, (int)(getenv("VLN_LSTM_STAMPS") != nullptr)));
+  return 0;
+}
+
+// NB = 16 unless the launch would then need more clusters than can be resident at once (a second wave doubles the
+// serial latency chain); VLN_LSTM_NB=16|32 forces it.
+template <int H>
+int pick_nb(int B, int n_dir, bool fwd) {
+  static int max16[2] = {-1, -1};
+  const char* e = getenv("VLN_LSTM_NB");
+  if (e && !strcmp(e, "32")) return 32;
+  if (e && !strcmp(e, "16")) return 16;
+  int& m = max16[fwd ? 0 : 1];
+  if (m < 0) {
+    int v = 0;
+    int rc;
+    if (fwd) {
+      cudaFuncSetAttribute(lstm_tc_fwd_kernel<H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF<H, 16>::kSmem);
+      rc = max_active_clusters(lstm_tc_fwd_kernel<H, 16>, LayF<H, 16>::kSmem, H / kHS, &v);
+    } else {
+      cudaFuncSetAttribute(lstm_tc_bwd_kernel<H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayB<H, 16>::kSmem);
+      rc = max_active_clusters(lstm_tc_bwd_kernel<H, 16>, LayB<H, 16>::kSmem, H / kHS, &v);
+    }
+    m = (rc == 0 && v > 0) ? v : 14;
+  }
+  return ((B + 15) / 16) * n_dir <= m ? 16 : 32;
+}
+
+template <int H, int NB>
+int launch_fwd(DirF d0, DirF d1, int n_dir, const int32_t* lengths, int B, int L, int ld_out, int ld_last, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    VLN_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF<H, NB>::kSmem));
+    configured = true;
+  }
+  return launch_tc(lstm_tc_fwd_kernel<H, NB>, LayF<H, NB>::kSmem, H / kHS, NB, n_dir, B, stream, d0, d1, lengths, L, ld_out, ld_last);
+}
+template <int H, int NB>
+int launch_bwd(DirB d0, DirB d1, int n_dir, const int32_t* lengths, int B, int L, int ld_out, int ld_last, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    VLN_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayB<H, NB>::kSmem));
+    configured = true;
+  }
+  return launch_tc(lstm_tc_bwd_kernel<H, NB>, LayB<H, NB>::kSmem, H / kHS, NB, n_dir, B, stream, d0, d1, lengths, L, ld_out, ld_last);
+}
+
+}  // namespace
+
+extern "C" int vln_debug_lstm_tc_stamps(unsigned long long* out_host /*[16]*/) {
+  VLN_CHECK_CUDA(cudaDeviceSynchronize());
+  VLN_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_tc_stamps, sizeof(unsigned long long) * 16));
+  return 0;
+}
+
+// Same contracts as vln_lstm_seq_fwd / vln_lstm_seq_bwd (csrc/lstm_seq.cu), which dispatch here by default.
+int vln_lstm_tc_fwd(const float* const* xproj, const float* const* w_hh, const int32_t* lengths, float* out,
+                    float* const* acts, float* const* cs, float* h_last, float* c_last, int B, int L, int H, int n_dir,
+                    cudaStream_t stream) {
+  DirF d[2] = {};
+  for (int k = 0; k < n_dir; ++k)
+    d[k] = DirF{xproj[k], w_hh[k], out + k * H, acts[k], cs[k], h_last + k * H, c_last + k * H, k};
+  const int ld = n_dir * H;
+  if (H == 256) {
+    if (pick_nb<256>(B, n_dir, true) == 16) return launch_fwd<256, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    return launch_fwd<256, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+  }
+  if (H == 128) {
+    if (pick_nb<128>(B, n_dir, true) == 16) return launch_fwd<128, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    return launch_fwd<128, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+  }
+  vln_set_error("vln_lstm_seq_fwd: hidden size %d per direction is not supported (128 or 256)", H);
+  return -1;
+}
+
+int vln_lstm_tc_bwd(const float* const* w_hh, const int32_t* lengths, const float* const* acts, const float* const* cs,
+                    const float* d_out, const float* d_hlast, const float* d_clast, float* const* d_xproj, int B, int L,
+                    int H, int n_dir, cudaStream_t stream) {
+  DirB d[2] = {};
+  for (int k = 0; k < n_dir; ++k)
+    d[k] = DirB{w_hh[k], acts[k], cs[k], d_out ? d_out + k * H : nullptr, d_hlast ? d_hlast + k * H : nullptr,
+                d_clast ? d_clast + k * H : nullptr, d_xproj[k], k};
+  const int ld = n_dir * H;
+  if (H == 256) {
+    if (pick_nb<256>(B, n_dir, false) == 16) return launch_bwd<256, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    return launch_bwd<256, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+  }
+  if (H == 128) {
+    if (pick_nb<128>(B, n_dir, false) == 16) return launch_bwd<128, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    return launch_bwd<128, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+  }
+  vln_set_error("vln_lstm_seq_bwd: hidden size %d per direction is not supported (128 or 256)", H);
+  return -1;
+}

@@ -243,6 +243,10 @@ int vln_lstm_seq_fwd(const float* const* xproj, const float* const* w_hh, const 
 int vln_lstm_seq_bwd(const float* const* w_hh, const int32_t* lengths, const float* const* acts,
                      const float* const* cs, const float* d_out, const float* d_hlast, const float* d_clast,
                      float* const* d_xproj, int B, int L, int H, int n_dir, void* stream);
+/* Which recurrence kernels the two entry points above run: 1 = tcgen05 (W_hh resident in tensor memory, 16 or 32
+ * batch rows per cluster; csrc/lstm_tc.cu, the default), 0 = mma.sync (weights in registers, 8 rows per cluster;
+ * csrc/lstm_seq.cu), -1 = back to the VLN_LSTM_VARIANT environment default.  A tuning / testing knob. */
+int vln_lstm_set_variant(int variant);
 
 /* Action head (envdrop.py:166-195, follower.py:107-135, monitor.py:143-176): masked
  * log-softmax, CE(ignore_index=-1), argmax / Philox-sampled / teacher action, log-prob and

@@ -411,9 +411,21 @@ def test_fused_clip_optimizer(setup, kind):
         assert relerr(flat, torch.cat([r.detach() for r in ref])) < 2e-5
 
 
-@pytest.mark.parametrize("H,E,B,L,ndir", [(256, 256, 64, 80, 2), (128, 300, 19, 33, 2), (256, 64, 5, 12, 1)])
-def test_lstm_layer_matches_oracle(setup, H, E, B, L, ndir):
-    """Persistent cluster LSTM (fwd + BPTT) vs the oracle's masked recurrence (== packed nn.LSTM)."""
+@pytest.fixture
+def lstm_variant(request):
+    """Selects the recurrence kernels: 1 = tcgen05 (TMEM-resident W_hh), 0 = mma.sync (register-resident W_hh)."""
+    from clvln_b200 import _lib
+    _lib.check(_lib.lib().vln_lstm_set_variant(request.param))
+    yield request.param
+    _lib.check(_lib.lib().vln_lstm_set_variant(-1))
+
+
+@pytest.mark.parametrize("lstm_variant", [1, 0], indirect=True, ids=["tcgen05", "mma"])
+@pytest.mark.parametrize("H,E,B,L,ndir", [(256, 256, 64, 80, 2), (128, 300, 19, 33, 2), (256, 64, 5, 12, 1),
+                                          (256, 128, 128, 40, 2), (128, 64, 150, 21, 2)])
+def test_lstm_layer_matches_oracle(setup, lstm_variant, H, E, B, L, ndir):
+    """Persistent cluster LSTM (fwd + BPTT) vs the oracle's masked recurrence (== packed nn.LSTM); B = 128 / 150
+    take the 32-rows-per-cluster instantiation of the tcgen05 kernels."""
     from oracle import port_modules as P
     _, _, ops, dev = setup
     torch.manual_seed(H + B)

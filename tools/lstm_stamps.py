@@ -33,6 +33,14 @@ names = ["mma + gate stores", "syncthreads", "pointwise + global stores", "st.as
 print(", ".join(f"{n}={buf[i + 1] - buf[i]}" for i, n in enumerate(names)), "cycles; step total", buf[5] - buf[0])
 print("kernel: prologue (weight fragments, barrier init, cluster sync) = %d cycles, %d steps = %d cycles (%.0f per step), epilogue = %d"
       % (buf[7] - buf[6], L, buf[8] - buf[7], (buf[8] - buf[7]) / L, buf[9] - buf[8]))
+L_.vln_debug_lstm_tc_stamps.argtypes = [C.c_void_p]
+tb = (C.c_ulonglong * 16)()
+L_.vln_debug_lstm_tc_stamps(tb)
+if tb[0]:
+    print("tcgen05 fwd step 10 (cycles from loop top): h arrived=%d, MMAs issued=%d, accumulator ready=%d, TMEM->smem=%d, "
+          "syncthreads=%d, cell update=%d, sends issued=%d" % tuple(int(tb[i]) - int(tb[0]) for i in range(1, 8)))
+    print("tcgen05 fwd kernel: zero+alloc+weights->TMEM=%d, cluster sync=%d, %d steps=%d (%.0f per step)"
+          % (tb[9] - tb[8], tb[10] - tb[9], L, tb[11] - tb[10], (tb[11] - tb[10]) / L))
 L_.vln_debug_lstm_occupancy.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
 f, b = C.c_int(0), C.c_int(0)
 for h in (256, 128):
