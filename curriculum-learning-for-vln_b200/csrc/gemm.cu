@@ -75,17 +75,23 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// (called by a whole converged warp with warp-uniform operands; one elected lane issues: with the operands in
+// uniform registers the issue loop is UIADD3 + UTCHMMA, instead of ELECT + four R2UR.BROADCAST per MMA)
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -131,7 +137,8 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
   uint64_t* acc_done = bars + 3 * C::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);           // warp-uniform by construction
   __shared__ unsigned int slot_s;
   unsigned int slot = 0;
   if (dbg && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -172,7 +179,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (tid == 0) STAMP(1);
 
   if (n_iter > 0) {
@@ -194,31 +201,32 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
         }
       }
     } else if (warp == 1) {
-      // ---------------- MMA issuer ----------------
-      if (lane == 0) {
-        // instruction descriptor: D = F32, A = B = BF16, both K-major, N = MP, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MP >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
-        for (int it = 0; it < n_iter; ++it) {
-          const int s = it % C::kStages;
-          const uint32_t ph = (it / C::kStages) & 1u;
-          mbar_wait(&full_w[s], ph);
-          if (it == 0) STAMP(2);
-          mbar_wait(&full_x[s], ph);
-          if (it == 0) STAMP(3);
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(base + (size_t)s * C::kStageBytes), a_lo = a_hi + C::kABytes;
-          const uint32_t b_hi = a_lo + C::kABytes, b_lo = b_hi + C::kBBytes;
+      // ---------------- MMA issuer (whole warp converged, one elected lane issues) ----------------
+      // instruction descriptor: D = F32, A = B = BF16, both K-major, N = MP, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MP >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+      const uint32_t base_addr = smem_u32(base);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1u;
+        mbar_wait(&full_w[s], ph);
+        if (it == 0 && lane == 0) STAMP(2);
+        mbar_wait(&full_x[s], ph);
+        if (it == 0 && lane == 0) STAMP(3);
+        tc_fence_after();
+        const uint32_t a_hi = base_addr + (uint32_t)s * C::kStageBytes, a_lo = a_hi + C::kABytes;
+        const uint32_t b_hi = a_lo + C::kABytes, b_lo = b_hi + C::kBBytes;
+        const uint64_t da_hi = make_sdesc(a_hi), da_lo = make_sdesc(a_lo), db_hi = make_sdesc(b_hi), db_lo = make_sdesc(b_lo);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint32_t ko = k * 32;                      // 16 bf16 = 32 bytes along the swizzled row
-            umma_bf16(tmem_d, make_sdesc(a_hi + ko), make_sdesc(b_hi + ko), idesc, (it | k) != 0);
-            umma_bf16(tmem_d, make_sdesc(a_hi + ko), make_sdesc(b_lo + ko), idesc, 1u);
-            umma_bf16(tmem_d, make_sdesc(a_lo + ko), make_sdesc(b_hi + ko), idesc, 1u);
-          }
-          umma_commit(&empty[s]);                            // frees the stage when these MMAs retire
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);              // 16 bf16 = 32 bytes along the swizzled row, in 16-byte units
+          umma_bf16(tmem_d, da_hi + ko, db_hi + ko, idesc, (it | k) != 0);
+          umma_bf16(tmem_d, da_hi + ko, db_lo + ko, idesc, 1u);
+          umma_bf16(tmem_d, da_lo + ko, db_hi + ko, idesc, 1u);
         }
-        umma_commit(acc_done);
+        umma_commit(&empty[s]);                              // frees the stage when these MMAs retire
       }
+      umma_commit(acc_done);
+      __syncwarp();
     } else if (warp >= 4) {
       // ---------------- activation converters: raw fp32 tile (TMA) -> bf16 hi/lo, 128B-swizzled rows ----------------
       // A row of the raw tile is 64 floats = 16 float4; lane l of a warp takes float4 (l % 16) of row (l / 16),

@@ -468,25 +468,48 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
   // forward visited t = 0..gmax-1 (or gmax-1..0 when reversed); walk it backwards
   int t = reverse ? 0 : gmax - 1;
   const int dt = reverse ? 1 : -1;
+  // saved activations / cell states / incoming gradient of the step are fetched one step ahead (registers), so the
+  // L2 round trip overlaps the previous step's product and exchange instead of heading every step's critical path
+  float pre[RPT][7];                                       // ig, fg, gg, og, c_t, c_{t-1}, d_out
+  auto load_step = [&](int tt) {
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int n = warp + 8 * j;
+      const int len = s_len[n];
+      const bool ok = tt >= 0 && tt < len;
+      const size_t o = (size_t)(b0 + n) * L + (ok ? tt : 0);
+      const float* ap = acts + o * (4 * H) + ug;
+      const int tp = tt - (reverse ? -1 : 1);                        // the step that produced c_{prev}
+      const bool okp = ok && tp >= 0 && tp < len;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pre[j][k] = ok ? __ldg(ap + k * H) : 0.f;
+      pre[j][4] = ok ? __ldg(cs + o * H + ug) : 0.f;
+      pre[j][5] = okp ? __ldg(cs + ((size_t)(b0 + n) * L + tp) * H + ug) : 0.f;
+      pre[j][6] = (ok && d_out) ? __ldg(d_out + o * ld_out + ug) : 0.f;
+    }
+  };
+  load_step(t);
   constexpr uint32_t idesc = make_idesc<NB>();
   for (int s = 0; s < gmax; ++s, t += dt) {
     const int buf = s & 1;
     const bool more = s + 1 < gmax;                      // dh of the step before the first one has no consumer
     if (tid == 0 && more) mbar_expect_tx(&bar_r[buf], C * NB * kHS * 4);
+    float cur[RPT][7];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j)
+#pragma unroll
+      for (int k = 0; k < 7; ++k) cur[j][k] = pre[j][k];
+    load_step(t + dt);
     // pointwise gradient for (row n = warp + 8j, unit lane); dgates -> d_xproj and, as bf16 hi / lo, the B tiles
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const int n = warp + 8 * j;
-      const int len = s_len[n];
       float dg[4] = {0.f, 0.f, 0.f, 0.f};
-      if (t < len) {
+      if (t < s_len[n]) {
         const size_t o = (size_t)(b0 + n) * L + t;
-        const float* ap = acts + o * (4 * H) + ug;
-        const float ig = ap[0], fg = ap[H], gg = ap[2 * H], og = ap[3 * H];
-        const float c1 = cs[o * H + ug];
-        const int tp = t - (reverse ? -1 : 1);                      // the step that produced c_{prev}
-        const float c0 = (tp >= 0 && tp < len) ? cs[((size_t)(b0 + n) * L + tp) * H + ug] : 0.f;
-        const float dht = dh[j] + (d_out ? d_out[o * ld_out + ug] : 0.f);
+        const float ig = cur[j][0], fg = cur[j][1], gg = cur[j][2], og = cur[j][3];
+        const float c1 = cur[j][4], c0 = cur[j][5];
+        const float dht = dh[j] + cur[j][6];
         const float tc = tanhf_(c1);
         const float dct = dc[j] + dht * og * (1.f - tc * tc);
         dg[0] = dct * gg * ig * (1.f - ig);
