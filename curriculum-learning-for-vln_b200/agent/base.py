@@ -27,10 +27,11 @@ class RolloutState:
     def __init__(self, store, ib, T):
         B, dev = ib.vp.shape[0], ib.vp.device
         self.store, self.goal, self.B, self.T = store, ib.goal, B, T
-        self.vp = torch.empty((T + 1, B), dtype=torch.int32, device=dev)
-        self.view = torch.empty((T + 1, B), dtype=torch.int32, device=dev)
+        # zero-filled: rows that stop taking part in a rollout early (paired rollouts) must stay valid table indices
+        self.vp = torch.zeros((T + 1, B), dtype=torch.int32, device=dev)
+        self.view = torch.zeros((T + 1, B), dtype=torch.int32, device=dev)
         self.ended = torch.zeros((T + 1, B), dtype=torch.uint8, device=dev)
-        self.dist = torch.empty((T + 1, B), dtype=torch.float32, device=dev)
+        self.dist = torch.zeros((T + 1, B), dtype=torch.float32, device=dev)
         self.n_active = torch.zeros((T,), dtype=torch.int32, device=dev)
         self.vp[0].copy_(ib.vp)
         self.view[0].copy_(ib.view)

@@ -7,6 +7,7 @@ with the per-step host work (numpy feature assembly :75-84, H2D copies, `.cpu()`
 by kernels and one batched critic call.  Dead reference paths (speaker back-translation :104-120,
 avoid_cyclic :167-172) are not carried over.
 """
+import dataclasses
 from collections import defaultdict
 
 import torch
@@ -53,6 +54,57 @@ class EnvDropAgent(BaseAgent):
         pose = ops.pose_feature(st.store, st.view[t])
         logit, (h_t, c_t), h_tilde = self.decoder(pose, pano, cands, h_tilde, h_t, c_t, ctx, ctx_mask)
         return logit, h_t, c_t, h_tilde
+
+    def rollout_pair(self, train_cl=False):
+        """The two rollouts of one EnvDrop training iteration (trainer.py:411-421: teacher-forced for the imitation
+        loss, then sampled on the SAME minibatch for A2C) stepped as ONE batch of 2B episodes: rows [0,B) sample,
+        rows [B,2B) follow the teacher and only take part in the first T_teacher steps.  Same losses as two
+        ``rollout`` calls (each half has its own dropout masks, as the two passes of the reference do), but the
+        encoder and the first T_teacher decoder steps stream the weights once instead of twice.  Sets ``loss`` /
+        ``ml_loss`` / ``rl_loss`` / ``logs`` like the two calls would."""
+        assert self.fused and self.device.type == "cuda"
+        ib = self.env.reset_index(restart=False)
+        store = self.store_of(self.env)
+        B = ib.vp.shape[0]
+        T_t, _ = self._horizon(ib, "teacher")
+        T, _ = self._horizon(ib, "sample")
+        T_t = min(T_t, T)
+        two = lambda x: torch.cat((x, x), 0)
+        ib2 = dataclasses.replace(ib, tokens=two(ib.tokens), lengths=two(ib.lengths), lengths_cpu=two(ib.lengths_cpu),
+                                  vp=two(ib.vp), view=two(ib.view), goal=two(ib.goal), index=two(ib.index))
+        prep = self._fused.prepare(self.rng, 2 * B, T, "sample", True, self.device, pair=(B, T_t))
+        ctx, h_t, c_t = self.encoder(ib2.tokens, ib2.lengths)
+        st = RolloutState(store, ib2, T + 1)
+        (ce, logps, ents, hiddens, logits, actions, targets, rewards, masks, last_h) = self._fused.run(
+            self.rng, st, ctx, ib2.lengths, h_t, c_t, T, "sample", True, 0, self.split_for(2 * B), prep, pair=(B, T_t))
+        n = st.steps
+        ml = ce[:T_t, B:].sum(0) if train_cl else ce[:T_t, B:].sum()
+        if self.trace is not None:
+            self.trace += [dict(logits=logits[t, B:], target=targets[t, B:], action=actions[t, B:]) for t in range(T_t)]
+            self.trace += [dict(logits=logits[t, :B], target=targets[t, :B], action=actions[t, :B]) for t in range(n)]
+        self.logs["entropy"].append(ents[:, :B].sum().detach())
+        with torch.no_grad():
+            last_value = self.critic(last_h[:B].contiguous())
+        values = self.critic(hiddens[:, :B].reshape(n * B, -1)).view(n, B)
+        loss_b, stats = ops.a2c_loss(logps[:, :B].contiguous(), ents[:, :B].contiguous(), values,
+                                     rewards[:, :B].contiguous(), masks[:, :B].contiguous(), last_value,
+                                     st.ended[n][:B].contiguous(), self.cfg.GAMMA, 0.01)
+        rl = loss_b if train_cl else loss_b.sum()
+        self.logs["total"].append(stats[0])
+        self.logs["critic_loss"].append(stats[1])
+        if self.cfg.RL_NORMALIZE == "total":
+            rl = rl / stats[0]
+        elif self.cfg.RL_NORMALIZE == "batch":
+            rl = rl / B
+        else:
+            assert self.cfg.RL_NORMALIZE == "none"
+        self.ml_loss, self.rl_loss = ml, rl
+        self.loss = {"ml_loss": ml * self.cfg.ML_WEIGHT / B, "rl_loss": rl}
+        if train_cl:
+            self.losses.append(self.loss["ml_loss"].sum().detach())
+        self.last_state = st
+        self.last_batch = ib
+        return []
 
     def rollout(self, train_ml=True, train_rl=False, train_cl=False, reset=True, restart=False, speaker=None,
                 avoid_cyclic=False, feedback="sample", return_traj=None):

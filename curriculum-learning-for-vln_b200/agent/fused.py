@@ -83,7 +83,7 @@ class FusedDecoder:
                 d.lstm.bias_hh, d.text_attn.linear_in.weight, d.text_attn.linear_out.weight,
                 d.visual_attn.linear_in.weight, d.cand_attn.weight]
 
-    def prepare(self, rng, B, T, feedback, bootstrap, device):
+    def prepare(self, rng, B, T, feedback, bootstrap, device, pair=None):
         """Before the encoder runs: hand out the dropout / sampling stream offsets of every decoder pass (in
         the call order of EnvDropDecoder.forward) and draw all feature-dropout keep-bits of the rollout with
         ONE kernel on a side stream, so that it overlaps with the instruction encoder."""
@@ -118,25 +118,38 @@ class FusedDecoder:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 stride = offs[1]["img"] - offs[0]["img"] if S > 1 else 0
-                _call("vln_feature_mask_bits", _ptr(MB), B * ops.N_VIEWS, S, pf, rng.ptr, offs[0]["img"], stride, _stream())
+                if pair is None:
+                    _call("vln_feature_mask_bits", _ptr(MB), B * ops.N_VIEWS, S, pf, rng.ptr, offs[0]["img"], stride, _stream())
+                else:        # rows [0, B_main) for every pass, the teacher-forced rows only for their T_teacher steps
+                    B_main, T_t = pair
+                    V = ops.N_VIEWS
+                    _call("vln_feature_mask_bits_ld", _ptr(MB), B_main * V, B * V, 0, S, pf, rng.ptr, offs[0]["img"], stride,
+                          _stream())
+                    _call("vln_feature_mask_bits_ld", _ptr(MB), (B - B_main) * V, B * V, B_main * V, T_t, pf, rng.ptr,
+                          offs[0]["img"], stride, _stream())
         return dict(offs=offs, MB=MB, side=side, p=p, pf=pf, S=S)
 
-    def run(self, rng, st, ctx, lengths, h0, c0, T, feedback, bootstrap, poll, split, prep=None):
+    def run(self, rng, st, ctx, lengths, h0, c0, T, feedback, bootstrap, poll, split, prep=None, pair=None):
+        """``pair = (B_main, T_teacher)``: the batch holds two rollouts of the same minibatch stepped together
+        (trainer.py:411-421) — rows [0, B_main) follow ``feedback`` for T steps, rows [B_main, B) are
+        teacher-forced and only take part in the first T_teacher steps (every launch of a later step covers the
+        row prefix [0, B_main) only)."""
+        assert pair is None or (poll == 0 and 0 < pair[0] < st.B and 0 < pair[1] <= T)
         if prep is None:
             prep = self.prepare(rng, st.B, T, feedback, bootstrap, ctx.device)
         if prep["side"] is not None:
             torch.cuda.current_stream().wait_stream(prep["side"])
             prep["side"] = None
         self._prep = prep
-        return _Rollout.apply(self, rng, st, lengths, T, feedback, bootstrap, poll, split, ctx, h0, c0, *self.params())
+        return _Rollout.apply(self, rng, st, lengths, T, feedback, bootstrap, poll, split, pair, ctx, h0, c0, *self.params())
 
 
-N_META = 9          # non-tensor arguments of _Rollout.apply before (ctx, h0, c0, *params)
+N_META = 10         # non-tensor arguments of _Rollout.apply before (ctx, h0, c0, *params)
 
 
 class _Rollout(torch.autograd.Function):
     @staticmethod
-    def forward(fctx, fd, rng, st, lengths, T, feedback, bootstrap, poll, split, ctx, h0, c0, *params):
+    def forward(fctx, fd, rng, st, lengths, T, feedback, bootstrap, poll, split, pair, ctx, h0, c0, *params):
         dec = fd.dec
         w_act, b_act, w_ih, w_hh, b_ih, b_hh = [q.detach() for q in params[:6]]
         ctx, h0, c0 = ops._f32c(ctx.detach()), ops._f32c(h0.detach()), ops._f32c(c0.detach())
@@ -149,6 +162,15 @@ class _Rollout(torch.autograd.Function):
         fb = ops.FEEDBACK[feedback]
         S = T + (1 if bootstrap else 0)                       # decoder passes (the bootstrap one only up to h_1)
         rp = rng.ptr
+        B_all = B
+        B_main, T_pair = pair if pair is not None else (B, S + 1)
+        if pair is not None:
+            fb |= (B_main + 1) << 8                           # rows >= B_main are teacher-forced (vln_policy_env_act_fwd)
+
+        def rows(t):                                          # episodes that take part in decoder pass t
+            return B_all if t < T_pair else B_main
+        # rows that sit out later steps must read as zeros (finite) in the stacked weight-gradient GEMMs
+        alloc = torch.zeros if pair is not None else torch.empty
 
         # ---- weights: bf16 hi/lo splits, refreshed once per optimiser step ----
         s_cat = fd.cat.fresh(w_ih, w_hh)
@@ -169,22 +191,22 @@ class _Rollout(torch.autograd.Function):
             return t_
         Q, GATES = carve(S, B, F), carve(S, B, G4)
         TQ, PRE, TGT = carve(T, B, H), carve(T, B, H), carve(T, B, F)
-        XH = torch.empty((S + 1, B, KX), device=dev)
-        HQ = torch.empty((S + 1, B, H), device=dev)
-        HC = torch.empty((T, B, H), device=dev)
-        ACT = torch.empty((S + 1, B, H_ACT), device=dev)
-        ACTS = torch.empty((S, B, G4), device=dev)
-        CS = torch.empty((S + 1, B, H), device=dev)
-        H1 = torch.empty((S, B, H), device=dev)
-        WH = torch.empty((T, B, 2 * H), device=dev)
-        ATTV = torch.empty((S, B, ops.N_VIEWS), device=dev)
-        ATTC = torch.empty((T, B, L), device=dev)
-        LOGIT = torch.empty((T, B, ops.NSLOT), device=dev)
-        PROBS = torch.empty((T, B, ops.NSLOT), device=dev)
+        XH = alloc((S + 1, B, KX), device=dev)
+        HQ = alloc((S + 1, B, H), device=dev)
+        HC = alloc((T, B, H), device=dev)
+        ACT = alloc((S + 1, B, H_ACT), device=dev)
+        ACTS = alloc((S, B, G4), device=dev)
+        CS = alloc((S + 1, B, H), device=dev)
+        H1 = alloc((S, B, H), device=dev)
+        WH = alloc((T, B, 2 * H), device=dev)
+        ATTV = alloc((S, B, ops.N_VIEWS), device=dev)
+        ATTC = alloc((T, B, L), device=dev)
+        LOGIT = alloc((T, B, ops.NSLOT), device=dev)
+        PROBS = alloc((T, B, ops.NSLOT), device=dev)
         CE, LOGP, ENT = (torch.zeros((T, B), device=dev) for _ in range(3))
         REWARD, MASK = torch.zeros((T, B), device=dev), torch.zeros((T, B), device=dev)
         ACTION = torch.full((T, B), -1, dtype=torch.int32, device=dev)
-        TEACH = torch.empty((T + 1, B), dtype=torch.int32, device=dev)
+        TEACH = torch.full((T + 1, B), -1, dtype=torch.int32, device=dev)
         TEACH[0].copy_(st.teacher)
         CS[0].copy_(c0)
 
@@ -194,17 +216,18 @@ class _Rollout(torch.autograd.Function):
 
         def act_embed(t):
             _call("vln_envdrop_act_fwd", _ptr(st.view[t]), _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t]),
-                  _ptr(XH[t]), KX, B, H_ACT, p, rp, offs[t]["act"], _stream())
+                  _ptr(XH[t]), KX, rows(t), H_ACT, p, rp, offs[t]["act"], _stream())
 
         def visual_and_lstm(t, need_drop, q_done=False):
+            Bt = rows(t)
             if not q_done:
-                _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, B, None, _p(Q[t]), F)
+                _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, Bt, None, _p(Q[t]), F)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4), _ptr(Q[t]), F,
-                  _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, B, 0, pf, rp, offs[t]["img"],
+                  _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, Bt, 0, pf, rp, offs[t]["img"],
                   _ptr(MB[t]) if MB is not None else None, split, _stream())
-            _gemm(s_cat.hi, s_cat.lo, G4, KX, _p(XH[t]), KX, B, _ptr(bsum), _p(GATES[t]), G4)
+            _gemm(s_cat.hi, s_cat.lo, G4, KX, _p(XH[t]), KX, Bt, _ptr(bsum), _p(GATES[t]), G4)
             _call("vln_lstm_pointwise_drop_fwd", _ptr(GATES[t]), _ptr(CS[t]), _ptr(H1[t]), _ptr(CS[t + 1]),
-                  _ptr(ACTS[t]), _p(WH[t], H) if need_drop else None, 2 * H, B, H, p, rp, offs[t]["h1"], _stream())
+                  _ptr(ACTS[t]), _p(WH[t], H) if need_drop else None, 2 * H, Bt, H, p, rp, offs[t]["h1"], _stream())
 
         _call("vln_envdrop_state_fwd", _ptr(h0), 0, _p(XH[0], H_ACT + F), KX, _ptr(HQ[0]), None, B, H, p, rp,
               offs[0]["hprev"], 0, _stream())
@@ -212,22 +235,23 @@ class _Rollout(torch.autograd.Function):
         n = 0
         paired = B <= 128
         for t in range(T):
+            Bt = rows(t)
             visual_and_lstm(t, True, q_done=paired and t > 0)
-            _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, B, None, _p(TQ[t]), H)
-            _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, B, L,
+            _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, Bt, None, _p(TQ[t]), H)
+            _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, Bt, L,
                   H, _stream())
-            _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, B, None, _p(PRE[t]), H)
+            _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, Bt, None, _p(PRE[t]), H)
             more = t + 1 < S
             _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
-                  _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), B, H, p, rp,
+                  _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), Bt, H, p, rp,
                   offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _stream())
             if paired and more:      # tgt_t = W_cand hc_t and q_{t+1} = W_vin hq_{t+1} both only wait for h~_t: one launch
                 _call("vln_linear_bf16x3_pair", _ptr(s_cand.hi), _ptr(s_cand.lo), _ptr(HC[t]), _ptr(TGT[t]), _ptr(s_vin.hi),
-                      _ptr(s_vin.lo), _ptr(HQ[t + 1]), _ptr(Q[t + 1]), F, H, H, B, F, _stream())
+                      _ptr(s_vin.lo), _ptr(HQ[t + 1]), _ptr(Q[t + 1]), F, H, H, Bt, F, _stream())
             else:
-                _gemm(s_cand.hi, s_cand.lo, F, H, _p(HC[t]), H, B, None, _p(TGT[t]), F)
+                _gemm(s_cand.hi, s_cand.lo, F, H, _p(HC[t]), H, Bt, None, _p(TGT[t]), F)
             _call("vln_cand_logits_fwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
-                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(TGT[t]), None, _ptr(LOGIT[t]), B, pf, rp,
+                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(TGT[t]), None, _ptr(LOGIT[t]), Bt, pf, rp,
                   offs[t]["cand"], _stream())
             # action head + simulator transition + the next pass's action embedding: one launch
             _call("vln_policy_env_act_fwd", _ptr(LOGIT[t]), _ptr(TEACH[t]), fb, rp, offs[t]["sample"], _ptr(CE[t]),
@@ -238,7 +262,7 @@ class _Rollout(torch.autograd.Function):
                   _ptr(st.vp[t + 1]), _ptr(st.view[t + 1]), _ptr(st.ended[t + 1]), _ptr(st.dist[t + 1]),
                   _ptr(TEACH[t + 1]), _ptr(REWARD[t]), _ptr(MASK[t]), _ptr(st.n_active[t:t + 1]),
                   _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t + 1]) if more else None,
-                  _ptr(XH[t + 1]) if more else None, KX, H_ACT, p, offs[t + 1]["act"] if more else 0, B, _stream())
+                  _ptr(XH[t + 1]) if more else None, KX, H_ACT, p, offs[t + 1]["act"] if more else 0, Bt, _stream())
             st.steps = n = t + 1
             if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
                 break
@@ -247,7 +271,7 @@ class _Rollout(torch.autograd.Function):
         st.teacher = TEACH[n]
 
         fctx.fd, fctx.st, fctx.rp, fctx.MB = fd, st, rp, MB
-        fctx.cfg = (n, B, L, H, p, pf, split, offs)
+        fctx.cfg = (n, B, L, H, p, pf, split, offs, B_main, T_pair)
         fctx.splits = (s_cat, s_vin, s_tin, s_out, s_cand)
         fctx.save_for_backward(ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH)
         outs = (CE[:n], LOGP[:n], ENT[:n], H1[:n], LOGIT[:n], ACTION[:n], TEACH[:n], REWARD[:n], MASK[:n],
@@ -258,7 +282,12 @@ class _Rollout(torch.autograd.Function):
     @staticmethod
     def backward(fctx, d_ce, d_logp, d_ent, d_h1, *_unused):
         ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH = fctx.saved_tensors
-        n, B, L, H, p, pf, split, offs = fctx.cfg
+        n, B, L, H, p, pf, split, offs, B_main, T_pair = fctx.cfg
+        paired_rollouts = B_main < B
+        alloc = torch.zeros if paired_rollouts else torch.empty
+
+        def rows(t):
+            return B if t < T_pair else B_main
         s_cat, s_vin, s_tin, s_out, s_cand = fctx.splits
         st, rp, MB = fctx.st, fctx.rp, fctx.MB
         store = st.store
@@ -278,14 +307,14 @@ class _Rollout(torch.autograd.Function):
             cur[0] += k
             return t_
         DHC, DWH, DXH, DHQ = carve(n, B, H), carve(n, B, 2 * H), carve(n, B, KX), carve(n, B, H)
-        DTGT = torch.empty((n, B, F), device=dev)
-        DPRE = torch.empty((n, B, H), device=dev)
-        DTQ = torch.empty((n, B, H), device=dev)
-        DGATES = torch.empty((n, B, G4), device=dev)
-        DQ = torch.empty((n, B, F), device=dev)
-        DACT = torch.empty((n, B, H_ACT), device=dev)
-        DC = torch.empty((2, B, H), device=dev)
-        DLC = torch.empty((n, B, L), device=dev)                  # d(logit) of the text attention, per step
+        DTGT = alloc((n, B, F), device=dev)
+        DPRE = alloc((n, B, H), device=dev)
+        DTQ = alloc((n, B, H), device=dev)
+        DGATES = alloc((n, B, G4), device=dev)
+        DQ = alloc((n, B, F), device=dev)
+        DACT = alloc((n, B, H_ACT), device=dev)
+        DC = alloc((2, B, H), device=dev)
+        DLC = alloc((n, B, L), device=dev)                  # d(logit) of the text attention, per step
 
         # ---- off the recursion: candidate-logit backward of ALL steps in one launch, then d(h~_drop) = dtgt W_cand
         #      as a stack of 128-row GEMMs (none of it depends on the backward-in-time chain) ----
@@ -297,21 +326,22 @@ class _Rollout(torch.autograd.Function):
         _gemm(s_cand.hi_t, s_cand.lo_t, H, F, _p(DTGT), F, n * B, None, _p(DHC), H)
         for t in range(n - 1, -1, -1):
             last = t == n - 1
+            Bt = rows(t)            # rows that sat out step t+1 see zero carried gradients (zero-filled slab / DC)
             _call("vln_envdrop_state_bwd", _ptr(DHC[t]), None if last else _p(DXH[t + 1], OH), KX,
-                  None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), B, H, p, rp,
+                  None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), Bt, H, p, rp,
                   0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
-            _gemm(s_out.hi_t, s_out.lo_t, 2 * H, H, _p(DPRE[t]), H, B, None, _p(DWH[t]), 2 * H)
+            _gemm(s_out.hi_t, s_out.lo_t, 2 * H, H, _p(DPRE[t]), H, Bt, None, _p(DWH[t]), 2 * H)
             _call("vln_ctx_attn_bwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H, None,
-                  _ptr(DTQ[t]), None, _ptr(DLC[t]), B, L, H, _stream())
-            _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, B, None, _p(DWH[t], H), 2 * H, accumulate=1)
+                  _ptr(DTQ[t]), None, _ptr(DLC[t]), Bt, L, H, _stream())
+            _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, Bt, None, _p(DWH[t], H), 2 * H, accumulate=1)
             _call("vln_lstm_pointwise_drop_bwd", _ptr(ACTS[t]), _ptr(CS[t]), _ptr(CS[t + 1]), _p(DWH[t], H), 2 * H,
                   _ptr(d_h1[t]) if d_h1 is not None else None, None if last else _ptr(DC[(t + 1) & 1]),
-                  _ptr(DGATES[t]), _ptr(DC[t & 1]), B, H, p, rp, offs[t]["h1"], _stream())
-            _gemm(s_cat.hi_t, s_cat.lo_t, KX, G4, _p(DGATES[t]), G4, B, None, _p(DXH[t]), KX)
+                  _ptr(DGATES[t]), _ptr(DC[t & 1]), Bt, H, p, rp, offs[t]["h1"], _stream())
+            _gemm(s_cat.hi_t, s_cat.lo_t, KX, G4, _p(DGATES[t]), G4, Bt, None, _p(DXH[t]), KX)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4),
-                  _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, B, 1, pf, rp,
+                  _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, Bt, 1, pf, rp,
                   offs[t]["img"], _ptr(MB[t]) if MB is not None else None, split, _stream())
-            _gemm(s_vin.hi_t, s_vin.lo_t, H, F, _p(DQ[t]), F, B, None, _p(DHQ[t]), H)
+            _gemm(s_vin.hi_t, s_vin.lo_t, H, F, _p(DQ[t]), F, Bt, None, _p(DHQ[t]), H)
         _call("vln_envdrop_act_bwd", _ptr(DXH), KX, _ptr(ACT), _ptr(DACT), B, H_ACT, n, p, rp, offs[0]["act"],
               (offs[1]["act"] - offs[0]["act"]) if len(offs) > 1 else 0, _stream())
         d_h0 = torch.empty((B, H), device=dev)

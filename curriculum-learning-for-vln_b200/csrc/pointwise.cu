@@ -258,8 +258,10 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t n, float
 // each half of the row (one CTA of the panorama kernel's cluster) is 128 contiguous bytes, and lane c % 32
 // of a warp reads the four bytes of its four 16-byte column chunks at once.
 // Same bits as vln_dropout_mask on the dense [rows, 2048] tensor with call_off = off0 + t * off_stride.
+// The buffer holds ld_rows rows per step; rows [row0, row0 + rows) of each step are written (numbered row0.. in the stream).
 __global__ void feature_mask_bits_kernel(uint8_t* __restrict__ bits, int64_t rows, int n_steps, float p,
-                                         const uint64_t* __restrict__ rng, uint64_t off0, uint64_t off_stride) {
+                                         const uint64_t* __restrict__ rng, uint64_t off0, uint64_t off_stride,
+                                         int64_t ld_rows, int64_t row0) {
   const int64_t total = rows * 256 * n_steps;
   const uint32_t thr = drop_threshold(p);
   const uint64_t seed = rng[0], base = rng[1];
@@ -267,12 +269,12 @@ __global__ void feature_mask_bits_kernel(uint8_t* __restrict__ bits, int64_t row
     const int64_t row_t = o >> 8;                                   // (t, row)
     const int w = (int)(o & 255);                                   // byte position inside the row
     const int c = (w >> 7) * 128 + (w & 3) * 32 + ((w & 127) >> 2);  // Philox block of the row stored there
-    const int64_t t = row_t / rows, row = row_t - t * rows;
+    const int64_t t = row_t / rows, row = row0 + row_t - t * rows;
     const Philox8 r = philox8(seed, base + off0 + (uint64_t)t * off_stride, (uint64_t)(row * 256 + c));
     uint32_t b = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) b |= (philox_keep(r, j, thr) ? 1u : 0u) << j;
-    bits[o] = (uint8_t)b;
+    bits[(t * ld_rows + row) * 256 + w] = (uint8_t)b;
   }
 }
 
@@ -582,7 +584,21 @@ extern "C" int vln_feature_mask_bits(uint8_t* bits, int64_t rows, int n_steps, f
   const int64_t total = rows * 256 * n_steps;
   const int64_t want = (total + 255) / 256;
   const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-  feature_mask_bits_kernel<<<grid, 256, 0, STREAM>>>(bits, rows, n_steps, p, rng, off0, off_stride);
+  feature_mask_bits_kernel<<<grid, 256, 0, STREAM>>>(bits, rows, n_steps, p, rng, off0, off_stride, rows, 0);
+  VLN_LAUNCH_OK();
+  return 0;
+}
+
+// The same bits for a sub-block of a larger buffer: steps [0, n_steps), rows [row0, row0 + rows) of a buffer with
+// ld_rows rows per step (paired rollouts: the teacher-forced half only needs the first T_teacher steps).
+extern "C" int vln_feature_mask_bits_ld(uint8_t* bits, int64_t rows, int64_t ld_rows, int64_t row0, int n_steps, float p,
+                                        const uint64_t* rng, uint64_t off0, uint64_t off_stride, void* stream) {
+  VLN_REQUIRE(bits && rng && rows > 0 && n_steps > 0 && p > 0.f && p < 1.f && row0 >= 0 && row0 + rows <= ld_rows,
+              "bad arguments");
+  const int64_t total = rows * 256 * n_steps;
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  feature_mask_bits_kernel<<<grid, 256, 0, STREAM>>>(bits, rows, n_steps, p, rng, off0, off_stride, ld_rows, row0);
   VLN_LAUNCH_OK();
   return 0;
 }

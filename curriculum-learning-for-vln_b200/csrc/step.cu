@@ -202,10 +202,14 @@ __global__ void policy_env_act_kernel(const float* __restrict__ logits, const in
   const float lp = x - m - logf(s);
   const float ent = -warp_sum(p > 0.f ? p * lp : 0.f);
   const int tg = target ? target[b] : -1;
+  // feedback = mode | (teacher_from + 1) << 8: rows >= teacher_from follow the teacher whatever the mode (the
+  // teacher-forced and the sampled rollout of one EnvDrop iteration stepped as one launch, trainer.py:411-421)
+  const int t_from = feedback >> 8;
+  const int mode = (t_from > 0 && b >= t_from - 1) ? 0 : (feedback & 3);
   int act_id;
-  if (feedback == 0) {
+  if (mode == 0) {
     act_id = tg;
-  } else if (feedback == 1) {
+  } else if (mode == 1) {
     act_id = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
   } else {
     const float u = philox_uniform(philox8(rng[0], rng[1] + off_sample, (uint64_t)b), 0);
@@ -417,7 +421,9 @@ extern "C" int vln_policy_env_act_fwd(const float* logits, const int32_t* target
                   cand_vp && cand_view && n_cand && next_hop && dist_tbl && sq_off && vp_local && vp_out && view_out &&
                   ended_out && dist_out && teacher_out && reward && mask && B > 0,
               "bad arguments");
-  VLN_REQUIRE(feedback >= 0 && feedback <= 2 && (feedback != 0 || target) && (feedback != 2 || rng), "bad feedback mode");
+  VLN_REQUIRE(feedback >= 0 && (feedback & 3) <= 2 && ((feedback & 3) != 0 || target) && ((feedback & 3) != 2 || rng) &&
+                  ((feedback >> 8) == 0 || target),
+              "bad feedback mode");
   VLN_REQUIRE(!xh || (pose4 && w_act && b_act && act && E > 0 && (p_act == 0.f || rng)), "action embedding needs its weights");
   EnvTables env{cand_vp, cand_view, n_cand, next_hop, dist_tbl, sq_off, vp_local};
   VLN_CHECK_CUDA(vln_launch_chain(policy_env_act_kernel, dim3((B + 3) / 4), dim3(128), 0, STREAM, logits, target, feedback,

@@ -36,10 +36,20 @@ class TrainStep:
         self.feedback = cfg.AGENT.FEEDBACK
         self.weights = weights              # SelfPacedCurriculum instance (train_cl) or None
         self.item_loss = None
+        # EnvDrop: step the teacher-forced and the sampled rollout of an iteration as one batch (agent.rollout_pair)
+        self.pair_rollouts = os.environ.get("VLN_PAIR_ROLLOUTS", "1") != "0"
 
     def losses(self):
         """Run the rollouts; return (loss to differentiate, per-item loss record or None)."""
         ag, cl = self.agent, self.weights is not None
+        if self.name == "ENVDROP" and self.feedback == "sample" and self.pair_rollouts and getattr(ag, "fused", False) \
+                and ag.device.type == "cuda" and ag.trace is None:
+            ag.rollout_pair(train_cl=cl)                       # both rollouts of the iteration as one batch of 2B episodes
+            cur = ag.loss["ml_loss"] + ag.loss["rl_loss"]
+            if not cl:
+                return cur, None
+            w = self.weights.weight[ag.last_batch.index]
+            return torch.dot(w, cur), ag.loss["ml_loss"].detach() * cur.shape[0]
         if self.name == "ENVDROP":
             ag.rollout(train_ml=True, train_rl=False, train_cl=cl, feedback="teacher")
             ml = ag.loss["ml_loss"]

@@ -94,6 +94,10 @@ int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int32_t* view,
  * Byte (c/128)*128 + (c%32)*4 + (c%128)/32 of a row = keep-bits of features [8c, 8c+8). */
 int vln_feature_mask_bits(uint8_t* bits, int64_t rows, int n_steps, float p, const uint64_t* rng,
                           uint64_t off0, uint64_t off_stride, void* stream);
+/* The same bits for rows [row0, row0 + rows) of the first n_steps steps of a buffer that holds ld_rows rows per
+ * step (paired rollouts: the teacher-forced half of the batch only lives for the first T_teacher steps). */
+int vln_feature_mask_bits_ld(uint8_t* bits, int64_t rows, int64_t ld_rows, int64_t row0, int n_steps, float p,
+                             const uint64_t* rng, uint64_t off0, uint64_t off_stride, void* stream);
 
 /* Candidate logits (EnvDropDecoder.candidate_attn policy.py:199-206; also ActionScoring
  * units.py:173-185 after folding its Linear layers into tgt/bias on the host side):
@@ -180,7 +184,10 @@ int vln_envdrop_act_bwd(const float* d_xh, int ld_dxh, const float* act, float* 
                         void* stream);
 /* vln_policy_fwd + vln_env_step + vln_envdrop_act_fwd (for the NEW view) in one launch, one warp per
  * episode: the tail of a rollout step (envdrop.py:177-219) and the head of the next (policy.py:222-223).
- * xh may be NULL (no following decoder pass): then the action embedding is skipped. */
+ * xh may be NULL (no following decoder pass): then the action embedding is skipped.
+ * feedback = mode (0 teacher, 1 argmax, 2 sample) | (teacher_from + 1) << 8: with the upper field set, episodes
+ * b >= teacher_from follow the teacher whatever the mode — the teacher-forced and the sampled rollout of one
+ * EnvDrop iteration (trainer.py:411-421) stepped as one batch. */
 int vln_policy_env_act_fwd(const float* logits, const int32_t* target, int feedback, const uint64_t* rng,
                            uint64_t off_sample, float* ce, int32_t* action, float* logp, float* entropy,
                            float* probs, const int32_t* vp_in, const int32_t* view_in, const uint8_t* ended_in,

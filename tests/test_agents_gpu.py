@@ -250,6 +250,37 @@ def test_train_step_and_flat_optimizer():
         assert flat.data_ptr() <= p.data_ptr() < flat.data_ptr() + flat.numel() * 4
 
 
+@pytest.mark.parametrize("train_cl", [False, True], ids=["sum", "per_item"])
+def test_paired_rollouts_equal_separate_rollouts(train_cl):
+    """agent.rollout_pair (teacher-forced + sampled rollout of one iteration stepped as one batch of 2B episodes,
+    the teacher half dropping out after its last step) == the two rollout() calls of trainer.py:411-421: same
+    imitation / A2C losses and gradients.  Dropout off so both paths are the same function of the weights (each
+    half draws its own masks otherwise); the sampled actions use the same Philox offsets in both paths."""
+    out = []
+    for pair in (False, True):
+        agent, pag, env, penv, sds, cfg = _setup("ENVDROP", B=8)
+        agent.train()
+        agent.sync_every = 0
+        agent.encoder.drop_ratio = agent.decoder.drop_ratio = agent.decoder.feat_drop_ratio = 0.0
+        agent.critic.state2value[2].p = 0.0
+        if pair:
+            agent.rollout_pair(train_cl=train_cl)
+        else:
+            agent.rollout(train_ml=True, train_rl=False, train_cl=train_cl, feedback="teacher")
+            ml = agent.loss["ml_loss"]
+            agent.rollout(train_ml=False, train_rl=True, train_cl=train_cl, restart=True, feedback="sample")
+            agent.loss = {"ml_loss": ml, "rl_loss": agent.loss["rl_loss"]}
+        ml, rl = agent.loss["ml_loss"], agent.loss["rl_loss"]
+        (ml + rl).sum().backward()
+        out.append((ml.detach().cpu(), rl.detach().cpu(), _grads(agent.trainable_params()),
+                    agent.last_state.vp[:, :8].cpu(), [float(x) for x in agent.logs["total"]]))
+    (ml0, rl0, g0, vp0, tot0), (ml1, rl1, g1, vp1, tot1) = out
+    assert torch.equal(vp0, vp1[:vp0.shape[0]])                      # the sampled half walked the same trajectories
+    assert tot0 == tot1
+    assert _rel(ml1, ml0) < 1e-4 and _rel(rl1, rl0) < 1e-4
+    assert _cos(g1, g0) > 0.99999 and _rel(g1, g0) < 1e-3
+
+
 def test_graph_replay_tracks_the_optimiser():
     """CUDA-graph replays of the iteration must see the weights the fused optimiser wrote (the bf16
     weight splits are re-derived inside the graph): graphed steps == eager steps.  Dropout off and

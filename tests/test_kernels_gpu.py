@@ -539,6 +539,11 @@ def test_feature_mask_bits_equal_dropout_mask(setup):
         keep = ops.dropout_mask((B * 36, 256, 8), p, rng, 4 + 7 * s).to(torch.int32)      # [rows, block, lane]
         want = (keep * w).sum(2).to(torch.uint8)                                          # byte of block c
         assert torch.equal(bits[s][:, pos], want)
+    # sub-block generation (paired rollouts): rows [0, 2*36) of every step + rows [2*36, 5*36) of the first 2 steps
+    sub = torch.zeros_like(bits)
+    ops._call("vln_feature_mask_bits_ld", ops._ptr(sub), 2 * 36, B * 36, 0, S, p, rng.ptr, 4, 7, ops._stream())
+    ops._call("vln_feature_mask_bits_ld", ops._ptr(sub), 3 * 36, B * 36, 2 * 36, 2, p, rng.ptr, 4, 7, ops._stream())
+    assert torch.equal(sub[:2], bits[:2]) and torch.equal(sub[2, :72], bits[2, :72]) and int(sub[2, 72:].sum()) == 0
 
 
 @pytest.mark.parametrize("mode", [0, 1])

@@ -44,10 +44,13 @@ def main():
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     tot, cnt = defaultdict(float), defaultdict(int)
     spans = []
+    durs = defaultdict(list)
     for e in evs:
         name = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("<")[0].split("(")[0]
-        tot[name] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+        d = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        tot[name] += d
         cnt[name] += 1
+        durs[name].append(d)
         spans.append((e.time_range.start, e.time_range.end))
     spans.sort()
     busy = sum(b - a for a, b in spans)
@@ -58,6 +61,15 @@ def main():
              "| kernel | launches/iter | total us/iter | share | avg us |", "|---|---:|---:|---:|---:|"]
     for k in sorted(tot, key=tot.get, reverse=True)[:40]:
         lines.append(f"| {k[:70]} | {cnt[k] / n_it:.0f} | {tot[k] / n_it:.1f} | {100 * tot[k] / total:.1f}% | {tot[k] / cnt[k]:.2f} |")
+    # duration histogram (1 us buckets) of the step-chain kernels: separates the GEMM shapes
+    for k in ("linear_bf16x3_kernel", "pano_attn_kernel", "ctx_attn_kernel"):
+        if k in durs:
+            h = defaultdict(int)
+            for d in durs[k]:
+                h[int(d)] += 1
+            lines.append("")
+            lines.append(f"{k} durations (us bucket: launches/iter): " +
+                         ", ".join(f"{b}-{b + 1}: {h[b] / n_it:.0f}" for b in sorted(h)))
     text = "\n".join(lines)
     print(text)
     if len(sys.argv) > 1:
