@@ -264,6 +264,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world_size > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps the version banner off stdout (one JSON line)
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     import clvln_b200  # noqa: F401
     from clvln_b200 import ops, utils, _lib

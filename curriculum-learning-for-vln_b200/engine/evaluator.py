@@ -1,7 +1,34 @@
 """Navigation metrics on the World's distance tables (reference: src/engine/evaluator.py:10-146,
-src/utils/dtw.py:60-82): nav / oracle error, steps, length, success and oracle rates, SPL, nDTW,
-SDTW.  Off the training hot path (runs every EVAL_INTERVAL epochs); kept as host code."""
+src/utils/dtw.py:60-82, src/utils/cls.py:62-90): nav / oracle error, steps, length, success and oracle
+rates, SPL, nDTW, SDTW, CLS.  Off the training hot path (runs every EVAL_INTERVAL epochs); kept as host code.
+
+`dtw_scores` / `cls_score` take a distance function, so they are checked against the reference's own known-answer
+doctests (dtw.py:26-34, cls.py:31-39: a 3x4 grid graph) in tests/test_host_cpu.py."""
 import numpy as np
+
+
+def dtw_scores(dist, pred, ref, threshold=3.0):
+    """(dtw, ndtw, sdtw) of DTW.__call__ (dtw.py:60-82); `dist(a, b)` = shortest-path distance."""
+    m = np.full((len(pred) + 1, len(ref) + 1), np.inf)
+    m[0][0] = 0
+    for i in range(1, len(pred) + 1):
+        for j in range(1, len(ref) + 1):
+            m[i][j] = float(dist(pred[i - 1], ref[j - 1])) + min(m[i - 1][j], m[i][j - 1], m[i - 1][j - 1])
+    dtw = m[len(pred)][len(ref)]
+    ndtw = float(np.exp(-dtw / (threshold * len(ref))))
+    return float(dtw), ndtw, ndtw * (float(dist(pred[-1], ref[-1])) <= threshold)
+
+
+def cls_score(dist, prediction, reference, threshold=3.0):
+    """CLS.__call__ (cls.py:62-90) with its argument order: coverage of `reference` by `prediction`, weighted by
+    the length score.  (The reference's evaluator passes (predicted_path, gt_path) into these two slots,
+    evaluator.py:81-82 — i.e. it measures how well the ground truth covers the prediction; kept as is.)"""
+    def length(nodes):
+        return float(np.sum([dist(a, b) for a, b in zip(nodes[:-1], nodes[1:])]))
+    coverage = np.mean([np.exp(-np.min([dist(u, v) for v in prediction]) / threshold) for u in reference])
+    expected = coverage * length(reference)
+    score = expected / (expected + np.abs(expected - length(prediction)))
+    return float(coverage * score)
 
 
 class Evaluation:
@@ -12,20 +39,13 @@ class Evaluation:
         self.gt = {it["instr_id"]: it for it in env.data}
 
     def _dtw(self, pred, ref):
-        w = self.env.world
-        m = np.full((len(pred) + 1, len(ref) + 1), np.inf)
-        m[0][0] = 0
-        for i in range(1, len(pred) + 1):
-            for j in range(1, len(ref) + 1):
-                m[i][j] = float(w.distance(pred[i - 1], ref[j - 1])) + min(m[i - 1][j], m[i][j - 1], m[i - 1][j - 1])
-        dtw = m[len(pred)][len(ref)]
-        ndtw = float(np.exp(-dtw / (self.error_margin * len(ref))))
-        return ndtw, ndtw * (float(w.distance(pred[-1], ref[-1])) <= self.error_margin)
+        _, ndtw, sdtw = dtw_scores(self.env.world.distance, pred, ref, self.error_margin)
+        return ndtw, sdtw
 
     def score(self, results):
         env, w = self.env, self.env.world
         s = {k: [] for k in ("nav_errors", "oracle_errors", "trajectory_steps", "trajectory_lengths",
-                             "success_path_length", "ndtws", "sdtws")}
+                             "success_path_length", "ndtws", "sdtws", "clss")}
         seen = set()
         for item in results:
             iid = item["instr_id"]
@@ -47,12 +67,14 @@ class Evaluation:
             s["success_path_length"].append(ok * d0 / max(d0, length, 1e-9))
             nd, sd = self._dtw(path, gt["path_g"])
             s["ndtws"].append(nd), s["sdtws"].append(sd)
+            # evaluator.py:81-82: cls_worker(predicted_path, gt['path']) -> CLS.__call__(prediction=pred, reference=gt)
+            s["clss"].append(cls_score(w.distance, path, gt["path_g"], self.error_margin))
         assert len(seen) == len(self.gt), f"missing {len(self.gt) - len(seen)} of {len(self.gt)} instruction ids"
         n = float(len(seen))
         summary = {"nav_error": float(np.average(s["nav_errors"])), "oracle_error": float(np.average(s["oracle_errors"])),
                    "steps": float(np.average(s["trajectory_steps"])), "lengths": float(np.average(s["trajectory_lengths"])),
                    "spl": float(np.average(s["success_path_length"])), "ndtw": float(np.average(s["ndtws"])),
-                   "sdtw": float(np.average(s["sdtws"])),
+                   "sdtw": float(np.average(s["sdtws"])), "cls": float(np.average(s["clss"])),
                    "success_rate": sum(e < self.error_margin for e in s["nav_errors"]) / n,
                    "oracle_rate": sum(e < self.error_margin for e in s["oracle_errors"]) / n}
         return summary, s

@@ -245,3 +245,23 @@ def test_two_rank_gloo_sharding_and_curriculum_allgather():
         assert not set(a) & set(b) and len(a) == len(b) == 8           # disjoint shards of the global batch
     idx = torch.tensor(seen0[-1] + seen1[-1])
     assert torch.allclose(l0[idx], idx.float() * 0.01 + 2)
+
+
+def test_dtw_cls_known_answers():
+    """The reference's only known-answer vectors (doctests of src/utils/dtw.py:26-34 and src/utils/cls.py:31-39,
+    3x4 grid graph with unit edges) reproduced by engine/evaluator.py's dtw_scores / cls_score."""
+    import networkx as nx
+    from clvln_b200.engine.evaluator import cls_score, dtw_scores
+    d = dict(nx.all_pairs_dijkstra_path_length(nx.grid_graph([3, 4])))
+    dist = lambda a, b: d[a][b]
+    prediction = [(0, 0), (1, 0), (2, 0), (3, 0)]
+    reference = [(0, 0), (1, 0), (2, 1), (3, 2)]
+    dtw, ndtw, sdtw = dtw_scores(dist, prediction, reference)
+    assert np.isclose(dtw, 3.0) and np.isclose(ndtw, 0.77880078307140488) and np.isclose(sdtw, 0.77880078307140488)
+    assert np.isclose(dtw_scores(dist, prediction[:2], reference)[2], 0.0)
+    reference = [(0, 0), (1, 0), (1, 1), (2, 1), (2, 2), (3, 2)]
+    assert np.isclose(cls_score(dist, reference, reference), 1.0)
+    prediction = [(0, 0), (0, 1), (1, 1), (2, 1), (3, 1), (3, 2)]
+    assert np.isclose(cls_score(dist, reference, prediction), 0.81994915125863865)      # doctest call order cls(reference, prediction)
+    prediction = [(0, 1), (1, 1), (2, 1), (3, 1)]
+    assert np.isclose(cls_score(dist, reference, prediction), 0.44197196102702557)

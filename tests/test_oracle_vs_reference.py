@@ -26,3 +26,13 @@ def test_reference_env_matches_world_tables():
 def test_port_rollouts_match_reference_agents():
     """Real Follower/Monitor/EnvDrop agents' rollout + backward == port: loss, grads, trajectories."""
     runpy.run_path(os.path.join(HERE, "_ref_check_rollout.py"), run_name="__main__")
+
+
+def test_ingest_matches_reference_loaders():
+    """environ/ingest.py == ImageFeatures.read_in, load_nav_graphs + networkx paths (ties), Tokenizer."""
+    runpy.run_path(os.path.join(HERE, "_ref_check_ingest.py"), run_name="__main__")
+
+
+def test_evaluator_matches_reference_evaluation():
+    """engine/evaluator.py (nav/oracle error, SPL, nDTW, SDTW, CLS, rates) == src/engine/evaluator.py Evaluation.score."""
+    runpy.run_path(os.path.join(HERE, "_ref_check_eval.py"), run_name="__main__")
