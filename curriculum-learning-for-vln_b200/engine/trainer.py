@@ -94,8 +94,15 @@ class ClassicTrainer:
     def pick_env(self, train_env, ep):
         return train_env
 
-    def make_step(self, cfg, agent):
-        return TrainStep(cfg, agent)
+    def make_step(self, cfg, agent, weights=None):
+        """The iteration body: CUDA-graph replay for the fused EnvDrop rollout on a GPU (engine/graphs.py), the
+        eager TrainStep otherwise (drop-in module path of Follower / Self-Monitor, CPU-side tests)."""
+        if (cfg.MODEL.NAME == "ENVDROP" and getattr(agent, "fused", False) and agent.device.type == "cuda"
+                and os.environ.get("VLN_TRAIN_GRAPH", "1") != "0"):
+            from .graphs import GraphedTrainStep
+            agent.sync_every = 0                  # fixed-length sampled rollouts (ended episodes are masked): no host polls
+            return GraphedTrainStep(cfg, agent, weights=weights)
+        return TrainStep(cfg, agent, weights=weights)
 
     def after_epoch(self, ep, step):
         pass
@@ -193,8 +200,8 @@ class SelfPacedCurriculum(ClassicTrainer):
     def pick_env(self, train_env, ep):
         return self.train_env
 
-    def make_step(self, cfg, agent):
-        return TrainStep(cfg, agent, weights=self)
+    def make_step(self, cfg, agent, weights=None):
+        return super().make_step(cfg, agent, weights=self)
 
     def record(self, index, item_loss):
         """loss_for_item[idx] = loss (curriculum.py:311-314).  Under data parallelism every rank
@@ -239,7 +246,7 @@ class SelfPacedCurriculum(ClassicTrainer):
             a_norm = torch.norm(self.a, p=2)
             new_w = w + self.a * (self.c - torch.dot(self.a, w)) / (a_norm * a_norm)
             new_w[new_w <= 0.0] = 0.001
-            self.weight = new_w
+            self.weight.copy_(new_w)        # in place: a captured CUDA graph keeps reading this very tensor
 
 
 def build_trainer(cfg, train_env, device):

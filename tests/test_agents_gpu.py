@@ -305,3 +305,78 @@ def test_graph_replay_tracks_the_optimiser():
     num = sum(float((a - b).norm()) ** 2 for a, b in zip(p0, p1)) ** 0.5
     den = sum(float((a - i).norm()) ** 2 for a, i in zip(p0, i0)) ** 0.5
     assert num <= 0.25 * den, (num, den)
+
+
+def _cl_setup(kind, B, n_items=120):
+    import clvln_b200  # noqa: F401
+    from clvln_b200 import utils
+    from clvln_b200.agent import build_agent
+    from clvln_b200.environ import make_world, make_items, split_rounds
+    dev = torch.device("cuda:0")
+    world = make_world(n_scans=3, seed=2)
+    items = make_items(world, n_items, seed=2)
+    cfg = utils.agent_cfg(kind)
+    cfg.AGENT.MAX_EPISODE_LEN = KINDS[kind]
+    cfg.TRAIN.BATCH_SIZE = B
+    cfg.TRAIN.MAX_EPOCH, cfg.TRAIN.ITER_PER_EPOCH = 3, 3
+    torch.manual_seed(2020)
+    agent = build_agent(cfg, utils.StubTokenizer(), dev)
+    return world, split_rounds(items), cfg, agent, dev
+
+
+def test_self_paced_envdrop_trainer_end_to_end():
+    """BASELINE config 4 in small: EnvDrop + TRAIN.CLMODE=SELF-PACE through build_trainer(...).train (graph-replayed
+    iterations): per-item losses land at the visited dataset indices, the pace update of curriculum.py:402-448 runs on
+    the device-resident weight vector the captured graph reads, parameters move, losses stay finite."""
+    from clvln_b200.engine import build_trainer
+    from clvln_b200.engine.graphs import GraphedTrainStep
+    from clvln_b200.environ import CLR2RBatch
+    world, rounds, cfg, agent, dev = _cl_setup("ENVDROP", B=8)
+    cfg.TRAIN.CLMODE = "SELF-PACE"
+    sp = cfg.TRAIN.SELF_PACE
+    sp.FUNC, sp.LAMB, sp.MIU, sp.WCTRL, sp.CRATE, sp.INTERVAL, sp.BURN_IN, sp.STRATEGY = "linear", 2.0, 2.0, 0.5, 1.0, 1, 1, "epoch"
+    random.seed(2020)
+    env = CLR2RBatch(world, rounds, batch_size=8, c_rate=sp.CRATE, device=dev)
+    trainer = build_trainer(cfg, env, dev)
+    assert isinstance(trainer.make_step(cfg, agent), GraphedTrainStep)
+    w0 = trainer.weight.clone()
+    wptr = trainer.weight.data_ptr()
+    p0 = [p.detach().clone() for p in agent.trainable_params()]
+    visited = set()
+    orig = trainer.record
+
+    def record(index, item):
+        visited.update(index.tolist())
+        assert item.shape == index.shape and bool(torch.isfinite(item).all())
+        orig(index, item)
+    trainer.record = record
+    trainer.train(cfg, agent, None, env, None, log=lambda *_: None)
+    assert len(trainer.history) == 3 and all(np.isfinite(h["loss_sum"]) for h in trainer.history)
+    nz = set(torch.nonzero(trainer.loss_for_item).flatten().tolist())
+    assert nz and nz <= visited and len(visited) <= 3 * 3 * 8
+    assert trainer.weight.data_ptr() == wptr and not torch.equal(trainer.weight, w0)      # updated in place
+    assert float(trainer.weight.min()) > 0.0
+    assert max(_rel(a, b) for a, b in zip(agent.trainable_params(), p0)) > 1e-4
+
+
+def test_naive_curriculum_monitor_trainer_end_to_end():
+    """BASELINE config 3 in small: Self-Monitor + TRAIN.CLMODE=NAIVE (round switch every epoch here) through
+    build_trainer(...).train on the drop-in module path."""
+    from clvln_b200.engine import build_trainer, NaiveCurriculum
+    from clvln_b200.environ import R2RBatch
+    world, rounds, cfg, agent, dev = _cl_setup("SELF-MONITOR", B=8)
+    cfg.TRAIN.CLMODE = "NAIVE"
+    random.seed(2020)
+    envs = {f"round_{k}": R2RBatch(world, [it for j in range(1, k + 1) for it in rounds[j]], batch_size=8, device=dev)
+            for k in range(1, 6)}
+    trainer = build_trainer(cfg, envs, dev)
+    assert isinstance(trainer, NaiveCurriculum)
+    trainer.switch_epoch = 1
+    seen = []
+    pick = trainer.pick_env
+    trainer.pick_env = lambda te, ep: seen.append(pick(te, ep)) or seen[-1]
+    p0 = [p.detach().clone() for p in agent.trainable_params()]
+    trainer.train(cfg, agent, None, envs, None, log=lambda *_: None)
+    assert seen == [envs["round_1"], envs["round_2"], envs["round_3"]]
+    assert all(np.isfinite(h["loss_sum"]) for h in trainer.history)
+    assert max(_rel(a, b) for a, b in zip(agent.trainable_params(), p0)) > 1e-4
