@@ -3,7 +3,7 @@
 // directions.  Same contract as csrc/lstm_seq.cu (the mma.sync version, kept behind VLN_LSTM_VARIANT=mma);
 // what changes is where the recurrent product runs:
 //
-//   * a thread-block CLUSTER of C = H/32 CTAs owns NB (16 or 32) batch rows for the whole sequence; CTA r owns
+//   * a thread-block CLUSTER of C = H/32 CTAs owns NB (16, 24 or 32) batch rows for the whole sequence; CTA r owns
 //     hidden units [32r, 32r+32), i.e. 128 gate rows (i,f,g,o x 32) of W_hh;
 //   * those 128 x H weights stay resident in TENSOR MEMORY for all timesteps as the A operand of
 //     tcgen05.mma (bf16 hi and lo halves, two bf16 per 32-bit column: lane = gate row, H/2 + H/2 columns),
@@ -101,6 +101,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// NB (16, 24 or 32) consecutive accumulator columns of this thread's TMEM lane
+template <int NB>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+#pragma unroll
+  for (int cg = 0; cg < NB / 16; ++cg) tmem_ld16(taddr + cg * 16, v + cg * 16);
+  if constexpr (NB % 16 == 8) tmem_ld8(taddr + (NB / 16) * 16, v + (NB / 16) * 16);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 __device__ __forceinline__ float bf16_val(uint32_t bits) { return __uint_as_float(bits << 16); }
@@ -290,9 +304,7 @@ lstm_tc_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B,
       TSTAMP(3, tid == 128 && s == 10);
       tc_fence_after();
       uint32_t v[NB];
-#pragma unroll
-      for (int cg = 0; cg < NB / 16; ++cg) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + S::kColD + cg * 16, v + cg * 16);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld_cols<NB>(tmem + ((uint32_t)(q * 32) << 16) + S::kColD, v);
 #pragma unroll
       for (int n = 0; n < NB; ++n) g[n * kGP + q * kHS + lane] = __uint_as_float(v[n]);
       tc_fence_before();
@@ -558,9 +570,7 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
       mbar_wait_g(bar_acc, (uint32_t)s & 1u);
       tc_fence_after();
       uint32_t v[NB];
-#pragma unroll
-      for (int cg = 0; cg < NB / 16; ++cg) tmem_ld16(tmem + ((uint32_t)(qq * 32) << 16) + mt * 32 + cg * 16, v + cg * 16);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tmem_ld_cols<NB>(tmem + ((uint32_t)(qq * 32) << 16) + mt * 32, v);
       const uint32_t owner = (uint32_t)(mt * 4 + qq);
 #pragma unroll
       for (int n4 = 0; n4 < NB / 4; ++n4) {
@@ -630,28 +640,32 @@ int launch_tc(K kernel, size_t smem, int C, int NB, int n_dir, int B, cudaStream
   return 0;
 }
 
-// NB = 16 unless the launch would then need more clusters than can be resident at once (a second wave doubles the
-// serial latency chain); VLN_LSTM_NB=16|32 forces it.
+// The smallest NB in {16, 24, 32} whose launch fits in ONE wave of resident clusters (a second wave doubles the serial
+// latency chain; a larger NB lengthens every step: MMA N, gate math and the h exchange all scale with it);
+// VLN_LSTM_NB=16|24|32 forces it.
 template <int H>
 int pick_nb(int B, int n_dir, bool fwd) {
   static int max16[2] = {-1, -1};
   const char* e = getenv("VLN_LSTM_NB");
   if (e && !strcmp(e, "32")) return 32;
+  if (e && !strcmp(e, "24")) return 24;
   if (e && !strcmp(e, "16")) return 16;
   int& m = max16[fwd ? 0 : 1];
   if (m < 0) {
     int v = 0;
     int rc;
     if (fwd) {
-      cudaFuncSetAttribute(lstm_tc_fwd_kernel<H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF<H, 16>::kSmem);
-      rc = max_active_clusters(lstm_tc_fwd_kernel<H, 16>, LayF<H, 16>::kSmem, H / kHS, &v);
+      cudaFuncSetAttribute(lstm_tc_fwd_kernel<H, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF<H, 32>::kSmem);
+      rc = max_active_clusters(lstm_tc_fwd_kernel<H, 32>, LayF<H, 32>::kSmem, H / kHS, &v);
     } else {
-      cudaFuncSetAttribute(lstm_tc_bwd_kernel<H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayB<H, 16>::kSmem);
-      rc = max_active_clusters(lstm_tc_bwd_kernel<H, 16>, LayB<H, 16>::kSmem, H / kHS, &v);
+      cudaFuncSetAttribute(lstm_tc_bwd_kernel<H, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayB<H, 32>::kSmem);
+      rc = max_active_clusters(lstm_tc_bwd_kernel<H, 32>, LayB<H, 32>::kSmem, H / kHS, &v);
     }
     m = (rc == 0 && v > 0) ? v : 14;
   }
-  return ((B + 15) / 16) * n_dir <= m ? 16 : 32;
+  for (int nb = 16; nb < 32; nb += 8)
+    if (((B + nb - 1) / nb) * n_dir <= m) return nb;
+  return 32;
 }
 
 template <int H, int NB>
@@ -690,11 +704,15 @@ int vln_lstm_tc_fwd(const float* const* xproj, const float* const* w_hh, const i
     d[k] = DirF{xproj[k], w_hh[k], out + k * H, acts[k], cs[k], h_last + k * H, c_last + k * H, k};
   const int ld = n_dir * H;
   if (H == 256) {
-    if (pick_nb<256>(B, n_dir, true) == 16) return launch_fwd<256, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    const int nb = pick_nb<256>(B, n_dir, true);
+    if (nb == 16) return launch_fwd<256, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    if (nb == 24) return launch_fwd<256, 24>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
     return launch_fwd<256, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
   }
   if (H == 128) {
-    if (pick_nb<128>(B, n_dir, true) == 16) return launch_fwd<128, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    const int nb = pick_nb<128>(B, n_dir, true);
+    if (nb == 16) return launch_fwd<128, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    if (nb == 24) return launch_fwd<128, 24>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
     return launch_fwd<128, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
   }
   vln_set_error("vln_lstm_seq_fwd: hidden size %d per direction is not supported (128 or 256)", H);
@@ -710,11 +728,15 @@ int vln_lstm_tc_bwd(const float* const* w_hh, const int32_t* lengths, const floa
                 d_clast ? d_clast + k * H : nullptr, d_xproj[k], k};
   const int ld = n_dir * H;
   if (H == 256) {
-    if (pick_nb<256>(B, n_dir, false) == 16) return launch_bwd<256, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    const int nb = pick_nb<256>(B, n_dir, false);
+    if (nb == 16) return launch_bwd<256, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    if (nb == 24) return launch_bwd<256, 24>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
     return launch_bwd<256, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
   }
   if (H == 128) {
-    if (pick_nb<128>(B, n_dir, false) == 16) return launch_bwd<128, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    const int nb = pick_nb<128>(B, n_dir, false);
+    if (nb == 16) return launch_bwd<128, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+    if (nb == 24) return launch_bwd<128, 24>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
     return launch_bwd<128, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
   }
   vln_set_error("vln_lstm_seq_bwd: hidden size %d per direction is not supported (128 or 256)", H);

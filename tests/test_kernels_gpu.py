@@ -423,7 +423,7 @@ def lstm_variant(request):
 @pytest.mark.parametrize("lstm_variant", [1, 0], indirect=True, ids=["tcgen05", "mma"])
 @pytest.mark.parametrize("H,E,B,L,ndir", [(256, 256, 64, 80, 2), (128, 300, 19, 33, 2), (256, 64, 5, 12, 1),
                                           (256, 128, 128, 40, 2), (128, 64, 150, 21, 2)])
-def test_lstm_layer_matches_oracle(setup, lstm_variant, H, E, B, L, ndir):
+def test_lstm_layer_matches_oracle(setup, lstm_variant, H, E, B, L, ndir, nb=None):
     """Persistent cluster LSTM (fwd + BPTT) vs the oracle's masked recurrence (== packed nn.LSTM); B = 128 / 150
     take the 32-rows-per-cluster instantiation of the tcgen05 kernels."""
     from oracle import port_modules as P
@@ -453,6 +453,15 @@ def test_lstm_layer_matches_oracle(setup, lstm_variant, H, E, B, L, ndir):
     for wm, wr in zip(mine, ref):
         for a, b in zip(wm, wr):
             assert relerr(a.grad, b.grad) < 2e-4
+
+
+
+@pytest.mark.parametrize("lstm_variant", [1], indirect=True, ids=["tcgen05"])
+@pytest.mark.parametrize("nb", [16, 24, 32])
+def test_lstm_tcgen05_rows_per_cluster(setup, lstm_variant, nb, monkeypatch):
+    """Every rows-per-cluster instantiation (MMA N = 16 / 24 / 32) of the tcgen05 recurrence, ragged batch of 45."""
+    monkeypatch.setenv("VLN_LSTM_NB", str(nb))
+    test_lstm_layer_matches_oracle(setup, lstm_variant, 256, 128, 45, 30, 2)
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 2048, 2240), (64, 2176, 512), (7, 512, 1024), (100, 2048, 512), (64, 64, 128),
