@@ -292,6 +292,8 @@ def run_b200(args):
     agent.train()
     agent.sync_every = 0                                  # fixed-length sampled rollouts: no host polls
     step = GraphedTrainStep(cfg, agent) if args.graph else TrainStep(cfg, agent)
+    if args.graph:
+        step.prefetch_next = True                         # e2e: the next minibatch is assembled + copied under this step's kernels
 
     def barrier():
         if world_size > 1:

@@ -34,6 +34,11 @@ class GraphedTrainStep(TrainStep):
         self.static = None
         self.warmup = warmup
         self.full_length = cfg.MODEL.NAME == "SELF-MONITOR"
+        # draw + stage the NEXT minibatch right after this iteration is launched, so that the host-side assembly
+        # and its H2D copies overlap the GPU's work instead of following the caller's loss read-back.  The order of
+        # minibatches is unchanged; callers switch it off for the last iteration before they touch the env / the
+        # global `random` stream themselves (epoch end: evaluation, curriculum round switch).
+        self.prefetch_next = False
 
     def _body(self):
         self.opt.zero_grad()
@@ -95,4 +100,6 @@ class GraphedTrainStep(TrainStep):
         self.opt.step()
         if item is not None:
             self.weights.record(st.index, item)
+        if self.prefetch_next and not env._staged:
+            env.prefetch(1, full_length=self.full_length)
         return loss

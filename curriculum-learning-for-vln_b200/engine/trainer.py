@@ -125,7 +125,11 @@ class ClassicTrainer:
             agent.env = self.pick_env(train_env, ep)
             agent.train()
             agent.reset_loss()
-            rec = [step() for _ in range(tc.ITER_PER_EPOCH)]
+            rec = []
+            for it in range(tc.ITER_PER_EPOCH):
+                if hasattr(step, "prefetch_next"):           # stage the next minibatch under this iteration's GPU work,
+                    step.prefetch_next = it + 1 < tc.ITER_PER_EPOCH      # except across the epoch boundary (eval / env switch)
+                rec.append(step())
             rec = torch.stack(rec).cpu().numpy()                     # the epoch's only loss read-back
             info = {"epoch": ep, "loss_sum": float(rec.sum()), "loss_avg": float(rec.mean()),
                     "loss_min": float(rec.min()), "loss_max": float(rec.max()),
