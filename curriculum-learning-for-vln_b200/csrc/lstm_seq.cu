@@ -551,7 +551,7 @@ extern "C" int vln_lstm_seq_fwd(const float* const* xproj, const float* const* w
     VLN_REQUIRE(((uintptr_t)w_hh[k] & 15) == 0, "w_hh must be 16-byte aligned");
     d[k] = DirF{xproj[k], w_hh[k], out + k * H, acts[k], cs[k], h_last + k * H, c_last + k * H, k};
   }
-  if (use_tc() && (H == 256 || H == 128))
+  if ((use_tc() && (H == 256 || H == 128)) || H == 512)        // 512 per direction exists on the tcgen05 path only
     return vln_lstm_tc_fwd(xproj, w_hh, lengths, out, acts, cs, h_last, c_last, B, L, H, n_dir, (cudaStream_t)stream);
   if (H == 256) return launch_fwd<256>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);
   if (H == 128) return launch_fwd<128>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);
@@ -571,7 +571,7 @@ extern "C" int vln_lstm_seq_bwd(const float* const* w_hh, const int32_t* lengths
     d[k] = DirB{w_hh[k], acts[k], cs[k], d_out ? d_out + k * H : nullptr, d_hlast ? d_hlast + k * H : nullptr,
                 d_clast ? d_clast + k * H : nullptr, d_xproj[k], k};
   }
-  if (use_tc() && (H == 256 || H == 128))
+  if ((use_tc() && (H == 256 || H == 128)) || H == 512)
     return vln_lstm_tc_bwd(w_hh, lengths, acts, cs, d_out, d_hlast, d_clast, d_xproj, B, L, H, n_dir, (cudaStream_t)stream);
   if (H == 256) return launch_bwd<256>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);
   if (H == 128) return launch_bwd<128>(d[0], d[1], n_dir, lengths, B, L, n_dir * H, n_dir * H, (cudaStream_t)stream);

@@ -81,6 +81,17 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// D[tmem] (+)= A[smem] . B[smem]  (both K-major swizzled tiles): used for the lo half of the weights when H = 512
+// leaves no tensor-memory columns for it
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"
@@ -169,13 +180,20 @@ struct LayF {
   static constexpr int KB = H / 64;                       // 64-wide k-blocks of the B operand (h_{t-1})
   static constexpr int kTile = NB * 128;                  // bytes of one k-block tile: NB rows x 128 B
   static constexpr int kHBytes = 2 * 2 * KB * kTile;      // [buffer][hi/lo][k-block]
-  static constexpr int kGOff = kHBytes;                   // float g[NB][kGP]: activated gates
+  // H = 512: hi (256 columns) + lo (256) + accumulator exceed the 512 tensor-memory columns, so the lo half of the
+  // weights lives in shared memory as a K-major 128B-swizzled A operand (KB tiles of 128 rows x 128 B)
+  static constexpr bool kLoSmem = H > 256;
+  static constexpr int kALoOff = kHBytes;
+  static constexpr int kALoBytes = kLoSmem ? KB * kRows * 128 : 0;
+  static constexpr int kGOff = kHBytes + kALoBytes;       // float g[NB][kGP]: activated gates
   static constexpr int kStageOff = kGOff + NB * kGP * 4;  // uint16 stage[hi/lo][NB][32]: this CTA's new h slice
   static constexpr int kLenOff = kStageOff + 2 * NB * kHS * 2;
   static constexpr int kBarOff = kLenOff + NB * 4;
   static constexpr int kSmem = kBarOff + 64 + 1024;       // + barriers/TMEM slot + 1 KB alignment slack
   static constexpr int kColD = 0, kColAhi = 32, kColAlo = 32 + H / 2;
   static constexpr int kTmemCols = (32 + H) <= 256 ? 256 : 512;
+  static_assert(kLoSmem ? (32 + H / 2 <= 512) : (32 + H <= 512), "tensor-memory columns");
+  static_assert(kSmem <= 227 * 1024, "shared memory");
 };
 
 template <int H, int NB>
@@ -244,11 +262,17 @@ lstm_tc_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B,
         split_pair(f.z, f.w, hi[2 * qd + 1], lo[2 * qd + 1]);
       }
       tmem_st8(lane_base + S::kColAhi + 8 * j, hi);
-      tmem_st8(lane_base + S::kColAlo + 8 * j, lo);
+      if constexpr (S::kLoSmem) {     // 16 k = two 16-byte chunks of row lr in k-block j / 4
+        uint8_t* row = base + S::kALoOff + (size_t)(j >> 2) * (kRows * 128) + lr * 128;
+        *reinterpret_cast<uint4*>(row + ((((j & 3) * 2 + 0) ^ (lr & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(row + ((((j & 3) * 2 + 1) ^ (lr & 7)) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      } else {
+        tmem_st8(lane_base + S::kColAlo + 8 * j, lo);
+      }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-  fence_proxy_async();              // the zero-filled h tiles are read by the tensor core (async proxy)
+  fence_proxy_async();              // the zero-filled h tiles (and the lo weights) are read through the async proxy
   tc_fence_before();
   TSTAMP(9, tid == 0);
   cluster_sync_all();               // barriers initialised + buffers zeroed cluster-wide before any DSMEM traffic
@@ -288,12 +312,18 @@ lstm_tc_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B,
       const uint32_t bh = hb_addr + (uint32_t)((cur * 2 + 0) * KB * S::kTile);
       const uint32_t bl = hb_addr + (uint32_t)((cur * 2 + 1) * KB * S::kTile);
       const uint64_t dh0 = sdesc_sw128(bh), dl0 = sdesc_sw128(bl);
+      [[maybe_unused]] const uint64_t alo0 = sdesc_sw128(hb_addr + S::kALoOff);
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint64_t inc = (uint64_t)(((ks >> 2) * S::kTile + (ks & 3) * 32) >> 4);   // address field is in 16-byte units
         umma_ts(tmem + S::kColD, tmem + S::kColAhi + 8 * ks, dh0 + inc, idesc, ks != 0);
         umma_ts(tmem + S::kColD, tmem + S::kColAhi + 8 * ks, dl0 + inc, idesc, 1u);
-        umma_ts(tmem + S::kColD, tmem + S::kColAlo + 8 * ks, dh0 + inc, idesc, 1u);
+        if constexpr (S::kLoSmem) {
+          const uint64_t ainc = (uint64_t)(((ks >> 2) * (kRows * 128) + (ks & 3) * 32) >> 4);
+          umma_ss(tmem + S::kColD, alo0 + ainc, dh0 + inc, idesc, 1u);
+        } else {
+          umma_ts(tmem + S::kColD, tmem + S::kColAlo + 8 * ks, dh0 + inc, idesc, 1u);
+        }
       }
       umma_commit(bar_acc);
       __syncwarp();
@@ -387,13 +417,19 @@ struct LayB {
   static constexpr int MT = H / 128;                      // 128-column M-tiles of dh
   static constexpr int kTile = NB * 128;                  // one 64-wide k-block of the dgates operand
   static constexpr int kDgBytes = 2 * 2 * kTile;          // [hi/lo][k-block]
-  static constexpr int kRecvOff = kDgBytes;               // float recv[2][C][NB/4][32][4]: partial dh for my units
+  static constexpr bool kLoSmem = H > 256;                // lo half of W^T in shared memory: [MT][2 k-blocks][128 x 128 B]
+  static constexpr int kALoOff = (kDgBytes + 1023) / 1024 * 1024;
+  static constexpr int kALoBytes = kLoSmem ? MT * 2 * kRows * 128 : 0;
+  static constexpr int kRecvOff = kALoOff + kALoBytes;    // float recv[2][C][NB/4][32][4]: partial dh for my units
   static constexpr int kRecvBytes = 2 * C * NB * kHS * 4;
   static constexpr int kLenOff = kRecvOff + kRecvBytes;
   static constexpr int kBarOff = kLenOff + NB * 4;
   static constexpr int kSmem = kBarOff + 64 + 1024;
-  static constexpr int kColAhi = 64, kColAlo = 64 + MT * 64;    // D[mt] at column mt * 32
-  static constexpr int kTmemCols = (64 + 2 * MT * 64) <= 256 ? 256 : 512;
+  static constexpr int kColAhi = MT * 32 > 64 ? MT * 32 : 64, kColAlo = kColAhi + MT * 64;    // D[mt] at column mt * 32
+  static constexpr int kColD(int mt) { return mt * 32; }
+  static constexpr int kTmemCols = (MT * 32 + 2 * MT * 64) <= 256 ? 256 : 512;
+  static_assert(kLoSmem ? (MT * 32 + MT * 64 <= 512) : (MT <= 2), "tensor-memory columns");
+  static_assert(kSmem <= 227 * 1024, "shared memory");
 };
 
 template <int H, int NB>
@@ -446,9 +482,9 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
 
   // resident W^T restricted to this CTA's gate rows: dh[k][n] = sum_lr W[lr][k] dg[n][lr];  A[m = column k][kk = local row];
   // M-tile mt is written by warps 4mt .. 4mt+3 (TMEM lane = k % 128)
-  if (warp < 4 * MT) {
-    const int mt = warp >> 2;
+  for (int mt = warp >> 2; mt < MT; mt += 2) {
     const int k = mt * 128 + (warp & 3) * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;                 // TMEM lane = row of the A tile
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 2
     for (int j = 0; j < KS; ++j) {
@@ -461,10 +497,17 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
         split_pair(w0, w1, hi[p], lo[p]);
       }
       tmem_st8(lane_base + S::kColAhi + mt * 64 + 8 * j, hi);
-      tmem_st8(lane_base + S::kColAlo + mt * 64 + 8 * j, lo);
+      if constexpr (S::kLoSmem) {
+        uint8_t* rp = base + S::kALoOff + (size_t)(mt * 2 + (j >> 2)) * (kRows * 128) + row * 128;
+        *reinterpret_cast<uint4*>(rp + ((((j & 3) * 2 + 0) ^ (row & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(rp + ((((j & 3) * 2 + 1) ^ (row & 7)) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      } else {
+        tmem_st8(lane_base + S::kColAlo + mt * 64 + 8 * j, lo);
+      }
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  fence_proxy_async();
   const int ug = rank * kHS + lane;
   float dh[RPT], dc[RPT];
 #pragma unroll
@@ -551,6 +594,7 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
     if (warp == 0) {
       tc_fence_after();
       const uint64_t dh0 = sdesc_sw128(dg_addr), dl0 = sdesc_sw128(dg_addr + 2 * S::kTile);
+      [[maybe_unused]] const uint64_t alo0 = sdesc_sw128(dg_addr + S::kALoOff);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -558,24 +602,33 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
           const uint64_t inc = (uint64_t)(((ks >> 2) * S::kTile + (ks & 3) * 32) >> 4);
           umma_ts(tmem + mt * 32, tmem + S::kColAhi + mt * 64 + 8 * ks, dh0 + inc, idesc, ks != 0);
           umma_ts(tmem + mt * 32, tmem + S::kColAhi + mt * 64 + 8 * ks, dl0 + inc, idesc, 1u);
-          umma_ts(tmem + mt * 32, tmem + S::kColAlo + mt * 64 + 8 * ks, dh0 + inc, idesc, 1u);
+          if constexpr (S::kLoSmem) {
+            const uint64_t ainc = (uint64_t)(((mt * 2 + (ks >> 2)) * (kRows * 128) + (ks & 3) * 32) >> 4);
+            umma_ss(tmem + mt * 32, alo0 + ainc, dh0 + inc, idesc, 1u);
+          } else {
+            umma_ts(tmem + mt * 32, tmem + S::kColAlo + mt * 64 + 8 * ks, dh0 + inc, idesc, 1u);
+          }
         }
       }
       umma_commit(bar_acc);
     }
     __syncwarp();
-    if (warp < 4 * MT) {
+    {
       // reduce-scatter: TMEM lane = column k of M-tile mt -> owner CTA k / 32, slot [my rank][n / 4][k % 32][n % 4]
-      const int mt = warp >> 2, qq = warp & 3;
-      mbar_wait_g(bar_acc, (uint32_t)s & 1u);
-      tc_fence_after();
-      uint32_t v[NB];
-      tmem_ld_cols<NB>(tmem + ((uint32_t)(qq * 32) << 16) + mt * 32, v);
-      const uint32_t owner = (uint32_t)(mt * 4 + qq);
+      const int qq = warp & 3;
+      if ((warp >> 2) < MT) {
+        mbar_wait_g(bar_acc, (uint32_t)s & 1u);
+        tc_fence_after();
+      }
+      for (int mt = warp >> 2; mt < MT; mt += 2) {
+        uint32_t v[NB];
+        tmem_ld_cols<NB>(tmem + ((uint32_t)(qq * 32) << 16) + mt * 32, v);
+        const uint32_t owner = (uint32_t)(mt * 4 + qq);
 #pragma unroll
-      for (int n4 = 0; n4 < NB / 4; ++n4) {
-        float* dst = recv + ((size_t)((buf * C + rank) * (NB / 4) + n4) * kHS + lane) * 4;
-        dsmem_st_async_v4(dst, &bar_r[buf], owner, make_uint4(v[4 * n4], v[4 * n4 + 1], v[4 * n4 + 2], v[4 * n4 + 3]));
+        for (int n4 = 0; n4 < NB / 4; ++n4) {
+          float* dst = recv + ((size_t)((buf * C + rank) * (NB / 4) + n4) * kHS + lane) * 4;
+          dsmem_st_async_v4(dst, &bar_r[buf], owner, make_uint4(v[4 * n4], v[4 * n4 + 1], v[4 * n4 + 2], v[4 * n4 + 3]));
+        }
       }
       tc_fence_before();
     }
@@ -673,6 +726,8 @@ int launch_fwd(DirF d0, DirF d1, int n_dir, const int32_t* lengths, int B, int L
   static bool configured = false;
   if (!configured) {
     VLN_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayF<H, NB>::kSmem));
+    if (H / kHS > 8)                                          // 16-CTA clusters (H = 512) are beyond the portable size
+      VLN_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_fwd_kernel<H, NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   return launch_tc(lstm_tc_fwd_kernel<H, NB>, LayF<H, NB>::kSmem, H / kHS, NB, n_dir, B, stream, d0, d1, lengths, L, ld_out, ld_last);
@@ -682,6 +737,8 @@ int launch_bwd(DirB d0, DirB d1, int n_dir, const int32_t* lengths, int B, int L
   static bool configured = false;
   if (!configured) {
     VLN_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, LayB<H, NB>::kSmem));
+    if (H / kHS > 8)
+      VLN_CHECK_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_kernel<H, NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   return launch_tc(lstm_tc_bwd_kernel<H, NB>, LayB<H, NB>::kSmem, H / kHS, NB, n_dir, B, stream, d0, d1, lengths, L, ld_out, ld_last);
@@ -715,7 +772,9 @@ int vln_lstm_tc_fwd(const float* const* xproj, const float* const* w_hh, const i
     if (nb == 24) return launch_fwd<128, 24>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
     return launch_fwd<128, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
   }
-  vln_set_error("vln_lstm_seq_fwd: hidden size %d per direction is not supported (128 or 256)", H);
+  if (H == 512)     // Self-Monitor's uni-directional encoder: 16-CTA clusters, lo weights in shared memory, 16 rows per cluster
+    return launch_fwd<512, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+  vln_set_error("vln_lstm_seq_fwd: hidden size %d per direction is not supported (128, 256 or 512)", H);
   return -1;
 }
 
@@ -739,6 +798,7 @@ int vln_lstm_tc_bwd(const float* const* w_hh, const int32_t* lengths, const floa
     if (nb == 24) return launch_bwd<128, 24>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
     return launch_bwd<128, 32>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
   }
-  vln_set_error("vln_lstm_seq_bwd: hidden size %d per direction is not supported (128 or 256)", H);
+  if (H == 512) return launch_bwd<512, 16>(d[0], d[1], n_dir, lengths, B, L, ld, ld, stream);
+  vln_set_error("vln_lstm_seq_bwd: hidden size %d per direction is not supported (128, 256 or 512)", H);
   return -1;
 }

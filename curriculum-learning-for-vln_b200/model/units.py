@@ -124,11 +124,11 @@ class EncoderLSTM(KernelModule):
                 xprojs.append(ops.linear(x.reshape(B * L, -1), w_ih, bias).view(B, L, -1))
                 whhs.append(w_hh)
             if self.hidden_size in ops.LSTM_KERNEL_H:
-                # persistent cluster kernel: W_hh resident in SMEM, both directions in one launch
+                # persistent cluster kernel (tcgen05, W_hh resident in tensor memory), both directions in one launch:
+                # 128 / 256 per direction (Follower, EnvDrop) and 512 (Self-Monitor's uni-directional encoder)
                 x, h_last, c_last = ops.lstm_layer(xprojs, whhs, lengths)
             else:
-                # TODO(kernel): hidden sizes other than 128/256 per direction (Self-Monitor's 512) still run
-                # the step-by-step recurrence (one pointwise kernel + one GEMM per timestep)
+                # other hidden sizes: step-by-step recurrence (one pointwise kernel + one GEMM per timestep)
                 res = [ops.lstm_sequence(xp, lengths, w, reverse=bool(d)) for d, (xp, w) in enumerate(zip(xprojs, whhs))]
                 x = torch.cat([r[0] for r in res], 2) if len(res) > 1 else res[0][0]
                 h_last = torch.cat([r[1] for r in res], 1) if len(res) > 1 else res[0][1]

@@ -556,7 +556,7 @@ def lstm_layer(xproj, w_hh, lengths):
     return _LstmLayer.apply(_i32c(lengths), len(xproj), *xproj, *w_hh)
 
 
-LSTM_KERNEL_H = (128, 256)
+LSTM_KERNEL_H = (128, 256, 512)
 
 
 # ---- action head ---------------------------------------------------------------------------------------

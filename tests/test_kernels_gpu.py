@@ -422,10 +422,12 @@ def lstm_variant(request):
 
 @pytest.mark.parametrize("lstm_variant", [1, 0], indirect=True, ids=["tcgen05", "mma"])
 @pytest.mark.parametrize("H,E,B,L,ndir", [(256, 256, 64, 80, 2), (128, 300, 19, 33, 2), (256, 64, 5, 12, 1),
-                                          (256, 128, 128, 40, 2), (128, 64, 150, 21, 2)])
+                                          (256, 128, 128, 40, 2), (128, 64, 150, 21, 2), (512, 256, 64, 40, 1),
+                                          (512, 64, 21, 13, 2)])
 def test_lstm_layer_matches_oracle(setup, lstm_variant, H, E, B, L, ndir, nb=None):
     """Persistent cluster LSTM (fwd + BPTT) vs the oracle's masked recurrence (== packed nn.LSTM); B = 128 / 150
-    take the 32-rows-per-cluster instantiation of the tcgen05 kernels."""
+    take the 24-rows-per-cluster instantiation of the tcgen05 kernels; H = 512 (Self-Monitor's uni-directional
+    encoder) runs 16-CTA clusters with the lo half of W_hh in shared memory (tcgen05 path in both variants)."""
     from oracle import port_modules as P
     _, _, ops, dev = setup
     torch.manual_seed(H + B)
