@@ -83,6 +83,18 @@ class PhiloxDropout(KernelModule):
         return self._drop(x, self.p, self.tag)
 
 
+class KernelLinear(nn.Linear):
+    """nn.Linear whose forward runs on the tcgen05 bf16x3 kernel (ops.linear: skinny or tall launch by row count);
+    same parameters / state_dict keys, so it can sit inside the nn.Sequential of MLPwithBN (units.py:218-236 — the
+    (B*C) x 2176 x 1024 projection that dominates a Self-Monitor step)."""
+
+    def forward(self, x):
+        if not x.is_cuda or x.dtype != torch.float32:
+            return super().forward(x)
+        y = ops.linear(x.reshape(-1, x.shape[-1]), self.weight, self.bias)
+        return y.view(*x.shape[:-1], self.weight.shape[0])
+
+
 class EncoderLSTM(KernelModule):
     def __init__(self, vocab_size, embed_size, hidden_size, padding_idx, drop_ratio=0.5, bidirectional=False,
                  num_layers=1, glove=None):
@@ -226,7 +238,7 @@ class MLPwithBN(KernelModule):
             layers.append(nn.BatchNorm1d(input_size))
         dims = [input_size] + list(hidden_size)
         for d_in, d_out in zip(dims[:-1], dims[1:]):
-            layers.append(nn.Linear(d_in, d_out, bias=use_bias))
+            layers.append(KernelLinear(d_in, d_out, bias=use_bias))
             if use_bn:
                 layers.append(nn.BatchNorm1d(d_out))
             if dropout > 0:
@@ -235,7 +247,7 @@ class MLPwithBN(KernelModule):
                 layers.append(nn.ReLU(inplace=True))
         self.out_size = hidden_size[-1]
         if out_size:
-            layers.append(nn.Linear(dims[-1], out_size, bias=use_bias))
+            layers.append(KernelLinear(dims[-1], out_size, bias=use_bias))
             self.out_size = out_size
         self.mlp = nn.Sequential(*layers)
 
