@@ -76,6 +76,8 @@ class FusedDecoder:
         self.cat = _CatSplit()
         self._side = None
         self._prep = None
+        self.async_wgrad = False       # set by TrainStep (which always differentiates with .backward() into .grad buffers)
+        self._wgrad_stream = None
 
     def params(self):
         d = self.dec
@@ -354,17 +356,41 @@ class _Rollout(torch.autograd.Function):
         d_ctx.baddbmm_(DLC.permute(1, 2, 0), TQ[:n].transpose(0, 1))
 
         # ---- weight gradients: one GEMM per weight over all n*B rows ----
-        nb = n * B
-        dG = DGATES.view(nb, G4)
-        d_wcat = ops.wgrad(dG, XH[:n].reshape(nb, KX))
-        d_b = dG.sum(0)
-        d_w_tin = ops.wgrad(DTQ.view(nb, H), WH[:n, :, H:].reshape(nb, H))
-        d_w_out = ops.wgrad(DPRE.view(nb, H), WH[:n].reshape(nb, 2 * H))
-        d_w_vin = ops.wgrad(DQ.view(nb, F), HQ[:n].reshape(nb, H))
-        d_w_cand = ops.wgrad(DTGT.view(nb, F), HC[:n].reshape(nb, H))
-        pose = store.pose128[st.view[:n].reshape(-1).long()]
-        dA = DACT.view(nb, H_ACT)
-        d_w_act = ops.wgrad(dA, pose)
-        d_b_act = dA.sum(0)
-        return (None,) * N_META + (d_ctx, d_h0, d_c0, d_w_act, d_b_act, d_wcat[:, :OH], d_wcat[:, OH:], d_b, d_b,
-                                   d_w_tin, d_w_out, d_w_vin, d_w_cand)
+        def weight_grads():
+            nb = n * B
+            dG = DGATES.view(nb, G4)
+            d_wcat = ops.wgrad(dG, XH[:n].reshape(nb, KX))
+            d_b = dG.sum(0)
+            d_w_tin = ops.wgrad(DTQ.view(nb, H), WH[:n, :, H:].reshape(nb, H))
+            d_w_out = ops.wgrad(DPRE.view(nb, H), WH[:n].reshape(nb, 2 * H))
+            d_w_vin = ops.wgrad(DQ.view(nb, F), HQ[:n].reshape(nb, H))
+            d_w_cand = ops.wgrad(DTGT.view(nb, F), HC[:n].reshape(nb, H))
+            pose = store.pose128[st.view[:n].reshape(-1).long()]
+            dA = DACT.view(nb, H_ACT)
+            d_w_act = ops.wgrad(dA, pose)
+            d_b_act = dA.sum(0)
+            return (d_w_act, d_b_act, d_wcat[:, :OH], d_wcat[:, OH:], d_b, d_b, d_w_tin, d_w_out, d_w_vin, d_w_cand)
+
+        fd = fctx.fd
+        params = fd.params()
+        if fd.async_wgrad and all(q.grad is not None for q in params):
+            # Nothing downstream of this node needs the weight gradients (the encoder's backward only takes d_ctx /
+            # d_h0 / d_c0), so their GEMMs run on a side stream underneath the encoder's latency-bound BPTT kernel and
+            # accumulate straight into the flat gradient buffer; the calling stream joins when the backward pass ends.
+            main = torch.cuda.current_stream()
+            if fd._wgrad_stream is None:
+                fd._wgrad_stream = torch.cuda.Stream()
+            side = fd._wgrad_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                grads = weight_grads()
+                for q, g_ in zip(params, grads):
+                    q.grad.add_(g_)
+            keep = [grads, DGATES, XH, WH, HQ, HC, DTQ, DPRE, DQ, DTGT, DACT]    # alive until the join (allocator safety)
+
+            def join():
+                torch.cuda.current_stream().wait_stream(side)
+                keep.clear()
+            torch.autograd.Variable._execution_engine.queue_callback(join)
+            return (None,) * N_META + (d_ctx, d_h0, d_c0) + (None,) * 10
+        return (None,) * N_META + (d_ctx, d_h0, d_c0) + weight_grads()

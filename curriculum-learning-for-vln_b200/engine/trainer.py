@@ -38,6 +38,9 @@ class TrainStep:
         self.item_loss = None
         # EnvDrop: step the teacher-forced and the sampled rollout of an iteration as one batch (agent.rollout_pair)
         self.pair_rollouts = os.environ.get("VLN_PAIR_ROLLOUTS", "1") != "0"
+        # the fused rollout's weight-gradient GEMMs run on a side stream under the encoder's backward (agent/fused.py)
+        if getattr(agent, "_fused", None) is not None and agent.device.type == "cuda":
+            agent._fused.async_wgrad = os.environ.get("VLN_ASYNC_WGRAD", "1") != "0"
 
     def losses(self):
         """Run the rollouts; return (loss to differentiate, per-item loss record or None)."""
