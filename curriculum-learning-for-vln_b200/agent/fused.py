@@ -59,11 +59,12 @@ class _CatSplit:
 
 
 def _gemm(hi, lo, N, K, x, ldx, M, bias, y, ldy, accumulate=1):
-    """y[M,N] += x[M,K] W^T (+ bias) on the tcgen05 kernel, in row blocks of 128 (y starts zero-filled)."""
-    for m0 in range(0, M, 128):
-        m = min(128, M - m0)
-        _call("vln_linear_bf16x3", _ptr(hi), _ptr(lo), N, K, C.c_void_p(x.value + 4 * m0 * ldx), ldx, m, bias,
-              C.c_void_p(y.value + 4 * m0 * ldy), ldy, accumulate, 0, _stream())
+    """y[M,N] += x[M,K] W^T (+ bias) on the tcgen05 kernel (y starts zero-filled): one split-K launch for a batch of
+    at most 128 rows, one tall launch (128 x 128 output blocks) for the stacked rows of a whole rollout."""
+    if M <= 128:
+        _call("vln_linear_bf16x3", _ptr(hi), _ptr(lo), N, K, x, ldx, M, bias, y, ldy, accumulate, 0, _stream())
+    else:
+        _call("vln_linear_bf16x3_tall", _ptr(hi), _ptr(lo), N, K, x, ldx, M, bias, y, ldy, accumulate, _stream())
 
 
 class FusedDecoder:

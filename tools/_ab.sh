@@ -1,3 +1,3 @@
 timeout 600 python -m pytest tests/test_agents_gpu.py -m gpu -x -q 2>&1 | tail -2
-for v in 1 0; do VLN_ASYNC_WGRAD=$v python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import sys, json; d=json.loads(sys.stdin.read()); print('async_wgrad=$v', d['value'], d['ms_per_step'], d['e2e']['value'])"; done
+python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
