@@ -72,7 +72,7 @@ class EnvDropAgent(BaseAgent):
         two = lambda x: torch.cat((x, x), 0)
         ib2 = dataclasses.replace(ib, tokens=two(ib.tokens), lengths=two(ib.lengths), lengths_cpu=two(ib.lengths_cpu),
                                   vp=two(ib.vp), view=two(ib.view), goal=two(ib.goal), index=two(ib.index))
-        prep = self._fused.prepare(self.rng, 2 * B, T, "sample", True, self.device, pair=(B, T_t))
+        prep = self._fused.prepare(self.rng, 2 * B, T, "sample", True, self.device, pair=(B, T_t), L=ib2.tokens.shape[1])
         ctx, h_t, c_t = self.encoder(ib2.tokens, ib2.lengths)
         st = RolloutState(store, ib2, T + 1)
         (ce, logps, ents, hiddens, logits, actions, targets, rewards, masks, last_h) = self._fused.run(
@@ -118,7 +118,7 @@ class EnvDropAgent(BaseAgent):
         use_fused = self.fused and self.device.type == "cuda"
         prep = None
         if use_fused:            # decoder stream offsets + the rollout's feature-dropout bits (side stream, overlaps the encoder)
-            prep = self._fused.prepare(self.rng, B, T, feedback, train_rl, self.device)
+            prep = self._fused.prepare(self.rng, B, T, feedback, train_rl, self.device, L=ib.tokens.shape[1])
         ctx, h_t, c_t = self.encoder(ib.tokens, ib.lengths)
         ctx_mask = LengthMask(ib.lengths, ctx.shape[1])
         st = RolloutState(store, ib, T + (1 if train_rl else 0))

@@ -67,6 +67,46 @@ def _gemm(hi, lo, N, K, x, ldx, M, bias, y, ldy, accumulate=1):
         _call("vln_linear_bf16x3_tall", _ptr(hi), _ptr(lo), N, K, x, ldx, M, bias, y, ldy, accumulate, _stream())
 
 
+def _carver(total, dev):
+    slab = torch.zeros(total, device=dev)
+    cur = [0]
+
+    def carve(*shape):
+        k = 1
+        for s_ in shape:
+            k *= s_
+        t_ = slab[cur[0]:cur[0] + k].view(*shape)
+        cur[0] += k
+        return t_
+    return carve
+
+
+def _make_buffers(S, T, B, L, H, dev, paired_rollouts):
+    """Work buffers of one rollout, forward and backward.  The GEMM outputs (split-K partial sums meet there) come
+    out of zero-filled slabs; with paired rollouts the stacked per-step buffers are zero-filled too (rows that sit
+    out later steps must read as finite zeros in the stacked weight-gradient GEMMs).  ~0.5 GB of fills per
+    iteration at B = 128: FusedDecoder.prepare issues them on the side stream, under the instruction encoder."""
+    F, G4, KX = ops.F_DIM, 4 * H, H_ACT + ops.F_DIM + H
+    alloc = torch.zeros if paired_rollouts else torch.empty
+    c = _carver(S * B * (F + G4) + T * B * (H + H + F), dev)
+    f = dict(Q=c(S, B, F), GATES=c(S, B, G4), TQ=c(T, B, H), PRE=c(T, B, H), TGT=c(T, B, F),
+             XH=alloc((S + 1, B, KX), device=dev), HQ=alloc((S + 1, B, H), device=dev), HC=alloc((T, B, H), device=dev),
+             ACT=alloc((S + 1, B, H_ACT), device=dev), ACTS=alloc((S, B, G4), device=dev),
+             CS=alloc((S + 1, B, H), device=dev), H1=alloc((S, B, H), device=dev), WH=alloc((T, B, 2 * H), device=dev),
+             ATTV=alloc((S, B, ops.N_VIEWS), device=dev), ATTC=alloc((T, B, L), device=dev),
+             LOGIT=alloc((T, B, ops.NSLOT), device=dev), PROBS=alloc((T, B, ops.NSLOT), device=dev),
+             CE=torch.zeros((T, B), device=dev), LOGP=torch.zeros((T, B), device=dev), ENT=torch.zeros((T, B), device=dev),
+             REWARD=torch.zeros((T, B), device=dev), MASK=torch.zeros((T, B), device=dev),
+             ACTION=torch.full((T, B), -1, dtype=torch.int32, device=dev),
+             TEACH=torch.full((T + 1, B), -1, dtype=torch.int32, device=dev))
+    c = _carver(T * B * (H + 2 * H + KX + H), dev)
+    b = dict(DHC=c(T, B, H), DWH=c(T, B, 2 * H), DXH=c(T, B, KX), DHQ=c(T, B, H),
+             DTGT=alloc((T, B, F), device=dev), DPRE=alloc((T, B, H), device=dev), DTQ=alloc((T, B, H), device=dev),
+             DGATES=alloc((T, B, G4), device=dev), DQ=alloc((T, B, F), device=dev), DACT=alloc((T, B, H_ACT), device=dev),
+             DC=alloc((2, B, H), device=dev), DLC=alloc((T, B, L), device=dev))
+    return f, b
+
+
 class FusedDecoder:
     """The EnvDrop decoder rollout as one autograd node.  ``run`` returns per-step stacks
     (ce, logp, entropy [n,B]; h_1 [n,B,H]) that carry gradients, plus detached logits / actions /
@@ -86,7 +126,7 @@ class FusedDecoder:
                 d.lstm.bias_hh, d.text_attn.linear_in.weight, d.text_attn.linear_out.weight,
                 d.visual_attn.linear_in.weight, d.cand_attn.weight]
 
-    def prepare(self, rng, B, T, feedback, bootstrap, device, pair=None):
+    def prepare(self, rng, B, T, feedback, bootstrap, device, pair=None, L=None):
         """Before the encoder runs: hand out the dropout / sampling stream offsets of every decoder pass (in
         the call order of EnvDropDecoder.forward) and draw all feature-dropout keep-bits of the rollout with
         ONE kernel on a side stream, so that it overlaps with the instruction encoder."""
@@ -111,14 +151,15 @@ class FusedDecoder:
             if fb == 2 and t < T:
                 d["sample"] = rng.next()
             offs.append(d)
-        MB, side = None, None
-        if pf > 0.0:
+        MB, side, bufs = None, None, None
+        if pf > 0.0 or L is not None:
             main = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream()
             side = self._side
+            side.wait_stream(main)      # also orders this iteration's fills after every earlier use of recycled blocks
+        if pf > 0.0:
             MB = torch.empty((S, B * ops.N_VIEWS, ops.IMG_DIM // 8), dtype=torch.uint8, device=device)   # owned by `main`
-            side.wait_stream(main)
             with torch.cuda.stream(side):
                 stride = offs[1]["img"] - offs[0]["img"] if S > 1 else 0
                 if pair is None:
@@ -130,7 +171,13 @@ class FusedDecoder:
                           _stream())
                     _call("vln_feature_mask_bits_ld", _ptr(MB), (B - B_main) * V, B * V, B_main * V, T_t, pf, rng.ptr,
                           offs[0]["img"], stride, _stream())
-        return dict(offs=offs, MB=MB, side=side, p=p, pf=pf, S=S)
+        if L is not None:               # the rollout's work buffers: allocated + zero-filled under the encoder
+            with torch.cuda.stream(side):
+                bufs = _make_buffers(S, T, B, L, dec.hidden_size, device, pair is not None)
+                for d_ in bufs:
+                    for t_ in d_.values():
+                        t_.record_stream(main)
+        return dict(offs=offs, MB=MB, side=side, p=p, pf=pf, S=S, bufs=bufs, shape=(S, T, B, L))
 
     def run(self, rng, st, ctx, lengths, h0, c0, T, feedback, bootstrap, poll, split, prep=None, pair=None):
         """``pair = (B_main, T_teacher)``: the batch holds two rollouts of the same minibatch stepped together
@@ -172,48 +219,26 @@ class _Rollout(torch.autograd.Function):
 
         def rows(t):                                          # episodes that take part in decoder pass t
             return B_all if t < T_pair else B_main
-        # rows that sit out later steps must read as zeros (finite) in the stacked weight-gradient GEMMs
-        alloc = torch.zeros if pair is not None else torch.empty
-
         # ---- weights: bf16 hi/lo splits, refreshed once per optimiser step ----
         s_cat = fd.cat.fresh(w_ih, w_hh)
         s_tin, s_out, s_vin, s_cand = (ops._split_of(w) for w in params[6:10])
         bsum = (b_ih + b_hh).contiguous()
         w_act = w_act.view(H_ACT, 4, 32).sum(2).contiguous()        # group sums: the angle feature is 4 values x32
 
-        # ---- buffers: the GEMM outputs (split-K partial sums meet there) come out of one zero-filled slab ----
-        slab = torch.zeros(S * B * (F + G4) + T * B * (H + H + F), device=dev)
-        cur = [0]
-
-        def carve(*shape):
-            k = 1
-            for s_ in shape:
-                k *= s_
-            t_ = slab[cur[0]:cur[0] + k].view(*shape)
-            cur[0] += k
-            return t_
-        Q, GATES = carve(S, B, F), carve(S, B, G4)
-        TQ, PRE, TGT = carve(T, B, H), carve(T, B, H), carve(T, B, F)
-        XH = alloc((S + 1, B, KX), device=dev)
-        HQ = alloc((S + 1, B, H), device=dev)
-        HC = alloc((T, B, H), device=dev)
-        ACT = alloc((S + 1, B, H_ACT), device=dev)
-        ACTS = alloc((S, B, G4), device=dev)
-        CS = alloc((S + 1, B, H), device=dev)
-        H1 = alloc((S, B, H), device=dev)
-        WH = alloc((T, B, 2 * H), device=dev)
-        ATTV = alloc((S, B, ops.N_VIEWS), device=dev)
-        ATTC = alloc((T, B, L), device=dev)
-        LOGIT = alloc((T, B, ops.NSLOT), device=dev)
-        PROBS = alloc((T, B, ops.NSLOT), device=dev)
-        CE, LOGP, ENT = (torch.zeros((T, B), device=dev) for _ in range(3))
-        REWARD, MASK = torch.zeros((T, B), device=dev), torch.zeros((T, B), device=dev)
-        ACTION = torch.full((T, B), -1, dtype=torch.int32, device=dev)
-        TEACH = torch.full((T + 1, B), -1, dtype=torch.int32, device=dev)
+        # ---- buffers (zero-filled GEMM output slabs, stacked per-step tensors): prepared under the encoder if possible ----
+        prep = fd._prep
+        if prep.get("bufs") is not None and prep["shape"] == (S, T, B, L):
+            fb_, bb_ = prep["bufs"]
+        else:
+            fb_, bb_ = _make_buffers(S, T, B, L, H, dev, pair is not None)
+        prep["bufs"] = None
+        Q, GATES, TQ, PRE, TGT = fb_["Q"], fb_["GATES"], fb_["TQ"], fb_["PRE"], fb_["TGT"]
+        XH, HQ, HC, ACT, ACTS, CS, H1, WH = (fb_[k] for k in ("XH", "HQ", "HC", "ACT", "ACTS", "CS", "H1", "WH"))
+        ATTV, ATTC, LOGIT, PROBS = fb_["ATTV"], fb_["ATTC"], fb_["LOGIT"], fb_["PROBS"]
+        CE, LOGP, ENT, REWARD, MASK, ACTION, TEACH = (fb_[k] for k in ("CE", "LOGP", "ENT", "REWARD", "MASK", "ACTION", "TEACH"))
         TEACH[0].copy_(st.teacher)
         CS[0].copy_(c0)
 
-        prep = fd._prep
         offs, MB = prep["offs"], prep["MB"]
         assert prep["S"] == S and prep["p"] == p and prep["pf"] == pf
 
@@ -273,7 +298,7 @@ class _Rollout(torch.autograd.Function):
             visual_and_lstm(n, False, q_done=paired and n > 0)
         st.teacher = TEACH[n]
 
-        fctx.fd, fctx.st, fctx.rp, fctx.MB = fd, st, rp, MB
+        fctx.fd, fctx.st, fctx.rp, fctx.MB, fctx.bwd_bufs = fd, st, rp, MB, bb_
         fctx.cfg = (n, B, L, H, p, pf, split, offs, B_main, T_pair)
         fctx.splits = (s_cat, s_vin, s_tin, s_out, s_cand)
         fctx.save_for_backward(ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH)
@@ -286,8 +311,6 @@ class _Rollout(torch.autograd.Function):
     def backward(fctx, d_ce, d_logp, d_ent, d_h1, *_unused):
         ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH = fctx.saved_tensors
         n, B, L, H, p, pf, split, offs, B_main, T_pair = fctx.cfg
-        paired_rollouts = B_main < B
-        alloc = torch.zeros if paired_rollouts else torch.empty
 
         def rows(t):
             return B if t < T_pair else B_main
@@ -299,25 +322,10 @@ class _Rollout(torch.autograd.Function):
         OH = H_ACT + F                                          # column of h~ inside an XH row
         d_ce, d_logp, d_ent, d_h1 = (ops._f32c(g) if g is not None else None for g in (d_ce, d_logp, d_ent, d_h1))
 
-        slab = torch.zeros(n * B * (H + 2 * H + KX + H), device=dev)
-        cur = [0]
-
-        def carve(*shape):
-            k = 1
-            for s_ in shape:
-                k *= s_
-            t_ = slab[cur[0]:cur[0] + k].view(*shape)
-            cur[0] += k
-            return t_
-        DHC, DWH, DXH, DHQ = carve(n, B, H), carve(n, B, 2 * H), carve(n, B, KX), carve(n, B, H)
-        DTGT = alloc((n, B, F), device=dev)
-        DPRE = alloc((n, B, H), device=dev)
-        DTQ = alloc((n, B, H), device=dev)
-        DGATES = alloc((n, B, G4), device=dev)
-        DQ = alloc((n, B, F), device=dev)
-        DACT = alloc((n, B, H_ACT), device=dev)
-        DC = alloc((2, B, H), device=dev)
-        DLC = alloc((n, B, L), device=dev)                  # d(logit) of the text attention, per step
+        bb_ = fctx.bwd_bufs                                       # zero-filled in prepare(): [T, B, ...], the first n steps used
+        DHC, DWH, DXH, DHQ = bb_["DHC"][:n], bb_["DWH"][:n], bb_["DXH"][:n], bb_["DHQ"][:n]
+        DTGT, DPRE, DTQ, DGATES = bb_["DTGT"][:n], bb_["DPRE"][:n], bb_["DTQ"][:n], bb_["DGATES"][:n]
+        DQ, DACT, DC, DLC = bb_["DQ"][:n], bb_["DACT"][:n], bb_["DC"], bb_["DLC"][:n]
 
         # ---- off the recursion: candidate-logit backward of ALL steps in one launch, then d(h~_drop) = dtgt W_cand
         #      as a stack of 128-row GEMMs (none of it depends on the backward-in-time chain) ----
