@@ -61,6 +61,8 @@ _SIGS = {
     "vln_envdrop_act_bwd": ([_p, _i, _p, _p, _i, _i, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_policy_env_act_fwd": ([_p, _p, _i, _p, _u64] + [_p] * 5 + [_p] * 5 + [_p] * 7 + [_p] * 8 + [_p] * 5
                                + [_i, _i, _f, _u64, _i, _p], _i),
+    "vln_cand_policy_env_act_fwd": ([_p] * 6 + [_f, _u64, _p, _i, _p, _u64] + [_p] * 5 + [_p] * 3 + [_p] * 7 + [_p] * 8
+                                    + [_p] * 5 + [_i, _i, _f, _u64, _i, _p], _i),
     "vln_cand_logits_bwd_policy": ([_p] * 14 + [_i, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_cand_logits_fwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),
     "vln_cand_logits_bwd": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _u64, _p], _i),

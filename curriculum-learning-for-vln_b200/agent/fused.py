@@ -31,6 +31,7 @@ from .. import ops
 from ..ops import _call, _ptr, _stream
 
 H_ACT = 64
+FUSE_TAIL = [__import__("os").environ.get("VLN_FUSE_TAIL", "1") != "0"]   # candidate logits + policy/env/act as one launch
 
 
 def _p(t, off=0):
@@ -278,19 +279,32 @@ class _Rollout(torch.autograd.Function):
                       _ptr(s_vin.lo), _ptr(HQ[t + 1]), _ptr(Q[t + 1]), F, H, H, Bt, F, _stream())
             else:
                 _gemm(s_cand.hi, s_cand.lo, F, H, _p(HC[t]), H, Bt, None, _p(TGT[t]), F)
-            _call("vln_cand_logits_fwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
-                  _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(TGT[t]), None, _ptr(LOGIT[t]), Bt, pf, rp,
-                  offs[t]["cand"], _stream())
-            # action head + simulator transition + the next pass's action embedding: one launch
-            _call("vln_policy_env_act_fwd", _ptr(LOGIT[t]), _ptr(TEACH[t]), fb, rp, offs[t]["sample"], _ptr(CE[t]),
-                  _ptr(ACTION[t]), _ptr(LOGP[t]), _ptr(ENT[t]), _ptr(PROBS[t]),
-                  _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(st.ended[t]), _ptr(st.dist[t]), _ptr(st.goal),
-                  _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand), _ptr(store.next_hop),
-                  _ptr(store.dist), _ptr(store.sq_off), _ptr(store.vp_local),
-                  _ptr(st.vp[t + 1]), _ptr(st.view[t + 1]), _ptr(st.ended[t + 1]), _ptr(st.dist[t + 1]),
-                  _ptr(TEACH[t + 1]), _ptr(REWARD[t]), _ptr(MASK[t]), _ptr(st.n_active[t:t + 1]),
-                  _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t + 1]) if more else None,
-                  _ptr(XH[t + 1]) if more else None, KX, H_ACT, p, offs[t + 1]["act"] if more else 0, Bt, _stream())
+            if FUSE_TAIL[0]:
+                # candidate logits + action head + simulator transition + the next pass's action embedding: one launch
+                _call("vln_cand_policy_env_act_fwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_ang4),
+                      _ptr(TGT[t]), _ptr(LOGIT[t]), pf, offs[t]["cand"], _ptr(TEACH[t]), fb, rp, offs[t]["sample"],
+                      _ptr(CE[t]), _ptr(ACTION[t]), _ptr(LOGP[t]), _ptr(ENT[t]), _ptr(PROBS[t]),
+                      _ptr(st.ended[t]), _ptr(st.dist[t]), _ptr(st.goal),
+                      _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand), _ptr(store.next_hop),
+                      _ptr(store.dist), _ptr(store.sq_off), _ptr(store.vp_local),
+                      _ptr(st.vp[t + 1]), _ptr(st.view[t + 1]), _ptr(st.ended[t + 1]), _ptr(st.dist[t + 1]),
+                      _ptr(TEACH[t + 1]), _ptr(REWARD[t]), _ptr(MASK[t]), _ptr(st.n_active[t:t + 1]),
+                      _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t + 1]) if more else None,
+                      _ptr(XH[t + 1]) if more else None, KX, H_ACT, p, offs[t + 1]["act"] if more else 0, Bt, _stream())
+            else:
+                _call("vln_cand_logits_fwd", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.cand_view),
+                      _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(TGT[t]), None, _ptr(LOGIT[t]), Bt, pf, rp,
+                      offs[t]["cand"], _stream())
+                # action head + simulator transition + the next pass's action embedding: one launch
+                _call("vln_policy_env_act_fwd", _ptr(LOGIT[t]), _ptr(TEACH[t]), fb, rp, offs[t]["sample"], _ptr(CE[t]),
+                      _ptr(ACTION[t]), _ptr(LOGP[t]), _ptr(ENT[t]), _ptr(PROBS[t]),
+                      _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(st.ended[t]), _ptr(st.dist[t]), _ptr(st.goal),
+                      _ptr(store.cand_vp), _ptr(store.cand_view), _ptr(store.n_cand), _ptr(store.next_hop),
+                      _ptr(store.dist), _ptr(store.sq_off), _ptr(store.vp_local),
+                      _ptr(st.vp[t + 1]), _ptr(st.view[t + 1]), _ptr(st.ended[t + 1]), _ptr(st.dist[t + 1]),
+                      _ptr(TEACH[t + 1]), _ptr(REWARD[t]), _ptr(MASK[t]), _ptr(st.n_active[t:t + 1]),
+                      _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t + 1]) if more else None,
+                      _ptr(XH[t + 1]) if more else None, KX, H_ACT, p, offs[t + 1]["act"] if more else 0, Bt, _stream())
             st.steps = n = t + 1
             if poll and (t + 1) % poll == 0 and t + 1 < T and st.all_ended(t):
                 break

@@ -198,6 +198,20 @@ int vln_policy_env_act_fwd(const float* logits, const int32_t* target, int feedb
                            int32_t* teacher_out, float* reward, float* mask, int32_t* n_active,
                            const float* pose4, const float* w_act, const float* b_act, float* act, float* xh,
                            int ld_xh, int E, float p_act, uint64_t off_act, int B, void* stream);
+/* vln_cand_logits_fwd (without bias) + vln_policy_env_act_fwd in ONE launch, one CTA per episode: the whole tail of
+ * a fused decoder step (policy.py:199-206, envdrop.py:166-219, policy.py:222-223).  Bit-identical results; the
+ * transition's index loads are issued ahead of / in parallel with the candidate rows instead of as a dependent chain.
+ * `logits` [B,16] is written as well (saved for the backward pass). */
+int vln_cand_policy_env_act_fwd(const vln_ctx* ctx, const int32_t* vp_in, const int32_t* view_in, const float* cand_ang4,
+                                const float* tgt, float* logits, float drop_p, uint64_t off_cand, const int32_t* target,
+                                int feedback, const uint64_t* rng, uint64_t off_sample, float* ce, int32_t* action,
+                                float* logp, float* entropy, float* probs, const uint8_t* ended_in, const float* dist_in,
+                                const int32_t* goal, const int32_t* cand_vp, const int32_t* cand_view,
+                                const int32_t* n_cand, const int32_t* next_hop, const float* dist_tbl,
+                                const int64_t* sq_off, const int32_t* vp_local, int32_t* vp_out, int32_t* view_out,
+                                uint8_t* ended_out, float* dist_out, int32_t* teacher_out, float* reward, float* mask,
+                                int32_t* n_active, const float* pose4, const float* w_act, const float* b_act, float* act,
+                                float* xh, int ld_xh, int E, float p_act, uint64_t off_act, int B, void* stream);
 /* vln_policy_bwd folded into vln_cand_logits_bwd: dlogits are computed from the action head's saved
  * probs / target / action / entropy and the incoming g_ce / g_logp / g_ent (each nullable).  Covers
  * n_steps decoder steps in one launch (none of its inputs depends on the backward recursion): every array

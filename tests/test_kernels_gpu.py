@@ -659,6 +659,52 @@ def test_policy_env_act_equals_separate_kernels(setup):
         assert relerr(act, ref) < 1e-5
 
 
+@pytest.mark.parametrize("pf", [0.0, 0.3])
+def test_fused_step_tail_equals_separate_kernels(setup, pf):
+    """vln_cand_policy_env_act_fwd == vln_cand_logits_fwd followed by vln_policy_env_act_fwd, bit for bit (logits,
+    probabilities, actions, new state, teacher slot, rewards, action embedding), incl. per-row teacher forcing."""
+    world, store, ops, dev = setup
+    B, E, p = 41, 64, 0.5
+    torch.manual_seed(3)
+    vp, view = rand_state(world, B, dev, 12)
+    goal = vp.clone()
+    goal[::3] = store.cand_vp[vp[::3].long(), 0]                  # a neighbour as the goal: non-trivial teacher slots
+    ended = (torch.rand(B, device=dev) < 0.2).to(torch.uint8)
+    teacher, dist = ops.env_observe(store, vp, ended, goal)
+    tgt = torch.randn(B, 2176, device=dev) * 0.05
+    rng = ops.Rng(5, dev)
+    w_act, b_act = torch.randn(E, 128, device=dev) * 0.1, torch.randn(E, device=dev) * 0.1
+    wg = w_act.view(E, 4, 32).sum(2).contiguous()
+    P = ops._ptr
+
+    def outputs():
+        return dict(logits=torch.empty(B, 16, device=dev), ce=torch.empty(B, device=dev),
+                    action=torch.empty(B, dtype=torch.int32, device=dev), logp=torch.empty(B, device=dev),
+                    ent=torch.empty(B, device=dev), probs=torch.empty(B, 16, device=dev), vp=torch.empty_like(vp),
+                    view=torch.empty_like(view), ended=torch.empty_like(ended), dist=torch.empty_like(dist),
+                    teacher=torch.empty_like(teacher), reward=torch.empty(B, device=dev), mask=torch.empty(B, device=dev),
+                    n_active=torch.zeros(1, dtype=torch.int32, device=dev), act=torch.empty(B, E, device=dev),
+                    xh=torch.zeros(B, 96, device=dev))
+    for fb in (0, 1, 2, 2 | ((B // 2 + 1) << 8)):
+        a, o = outputs(), outputs()
+        ops._call("vln_cand_logits_fwd", store.handle, P(vp), P(view), P(store.cand_view), P(store.cand_ang4), P(store.n_cand),
+                  P(tgt), None, P(a["logits"]), B, pf, rng.ptr, 7, ops._stream())
+        ops._call("vln_policy_env_act_fwd", P(a["logits"]), P(teacher), fb, rng.ptr, 3, P(a["ce"]), P(a["action"]), P(a["logp"]),
+                  P(a["ent"]), P(a["probs"]), P(vp), P(view), P(ended), P(dist), P(goal), P(store.cand_vp), P(store.cand_view),
+                  P(store.n_cand), P(store.next_hop), P(store.dist), P(store.sq_off), P(store.vp_local), P(a["vp"]),
+                  P(a["view"]), P(a["ended"]), P(a["dist"]), P(a["teacher"]), P(a["reward"]), P(a["mask"]), P(a["n_active"]),
+                  P(store.pose4), P(wg), P(b_act), P(a["act"]), P(a["xh"]), 96, E, p, 4, B, ops._stream())
+        ops._call("vln_cand_policy_env_act_fwd", store.handle, P(vp), P(view), P(store.cand_ang4), P(tgt), P(o["logits"]), pf, 7,
+                  P(teacher), fb, rng.ptr, 3, P(o["ce"]), P(o["action"]), P(o["logp"]), P(o["ent"]), P(o["probs"]),
+                  P(ended), P(dist), P(goal), P(store.cand_vp), P(store.cand_view), P(store.n_cand), P(store.next_hop),
+                  P(store.dist), P(store.sq_off), P(store.vp_local), P(o["vp"]), P(o["view"]), P(o["ended"]), P(o["dist"]),
+                  P(o["teacher"]), P(o["reward"]), P(o["mask"]), P(o["n_active"]), P(store.pose4), P(wg), P(b_act), P(o["act"]),
+                  P(o["xh"]), 96, E, p, 4, B, ops._stream())
+        for k in a:
+            assert torch.equal(a[k], o[k]), (fb, k)
+        assert bool((a["teacher"][a["ended"] == 0] >= 0).all())
+
+
 def test_cand_bwd_policy_stacked_steps(setup):
     """vln_cand_logits_bwd_policy over [n_steps, B] stacked rows == vln_policy_bwd + vln_cand_logits_bwd per step."""
     world, store, ops, dev = setup
