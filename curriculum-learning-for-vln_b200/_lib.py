@@ -51,8 +51,8 @@ _SIGS = {
     "vln_pano_attn_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _f, _p, _u64, _p, _i, _p], _i),
     "vln_feature_mask_bits": ([_p, _i64, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_feature_mask_bits_ld": ([_p, _i64, _i64, _i64, _i, _f, _p, _u64, _u64, _p], _i),
-    "vln_ctx_attn_fwd_ld": ([_p, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
-    "vln_ctx_attn_bwd_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p], _i),
+    "vln_ctx_attn_fwd_ld": ([_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p], _i),
+    "vln_ctx_attn_bwd_ld": ([_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p], _i),
     "vln_lstm_pointwise_drop_fwd": ([_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _u64, _p], _i),
     "vln_lstm_pointwise_drop_bwd": ([_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _p], _i),
     "vln_envdrop_state_fwd": ([_p, _i, _p, _i, _p, _p, _i, _i, _f, _p, _u64, _u64, _p], _i),

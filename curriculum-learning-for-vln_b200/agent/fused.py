@@ -268,7 +268,7 @@ class _Rollout(torch.autograd.Function):
             visual_and_lstm(t, True, q_done=paired and t > 0)
             _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, Bt, None, _p(TQ[t]), H)
             _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, Bt, L,
-                  H, _stream())
+                  H, 1 if t > 0 else 0, _stream())
             _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, Bt, None, _p(PRE[t]), H)
             more = t + 1 < S
             _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
@@ -357,14 +357,14 @@ class _Rollout(torch.autograd.Function):
                   0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
             _gemm(s_out.hi_t, s_out.lo_t, 2 * H, H, _p(DPRE[t]), H, Bt, None, _p(DWH[t]), 2 * H)
             _call("vln_ctx_attn_bwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H, None,
-                  _ptr(DTQ[t]), None, _ptr(DLC[t]), Bt, L, H, _stream())
+                  _ptr(DTQ[t]), None, _ptr(DLC[t]), Bt, L, H, 1, _stream())
             _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, Bt, None, _p(DWH[t], H), 2 * H, accumulate=1)
             _call("vln_lstm_pointwise_drop_bwd", _ptr(ACTS[t]), _ptr(CS[t]), _ptr(CS[t + 1]), _p(DWH[t], H), 2 * H,
                   _ptr(d_h1[t]) if d_h1 is not None else None, None if last else _ptr(DC[(t + 1) & 1]),
                   _ptr(DGATES[t]), _ptr(DC[t & 1]), Bt, H, p, rp, offs[t]["h1"], _stream())
             _gemm(s_cat.hi_t, s_cat.lo_t, KX, G4, _p(DGATES[t]), G4, Bt, None, _p(DXH[t]), KX)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4),
-                  _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, Bt, 1, pf, rp,
+                  _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, Bt, 1 | 2, pf, rp,
                   offs[t]["img"], _ptr(MB[t]) if MB is not None else None, split, _stream())
             _gemm(s_vin.hi_t, s_vin.lo_t, H, F, _p(DQ[t]), F, Bt, None, _p(DHQ[t]), H)
         _call("vln_envdrop_act_bwd", _ptr(DXH), KX, _ptr(ACT), _ptr(DACT), B, H_ACT, n, p, rp, offs[0]["act"],

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_attn_kernel(
     float* __restrict__ attn, float* __restrict__ weighted,            // fwd outputs (attn is an input in bwd)
     const float* __restrict__ d_weighted, const float* __restrict__ d_attn_ext, float* __restrict__ d_tgt,
     float* __restrict__ d_context, float* __restrict__ dlogit_out,       // bwd
-    int mode, int L, int H, int ld_w, int staged) {
+    int mode, int L, int H, int ld_w, int staged, int ctx_ready) {
   extern __shared__ __align__(128) uint8_t smem[];
   float* vec = reinterpret_cast<float*>(smem);           // [H]  tgt (fwd) / d_weighted (bwd)
   float* tg = vec + H;                                   // [H]  tgt (bwd only)
@@ -46,7 +46,10 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_attn_kernel(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   pdl_trigger();
-  pdl_wait();
+  // ctx_ready: context / lengths (and, backward, the saved attention and tgt) were complete before the preceding kernel
+  // started — true for every decoder step but the first — so the tile copy is requested BEFORE the programmatic
+  // dependency wait and lands while the predecessor (the GEMM that produces tgt / d_weighted) is still finishing.
+  if (!ctx_ready) pdl_wait();
   const int len = max(0, min(lengths[b], L));
   const uint32_t bytes = (uint32_t)len * (uint32_t)H * 4u;
 
@@ -58,12 +61,13 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_attn_kernel(
       bulk_g2s(const_cast<float*>(tile), context + (size_t)b * L * H, bytes, bar);
     }
   }
-  const float* v_in = mode == 0 ? tgt + (size_t)b * H : d_weighted + (size_t)b * ld_w;
-  for (int i = tid; i < H; i += kThreads) {
-    vec[i] = v_in[i];
-    if (mode == 1) tg[i] = tgt[(size_t)b * H + i];
+  if (mode == 1) {
+    for (int i = tid; i < H; i += kThreads) tg[i] = tgt[(size_t)b * H + i];
+    if (tid < L) av[tid] = tid < len ? attn[(size_t)b * L + tid] : 0.f;
   }
-  if (mode == 1 && tid < L) av[tid] = tid < len ? attn[(size_t)b * L + tid] : 0.f;
+  if (ctx_ready) pdl_wait();
+  const float* v_in = mode == 0 ? tgt + (size_t)b * H : d_weighted + (size_t)b * ld_w;
+  for (int i = tid; i < H; i += kThreads) vec[i] = v_in[i];
   __syncthreads();                                       // barrier initialised; vec / tg / av in place
   if (staged && len > 0) mbar_wait(bar, 0);
 
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_attn_kernel(
 
 int launch(const float* context, const float* tgt, const int32_t* lengths, float* attn, float* weighted,
            const float* d_weighted, const float* d_attn_ext, float* d_tgt, float* d_context, float* dlogit_out, int mode,
-           int B, int L, int H, int ld_w, cudaStream_t stream) {
+           int B, int L, int H, int ld_w, cudaStream_t stream, int ctx_ready = 0) {
   VLN_REQUIRE(L > 0 && L <= kMaxL, "L must be in 1..96");
   VLN_REQUIRE(H % 128 == 0 && H >= 128, "H must be a multiple of 128");
   VLN_REQUIRE(ld_w >= H, "row stride of weighted / d_weighted must be >= H");
@@ -174,35 +178,36 @@ int launch(const float* context, const float* tgt, const int32_t* lengths, float
     configured = smem;
   }
   VLN_CHECK_CUDA(vln_launch_chain(ctx_attn_kernel, dim3(B), dim3(kThreads), smem, stream, context, tgt, lengths, attn,
-                                  weighted, d_weighted, d_attn_ext, d_tgt, d_context, dlogit_out, mode, L, H, ld_w, staged));
+                                  weighted, d_weighted, d_attn_ext, d_tgt, d_context, dlogit_out, mode, L, H, ld_w, staged,
+                                  ctx_ready && staged ? 1 : 0));
   return 0;
 }
 
 }  // namespace
 
 extern "C" int vln_ctx_attn_fwd_ld(const float* context, const float* tgt, const int32_t* lengths, float* attn,
-                                   float* weighted, int ld_weighted, int B, int L, int H, void* stream) {
+                                   float* weighted, int ld_weighted, int B, int L, int H, int ctx_ready, void* stream) {
   VLN_REQUIRE(context && tgt && lengths && attn && weighted && B > 0, "bad arguments");
   return launch(context, tgt, lengths, attn, weighted, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, L, H,
-                ld_weighted, (cudaStream_t)stream);
+                ld_weighted, (cudaStream_t)stream, ctx_ready);
 }
 
 extern "C" int vln_ctx_attn_fwd(const float* context, const float* tgt, const int32_t* lengths, float* attn,
                                 float* weighted, int B, int L, int H, void* stream) {
-  return vln_ctx_attn_fwd_ld(context, tgt, lengths, attn, weighted, H, B, L, H, stream);
+  return vln_ctx_attn_fwd_ld(context, tgt, lengths, attn, weighted, H, B, L, H, 0, stream);
 }
 
 extern "C" int vln_ctx_attn_bwd_ld(const float* context, const float* tgt, const int32_t* lengths, const float* attn,
                                    const float* d_weighted, int ld_d_weighted, const float* d_attn_ext, float* d_tgt,
-                                   float* d_context, float* dlogit_out, int B, int L, int H, void* stream) {
+                                   float* d_context, float* dlogit_out, int B, int L, int H, int ctx_ready, void* stream) {
   VLN_REQUIRE(context && tgt && lengths && attn && d_weighted && d_tgt && B > 0, "bad arguments");
   return launch(context, tgt, lengths, const_cast<float*>(attn), nullptr, d_weighted, d_attn_ext, d_tgt, d_context,
-                dlogit_out, 1, B, L, H, ld_d_weighted, (cudaStream_t)stream);
+                dlogit_out, 1, B, L, H, ld_d_weighted, (cudaStream_t)stream, ctx_ready);
 }
 
 extern "C" int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* lengths, const float* attn,
                                 const float* d_weighted, const float* d_attn_ext, float* d_tgt, float* d_context,
                                 int B, int L, int H, void* stream) {
   return vln_ctx_attn_bwd_ld(context, tgt, lengths, attn, d_weighted, H, d_attn_ext, d_tgt, d_context, nullptr, B, L, H,
-                             stream);
+                             0, stream);
 }

@@ -82,7 +82,7 @@ struct Smem {
 __global__ void __launch_bounds__(kThreads, 1)
 pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ vp,
                  const int32_t* __restrict__ view, const float* __restrict__ loc4, const float* __restrict__ vec,
-                 float* __restrict__ attn_io, float* __restrict__ out, int B, int mode, float drop_p,
+                 float* __restrict__ attn_io, float* __restrict__ out, int B, int mode_in, float drop_p,
                  const uint64_t* __restrict__ rng, uint64_t call_off, int ld_vec, int ld_out,
                  const uint8_t* __restrict__ mask_bits, int dbg) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -91,6 +91,11 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   const int rank = (int)cluster_ctarank();                 // which half of the feature columns
   const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int col0 = rank * kHalf;
+  const int mode = mode_in & 1;
+  // mode bit 1: the indices, keep-bits and (backward) the saved attention were complete before the PRECEDING kernel
+  // started (backward pass: they date from the forward pass) — the first unit's rows are then requested before the
+  // programmatic-dependency wait, and the HBM round trip overlaps the predecessor's tail
+  const bool early = (mode_in & 2) != 0;
 
   int it = 0;
   if (dbg && blockIdx.x == 0 && tid == 0) g_pano_stamps[0] = (unsigned long long)clock64();
@@ -100,7 +105,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   fence_mbar_init();
   cluster_arrive();                                        // (waited for just before the first DSMEM store)
   __syncthreads();
-  pdl_wait();                                              // viewpoints, query and mask bits come from predecessors
+  if (!early) pdl_wait();                                  // viewpoints, query and mask bits come from predecessors
   if (dbg && blockIdx.x == 0 && tid == 0) g_pano_stamps[1] = (unsigned long long)clock64();
 
   // request row r of episode `ep` (this CTA's half, and its keep-bits) into unit buffer `ub`
@@ -146,6 +151,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
     // every warp requests the three rows it will consume in phase 1 (one warp issuing all 36-72 bulk copies
     // serialised ~30 cycles apiece: the first vectors were ready 1 us later with keep-bits than without)
     if (cid < B && lane < VLN_V / kWarps) request_row(cid, g0, warp + lane * kWarps, 0);
+    if (early) pdl_wait();                                 // the query / gradient vector comes from the predecessor
     prefetch_unit(cid, vw0, 0);
   }
 
@@ -348,7 +354,7 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
                                 uint64_t call_off, const uint8_t* mask_bits, int split, void* stream) {
   VLN_REQUIRE(ctx && vp && view && loc4 && vec && attn_io && out && B > 0, "bad arguments");
   VLN_REQUIRE(split == 1 || split == 2 || split == 4, "split (kernel variant) must be 1 = automatic, 2 = cluster, 4 = streaming");
-  VLN_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (forward) or 1 (backward)");
+  VLN_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (forward) or 1 (backward), + 2 = indices complete before the predecessor");
   VLN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");
   VLN_REQUIRE(drop_p == 0.f || rng || mask_bits, "dropout needs an rng state or pre-generated keep-bits");
   VLN_REQUIRE(!mask_bits || (drop_p > 0.f && ((uintptr_t)mask_bits & 15) == 0), "mask_bits: 16-byte aligned, with drop_p > 0");
@@ -362,7 +368,7 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
   static const int stream_min_b = getenv("VLN_PANO_STREAM_MIN_B") ? atoi(getenv("VLN_PANO_STREAM_MIN_B")) : 128;
   const bool stream_ok = drop_p == 0.f || mask_bits;        // the streaming kernel has no inline Philox
   if (stream_ok && (split == 4 || (split == 1 && B >= stream_min_b))) {
-    VLN_CHECK_CUDA(vln_pano_stream_launch(ctx, vp, view, loc4, vec, ld_vec, attn_io, out, ld_out, B, mode, drop_p, mask_bits,
+    VLN_CHECK_CUDA(vln_pano_stream_launch(ctx, vp, view, loc4, vec, ld_vec, attn_io, out, ld_out, B, mode & 1, drop_p, mask_bits,
                                           (cudaStream_t)stream));
     return 0;
   }

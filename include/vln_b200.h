@@ -83,7 +83,9 @@ int vln_pano_attn(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, co
  * and the backward can read its d(out) / saved forward output from there. */
 /* mask_bits (nullable): pre-generated keep-bits [B,36,256 bytes] of this step's feature dropout
  * (vln_feature_mask_bits) — the kernel then streams 256 mask bytes next to each 4 096-byte row instead of
- * running Philox inline (which made the kernel ALU-bound: 15.4 us vs 7.6 us per launch at B=64). */
+ * running Philox inline (which made the kernel ALU-bound: 15.4 us vs 7.6 us per launch at B=64).  * mode + 2 (row-strided entry point only): promises that vp / view / mask_bits (and, backward, attn_io) were
+ * complete before the PRECEDING kernel of the stream started — true throughout the backward pass, whose indices
+ * date from the forward pass — so the first rows are requested before the programmatic-dependency wait. */
 int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int32_t* view, const float* loc4,
                      const float* vec, int ld_vec, float* attn_io, const float* fwd_out, int ld_fwd,
                      float* out, int ld_out, int B, int mode, float drop_p, const uint64_t* rng,
@@ -128,14 +130,18 @@ int vln_ctx_attn_bwd(const float* context, const float* tgt, const int32_t* leng
 
 /* Row-strided variants: `weighted` (forward) / `d_weighted` (backward) rows are ld floats apart, so the
  * weighted context is written straight into cat((weighted, h)) (units.py:119) and its gradient read from there. */
+/* ctx_ready = 1 promises that `context` and `lengths` (backward: also `attn` and `tgt`) were complete before the
+ * PRECEDING kernel of the stream started (every decoder step but the first): the tile copy is then requested before
+ * the programmatic-dependency wait and overlaps the predecessor's tail. */
 int vln_ctx_attn_fwd_ld(const float* context, const float* tgt, const int32_t* lengths, float* attn,
-                        float* weighted, int ld_weighted, int B, int L, int H, void* stream);
+                        float* weighted, int ld_weighted, int B, int L, int H, int ctx_ready, void* stream);
 /* dlogit_out (nullable) [B,L] receives dlogit, so that d_context = sum over steps of
  * attn^T d_weighted + dlogit^T tgt can be ONE batched GEMM at the end of a rollout instead of a
  * read-modify-write of the whole context gradient per step (then pass d_context = NULL). */
 int vln_ctx_attn_bwd_ld(const float* context, const float* tgt, const int32_t* lengths,
                         const float* attn, const float* d_weighted, int ld_d_weighted, const float* d_attn_ext,
-                        float* d_tgt, float* d_context, float* dlogit_out, int B, int L, int H, void* stream);
+                        float* d_tgt, float* d_context, float* dlogit_out, int B, int L, int H, int ctx_ready,
+                        void* stream);
 
 /* nn.LSTMCell pointwise half (policy.py:53,159,238): gates [B,4H] (i,f,g,o pre-activations,
  * biases already added) + c0 -> h1, c1; acts [B,4H] keeps the activated gates for backward. */
