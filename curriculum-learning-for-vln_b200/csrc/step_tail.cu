@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   __shared__ float s_logit[VLN_NSLOT];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
   pdl_trigger();
-  pdl_wait();
+  // Everything up to the wait reads data that was complete long before the preceding kernel (the GEMM that produces
+  // tgt) started: this step's state was written by the previous step's tail, nine kernels back, and the tables are
+  // constant.  So the index chain and the candidate rows are in flight while that GEMM is still finishing.
   const int g = a.vp[b];
   const int vw_in = a.view[b];
   const int n = a.n_cand[g];
@@ -74,6 +76,17 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
     d_in = a.dist_in[b];
     vloc_g = a.vp_local[gl];
   }
+  // this warp's candidate row (8 x 16 bytes per lane) and its angle feature
+  uint4 xr[8];
+  float4 an = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < n) {
+    const int cv = a.cand_view[(size_t)g * VLN_CMAX + j];
+    an = __ldg(reinterpret_cast<const float4*>(a.cand_ang4 + (((size_t)g * VLN_CMAX + j) * 12 + (vw_in % 12)) * 4));
+    const uint4* src = reinterpret_cast<const uint4*>(a.table + ((size_t)g * VLN_V + cv) * VLN_IMG);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) xr[it] = __ldg(src + it * 32 + lane);
+  }
+  pdl_wait();
   // ---- candidate logits (cand_logits_fwd_kernel) ----
   for (int i = tid; i < VLN_F; i += 512) ts[i] = a.tgt[(size_t)b * VLN_F + i];
   __syncthreads();
@@ -84,10 +97,6 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   __syncthreads();
   float res;
   if (j < n) {
-    const int cv = a.cand_view[(size_t)g * VLN_CMAX + j];
-    const float* ang = a.cand_ang4 + (((size_t)g * VLN_CMAX + j) * 12 + (vw_in % 12)) * 4;
-    const float4 an = __ldg(reinterpret_cast<const float4*>(ang));
-    const uint4* src = reinterpret_cast<const uint4*>(a.table + ((size_t)g * VLN_V + cv) * VLN_IMG);
     const uint32_t thr = drop_threshold(a.drop_p);
     uint64_t seed = 0, offset = 0;
     if (a.drop_p > 0.f) { seed = a.rng[0]; offset = a.rng[1] + a.off_cand; }
@@ -95,7 +104,7 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int vi = it * 32 + lane;
-      uint4 x = __ldg(src + vi);
+      uint4 x = xr[it];
       if (a.drop_p > 0.f) {
         const uint64_t e = (((uint64_t)b * VLN_NSLOT + j) * VLN_IMG + (uint64_t)vi * 8) >> 3;
         x = apply_keep(x, philox8(seed, offset, e), thr);
