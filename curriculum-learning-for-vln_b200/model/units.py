@@ -133,7 +133,8 @@ class EncoderLSTM(KernelModule):
                 sfx = f"_l{layer}" + ("_reverse" if d else "")
                 w_ih, w_hh = getattr(self.lstm, "weight_ih" + sfx), getattr(self.lstm, "weight_hh" + sfx)
                 bias = getattr(self.lstm, "bias_ih" + sfx) + getattr(self.lstm, "bias_hh" + sfx)
-                xprojs.append(ops.linear(x.reshape(B * L, -1), w_ih, bias).view(B, L, -1))
+                # layer 0's dx only feeds the embedding gradient: TF32 library GEMM (see ops._LinearTall)
+                xprojs.append(ops.linear(x.reshape(B * L, -1), w_ih, bias, dx_tf32=(layer == 0)).view(B, L, -1))
                 whhs.append(w_hh)
             if self.hidden_size in ops.LSTM_KERNEL_H:
                 # persistent cluster kernel (tcgen05, W_hh resident in tensor memory), both directions in one launch:

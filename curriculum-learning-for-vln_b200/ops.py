@@ -248,15 +248,18 @@ def _tc_matmul_tall(x, hi, lo, N, K, bias=None):
 
 class _LinearTall(torch.autograd.Function):
     """Tall inputs (encoder input projection [B*L, E], batched critic [T*B, H]) on the same tcgen05 bf16x3
-    kernel, forward and input gradient; weight gradient through wgrad()."""
+    kernel, forward and input gradient; weight gradient through wgrad().  ``dx_tf32``: the input gradient as a
+    library TF32 GEMM instead — for the encoder's input projection, whose dx only feeds the embedding gradient
+    (same tolerance argument as wgrad(): 1024-long sums, gradient cosine unaffected) and whose K = 4H = 1024,
+    N = E = 256 shape keeps the two-stage tcgen05 pipeline latency-bound (47 us vs 12 us per direction)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, dx_tf32):
         x = _f32c(x)
         sw = _split_of(w)
         N, K = w.shape
         ctx.save_for_backward(x, w)
-        ctx.sw, ctx.has_b = sw, b is not None
+        ctx.sw, ctx.has_b, ctx.dx_tf32 = sw, b is not None, bool(dx_tf32)
         return _tc_matmul_tall(x, sw.hi, sw.lo, N, K, b.detach() if b is not None else None)
 
     @staticmethod
@@ -264,10 +267,20 @@ class _LinearTall(torch.autograd.Function):
         x, w = ctx.saved_tensors
         dy = _f32c(dy)
         N, K = w.shape
-        dx = _tc_matmul_tall(dy, ctx.sw.hi_t, ctx.sw.lo_t, K, N) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.dx_tf32 and WGRAD_TF32[0]:
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = True
+                try:
+                    dx = dy @ w.detach()
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+            else:
+                dx = _tc_matmul_tall(dy, ctx.sw.hi_t, ctx.sw.lo_t, K, N)
         dw = wgrad(dy, x) if ctx.needs_input_grad[1] else None
         db = dy.sum(0) if ctx.has_b and ctx.needs_input_grad[2] else None
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class _LinearLib(torch.autograd.Function):
@@ -289,7 +302,7 @@ class _LinearLib(torch.autograd.Function):
         return dx, dw, db
 
 
-def linear(x, w, b=None, acc=None):
+def linear(x, w, b=None, acc=None, dx_tf32=False):
     """y = x W^T + b (+ acc) on the tcgen05 bf16x3 kernel (csrc/gemm.cu): split-K skinny launches for at
     most 128 rows, 128x128 output blocks for taller inputs (encoder input projection, batched critic)."""
     ok = (USE_TC_LINEAR[0] and x.is_cuda and x.dim() == 2 and w.shape[1] % 64 == 0 and w.shape[0] % 4 == 0
@@ -297,7 +310,7 @@ def linear(x, w, b=None, acc=None):
     if ok and x.shape[0] <= 128:
         return _LinearTC.apply(x, w, b, acc)
     if ok and w.shape[0] % 64 == 0:
-        y = _LinearTall.apply(x, w, b)
+        y = _LinearTall.apply(x, w, b, dx_tf32)
         return y if acc is None else y + acc
     y = _LinearLib.apply(x, w, b) if x.dim() == 2 else F.linear(x, w, b)
     return y if acc is None else y + acc
