@@ -30,9 +30,10 @@ L_.vln_debug_lstm_stamps.argtypes = [C.c_void_p]
 buf = (C.c_ulonglong * 12)()
 L_.vln_debug_lstm_stamps(buf)
 names = ["mma + gate stores", "syncthreads", "pointwise + global stores", "st.async issue", "mbarrier wait"]
-print(", ".join(f"{n}={buf[i + 1] - buf[i]}" for i, n in enumerate(names)), "cycles; step total", buf[5] - buf[0])
-print("kernel: prologue (weight fragments, barrier init, cluster sync) = %d cycles, %d steps = %d cycles (%.0f per step), epilogue = %d"
-      % (buf[7] - buf[6], L, buf[8] - buf[7], (buf[8] - buf[7]) / L, buf[9] - buf[8]))
+if buf[0]:           # stamps of the mma.sync kernels (VLN_LSTM_VARIANT=mma)
+    print(", ".join(f"{n}={buf[i + 1] - buf[i]}" for i, n in enumerate(names)), "cycles; step total", buf[5] - buf[0])
+    print("kernel: prologue (weight fragments, barrier init, cluster sync) = %d cycles, %d steps = %d cycles (%.0f per step), epilogue = %d"
+          % (buf[7] - buf[6], L, buf[8] - buf[7], (buf[8] - buf[7]) / L, buf[9] - buf[8]))
 L_.vln_debug_lstm_tc_stamps.argtypes = [C.c_void_p]
 tb = (C.c_ulonglong * 16)()
 L_.vln_debug_lstm_tc_stamps(tb)
@@ -45,7 +46,8 @@ L_.vln_debug_lstm_occupancy.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
 f, b = C.c_int(0), C.c_int(0)
 for h in (256, 128):
     if L_.vln_debug_lstm_occupancy(h, C.byref(f), C.byref(b)) == 0:
-        print(f"H={h}: max resident clusters fwd={f.value} bwd={b.value} (a B=64 bidirectional launch has 16)")
+        print(f"H={h}: max resident clusters fwd={f.value} bwd={b.value} (mma.sync kernels, 8 rows per cluster: a B=64 "
+              f"bidirectional launch needs 16; the tcgen05 kernels take 16 / 24 / 32 rows per cluster)")
 # one wave or two?  time the launch at 8, 16, 24, 32 clusters (B = 32 .. 128, both directions)
 for Bx in (32, 56, 64, 96, 128):
     xp = [torch.randn(Bx, L, 4 * H, device=dev) * 0.1 for _ in range(2)]
@@ -58,4 +60,4 @@ for Bx in (32, 56, 64, 96, 128):
         ops.lstm_layer(xp, whh, ln)
     e1.record()
     torch.cuda.synchronize()
-    print("B=%d (%d clusters): fwd launch %.1f us" % (Bx, 2 * ((Bx + 7) // 8), e0.elapsed_time(e1) * 100))
+    print("B=%d, both directions: fwd launch %.1f us" % (Bx, e0.elapsed_time(e1) * 100))
