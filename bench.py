@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--small", action="store_true", help="tiny world (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-op", action="store_true",
+                    help="with --impl reference: add per-op CPU times (gather, panorama attention, LSTMCell, context "
+                         "attention, cross-entropy; SURVEY 8d) and the config-1 Follower iteration to the line")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("VLN_BENCH_GRAPH", "1")),
                     help="replay the iteration as CUDA graphs (1) or launch eagerly (0)")
     return ap.parse_args()
@@ -206,6 +209,96 @@ def cpu_iteration_factory(world_small, items, B, threads):
     return iteration
 
 
+def cpu_per_op(B, threads, world, items):
+    """Per-op host times of the reference algorithm (oracle restatement, fp32, all host threads), forward + backward,
+    at the EnvDrop step's shapes; plus one Follower teacher-forcing iteration at B=16 (BASELINE config 1)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from clvln_b200.environ.world import static_loc4
+    from oracle import port_modules as P
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+
+    def clock(fn, reps=5):
+        fn()
+        t0 = time.time()
+        for _ in range(reps):
+            fn()
+        return (time.time() - t0) / reps * 1e3
+
+    out = {}
+    vp = torch.randint(0, world.n_vp, (B,), generator=g)
+    view = torch.randint(0, 36, (B,), generator=g)
+    loc = torch.from_numpy(static_loc4())
+    table = world.table.float()
+
+    def gather():            # R2RBatch.observe concat + _feature_variable (common_env.py:309, base.py:141-147)
+        feats = [np.concatenate((table[int(v)].numpy(), np.repeat(loc[int(w)].numpy(), 32, axis=1)), 1) for v, w in zip(vp, view)]
+        return torch.from_numpy(np.stack(feats))
+    out["gather_pano_ms"] = clock(gather)
+    img = gather()
+    h = torch.randn(B, 512, generator=g, requires_grad=True)
+    w_in = (torch.randn(2176, 512, generator=g) * 0.02).requires_grad_(True)
+
+    def pano():
+        o, _ = P.soft_dot_attention(h, img, w_in)
+        o.sum().backward()
+    out["pano_attention_fwd_bwd_ms"] = clock(pano)
+    x = torch.randn(B, 2240, generator=g, requires_grad=True)
+    c = torch.randn(B, 512, generator=g)
+    w_ih = (torch.randn(2048, 2240, generator=g) * 0.02).requires_grad_(True)
+    w_hh = (torch.randn(2048, 512, generator=g) * 0.02).requires_grad_(True)
+    bz = torch.zeros(2048)
+
+    def cell():
+        h1, c1 = P.lstm_cell(x, h, c, w_ih, w_hh, bz, bz)
+        (h1.sum() + c1.sum()).backward()
+    out["lstm_cell_fwd_bwd_ms"] = clock(cell)
+    ctx = torch.randn(B, 80, 512, generator=g, requires_grad=True)
+    w_t = (torch.randn(512, 512, generator=g) * 0.02).requires_grad_(True)
+    w_o = (torch.randn(512, 1024, generator=g) * 0.02).requires_grad_(True)
+
+    def ctxa():
+        o, _ = P.soft_dot_attention(h, ctx, w_t, w_o)
+        o.sum().backward()
+    out["ctx_attention_fwd_bwd_ms"] = clock(ctxa)
+    logit = torch.randn(B, 16, generator=g, requires_grad=True)
+    tgt = torch.randint(0, 16, (B,), generator=g)
+
+    def ce():
+        F.cross_entropy(logit, tgt, ignore_index=-1, reduction="sum").backward()
+    out["cross_entropy_fwd_bwd_ms"] = clock(ce)
+    # config 1: Follower, teacher forcing, B=16, MAX_EPISODE_LEN=10
+    import random
+    from clvln_b200 import utils
+    from clvln_b200.model import EncoderLSTM, AttnDecoderLSTM
+    from oracle import port_env as PE, port_rollout as PR
+    cfg = utils.agent_cfg("FOLLOWER")
+    mc = cfg.MODEL.FOLLOWER
+    torch.manual_seed(2020)
+    mods = [EncoderLSTM(992, mc.WORD_EMB_SIZE, mc.HIDDEN_SIZE, 0, mc.DROP_RATE, mc.ENC_BIDIRECTION, mc.ENC_LAYERS),
+            AttnDecoderLSTM(mc.HIDDEN_SIZE, mc.DROP_RATE)]
+    sds = [{k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()} for m in mods]
+    params = [v for sd in sds for v in sd.values()]
+    opt = torch.optim.Adam(params, lr=cfg.TRAIN.LR)
+    random.seed(2020)
+    penv = PE.R2RBatchPort(PE.WorldView(world), items, batch_size=16)
+    ag = PR.Agent("FOLLOWER", sds[0], sds[1], None, hidden=mc.HIDDEN_SIZE, bidirectional=mc.ENC_BIDIRECTION,
+                  enc_layers=mc.ENC_LAYERS, episode_len=10)
+    drop = P.Drop("torch")
+
+    def follower():
+        _, ml = PR.rollout_follower(ag, penv, feedback="teacher", drop=drop)
+        opt.zero_grad()
+        ml.backward()
+        opt.step()
+    ms = clock(follower, reps=3)
+    out["follower_B16_teacher_iteration_ms"] = ms
+    out["follower_B16_episodes_per_s"] = 16 / (ms * 1e-3)
+    return {k: round(v, 3) for k, v in out.items()}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -244,7 +337,8 @@ def run_reference(args):
     dt = time.time() - t0
     v = B * args.steps / dt
     sample = f"{args.steps} full EnvDrop training iterations (teacher + 35-step sampled rollout + backward + clip + RMSprop) at B={B}, L=80, 8-scan synthetic world, fp32, {threads} torch threads"
-    print(json.dumps({
+    extra = {"per_op_ms": cpu_per_op(args.batch, threads, world, items)} if args.per_op else {}
+    print(json.dumps({**extra, 
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
