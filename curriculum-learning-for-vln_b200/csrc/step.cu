@@ -54,34 +54,60 @@ __device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// The four per-element kernels between the step's GEMMs (state_fwd/bwd, lstm_pw_drop_fwd/bwd) sit on the step's
+// latency chain with only B*H = 32 K elements: a thread takes kE = 2 consecutive elements (four threads share one
+// 8-element Philox block and each recomputes it), so the dependent chain of transcendentals per thread is a quarter
+// of the 8-per-thread layout the wider kernels use (4.5 -> ~2.5 us for the LSTM pointwise kernel at B = 64).
+constexpr int kE = 2;
+__device__ __forceinline__ void keepE(const Drop& d, uint64_t blk, int sub, float (&k)[kE]) {
+  if (!d.on) {
+#pragma unroll
+    for (int j = 0; j < kE; ++j) k[j] = 1.f;
+    return;
+  }
+  const Philox8 r = philox8(d.seed, d.offset, blk);
+#pragma unroll
+  for (int j = 0; j < kE; ++j) k[j] = philox_keep(r, sub + j, d.thr) ? d.scale : 0.f;
+}
+__device__ __forceinline__ void ldE(const float* p, float (&v)[kE]) {
+  const float2 a = *reinterpret_cast<const float2*>(p);
+  v[0] = a.x; v[1] = a.y;
+}
+__device__ __forceinline__ void stE(float* p, const float (&v)[kE]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+// thread -> (row b, first column h, Philox block of the dense [B,H] tensor, lane offset inside the block)
+#define ELEM_INDEX()                                                   \
+  const int i_ = blockIdx.x * blockDim.x + threadIdx.x;               \
+  const int per_row = H / kE;                                          \
+  if (i_ >= B * per_row) return;                                       \
+  const int b = i_ / per_row, h = (i_ - b * per_row) * kE;             \
+  const uint64_t i = ((uint64_t)b * H + h) >> 3;                       \
+  const int sub = h & 7
+
 // ---- h~ state: tanh + the two dropout sites that consume it -------------------------------------
 __global__ void state_fwd_kernel(const float* __restrict__ src, int apply_tanh, float* __restrict__ xh_next, int ld_xh,
                                  float* __restrict__ hq_next, float* __restrict__ hc_cur, int B, int H, float p,
                                  const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
   pdl_trigger();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // 8-element block index
-  const int hb = H / 8;
-  if (i >= B * hb) return;
-  const int b = i / hb, h = (i - b * hb) * 8;
-  float v[8], k[8], o[8];
-  ld8(src + (size_t)b * H + h, v);
+  ELEM_INDEX();
+  float v[kE], k[kE], o[kE];
+  ldE(src + (size_t)b * H + h, v);
   if (apply_tanh) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+    for (int j = 0; j < kE; ++j) v[j] = tanhf(v[j]);
   }
-  if (xh_next) st8(xh_next + (size_t)b * ld_xh + h, v);
+  if (xh_next) stE(xh_next + (size_t)b * ld_xh + h, v);
   if (hq_next) {
-    keep8(make_drop(p, rng, off_q), (uint64_t)i, k);
+    keepE(make_drop(p, rng, off_q), i, sub, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = v[j] * k[j];
-    st8(hq_next + (size_t)b * H + h, o);
+    for (int j = 0; j < kE; ++j) o[j] = v[j] * k[j];
+    stE(hq_next + (size_t)b * H + h, o);
   }
   if (hc_cur) {
-    keep8(make_drop(p, rng, off_c), (uint64_t)i, k);
+    keepE(make_drop(p, rng, off_c), i, sub, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = v[j] * k[j];
-    st8(hc_cur + (size_t)b * H + h, o);
+    for (int j = 0; j < kE; ++j) o[j] = v[j] * k[j];
+    stE(hc_cur + (size_t)b * H + h, o);
   }
 }
 
@@ -92,34 +118,31 @@ __global__ void state_bwd_kernel(const float* __restrict__ d_hc, const float* __
                                  const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
   pdl_trigger();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int hb = H / 8;
-  if (i >= B * hb) return;
-  const int b = i / hb, h = (i - b * hb) * 8;
-  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, v[8], k[8];
+  ELEM_INDEX();
+  float g[kE] = {0.f, 0.f}, v[kE], k[kE];
   if (d_hc) {
-    ld8(d_hc + (size_t)b * H + h, v);
-    keep8(make_drop(p, rng, off_c), (uint64_t)i, k);
+    ldE(d_hc + (size_t)b * H + h, v);
+    keepE(make_drop(p, rng, off_c), i, sub, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += v[j] * k[j];
+    for (int j = 0; j < kE; ++j) g[j] += v[j] * k[j];
   }
   if (d_xh_next) {
-    ld8(d_xh_next + (size_t)b * ld_dxh + h, v);
+    ldE(d_xh_next + (size_t)b * ld_dxh + h, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += v[j];
+    for (int j = 0; j < kE; ++j) g[j] += v[j];
   }
   if (d_hq_next) {
-    ld8(d_hq_next + (size_t)b * H + h, v);
-    keep8(make_drop(p, rng, off_q), (uint64_t)i, k);
+    ldE(d_hq_next + (size_t)b * H + h, v);
+    keepE(make_drop(p, rng, off_q), i, sub, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += v[j] * k[j];
+    for (int j = 0; j < kE; ++j) g[j] += v[j] * k[j];
   }
   if (apply_tanh) {
-    ld8(htilde + (size_t)b * ld_h + h, v);
+    ldE(htilde + (size_t)b * ld_h + h, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] *= 1.f - v[j] * v[j];
+    for (int j = 0; j < kE; ++j) g[j] *= 1.f - v[j] * v[j];
   }
-  st8(d_src + (size_t)b * H + h, g);
+  stE(d_src + (size_t)b * H + h, g);
 }
 
 // ---- action embedding of the agent's pose: drop(tanh(W_a angle128(view) + b_a)) ------------------
@@ -279,31 +302,28 @@ __global__ void lstm_pw_drop_fwd_kernel(const float* __restrict__ gates, const f
                                         const uint64_t* __restrict__ rng, uint64_t call_off) {
   pdl_trigger();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int hb = H / 8;
-  if (i >= B * hb) return;
-  const int b = i / hb, h = (i - b * hb) * 8;
+  ELEM_INDEX();
   const float* gr = gates + (size_t)b * 4 * H + h;
-  float gi[8], gf[8], gg[8], go[8], c[8], hh[8], k[8];
-  ld8(gr, gi); ld8(gr + H, gf); ld8(gr + 2 * H, gg); ld8(gr + 3 * H, go);
-  ld8(c0 + (size_t)b * H + h, c);
+  float gi[kE], gf[kE], gg[kE], go[kE], c[kE], hh[kE], k[kE];
+  ldE(gr, gi); ldE(gr + H, gf); ldE(gr + 2 * H, gg); ldE(gr + 3 * H, go);
+  ldE(c0 + (size_t)b * H + h, c);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < kE; ++j) {
     gi[j] = sigmoidf_(gi[j]); gf[j] = sigmoidf_(gf[j]); gg[j] = tanhf(gg[j]); go[j] = sigmoidf_(go[j]);
     c[j] = gf[j] * c[j] + gi[j] * gg[j];
     hh[j] = go[j] * tanhf(c[j]);
   }
-  st8(c1 + (size_t)b * H + h, c);
-  st8(h1 + (size_t)b * H + h, hh);
+  stE(c1 + (size_t)b * H + h, c);
+  stE(h1 + (size_t)b * H + h, hh);
   if (acts) {
     float* ar = acts + (size_t)b * 4 * H + h;
-    st8(ar, gi); st8(ar + H, gf); st8(ar + 2 * H, gg); st8(ar + 3 * H, go);
+    stE(ar, gi); stE(ar + H, gf); stE(ar + 2 * H, gg); stE(ar + 3 * H, go);
   }
   if (h1_drop) {
-    keep8(make_drop(p, rng, call_off), (uint64_t)i, k);
+    keepE(make_drop(p, rng, call_off), i, sub, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hh[j] *= k[j];
-    st8(h1_drop + (size_t)b * ld_drop + h, hh);
+    for (int j = 0; j < kE; ++j) hh[j] *= k[j];
+    stE(h1_drop + (size_t)b * ld_drop + h, hh);
   }
 }
 
@@ -315,36 +335,33 @@ __global__ void lstm_pw_drop_bwd_kernel(const float* __restrict__ acts, const fl
                                         const uint64_t* __restrict__ rng, uint64_t call_off) {
   pdl_trigger();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int hb = H / 8;
-  if (i >= B * hb) return;
-  const int b = i / hb, h = (i - b * hb) * 8;
+  ELEM_INDEX();
   const float* ar = acts + (size_t)b * 4 * H + h;
-  float gi[8], gf[8], gg[8], go[8], cp[8], cn[8], dh[8], dc[8], k[8], v[8];
-  ld8(ar, gi); ld8(ar + H, gf); ld8(ar + 2 * H, gg); ld8(ar + 3 * H, go);
-  ld8(c0 + (size_t)b * H + h, cp);
-  ld8(c1 + (size_t)b * H + h, cn);
+  float gi[kE], gf[kE], gg[kE], go[kE], cp[kE], cn[kE], dh[kE], dc[kE], k[kE], v[kE];
+  ldE(ar, gi); ldE(ar + H, gf); ldE(ar + 2 * H, gg); ldE(ar + 3 * H, go);
+  ldE(c0 + (size_t)b * H + h, cp);
+  ldE(c1 + (size_t)b * H + h, cn);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) dh[j] = 0.f;
+  for (int j = 0; j < kE; ++j) dh[j] = 0.f;
   if (d_h1_drop) {
-    ld8(d_h1_drop + (size_t)b * ld_drop + h, v);
-    keep8(make_drop(p, rng, call_off), (uint64_t)i, k);
+    ldE(d_h1_drop + (size_t)b * ld_drop + h, v);
+    keepE(make_drop(p, rng, call_off), i, sub, k);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dh[j] = v[j] * k[j];
+    for (int j = 0; j < kE; ++j) dh[j] = v[j] * k[j];
   }
   if (d_h1_extra) {
-    ld8(d_h1_extra + (size_t)b * H + h, v);
+    ldE(d_h1_extra + (size_t)b * H + h, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dh[j] += v[j];
+    for (int j = 0; j < kE; ++j) dh[j] += v[j];
   }
-  if (d_c1) ld8(d_c1 + (size_t)b * H + h, dc);
+  if (d_c1) ldE(d_c1 + (size_t)b * H + h, dc);
   else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dc[j] = 0.f;
+    for (int j = 0; j < kE; ++j) dc[j] = 0.f;
   }
-  float di[8], df[8], dg[8], dgo[8];
+  float di[kE], df[kE], dg[kE], dgo[kE];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < kE; ++j) {
     const float tc = tanhf(cn[j]);
     const float dcj = dc[j] + dh[j] * go[j] * (1.f - tc * tc);
     di[j] = dcj * gg[j] * gi[j] * (1.f - gi[j]);
@@ -354,8 +371,8 @@ __global__ void lstm_pw_drop_bwd_kernel(const float* __restrict__ acts, const fl
     dc[j] = dcj * gf[j];
   }
   float* dr = d_gates + (size_t)b * 4 * H + h;
-  st8(dr, di); st8(dr + H, df); st8(dr + 2 * H, dg); st8(dr + 3 * H, dgo);
-  st8(d_c0 + (size_t)b * H + h, dc);
+  stE(dr, di); stE(dr + H, df); stE(dr + 2 * H, dg); stE(dr + 3 * H, dgo);
+  stE(d_c0 + (size_t)b * H + h, dc);
 }
 
 }  // namespace
@@ -368,7 +385,7 @@ extern "C" int vln_envdrop_state_fwd(const float* src, int apply_tanh, float* xh
   VLN_REQUIRE(src && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
   VLN_REQUIRE(!xh_next || ld_xh % 4 == 0, "xh rows must be 16-byte aligned");
-  const int n = B * (H / 8);
+  const int n = B * (H / kE);                              // one thread per kE consecutive elements
   VLN_CHECK_CUDA(vln_launch_chain(state_fwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, src, apply_tanh, xh_next,
                                   ld_xh, hq_next, hc_cur, B, H, p, rng, off_q, off_c));
   return 0;
@@ -380,7 +397,7 @@ extern "C" int vln_envdrop_state_bwd(const float* d_hc, const float* d_xh_next, 
   VLN_REQUIRE(d_src && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
   VLN_REQUIRE(!apply_tanh || htilde, "tanh backward needs the saved h~");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
-  const int n = B * (H / 8);
+  const int n = B * (H / kE);                              // one thread per kE consecutive elements
   VLN_CHECK_CUDA(vln_launch_chain(state_bwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, d_hc, d_xh_next, ld_dxh,
                                   d_hq_next, htilde, ld_h, apply_tanh, d_src, B, H, p, rng, off_q, off_c));
   return 0;
@@ -438,7 +455,7 @@ extern "C" int vln_lstm_pointwise_drop_fwd(const float* gates, const float* c0, 
                                            uint64_t call_off, void* stream) {
   VLN_REQUIRE(gates && c0 && h1 && c1 && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng || !h1_drop), "dropout needs 0 <= p < 1 and an rng state");
-  const int n = B * (H / 8);
+  const int n = B * (H / kE);                              // one thread per kE consecutive elements
   VLN_CHECK_CUDA(vln_launch_chain(lstm_pw_drop_fwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, gates, c0, h1, c1,
                                   acts, h1_drop, ld_drop, B, H, p, rng, call_off));
   return 0;
@@ -450,7 +467,7 @@ extern "C" int vln_lstm_pointwise_drop_bwd(const float* acts, const float* c0, c
                                            void* stream) {
   VLN_REQUIRE(acts && c0 && c1 && d_gates && d_c0 && B > 0 && H > 0 && H % 8 == 0, "bad arguments");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng || !d_h1_drop), "dropout needs 0 <= p < 1 and an rng state");
-  const int n = B * (H / 8);
+  const int n = B * (H / kE);                              // one thread per kE consecutive elements
   VLN_CHECK_CUDA(vln_launch_chain(lstm_pw_drop_bwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, acts, c0, c1,
                                   d_h1_drop, ld_drop, d_h1_extra, d_c1, d_gates, d_c0, B, H, p, rng, call_off));
   return 0;
