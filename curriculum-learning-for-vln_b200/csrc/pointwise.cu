@@ -165,76 +165,77 @@ __global__ void embed_drop_fwd_kernel(const int64_t* __restrict__ tok, const flo
   }
 }
 
-// Its backward: d_emb[v, :] = sum over the rows r with tok[r] == v (in row order: deterministic, unlike an atomic
-// scatter; ATen's embedding_dense_backward sorts the indices instead) of mask(r, :) * d_y[r, :] / (1 - p); the
-// padding row gets zero (nn.Embedding(padding_idx=0), units.py:33).  One CTA per vocabulary entry, one thread per column.
-constexpr int kEmbChunk = 2048;
+// Its backward: d_emb[v, :] = sum over the rows r with tok[r] == v of mask(r, :) * d_y[r, :] / (1 - p); the padding
+// row gets zero (nn.Embedding(padding_idx=0), units.py:33).  One CTA per vocabulary entry; each of its 8 warps scans
+// a contiguous eighth of the token rows (32 per coalesced load + ballot) and accumulates the matching rows in row
+// order — a lane owns 8 consecutive columns, i.e. one Philox block per matching row — then the 8 partial sums are
+// added in warp order: deterministic, unlike an atomic scatter (ATen's embedding_dense_backward sorts instead).
 __global__ void __launch_bounds__(256)
 embed_drop_bwd_kernel(const int64_t* __restrict__ tok, const float* __restrict__ dy, float* __restrict__ d_emb, int64_t rows,
                       int E, int padding_idx, float p, const uint64_t* __restrict__ rng, uint64_t call_off) {
-  __shared__ int s_rows[kEmbChunk];
-  __shared__ int s_warp_cnt[8];
+  __shared__ float part[8][1024];
   const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t thr = drop_threshold(p);
   const float sc = 1.0f / (1.0f - p);
   const uint64_t seed = rng[0], off = rng[1] + call_off;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};                      // columns tid, tid + 256, ... (E <= 1024)
+  float acc[4][8];                                          // columns [256 c + 8 lane, +8), c < 4 (E <= 1024)
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
   if (v != padding_idx) {
-    for (int64_t base = 0; base < rows; base += kEmbChunk) {
-      // ordered compaction of the matching rows of this chunk (ballot + prefix over warps keeps row order);
-      // the chunk's tokens are fetched up front so the eight passes do not each wait for L2
-      int n_prev = 0;
-      bool hits[kEmbChunk / 256];
+    const int64_t per = ((rows + 7) / 8 + 31) / 32 * 32;    // rows per warp, a multiple of 32
+    const int64_t r_begin = warp * per, r_end = min(rows, r_begin + per);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += 128) {     // four coalesced token loads in flight
+      unsigned m[4];
 #pragma unroll
-      for (int i = 0; i < kEmbChunk / 256; ++i) {
-        const int64_t r = base + i * 256 + tid;
-        hits[i] = r < rows && __ldg(tok + r) == (int64_t)v;
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = r0 + u * 32 + lane;
+        m[u] = __ballot_sync(0xffffffffu, r < r_end && __ldg(tok + r) == (int64_t)v);
       }
 #pragma unroll
-      for (int i = 0; i < kEmbChunk / 256; ++i) {
-        const unsigned m = __ballot_sync(0xffffffffu, hits[i]);
-        if (lane == 0) s_warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        int before = n_prev;
-        for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
-        if (hits[i]) s_rows[before + __popc(m & ((1u << lane) - 1u))] = i * 256 + tid;
-        for (int w = 0; w < 8; ++w) n_prev += s_warp_cnt[w];
-        __syncthreads();
-      }
-      const int cnt = n_prev;                                 // identical in every thread
-      for (int k0 = 0; k0 < cnt; k0 += 4) {                   // four rows in flight, accumulated in row order
-        float val[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t r = base + s_rows[min(k0 + j, cnt - 1)];
+      for (int u = 0; u < 4; ++u) {
+        unsigned mm = m[u];
+        while (mm) {
+          const int bit = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const int64_t r = r0 + u * 32 + bit;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const int col = tid + c * 256;
-            val[j][c] = (k0 + j < cnt && col < E) ? __ldg(dy + r * E + col) : 0.f;
-          }
-        }
+            const int col = c * 256 + lane * 8;
+            if (col >= E) break;
+            if ((E & 7) == 0) {                             // the 8 columns are one Philox block of the dense [rows, E] tensor
+              const float4 a = __ldg(reinterpret_cast<const float4*>(dy + r * E + col));
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(dy + r * E + col) + 1);
+              const Philox8 ph = philox8(seed, off, (uint64_t)((r * E + col) >> 3));
+              const float x[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (k0 + j >= cnt) break;
-          const int64_t r = base + s_rows[k0 + j];
+              for (int j = 0; j < 8; ++j)
+                if (philox_keep(ph, j, thr)) acc[c][j] += x[j] * sc;
+            } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int col = tid + c * 256;
-            if (col < E) {
-              const int64_t idx = r * E + col;
-              const Philox8 ph = philox8(seed, off, (uint64_t)(idx >> 3));
-              if (philox_keep(ph, (int)(idx & 7), thr)) acc[c] += val[j][c] * sc;
+              for (int j = 0; j < 8; ++j) {
+                if (col + j < E) {
+                  const int64_t idx = r * E + col + j;
+                  if (philox_keep(philox8(seed, off, (uint64_t)(idx >> 3)), (int)(idx & 7), thr)) acc[c][j] += __ldg(dy + idx) * sc;
+                }
+              }
             }
           }
         }
       }
-      __syncthreads();
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int col = tid + c * 256;
-    if (col < E) d_emb[(size_t)v * E + col] = acc[c];
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[warp][c * 256 + lane * 8 + j] = acc[c][j];
+  __syncthreads();
+  for (int col = tid; col < E; col += 256) {
+    float s_ = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_ += part[w][col];
+    d_emb[(size_t)v * E + col] = s_;
   }
 }
 
