@@ -41,6 +41,9 @@ class TrainStep:
         # the fused rollout's weight-gradient GEMMs run on a side stream under the encoder's backward (agent/fused.py)
         if getattr(agent, "_fused", None) is not None and agent.device.type == "cuda":
             agent._fused.async_wgrad = os.environ.get("VLN_ASYNC_WGRAD", "1") != "0"
+        if agent.device.type == "cuda":           # same for the encoder's leaf gradients (ops._leaf_grads_async)
+            from .. import ops
+            ops.ASYNC_LEAF_GRADS[0] = os.environ.get("VLN_ASYNC_WGRAD", "1") != "0"
 
     def losses(self):
         """Run the rollouts; return (loss to differentiate, per-item loss record or None)."""

@@ -246,6 +246,35 @@ def _tc_matmul_tall(x, hi, lo, N, K, bias=None):
     return out
 
 
+ASYNC_LEAF_GRADS = [False]   # set by TrainStep: leaf (weight) gradients of the encoder on a side stream, into .grad
+_leaf_side = {}
+
+
+def _leaf_grads_async(pairs, keep):
+    """pairs: [(parameter, fn)] — fn() computes that parameter's gradient.  Nothing downstream in the backward pass
+    needs a leaf gradient, so they are computed on a side stream (under the kernels that carry the chain: the BPTT
+    recurrence, the input-gradient GEMM, the embedding backward) and accumulated straight into ``.grad``; the calling
+    stream joins when the backward pass ends.  ``keep`` holds the tensors the side stream reads until then."""
+    main = torch.cuda.current_stream()
+    dev = main.device
+    side = _leaf_side.get(dev)
+    if side is None:
+        side = _leaf_side[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        for q, fn in pairs:
+            q.grad.add_(fn())
+
+    def join():
+        torch.cuda.current_stream().wait_stream(side)
+        keep.clear()
+    torch.autograd.Variable._execution_engine.queue_callback(join)
+
+
+def _async_leaf_ok(*params):
+    return ASYNC_LEAF_GRADS[0] and all(isinstance(q, torch.nn.Parameter) and q.grad is not None for q in params)
+
+
 class _LinearTall(torch.autograd.Function):
     """Tall inputs (encoder input projection [B*L, E], batched critic [T*B, H]) on the same tcgen05 bf16x3
     kernel, forward and input gradient; weight gradient through wgrad().  ``dx_tf32``: the input gradient as a
@@ -259,7 +288,7 @@ class _LinearTall(torch.autograd.Function):
         sw = _split_of(w)
         N, K = w.shape
         ctx.save_for_backward(x, w)
-        ctx.sw, ctx.has_b, ctx.dx_tf32 = sw, b is not None, bool(dx_tf32)
+        ctx.sw, ctx.has_b, ctx.dx_tf32, ctx.w_param = sw, b is not None, bool(dx_tf32), w
         return _tc_matmul_tall(x, sw.hi, sw.lo, N, K, b.detach() if b is not None else None)
 
     @staticmethod
@@ -278,7 +307,12 @@ class _LinearTall(torch.autograd.Function):
                     torch.backends.cuda.matmul.allow_tf32 = prev
             else:
                 dx = _tc_matmul_tall(dy, ctx.sw.hi_t, ctx.sw.lo_t, K, N)
-        dw = wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if _async_leaf_ok(ctx.w_param):
+                _leaf_grads_async([(ctx.w_param, lambda: wgrad(dy, x))], [dy, x])
+            else:
+                dw = wgrad(dy, x)
         db = dy.sum(0) if ctx.has_b and ctx.needs_input_grad[2] else None
         return dx, dw, db, None
 
@@ -535,6 +569,7 @@ class _LstmLayer(torch.autograd.Function):
         _call("vln_lstm_seq_fwd", _ptr_array(xproj), _ptr_array(w_hh), _ptr(lengths), _ptr(out), _ptr_array(acts),
               _ptr_array(cs), _ptr(h_last), _ptr(c_last), B, L, H, n_dir, _stream())
         ctx.n_dir = n_dir
+        ctx.w_params = tuple(tensors[n_dir:2 * n_dir])
         ctx.save_for_backward(lengths, out, *w_hh, *acts, *cs)
         return out, h_last, c_last
 
@@ -552,15 +587,19 @@ class _LstmLayer(torch.autograd.Function):
         d_c = _f32c(d_c) if d_c is not None else None
         _call("vln_lstm_seq_bwd", _ptr_array(w_hh), _ptr(lengths), _ptr_array(acts), _ptr_array(cs), _ptr(d_out),
               _ptr(d_h), _ptr(d_c), _ptr_array(d_x), B, L, H, n, _stream())
-        d_w = []
-        for k in range(n):
+        def dw_of(k):
             hk = out[:, :, k * H:(k + 1) * H]
             hprev = torch.zeros_like(hk)
             if k == 0:
                 hprev[:, 1:] = hk[:, :-1]                       # h_{t-1}; zero initial state
             else:
                 hprev[:, :-1] = hk[:, 1:]                       # reversed direction: the previous step is t+1
-            d_w.append(wgrad(d_x[k].reshape(B * L, H4), hprev.reshape(B * L, H)))
+            return wgrad(d_x[k].reshape(B * L, H4), hprev.reshape(B * L, H))
+        if _async_leaf_ok(*ctx.w_params):
+            _leaf_grads_async([(ctx.w_params[k], (lambda k=k: dw_of(k))) for k in range(n)], [out, d_x])
+            d_w = [None] * n
+        else:
+            d_w = [dw_of(k) for k in range(n)]
         return (None, None, *d_x, *d_w)
 
 
