@@ -342,30 +342,25 @@ lstm_tc_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B,
     }
     __syncthreads();
     TSTAMP(5, tid == 0 && s == 10);
-    // gates + cell update for (row n = warp + 8j, unit lane); new h as bf16 hi / lo into the staging tile
-    float xc[RPT][4];
-#pragma unroll
-    for (int j = 0; j < RPT; ++j)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) xc[j][k] = xp[j][k];
-    load_x(t + dt);                                        // next step's input projection, in flight during the cell update
+    // gates + cell update for (row n = warp + 8j, unit lane); new h as bf16 hi / lo into the staging tile.  What the
+    // peers' next product waits for — the h slices — leaves first; the global stores of this step (out, cs, activated
+    // gates for the backward pass) and the prefetch of the next input projection follow, off the inter-CTA chain.
+    float sv_i[RPT], sv_f[RPT], sv_g[RPT], sv_o[RPT];
+    bool live[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const int n = warp + 8 * j;
       const float* gp = g + n * kGP + lane;
-      const float ig = sigmoidf_(gp[0] + xc[j][0]), fg = sigmoidf_(gp[32] + xc[j][1]), gg = tanhf_(gp[64] + xc[j][2]),
-                  og = sigmoidf_(gp[96] + xc[j][3]);
+      const float ig = sigmoidf_(gp[0] + xp[j][0]), fg = sigmoidf_(gp[32] + xp[j][1]), gg = tanhf_(gp[64] + xp[j][2]),
+                  og = sigmoidf_(gp[96] + xp[j][3]);
       const float c_new = fg * c_reg[j] + ig * gg;
       const float h_new = og * tanhf_(c_new);
-      if (t < s_len[n]) {                                  // rows past their length keep their state, outputs stay zero
+      live[j] = t < s_len[n];                              // rows past their length keep their state, outputs stay zero
+      if (live[j]) {
         c_reg[j] = c_new;
         h_reg[j] = h_new;
-        const size_t o = (size_t)(b0 + n) * L + t;
-        out[o * ld_out + ug] = h_new;
-        cs[o * H + ug] = c_new;
-        float* ap = acts + o * (4 * H) + ug;
-        ap[0] = ig; ap[H] = fg; ap[2 * H] = gg; ap[3 * H] = og;
       }
+      sv_i[j] = ig; sv_f[j] = fg; sv_g[j] = gg; sv_o[j] = og;
       const uint32_t hi16 = bf16_bits(h_reg[j]);
       stage[(0 * NB + n) * kHS + lane] = (uint16_t)hi16;
       stage[(1 * NB + n) * kHS + lane] = (uint16_t)bf16_bits(h_reg[j] - bf16_val(hi16));
@@ -387,6 +382,17 @@ lstm_tc_fwd_kernel(DirF d0, DirF d1, const int32_t* __restrict__ lengths, int B,
       }
     }
     TSTAMP(6, tid == 0 && s == 10);
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      if (live[j]) {
+        const size_t o = (size_t)(b0 + warp + 8 * j) * L + t;
+        out[o * ld_out + ug] = h_reg[j];
+        cs[o * H + ug] = c_reg[j];
+        float* ap = acts + o * (4 * H) + ug;
+        ap[0] = sv_i[j]; ap[H] = sv_f[j]; ap[2 * H] = sv_g[j]; ap[3 * H] = sv_o[j];
+      }
+    }
+    load_x(t + dt);                                        // next step's input projection (consumed after the next product)
     TSTAMP(7, tid == 0 && s == 10);
     // Buffer reuse needs no further barrier: a peer writes h[cur] again only in step s+1, which it enters after
     // it received THIS CTA's slice of step s — sent after this CTA's MMAs of step s (which read h[cur]) completed.
@@ -555,13 +561,16 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
 #pragma unroll
       for (int k = 0; k < 7; ++k) cur[j][k] = pre[j][k];
     load_step(t + dt);
-    // pointwise gradient for (row n = warp + 8j, unit lane); dgates -> d_xproj and, as bf16 hi / lo, the B tiles
+    // pointwise gradient for (row n = warp + 8j, unit lane); dgates as bf16 hi / lo into the B tiles first (the
+    // product waits for them), their global copy (d_xproj) after the product has been issued
+    float dgs[RPT][4];
+    bool live[RPT];
 #pragma unroll
     for (int j = 0; j < RPT; ++j) {
       const int n = warp + 8 * j;
       float dg[4] = {0.f, 0.f, 0.f, 0.f};
-      if (t < s_len[n]) {
-        const size_t o = (size_t)(b0 + n) * L + t;
+      live[j] = t < s_len[n];
+      if (live[j]) {
         const float ig = cur[j][0], fg = cur[j][1], gg = cur[j][2], og = cur[j][3];
         const float c1 = cur[j][4], c0 = cur[j][5];
         const float dht = dh[j] + cur[j][6];
@@ -572,9 +581,9 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
         dg[2] = dct * ig * (1.f - gg * gg);
         dg[3] = dht * tc * og * (1.f - og);
         dc[j] = dct * fg;
-        float* dp = d_xproj + o * (4 * H) + ug;
-        dp[0] = dg[0]; dp[H] = dg[1]; dp[2 * H] = dg[2]; dp[3 * H] = dg[3];
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dgs[j][k] = dg[k];
       if (more) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -587,7 +596,19 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
         }
       }
     }
-    if (!more) break;
+    auto store_dx = [&]() {
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        if (live[j]) {
+          float* dp = d_xproj + ((size_t)(b0 + warp + 8 * j) * L + t) * (4 * H) + ug;
+          dp[0] = dgs[j][0]; dp[H] = dgs[j][1]; dp[2 * H] = dgs[j][2]; dp[3 * H] = dgs[j][3];
+        }
+      }
+    };
+    if (!more) {
+      store_dx();
+      break;
+    }
     fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -613,6 +634,7 @@ lstm_tc_bwd_kernel(DirB d0, DirB d1, const int32_t* __restrict__ lengths, int B,
       umma_commit(bar_acc);
     }
     __syncwarp();
+    store_dx();                       // under the tensor-core product
     {
       // reduce-scatter: TMEM lane = column k of M-tile mt -> owner CTA k / 32, slot [my rank][n / 4][k % 32][n % 4]
       const int qq = warp & 3;
