@@ -382,3 +382,26 @@ def test_naive_curriculum_monitor_trainer_end_to_end():
     assert seen == [envs["round_1"], envs["round_2"], envs["round_3"]]
     assert all(np.isfinite(h["loss_sum"]) for h in trainer.history)
     assert max(_rel(a, b) for a, b in zip(agent.trainable_params(), p0)) > 1e-4
+
+
+def test_bench_cuda_arm_prints_the_contract_line():
+    """`bench.py` (small world, 2 steps): one JSON line with the contract's keys, device-side launches counted,
+    an end-to-end block with per-step H2D/D2H bytes, the clocks sample and the panorama-attention roofline."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--small", "--steps", "2", "--warmup", "3",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["value"] > 0
+    assert d["gpu_launches"] > 100 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
