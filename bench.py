@@ -152,6 +152,7 @@ def roofline_pano(store, ops, torch, B, split, peaks):
     return {"bound": "hbm", "kernel": "pano_attn fwd (fused gather + feature dropout + 36-view soft-dot attention)",
             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback",
+            "peak_spec": 8000.0, "frac_of_spec": round(achieved / 8000.0, 4),      # both denominators
             "us_per_launch": round(t * 1e6, 2), "episodes_per_launch": B, "split": split, "traffic": None,
             "note": "B=64 episodes per launch is the north-star shape: 9.4 MB per launch = 1.4 us at peak, so the launch is latency-bound; tools/microbench.py sweeps B up to 2048"}
 
