@@ -157,6 +157,62 @@ def roofline_pano(store, ops, torch, B, split, peaks):
             "note": "B=64 episodes per launch is the north-star shape: 9.4 MB per launch = 1.4 us at peak, so the launch is latency-bound; tools/microbench.py sweeps B up to 2048"}
 
 
+def roofline_others(ops, torch, B, peaks):
+    """The other kernel families of the iteration, each timed alone in bench.py (CUDA graph of 16 back-to-back
+    launches, CUDA events): the gates GEMM — the largest of the skinny tcgen05 linears that take a third of the
+    iteration — against the tensor peak and as streamed weight bytes (L2-resident: 22.5 MB of bf16 hi+lo per launch),
+    and the encoder recurrence (tcgen05, W_hh in tensor memory) as time per step of its 80-step latency chain."""
+    from clvln_b200.agent.fused import _gemm, _p
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = []
+
+    def time_graph(fn, n_in=16, reps=10):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n_in):
+                fn()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / (reps * n_in)
+
+    N, K = 2048, 2752
+    w = torch.randn(N, K, device=dev) * 0.02
+    sw = ops._SplitWeight(w).fresh(w)
+    x = torch.randn(B, K, device=dev)
+    y = torch.zeros(B, N, device=dev)
+    t = time_graph(lambda: _gemm(sw.hi, sw.lo, N, K, _p(x), K, B, None, _p(y), N))
+    tf = 3 * 2 * B * N * K / t / 1e12
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1350.0)))
+    out.append({"kernel": "linear_bf16x3 (LSTMCell gates, %dx%dx%d, bf16x3 = 3 MMAs per product)" % (N, K, B), "bound": "l2",
+                "us_per_launch": round(t * 1e6, 2), "weight_GBs_from_l2": round(N * K * 4 / t / 1e9, 1),
+                "achieved_tflops": round(tf, 1), "peak_tflops": peak_tf, "tensor_frac": round(tf / peak_tf, 4),
+                "note": "skinny (M = batch): bound by streaming the L2-resident weights (+ the activation tile every N-tile CTA re-reads), not by the tensor pipe"})
+    L, H = 80, 256
+    xproj = [torch.randn(B, L, 4 * H, device=dev) * 0.1 for _ in range(2)]
+    whh = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
+    lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
+    t = time_graph(lambda: ops.lstm_layer(xproj, whh, lengths), n_in=4, reps=5)
+    tf = 2 * 3 * 2 * B * L * 4 * H * H / t / 1e12
+    out.append({"kernel": "lstm_tc_fwd (encoder BiLSTM recurrence, B=%d, L=%d, H=%d per direction)" % (B, L, H), "bound": "latency",
+                "us_per_launch": round(t * 1e6, 1), "us_per_timestep": round(t * 1e6 / L, 3),
+                "achieved_tflops": round(tf, 2), "peak_tflops": peak_tf, "tensor_frac": round(tf / peak_tf, 5),
+                "note": "80 serial steps; per step and CTA 48 tcgen05.mma of 128x16x16 (8 cycles each) inside a ~2 900-cycle exchange / gate-math chain"})
+    return out
+
+
 def ncu_traffic(csv_name):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed `ncu --set full` capture
     (profiles/, trimmed by tools/ncu_trim.py); None when the capture is not there."""
@@ -446,6 +502,8 @@ def run_b200(args):
         out["roofline"]["sweep"] = [
             {k: r[k] for k in ("episodes_per_launch", "us_per_launch", "achieved", "frac")}
             for r in (roofline_pano(store, ops, torch, b, 1, peaks) for b in (256, 1024, 2048))]
+        if world_size == 1:
+            out["roofline"]["others"] = roofline_others(ops, torch, args.batch, peaks)
         if world_size == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             from clvln_b200.environ import make_world, make_items
