@@ -1,7 +1,7 @@
 #!/bin/bash
 # 1 -> 8 GPU weak-scaling lines of bench.py on one box + the reference arm with per-op host times
 O=gpurun_out; mkdir -p $O
-python bench.py --impl reference --steps 5 --warmup 1 --per-op 2> $O/ref.err | grep '^{' > $O/scale_ref.json; echo "reference rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 --per-op 2> $O/ref.err | grep '^{' > $O/scale_ref.json; echo "reference rc=$?"
 python bench.py --gpus 1 --steps 20 --warmup 5 2> $O/scale_1.err | grep '^{' > $O/scale_1.json; echo "N=1 rc=$?"
 for N in 2 4 8; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) \
