@@ -27,6 +27,11 @@ def test_cabi_library_exports_every_declared_symbol():
     assert declared == set(_lib.exported_symbols()), sorted(declared ^ set(_lib.exported_symbols()))
     L = _lib.lib()                                   # loads without a GPU; no compute calls here
     assert L.vln_version() >= 100
+    # the ctypes signatures follow the header: same number of parameters for every entry point
+    for name, params in re.findall(r"\b(vln_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib._SIGS[name][0]), (name, n, len(_lib._SIGS[name][0]))
 
 
 def _world(n_items=60, seed=3):
