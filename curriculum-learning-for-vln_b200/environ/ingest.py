@@ -25,7 +25,6 @@ R2RBatch, the agents) is unchanged.  Formats and the reference code that defines
 import base64
 import csv
 import json
-import math
 import os
 import re
 import string
@@ -34,7 +33,7 @@ import sys
 import numpy as np
 import torch
 
-from .world import CMAX, IMG_DIM, N_VIEWS, World
+from .world import CMAX, IMG_DIM, N_VIEWS, World, heading_to_view
 
 TSV_FIELDS = ["scanId", "viewpointId", "image_w", "image_h", "vfov", "features"]
 IMAGE_W, IMAGE_H, VFOV = 640, 480, 60          # ImageFeatures constants, misc.py:244-250
@@ -294,5 +293,5 @@ def items_from_r2r_json(path, world, tokenizer):
 
 def heading_to_start_view(heading):
     """viewIndex after newEpisode(scan, vp, heading, 0): the simulator snaps the heading to the 30-degree grid
-    on elevation row 1."""
-    return 12 + int(round((heading % (2 * math.pi)) / (math.pi / 6.0))) % 12
+    on elevation row 1; what R2RBatch does with each item's `heading`."""
+    return heading_to_view(heading)
