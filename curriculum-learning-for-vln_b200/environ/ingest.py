@@ -16,9 +16,10 @@ R2RBatch, the agents) is unchanged.  Formats and the reference code that defines
     Matterport simulator per (scan, viewpoint) and keeps, per navigable neighbour, the view with the
     smallest angular distance.  The simulator (MatterSim, C++, not vendored) is the only place that
     geometry is defined, so it is NOT re-derived here: the converter reads a JSON dump of the reference's
-    own `buffered_state_dict` — {"<scan>_<viewpoint>": [{"viewpointId", "pointId", "normalized_heading",
-    "elevation", "idx", "distance"}, ...]} — which `dump_candidates_with_reference` writes by running the
-    reference's make_candidate once over every viewpoint (needs MatterSim; run on the user's side).
+    own `buffered_state_dict`, verbatim (common_env.py:276-281) — {"<scan>_<viewpoint>": [{"scanId",
+    "absViewIndex", "nextViewpointId", "normalized_heading", "loc_elevation", "distance", "idx"}, ...]} — which
+    `dump_candidates_with_reference` writes by running the reference's make_candidate once over every viewpoint
+    (needs MatterSim; run on the user's side).
   * data/R2R_<split>.json + data/train_vocab.txt — episodes and the tokenizer vocabulary
     (load_datasets utils/misc.py:62-69, Tokenizer :91-157, R2RBatch.__init__ common_env.py:121-150).
 """
@@ -159,10 +160,10 @@ def candidates_to_tables(world, cache):
             assert len(cands) <= CMAX, f"{scan}_{vp}: {len(cands)} candidates (table width {CMAX})"
             world.n_cand[o + j] = len(cands)
             for k, c in enumerate(cands):
-                world.cand_vp[o + j, k] = o + local[c["viewpointId"]]
-                world.cand_view[o + j, k] = int(c["pointId"])
+                world.cand_vp[o + j, k] = o + local[c["nextViewpointId"]]
+                world.cand_view[o + j, k] = int(c["absViewIndex"])
                 world.cand_nheading[o + j, k] = float(c["normalized_heading"])
-                world.cand_elev[o + j, k] = float(c["elevation"])
+                world.cand_elev[o + j, k] = float(c["loc_elevation"])
     return world
 
 
@@ -173,9 +174,10 @@ def dump_candidates(world):
         s = int(world.vp_scan[g])
         o = int(world.scan_off[s])
         out[world.long_id(g)] = [
-            {"viewpointId": world.vp_names[s][int(world.cand_vp[g, k]) - o], "pointId": int(world.cand_view[g, k]),
-             "normalized_heading": float(world.cand_nheading[g, k]), "elevation": float(world.cand_elev[g, k]),
-             "idx": k + 1, "distance": 0.0}
+            {"scanId": world.scans[s], "absViewIndex": int(world.cand_view[g, k]),
+             "nextViewpointId": world.vp_names[s][int(world.cand_vp[g, k]) - o],
+             "normalized_heading": float(world.cand_nheading[g, k]), "loc_elevation": float(world.cand_elev[g, k]),
+             "distance": 0.0, "idx": k + 1}
             for k in range(int(world.n_cand[g]))]
     return out
 
@@ -184,13 +186,14 @@ def dump_candidates_with_reference(ref_env, scans_to_viewpoints, path):
     """Run on the user's side, with the reference importable and MatterSim installed: fills the reference
     R2RBatch's `buffered_state_dict` by calling its make_candidate(feature, scan, viewpoint, viewId=0)
     (common_env.py:225-297) for every viewpoint and writes the cache as JSON (features dropped)."""
-    keep = ("viewpointId", "pointId", "normalized_heading", "elevation", "idx", "distance")
+    def plain(v):                       # numpy scalars -> json
+        return v.item() if hasattr(v, "item") else v
     out = {}
     for scan, vps in scans_to_viewpoints.items():
         for vp in vps:
             long_id = f"{scan}_{vp}"
             ref_env.make_candidate(ref_env.env.features[long_id], scan, vp, 0)
-            out[long_id] = [{k: c[k] for k in keep} for c in ref_env.buffered_state_dict[long_id]]
+            out[long_id] = [{k: plain(v) for k, v in c.items()} for c in ref_env.buffered_state_dict[long_id]]
     with open(path, "w") as f:
         json.dump(out, f)
     return out

@@ -111,3 +111,30 @@ long = "walk , " * 100
 a, b = rt.encode_sentence(long), mt.encode_sentence(long)
 assert np.array_equal(a[0], b[0]) and a[1] == b[1] == 80 and b[0][-1] == mt.word_to_index["<EOS>"]
 print(f"tokenizer: {n} instructions encode identically (incl. unknown words and truncation)")
+
+# ---- candidate cache: the REAL R2RBatch.make_candidate (over the table-driven fake simulator) -> dump -> tables ----
+import random  # noqa: E402
+from clvln_b200.environ import make_items, make_world  # noqa: E402
+from oracle import ref_harness as H  # noqa: E402
+
+w = make_world(n_scans=2, seed=9)
+items = make_items(w, 24, seed=9)
+rsrc = H.install(w, {"train": items})
+import src.environ as renv  # noqa: E402
+random.seed(2020)
+ref_env = renv.R2RBatch(H.feature_store(w), batch_size=4, splits=["train"], tokenizer=H.StubTokenizer(items))
+dump = os.path.join(tmp, "cands.json")
+ingest.dump_candidates_with_reference(ref_env, {s: w.vp_names[i] for i, s in enumerate(w.scans)}, dump)
+w2 = make_world(n_scans=2, seed=9, with_table=False)
+for name in ("cand_vp", "cand_view", "cand_nheading", "cand_elev", "n_cand"):
+    getattr(w2, name)[...] = 0                         # wipe, then refill from the reference's cache
+ingest.candidates_to_tables(w2, json.load(open(dump)))
+w2.build_cand_angles()
+assert np.array_equal(w2.n_cand, w.n_cand) and np.array_equal(w2.cand_view, w.cand_view)
+for g in range(w.n_vp):
+    k = int(w.n_cand[g])
+    assert np.array_equal(w2.cand_vp[g, :k], w.cand_vp[g, :k])
+    assert np.allclose(w2.cand_elev[g, :k], w.cand_elev[g, :k], rtol=0, atol=1e-12)
+    assert np.allclose(w2.cand_nheading[g, :k], w.cand_nheading[g, :k], rtol=0, atol=1e-9)
+assert np.abs(w2.cand_ang4 - w.cand_ang4).max() < 1e-6
+print(f"candidate cache: reference make_candidate over {w.n_vp} viewpoints -> dump -> tables identical")
