@@ -36,3 +36,19 @@ def test_ingest_matches_reference_loaders():
 def test_evaluator_matches_reference_evaluation():
     """engine/evaluator.py (nav/oracle error, SPL, nDTW, SDTW, CLS, rates) == src/engine/evaluator.py Evaluation.score."""
     runpy.run_path(os.path.join(HERE, "_ref_check_eval.py"), run_name="__main__")
+
+
+def test_round_sizes_are_the_shipped_clr2r_rounds():
+    """split_rounds' default proportions (synthetic stand-in for the offline CLR2R difficulty split) are the instruction
+    counts of the reference's data/CLR2R/CLR2R_train_round[k]_v3.json files: 1037 / 1415 / 4897 / 4593 / 2097 = 14 039."""
+    import inspect
+    import json
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import split_rounds
+    sizes = inspect.signature(split_rounds).parameters["sizes"].default
+    data_dir = os.path.join(ref_loader.REF_TASK, "data", "CLR2R")
+    counted = []
+    for k in range(1, 6):
+        with open(os.path.join(data_dir, f"CLR2R_train_round[{k}]_v3.json")) as f:
+            counted.append(sum(len(it["instructions"]) for it in json.load(f)))
+    assert tuple(counted) == tuple(sizes) and sum(counted) == 14039
