@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--small", action="store_true", help="tiny world (debug)")
+    ap.add_argument("--lengths", default="80", choices=["80", "real"],
+                    help="instruction lengths: 80 for every row (headline, worst case) or drawn from the real R2R "
+                         "training distribution (mean 31.3; SURVEY 8d's second run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-op", action="store_true",
                     help="with --impl reference: add per-op CPU times (gather, panorama attention, LSTMCell, context "
@@ -53,15 +56,17 @@ def parse():
     return ap.parse_args()
 
 
-def build_world(small, device, with_table=True):
+def build_world(small, device, with_table=True, lengths="80"):
     import clvln_b200  # noqa: F401
     from clvln_b200.environ import make_world, make_items, full_world_sizes
+    from clvln_b200.environ.world import r2r_length_counts
+    kw = dict(fixed_len=80) if lengths == "80" else dict(length_counts=r2r_length_counts())
     if small:
         world = make_world(n_scans=6, seed=2020, device=device, with_table=with_table)
-        items = make_items(world, 2000, seed=2020, fixed_len=80)
+        items = make_items(world, 2000, seed=2020, **kw)
     else:
         world = make_world(sizes=full_world_sizes(), seed=2020, device=device, with_table=with_table)
-        items = make_items(world, 14039, seed=2020, fixed_len=80)
+        items = make_items(world, 14039, seed=2020, **kw)
     return world, items
 
 
@@ -432,7 +437,7 @@ def run_b200(args):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
 
-    world, items = build_world(args.small, dev)
+    world, items = build_world(args.small, dev, lengths=args.lengths)
     cfg = utils.agent_cfg("ENVDROP")
     cfg.TRAIN.BATCH_SIZE = args.batch
     random.seed(2020)
@@ -487,7 +492,8 @@ def run_b200(args):
                    "global_batch": args.batch * world_size, "parallelism": f"dp{world_size}",
                    "table": "%d viewpoints x 36 x 2048 bf16 = %.2f GB in HBM" % (world.n_vp, world.n_vp * 36 * 2048 * 2 / 1e9),
                    "l2": "inputs larger than L2: every step gathers random viewpoints from the %.2f GB table" % (world.n_vp * 36 * 2048 * 2 / 1e9),
-                   "cuda_graph": bool(args.graph)},
+                   "cuda_graph": bool(args.graph),
+                   "instruction_lengths": "80 for every row" if args.lengths == "80" else "real R2R training distribution (mean 31.3)"},
         "e2e": {"value": round(n_ep / t_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(t_e2e / args.steps * 1e3, 3)},
         "gpu_launches": launches, "clocks": clocks,

@@ -296,8 +296,17 @@ def full_world_sizes(seed=2020, n_scans=90, total=10567):
     return sizes
 
 
+def r2r_length_counts():
+    """counts[l] = number of R2R training instructions of encoded length l (0..80): the shipped data/R2R_train.json
+    tokenised with the reference's rules (oracle/make_length_hist.py wrote the file; mean 31.3, 0.6 % at 80)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r2r_train_lengths.json")) as f:
+        return json.load(f)["counts"]
+
+
 def make_items(world, n_items, seed=2020, max_len=80, fixed_len=None, vocab=992,
-               min_nodes=4, max_nodes=7, instr_per_path=1):
+               min_nodes=4, max_nodes=7, instr_per_path=1, length_counts=None):
     """R2R-shaped episodes: shortest path of 4..7 viewpoints, start heading snapped to 30 degrees,
     token ids U{4..vocab-1} framed by <BOS>=3 ... <EOS>=2 and padded with <PAD>=0
     (Tokenizer.encode_sentence, misc.py:139-157)."""
@@ -327,7 +336,12 @@ def make_items(world, n_items, seed=2020, max_len=80, fixed_len=None, vocab=992,
         for j in range(instr_per_path):
             if len(items) >= n_items:
                 break
-            length = fixed_len if fixed_len is not None else min(max_len, max(5, int(rng.gauss(31, 12))))
+            if fixed_len is not None:
+                length = fixed_len
+            elif length_counts is not None:          # the real R2R length distribution
+                length = min(max_len, max(3, rng.choices(range(len(length_counts)), weights=length_counts)[0]))
+            else:
+                length = min(max_len, max(5, int(rng.gauss(31, 12))))
             enc = np.zeros(max_len, np.int64)
             enc[0] = 3
             for k in range(1, length - 1):
