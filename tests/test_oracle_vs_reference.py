@@ -52,3 +52,23 @@ def test_round_sizes_are_the_shipped_clr2r_rounds():
         with open(os.path.join(data_dir, f"CLR2R_train_round[{k}]_v3.json")) as f:
             counted.append(sum(len(it["instructions"]) for it in json.load(f)))
     assert tuple(counted) == tuple(sizes) and sum(counted) == 14039
+
+
+def test_reference_yaml_configs_load_into_the_config_tree():
+    """Every configs/*/*.yaml of the reference merges into utils.get_cfg_defaults() (same keys as src/utils/config.py),
+    and the model node the agents read is there for each."""
+    import glob
+    import clvln_b200  # noqa: F401
+    from clvln_b200 import utils
+    files = sorted(glob.glob(os.path.join(ref_loader.REF_TASK, "configs", "*", "*.yaml")))
+    assert len(files) >= 6
+    seen = set()
+    for f in files:
+        cfg = utils.get_cfg_defaults()
+        cfg.merge_from_file(f)
+        assert cfg.MODEL.NAME in ("ENVDROP", "FOLLOWER", "SELF-MONITOR") and cfg.TRAIN.CLMODE in ("", "NAIVE", "SELF-PACE")
+        node = {"ENVDROP": "ENVDROP", "FOLLOWER": "FOLLOWER", "SELF-MONITOR": "MONITOR"}[cfg.MODEL.NAME]
+        mc = getattr(cfg.MODEL, node)
+        assert mc.HIDDEN_SIZE in (256, 512) and cfg.TRAIN.BATCH_SIZE > 0 and cfg.AGENT.MAX_EPISODE_LEN > 0
+        seen.add((cfg.MODEL.NAME, cfg.TRAIN.CLMODE))
+    assert {n for n, _ in seen} == {"ENVDROP", "FOLLOWER", "SELF-MONITOR"}
