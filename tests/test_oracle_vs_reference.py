@@ -72,3 +72,28 @@ def test_reference_yaml_configs_load_into_the_config_tree():
         assert mc.HIDDEN_SIZE in (256, 512) and cfg.TRAIN.BATCH_SIZE > 0 and cfg.AGENT.MAX_EPISODE_LEN > 0
         seen.add((cfg.MODEL.NAME, cfg.TRAIN.CLMODE))
     assert {n for n, _ in seen} == {"ENVDROP", "FOLLOWER", "SELF-MONITOR"}
+
+
+def test_state_dicts_are_interchangeable_with_the_reference_modules():
+    """Checkpoint compatibility: each of the five modules has exactly the reference module's state_dict keys
+    and shapes, so `load_state_dict(strict=True)` works in both directions (EnvDrop / Follower / Self-Monitor shapes)."""
+    import torch
+    import clvln_b200  # noqa: F401
+    from clvln_b200 import model as M
+    RU, RP = ref_loader.load_ref_models()
+    pairs = [
+        (M.EncoderLSTM(992, 256, 512, 0, 0.5, True, 1), RU.EncoderLSTM(992, 256, 512, 0, 0.5, True, 1)),      # EnvDrop
+        (M.EncoderLSTM(992, 300, 256, 0, 0.5, True, 2), RU.EncoderLSTM(992, 300, 256, 0, 0.5, True, 2)),      # Follower
+        (M.EncoderLSTM(992, 256, 512, 0, 0.5, False, 1), RU.EncoderLSTM(992, 256, 512, 0, 0.5, False, 1)),    # Self-Monitor
+        (M.EnvDropDecoder(512, 0.5, 0.3, 64), RP.EnvDropDecoder(512, 0.5, 0.3, 64)),
+        (M.AttnDecoderLSTM(256, 0.5), RP.AttnDecoderLSTM(256, 0.5)),
+        (M.MonitorDecoder(512, 0.5, 80, [1024]), RP.MonitorDecoder(512, 0.5, 80, [1024])),
+        (M.Critic(512, 0.5), RP.Critic(512, 0.5)),
+    ]
+    for mine, ref in pairs:
+        a, b = mine.state_dict(), ref.state_dict()
+        assert list(a.keys()) == list(b.keys()), (type(mine).__name__, sorted(set(a) ^ set(b)))
+        assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+        mine.load_state_dict(b, strict=True)
+        ref.load_state_dict(mine.state_dict(), strict=True)
+        assert all(torch.equal(mine.state_dict()[k], ref.state_dict()[k]) for k in a)
