@@ -97,3 +97,16 @@ def test_state_dicts_are_interchangeable_with_the_reference_modules():
         mine.load_state_dict(b, strict=True)
         ref.load_state_dict(mine.state_dict(), strict=True)
         assert all(torch.equal(mine.state_dict()[k], ref.state_dict()[k]) for k in a)
+
+
+def test_naive_curriculum_schedule_matches_reference():
+    """NaiveCurriculum.curriculum_strategy (curriculum.py:176-179): same round per epoch as the real class."""
+    import clvln_b200  # noqa: F401
+    from clvln_b200.engine import NaiveCurriculum
+    ref_loader.load_ref_agents()
+    from src.engine.curriculum import NaiveCurriculum as RefNaive
+    envs = {f"round_{k}": k for k in range(1, 6)}
+    for sw in (1, 7, 20):
+        ref, mine = RefNaive(switch_epoch=sw), NaiveCurriculum(switch_epoch=sw)
+        for ep in range(1, 8 * sw + 3):
+            assert mine.curriculum_strategy(envs, ep) == ref.curriculum_strategy(envs, ep)
