@@ -339,7 +339,8 @@ class _LinearLib(torch.autograd.Function):
 def linear(x, w, b=None, acc=None, dx_tf32=False):
     """y = x W^T + b (+ acc) on the tcgen05 bf16x3 kernel (csrc/gemm.cu): split-K skinny launches for at
     most 128 rows, 128x128 output blocks for taller inputs (encoder input projection, batched critic)."""
-    ok = (USE_TC_LINEAR[0] and x.is_cuda and x.dim() == 2 and w.shape[1] % 64 == 0 and w.shape[0] % 4 == 0
+    assert x.is_cuda, "ops.linear runs on the GPU only (there is no CPU path in this package)"
+    ok = (USE_TC_LINEAR[0] and x.dim() == 2 and w.shape[1] % 64 == 0 and w.shape[0] % 4 == 0
           and x.dtype == torch.float32)
     if ok and x.shape[0] <= 128:
         return _LinearTC.apply(x, w, b, acc)
