@@ -405,3 +405,39 @@ def test_bench_cuda_arm_prints_the_contract_line():
     assert d["gpu_launches"] > 100 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+
+
+def test_eval_loop_results_and_checkpoint_round_trip(tmp_path):
+    """The rest of the agent protocol main.py / the trainers use (base.py:63-112, envdrop.py:298-313): `test()` rolls the
+    validation env out with argmax actions until an instruction repeats, `get_results()` / `write_results()` hold one
+    trajectory per instr_id (starting at the episode's start viewpoint), the evaluator scores them, and
+    save_model -> load_model into a fresh agent reproduces the same trajectories."""
+    import json
+    from clvln_b200 import utils
+    from clvln_b200.agent import build_agent
+    from clvln_b200.engine import evaluate
+    agent, pag, env, penv, sds, cfg = _setup("ENVDROP", B=8, n_items=20)
+    agent.results_save_dir = str(tmp_path)
+    agent.eval()
+    agent.test(iters=None, feedback="argmax")
+    res = agent.get_results()
+    ids = [r["instr_id"] for r in res]
+    assert sorted(ids) == sorted(it["instr_id"] for it in env.data) and len(set(ids)) == len(ids)
+    start = {it["instr_id"]: it["path"][0] for it in env.data}
+    assert all(r["trajectory"][0][0] == start[r["instr_id"]] for r in res)
+    scores = evaluate(env, res)
+    for k in ("nav_error", "oracle_error", "steps", "lengths", "spl", "ndtw", "sdtw", "cls", "success_rate", "oracle_rate"):
+        assert np.isfinite(scores[k]), k
+    agent.write_results("val")
+    assert len(json.load(open(tmp_path / "val.json"))) == len(res)
+    ckpt = str(tmp_path / "ckpt.pt")
+    agent.save_model(ckpt, cfg=cfg, last_epoch=3)
+    torch.manual_seed(7)                                             # different init: the checkpoint must overwrite it
+    other = build_agent(cfg, utils.StubTokenizer(), agent.device)
+    meta = other.load_model(ckpt)
+    assert meta["last_epoch"] == 3 and set(meta) >= {"encoder_state_dict", "decoder_state_dict", "critic_state_dict"}
+    other.env = env
+    other.eval()
+    other.test(iters=None, feedback="argmax")
+    again = {r["instr_id"]: r["trajectory"] for r in other.get_results()}
+    assert all([tuple(p) for p in again[r["instr_id"]]] == [tuple(p) for p in r["trajectory"]] for r in res)
