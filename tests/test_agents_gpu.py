@@ -441,3 +441,34 @@ def test_eval_loop_results_and_checkpoint_round_trip(tmp_path):
     other.test(iters=None, feedback="argmax")
     again = {r["instr_id"]: r["trajectory"] for r in other.get_results()}
     assert all([tuple(p) for p in again[r["instr_id"]]] == [tuple(p) for p in r["trajectory"]] for r in res)
+
+
+def test_classic_trainer_with_validation_and_checkpoints(tmp_path):
+    """ClassicTrainer.train with a validation env and the evaluator (trainer.py:481-511): every EVAL_INTERVAL epochs the
+    agent is tested with argmax actions, scored, and the best / latest checkpoints are written the way the reference names
+    them; a run resumed from `latest` starts at last_epoch + 1 (trainer.py:378)."""
+    import os
+    from clvln_b200.engine import build_trainer, evaluate
+    from clvln_b200.environ import R2RBatch
+    world, rounds, cfg, agent, dev = _cl_setup("ENVDROP", B=8, n_items=60)
+    items = [it for k in range(1, 6) for it in rounds[k]]
+    random.seed(2020)
+    train_env = R2RBatch(world, items[:40], batch_size=8, device=dev)
+    val_env = R2RBatch(world, items[40:], batch_size=8, name="val_seen", device=dev)
+    cfg.TRAIN.MAX_EPOCH, cfg.TRAIN.ITER_PER_EPOCH, cfg.TRAIN.EVAL_INTERVAL = 2, 2, 1
+    cfg.OUTPUT.CKPT_DIR = str(tmp_path)
+    trainer = build_trainer(cfg, train_env, dev)
+    trainer.train(cfg, agent, None, train_env, {"val_seen": val_env}, evaluator=evaluate, log=lambda *_: None)
+    assert len(trainer.history) == 2 and all("val_seen" in h and 0.0 <= h["val_seen"]["success_rate"] <= 1.0 for h in trainer.history)
+    files = os.listdir(tmp_path)
+    latest = [f for f in files if f.startswith("latest_avgloss:")]
+    assert len(latest) == 1
+    assert all(np.isfinite(h["loss_avg"]) for h in trainer.history)
+    ckpt = torch.load(os.path.join(tmp_path, latest[0]), map_location="cpu", weights_only=False)
+    assert ckpt["last_epoch"] == 2 and "critic_state_dict" in ckpt
+    # resume: two more epochs start at epoch 3
+    cfg.OUTPUT.RESUME = latest[0][:-3]
+    cfg.TRAIN.MAX_EPOCH = 4
+    trainer2 = build_trainer(cfg, train_env, dev)
+    trainer2.train(cfg, agent, None, train_env, None, log=lambda *_: None)
+    assert [h["epoch"] for h in trainer2.history] == [3, 4]
