@@ -39,6 +39,11 @@ class GraphedTrainStep(TrainStep):
         # minibatches is unchanged; callers switch it off for the last iteration before they touch the env / the
         # global `random` stream themselves (epoch end: evaluation, curriculum round switch).
         self.prefetch_next = False
+        # warm-up iterations run on a side stream and the capture on its own: the AccumulateGrad nodes of the (persistent)
+        # parameters then see a different stream than the one they were created on; intended here, so silence the notice
+        fn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if fn is not None:
+            fn(False)
 
     def _body(self):
         self.opt.zero_grad()
