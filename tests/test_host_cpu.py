@@ -291,3 +291,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0 and "workload" in d["config"]
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package (or tools/, except nothing) may import it;
+    only tests/, __graft_entry__.smoke() and bench.py's CPU legs do."""
+    offenders = []
+    for top in ("curriculum-learning-for-vln_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for fn in files:
+                if fn.endswith(".py"):
+                    src = open(os.path.join(dirpath, fn)).read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                        offenders.append(os.path.join(dirpath, fn))
+    assert offenders == [], offenders
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    build_src = entry[entry.index("def build()"):entry.index("def smoke()")]
+    assert not re.search(r"(from|import)\s+oracle\b", build_src)          # build() compiles and imports the product only
