@@ -90,7 +90,11 @@ class BaseAgent:
         for m in self._modules():
             m.to(self.device)
         if self.device.type == "cuda":
-            self.rng = ops.Rng(2020, self.device)
+            # data parallel: every replica draws its own dropout masks / action samples (rank folded into the Philox
+            # seed); rank 0 keeps the single-GPU stream
+            import torch.distributed as dist
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+            self.rng = ops.Rng(2020 + 7919 * rank, self.device)
             for m in self._modules():
                 U.use_rng(m, self.rng)
 

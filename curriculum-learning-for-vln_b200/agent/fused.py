@@ -311,6 +311,8 @@ class _Rollout(torch.autograd.Function):
         if bootstrap:                                           # envdrop.py:225-237: h_1 of the state after the last step
             visual_and_lstm(n, False, q_done=paired and n > 0)
         st.teacher = TEACH[n]
+        # kept alive for inspection (tests read a CUDA-graph replay's logits / actions from these static buffers)
+        fd.last = dict(LOGIT=LOGIT, ACTION=ACTION, TEACH=TEACH, n=n)
 
         fctx.fd, fctx.st, fctx.rp, fctx.MB, fctx.bwd_bufs = fd, st, rp, MB, bb_
         fctx.cfg = (n, B, L, H, p, pf, split, offs, B_main, T_pair)

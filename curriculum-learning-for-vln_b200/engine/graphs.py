@@ -93,12 +93,25 @@ class GraphedTrainStep(TrainStep):
                 # re-derive every cached bf16 weight split, so the split kernels are part of the graph
                 ops.WEIGHT_EPOCH[0] += 1
                 c0 = ops.CALLS[0]
+                logs = getattr(ag, "logs", None)
+                n_log = {k: len(v) for k, v in logs.items()} if logs is not None else {}
                 with torch.cuda.graph(g):
                     loss, item = self._body()
-                self.graphs[key] = (g, loss, item, ops.CALLS[0] - c0)
-            g, loss, item, n_calls = self.graphs[key]
+                # device scalars the rollout appended to agent.logs (entropy / critic_loss / total, envdrop.py:193,257,
+                # 262): static outputs of the graph — every replay appends a copy, the capture's own entries go
+                stat = {}
+                if logs is not None:
+                    for k, v in logs.items():
+                        new = v[n_log.get(k, 0):]
+                        if new and all(torch.is_tensor(x) for x in new):
+                            stat[k] = list(new)
+                        del v[n_log.get(k, 0):]
+                self.graphs[key] = (g, loss, item, ops.CALLS[0] - c0, stat)
+            g, loss, item, n_calls, stat = self.graphs[key]
             g.replay()
             ops.CALLS[0] += n_calls
+            for k, refs in stat.items():
+                ag.logs[k] += [x.clone() for x in refs]
         finally:
             ag.env = env
             ag.sync_every = saved
@@ -107,4 +120,6 @@ class GraphedTrainStep(TrainStep):
             self.weights.record(st.index, item)
         if self.prefetch_next and not env._staged:
             env.prefetch(1, full_length=self.full_length)
-        return loss
+        # `loss` is the graph's static output buffer: hand out a copy, so that values kept across iterations (the
+        # trainers stack an epoch's losses and read them back once) are not overwritten by the next replay
+        return loss.clone()

@@ -20,6 +20,10 @@ import torch.distributed as dist
 from .. import ops
 
 KIND = {"rmsprop": 0, "adam": 1}
+# TRAIN.OPTIM as the reference reads it (trainer.py:17-21,65: optim_switcher.get(OPTIM, Adam) with the keys "adam",
+# "rms", "sgd"; the shipped EnvDrop YAMLs say "rms").  "rmsprop" is accepted as a spelling of "rms"; "sgd" has no
+# fused kernel here and is refused rather than silently replaced by another optimiser.
+OPTIM_NAMES = {"rms": "rmsprop", "rmsprop": "rmsprop", "adam": "adam", "": "adam"}
 
 
 class FlatOptimizer:
@@ -101,7 +105,10 @@ def build_optimizer(cfg, agent, process_group=None):
     """The reference's optimiser choice per agent: EnvDrop — one optimiser over encoder + decoder +
     critic with the encoder and decoder clipped to 40 separately (trainer.py:380-381, 423-427);
     Follower / Self-Monitor — Adam/RMSprop without clipping (trainer.py:66-67, 220)."""
-    kind = cfg.TRAIN.OPTIM if cfg.TRAIN.OPTIM in KIND else "adam"
+    name = str(cfg.TRAIN.OPTIM).lower()
+    if name not in OPTIM_NAMES:
+        raise NotImplementedError(f"TRAIN.OPTIM={cfg.TRAIN.OPTIM!r}: the fused update implements 'rms' (RMSprop) and 'adam'")
+    kind = OPTIM_NAMES[name]
     groups = [[p for p in m.parameters() if p.requires_grad] for m in agent._modules()]
     if cfg.MODEL.NAME == "ENVDROP":
         max_norms = [40.0, 40.0, 0.0]

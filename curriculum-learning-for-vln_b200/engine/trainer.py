@@ -114,7 +114,14 @@ class ClassicTrainer:
         pass
 
     def train(self, cfg, agent, tsboard_dir, train_env, valid_env, evaluator=None, log=print):
+        """``trainer.train(cfg, agent, cfg.OUTPUT.TSBOARD_DIR, train_env, valid_env)`` exactly as main.py:125 calls it:
+        with validation envs and no ``evaluator`` the reference's own scoring (Evaluation(...).score of
+        trainer.py:69-76, 481-511; engine/evaluator.py here) runs every EVAL_INTERVAL epochs and the best / latest
+        checkpoints are written under OUTPUT.CKPT_DIR."""
         tc = cfg.TRAIN
+        if valid_env and evaluator is None:
+            from .evaluator import evaluate as evaluator
+        rank0 = not _is_dist() or dist.get_rank() == 0
         start = tc.START_EPOCH
         if cfg.OUTPUT.RESUME:
             ckpt = agent.load_model(os.path.join(cfg.OUTPUT.CKPT_DIR, f"{cfg.OUTPUT.RESUME}.pt"))
@@ -149,20 +156,26 @@ class ClassicTrainer:
                 agent.eval()
                 for key, env in valid_env.items():
                     agent.env = env
-                    agent.test(iters=None, feedback="argmax")
+                    # data parallel: every rank scores the WHOLE split (an unsharded view of its env), so all ranks
+                    # consume the shared `random` stream identically, agree on `best`, and only rank 0 writes files
+                    with _unsharded(env):
+                        agent.test(iters=None, feedback="argmax")
                     scores = evaluator(env, agent.get_results())
                     info[key] = scores
                     if scores["success_rate"] > best.get(key, 0.0) and cfg.OUTPUT.CKPT_DIR:
                         best[key] = scores["success_rate"]
-                        _clean_dir(cfg.OUTPUT.CKPT_DIR, f"best_{key}")
-                        agent.save_model(os.path.join(cfg.OUTPUT.CKPT_DIR,
-                                                      "best_{}_SR:{:.4f}.pt".format(key, scores["success_rate"])),
-                                         cfg=cfg, last_epoch=ep)
+                        if rank0:
+                            _clean_dir(cfg.OUTPUT.CKPT_DIR, f"best_{key}")
+                            agent.save_model(os.path.join(cfg.OUTPUT.CKPT_DIR,
+                                                          "best_{}_SR:{:.4f}.pt".format(key, scores["success_rate"])),
+                                             cfg=cfg, last_epoch=ep)
             self.after_epoch(ep, step)
-            if cfg.OUTPUT.CKPT_DIR and (not _is_dist() or dist.get_rank() == 0):
+            if cfg.OUTPUT.CKPT_DIR and rank0:
                 _clean_dir(cfg.OUTPUT.CKPT_DIR, "latest_avgloss")
                 agent.save_model(os.path.join(cfg.OUTPUT.CKPT_DIR, "latest_avgloss:{:.4f}.pt".format(info["loss_avg"])),
                                  cfg=cfg, last_epoch=ep)
+            if cfg.OUTPUT.CKPT_DIR and _is_dist():
+                dist.barrier()                      # nobody races ahead of rank 0's checkpoint files
             history.append(info)
             log(f"\t Epoch [{ep}/{tc.MAX_EPOCH}] loss sum {info['loss_sum']:.4f} avg {info['loss_avg']:.4f} "
                 f"min {info['loss_min']:.4f} max {info['loss_max']:.4f} ({info['minutes']:.2f} min)")
@@ -269,6 +282,25 @@ def build_trainer(cfg, train_env, device):
         return SelfPacedCurriculum(train_env, device, pace_func=sp.FUNC, init_lamb=sp.LAMB, init_weight_ctrl=sp.WCTRL,
                                    miu=sp.MIU, interval=sp.INTERVAL, strategy=sp.STRATEGY, burn_in=sp.BURN_IN)
     return ClassicTrainer()
+
+
+class _unsharded:
+    """Temporarily make a data-parallel env hand out whole (world_size = 1) minibatches."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def __enter__(self):
+        e = self.env
+        self.saved = (getattr(e, "rank", 0), getattr(e, "world_size", 1))
+        if self.saved[1] > 1:
+            e.rank, e.world_size = 0, 1
+        return e
+
+    def __exit__(self, *exc):
+        if self.saved[1] > 1:
+            self.env.rank, self.env.world_size = self.saved
+        return False
 
 
 def _clean_dir(save_dir, key):

@@ -92,7 +92,7 @@ def agent_cfg(name, **over):
         cfg.MODEL.ENVDROP.merge_from_other(dict(WORD_EMB_SIZE=256, ACT_EMB_SIZE=64, HIDDEN_SIZE=512, DROP_RATE=0.5,
                                                 FEAT_DROP_RATE=0.3, ENC_BIDIRECTION=True, ENC_LAYERS=1,
                                                 ML_WEIGHT=0.2, GAMMA=0.9, RL_NORMALIZE="total"))
-        cfg.TRAIN.OPTIM, cfg.AGENT.MAX_EPISODE_LEN = "rmsprop", 35
+        cfg.TRAIN.OPTIM, cfg.AGENT.MAX_EPISODE_LEN = "rms", 35      # configs/envdrop/envdrop_config.yaml:18
     elif name == "FOLLOWER":
         cfg.MODEL.NAME = "FOLLOWER"
         cfg.MODEL.FOLLOWER.merge_from_other(dict(WORD_EMB_SIZE=300, HIDDEN_SIZE=256, DROP_RATE=0.5,
