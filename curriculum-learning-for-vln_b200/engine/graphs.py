@@ -106,10 +106,16 @@ class GraphedTrainStep(TrainStep):
                         if new and all(torch.is_tensor(x) for x in new):
                             stat[k] = list(new)
                         del v[n_log.get(k, 0):]
-                self.graphs[key] = (g, loss, item, ops.CALLS[0] - c0, stat)
-            g, loss, item, n_calls, stat = self.graphs[key]
+                # the rollout state / batch objects of THIS graph (static buffers the replay rewrites)
+                refs = (getattr(ag, "last_state", None), getattr(ag, "last_batch", None),
+                        getattr(getattr(ag, "_fused", None), "last", None))
+                self.graphs[key] = (g, loss, item, ops.CALLS[0] - c0, stat, refs)
+            g, loss, item, n_calls, stat, refs = self.graphs[key]
             g.replay()
             ops.CALLS[0] += n_calls
+            ag.last_state, ag.last_batch = refs[0], refs[1]
+            if getattr(ag, "_fused", None) is not None:
+                ag._fused.last = refs[2]
             for k, refs in stat.items():
                 ag.logs[k] += [x.clone() for x in refs]
         finally:
