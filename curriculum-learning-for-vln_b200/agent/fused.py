@@ -32,6 +32,8 @@ from ..ops import _call, _ptr, _stream
 
 H_ACT = 64
 FUSE_TAIL = [__import__("os").environ.get("VLN_FUSE_TAIL", "1") != "0"]   # candidate logits + policy/env/act as one launch
+# LSTM pointwise + text attention as one launch per step, linear_in folded into the context (csrc/ctx_step.cu)
+CTX_STEP = [__import__("os").environ.get("VLN_CTX_STEP", "1") != "0"]
 
 
 def _p(t, off=0):
@@ -247,7 +249,12 @@ class _Rollout(torch.autograd.Function):
             _call("vln_envdrop_act_fwd", _ptr(st.view[t]), _ptr(store.pose4), _ptr(w_act), _ptr(b_act), _ptr(ACT[t]),
                   _ptr(XH[t]), KX, rows(t), H_ACT, p, rp, offs[t]["act"], _stream())
 
-        def visual_and_lstm(t, need_drop, q_done=False):
+        # text-attention stage as one launch (csrc/ctx_step.cu): CW = ctx W_in once per rollout replaces the per-step
+        # query projection tq = W_in drop(h_1)  (logit_l = ctx_l . tq = CW_l . drop(h_1))
+        use_cs = CTX_STEP[0] and H == 512 and L <= 80
+        CW = ops._tc_matmul_tall(ctx.view(B * L, H), s_tin.hi_t, s_tin.lo_t, H, H).view(B, L, H) if use_cs else None
+
+        def visual_and_lstm(t, need_drop, q_done=False, pointwise=True):
             Bt = rows(t)
             if not q_done:
                 _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, Bt, None, _p(Q[t]), F)
@@ -255,6 +262,8 @@ class _Rollout(torch.autograd.Function):
                   _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, Bt, 0, pf, rp, offs[t]["img"],
                   _ptr(MB[t]) if MB is not None else None, split, _stream())
             _gemm(s_cat.hi, s_cat.lo, G4, KX, _p(XH[t]), KX, Bt, _ptr(bsum), _p(GATES[t]), G4)
+            if not pointwise:
+                return
             _call("vln_lstm_pointwise_drop_fwd", _ptr(GATES[t]), _ptr(CS[t]), _ptr(H1[t]), _ptr(CS[t + 1]),
                   _ptr(ACTS[t]), _p(WH[t], H) if need_drop else None, 2 * H, Bt, H, p, rp, offs[t]["h1"], _stream())
 
@@ -265,10 +274,15 @@ class _Rollout(torch.autograd.Function):
         paired = B <= 128
         for t in range(T):
             Bt = rows(t)
-            visual_and_lstm(t, True, q_done=paired and t > 0)
-            _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, Bt, None, _p(TQ[t]), H)
-            _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, Bt, L,
-                  H, 1 if t > 0 else 0, _stream())
+            visual_and_lstm(t, True, q_done=paired and t > 0, pointwise=not use_cs)
+            if use_cs:
+                _call("vln_envdrop_ctx_step_fwd", _ptr(GATES[t]), _ptr(CS[t]), _ptr(H1[t]), _ptr(CS[t + 1]), _ptr(ACTS[t]),
+                      _ptr(WH[t]), 2 * H, _ptr(ctx), _ptr(CW), _ptr(lengths), _ptr(ATTC[t]), Bt, L, H, p, rp,
+                      offs[t]["h1"], 1 if t > 0 else 0, _stream())
+            else:
+                _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, Bt, None, _p(TQ[t]), H)
+                _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, Bt,
+                      L, H, 1 if t > 0 else 0, _stream())
             _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, Bt, None, _p(PRE[t]), H)
             more = t + 1 < S
             _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
@@ -315,9 +329,10 @@ class _Rollout(torch.autograd.Function):
         fd.last = dict(LOGIT=LOGIT, ACTION=ACTION, TEACH=TEACH, n=n)
 
         fctx.fd, fctx.st, fctx.rp, fctx.MB, fctx.bwd_bufs = fd, st, rp, MB, bb_
-        fctx.cfg = (n, B, L, H, p, pf, split, offs, B_main, T_pair)
+        fctx.cfg = (n, B, L, H, p, pf, split, offs, B_main, T_pair, use_cs)
         fctx.splits = (s_cat, s_vin, s_tin, s_out, s_cand)
-        fctx.save_for_backward(ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH)
+        fctx.save_for_backward(ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, CW if use_cs else TQ, PROBS, ENT,
+                               ACTION, TEACH)
         outs = (CE[:n], LOGP[:n], ENT[:n], H1[:n], LOGIT[:n], ACTION[:n], TEACH[:n], REWARD[:n], MASK[:n],
                 H1[n].clone() if bootstrap else H1[:0].clone())
         fctx.mark_non_differentiable(*outs[4:])
@@ -326,7 +341,8 @@ class _Rollout(torch.autograd.Function):
     @staticmethod
     def backward(fctx, d_ce, d_logp, d_ent, d_h1, *_unused):
         ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH = fctx.saved_tensors
-        n, B, L, H, p, pf, split, offs, B_main, T_pair = fctx.cfg
+        n, B, L, H, p, pf, split, offs, B_main, T_pair, use_cs = fctx.cfg
+        CW = TQ                                                 # (the saved slot holds CW = ctx W_in with use_cs)
 
         def rows(t):
             return B if t < T_pair else B_main
@@ -358,12 +374,18 @@ class _Rollout(torch.autograd.Function):
                   None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), Bt, H, p, rp,
                   0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
             _gemm(s_out.hi_t, s_out.lo_t, 2 * H, H, _p(DPRE[t]), H, Bt, None, _p(DWH[t]), 2 * H)
-            _call("vln_ctx_attn_bwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H, None,
-                  _ptr(DTQ[t]), None, _ptr(DLC[t]), Bt, L, H, 1, _stream())
-            _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, Bt, None, _p(DWH[t], H), 2 * H, accumulate=1)
-            _call("vln_lstm_pointwise_drop_bwd", _ptr(ACTS[t]), _ptr(CS[t]), _ptr(CS[t + 1]), _p(DWH[t], H), 2 * H,
-                  _ptr(d_h1[t]) if d_h1 is not None else None, None if last else _ptr(DC[(t + 1) & 1]),
-                  _ptr(DGATES[t]), _ptr(DC[t & 1]), Bt, H, p, rp, offs[t]["h1"], _stream())
+            if use_cs:      # text attention backward + d drop(h_1) += sum_l dlogit_l CW_l + LSTM pointwise backward: one launch
+                _call("vln_envdrop_ctx_step_bwd", _ptr(ctx), _ptr(CW), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H,
+                      _ptr(DLC[t]), _ptr(ACTS[t]), _ptr(CS[t]), _ptr(CS[t + 1]),
+                      _ptr(d_h1[t]) if d_h1 is not None else None, None if last else _ptr(DC[(t + 1) & 1]),
+                      _ptr(DGATES[t]), _ptr(DC[t & 1]), Bt, L, H, p, rp, offs[t]["h1"], _stream())
+            else:
+                _call("vln_ctx_attn_bwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H, None,
+                      _ptr(DTQ[t]), None, _ptr(DLC[t]), Bt, L, H, 1, _stream())
+                _gemm(s_tin.hi_t, s_tin.lo_t, H, H, _p(DTQ[t]), H, Bt, None, _p(DWH[t], H), 2 * H, accumulate=1)
+                _call("vln_lstm_pointwise_drop_bwd", _ptr(ACTS[t]), _ptr(CS[t]), _ptr(CS[t + 1]), _p(DWH[t], H), 2 * H,
+                      _ptr(d_h1[t]) if d_h1 is not None else None, None if last else _ptr(DC[(t + 1) & 1]),
+                      _ptr(DGATES[t]), _ptr(DC[t & 1]), Bt, H, p, rp, offs[t]["h1"], _stream())
             _gemm(s_cat.hi_t, s_cat.lo_t, KX, G4, _p(DGATES[t]), G4, Bt, None, _p(DXH[t]), KX)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4),
                   _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, Bt, 1 | 2, pf, rp,
@@ -378,7 +400,12 @@ class _Rollout(torch.autograd.Function):
 
         # ---- d_ctx[b] = sum_t attn_t^T d_weighted_t + dlogit_t^T tq_t: one batched GEMM pair over all steps ----
         d_ctx = torch.bmm(ATTC[:n].permute(1, 2, 0), DWH[:, :, :H].transpose(0, 1))
-        d_ctx.baddbmm_(DLC.permute(1, 2, 0), TQ[:n].transpose(0, 1))
+        dCW = None
+        if use_cs:          # through CW = ctx W_in:  dCW = sum_t dlogit_t (x) drop(h_1)_t ,  d_ctx += dCW W_in^T
+            dCW = torch.bmm(DLC.permute(1, 2, 0), WH[:n, :, H:].transpose(0, 1))
+            _gemm(s_tin.hi, s_tin.lo, H, H, _p(dCW), H, B * L, None, _p(d_ctx), H, accumulate=1)
+        else:
+            d_ctx.baddbmm_(DLC.permute(1, 2, 0), TQ[:n].transpose(0, 1))
 
         # ---- weight gradients: one GEMM per weight over all n*B rows ----
         def weight_grads():
@@ -386,7 +413,10 @@ class _Rollout(torch.autograd.Function):
             dG = DGATES.view(nb, G4)
             d_wcat = ops.wgrad(dG, XH[:n].reshape(nb, KX))
             d_b = dG.sum(0)
-            d_w_tin = ops.wgrad(DTQ.view(nb, H), WH[:n, :, H:].reshape(nb, H))
+            if use_cs:      # dW_in[k, j] = sum_{b,l} ctx[b,l,k] dCW[b,l,j]
+                d_w_tin = ops.wgrad(ctx.reshape(B * L, H), dCW.view(B * L, H))
+            else:
+                d_w_tin = ops.wgrad(DTQ.view(nb, H), WH[:n, :, H:].reshape(nb, H))
             d_w_out = ops.wgrad(DPRE.view(nb, H), WH[:n].reshape(nb, 2 * H))
             d_w_vin = ops.wgrad(DQ.view(nb, F), HQ[:n].reshape(nb, H))
             d_w_cand = ops.wgrad(DTGT.view(nb, F), HC[:n].reshape(nb, H))
@@ -411,7 +441,7 @@ class _Rollout(torch.autograd.Function):
                 grads = weight_grads()
                 for q, g_ in zip(params, grads):
                     q.grad.add_(g_)
-            keep = [grads, DGATES, XH, WH, HQ, HC, DTQ, DPRE, DQ, DTGT, DACT]    # alive until the join (allocator safety)
+            keep = [grads, DGATES, XH, WH, HQ, HC, DTQ, DPRE, DQ, DTGT, DACT, dCW, ctx]    # alive until the join (allocator safety)
 
             def join():
                 torch.cuda.current_stream().wait_stream(side)

@@ -162,6 +162,27 @@ int vln_lstm_pointwise_drop_bwd(const float* acts, const float* c0, const float*
                                 float* d_c0, int B, int H, float p, const uint64_t* rng, uint64_t call_off,
                                 void* stream);
 
+/* Text-attention stage of a fused EnvDrop decoder step as ONE launch each way (policy.py:238-241 + units.py:107-118):
+ * nn.LSTMCell pointwise half (gates [B,4H] already hold the gate GEMM + biases) -> h_1, c_1 (+ saved activations),
+ * drop(h_1) -> wh[b, H:2H), then SoftDotAttention's masked softmax over the instruction and the weighted context
+ * -> wh[b, 0:H).  The query projection linear_in is folded into the context once per rollout: `cw` = ctx W_in
+ * [B,L,H] (logit_l = ctx_l . (W_in h) = cw_l . h), so no per-step GEMM sits between the LSTM cell and the attention.
+ * H must be 512 (one thread per hidden unit), L <= 80.  tiles_ready: ctx / cw / lengths were complete before the
+ * PRECEDING kernel started (both tiles are then requested ahead of the programmatic-dependency wait).
+ * Backward: dwh[b, 0:H) = d_weighted and dwh[b, H:2H) = the linear_out part of d drop(h_1) (both from the
+ * linear_out input-gradient GEMM); emits dlogit [B,L] (for d_ctx / d_cw, one batched GEMM per rollout), adds
+ * sum_l dlogit_l cw_l to d drop(h_1), undoes the dropout, adds d_h1_extra (nullable: the critic's gradient on h_1,
+ * envdrop.py:247) and runs the LSTMCell pointwise backward (d_c1 nullable) -> d_gates [B,4H], d_c0 [B,H]. */
+int vln_envdrop_ctx_step_fwd(const float* gates, const float* c0, float* h1, float* c1, float* acts, float* wh,
+                             int ld_wh, const float* ctx, const float* cw, const int32_t* lengths, float* attn,
+                             int B, int L, int H, float p, const uint64_t* rng, uint64_t call_off, int tiles_ready,
+                             void* stream);
+int vln_envdrop_ctx_step_bwd(const float* ctx, const float* cw, const int32_t* lengths, const float* attn,
+                             const float* dwh, int ld_dwh, float* dlogit_out, const float* acts, const float* c0,
+                             const float* c1, const float* d_h1_extra, const float* d_c1, float* d_gates,
+                             float* d_c0, int B, int L, int H, float p, const uint64_t* rng, uint64_t call_off,
+                             void* stream);
+
 /* Glue of the fused EnvDrop decoder step (EnvDropDecoder.forward policy.py:208-246): everything between
  * two grid-wide kernels of the step, writing into the operand rows of the next GEMM.
  * state_fwd: h~ = apply_tanh ? tanh(src) : src  (src = linear_out pre-activation, units.py:120, or the

@@ -801,3 +801,68 @@ def test_linear_pair_equals_two_launches(setup):
     for w, x, y in zip(ws, xs, ys):
         ref = x.double() @ w.double().t()
         assert relerr(y.double(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+@pytest.mark.parametrize("B,L", [(64, 80), (5, 33)])
+def test_ctx_step_equals_separate_kernels(setup, B, L, p):
+    """vln_envdrop_ctx_step_fwd/bwd (csrc/ctx_step.cu: LSTM pointwise + dropout + text attention in one launch, the
+    query projection folded into the context as CW = ctx W_in) against the three launches it replaces
+    (vln_lstm_pointwise_drop -> W_in GEMM -> vln_ctx_attn) in fp64-checked torch on the same inputs and masks."""
+    import ctypes as C
+    world, store, ops, dev = setup
+    H = 512
+    g = torch.Generator().manual_seed(B * 131 + L)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)
+    gates, c0 = r(B, 4 * H), r(B, H)
+    ctx = r(B, L, H) * 0.3
+    w_in = r(H, H) * 0.05
+    lengths = torch.randint(1, L + 1, (B,), generator=g).to(torch.int32).to(dev)
+    lengths[0] = L
+    cw = (ctx.double() @ w_in.double()).float().contiguous()
+    rng = ops.Rng(11, dev)
+    off = 5
+    h1, c1, acts = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev), torch.empty(B, 4 * H, device=dev)
+    wh = torch.zeros(B, 2 * H, device=dev)
+    attn = torch.full((B, L), -1.0, device=dev)
+    for ready in (0, 1):
+        ops._call("vln_envdrop_ctx_step_fwd", ops._ptr(gates), ops._ptr(c0), ops._ptr(h1), ops._ptr(c1), ops._ptr(acts),
+                  ops._ptr(wh), 2 * H, ops._ptr(ctx), ops._ptr(cw), ops._ptr(lengths), ops._ptr(attn), B, L, H, p, rng.ptr,
+                  off, ready, ops._stream())
+    # reference: the oracle's formulas in float64
+    i, f, gg, o = gates.double().chunk(4, 1)
+    i, f, gg, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(gg), torch.sigmoid(o)
+    c_ref = f * c0.double() + i * gg
+    h_ref = o * torch.tanh(c_ref)
+    keep = ops.dropout_mask((B, H), p, rng, off).double() / (1.0 - p) if p > 0 else torch.ones(B, H, device=dev).double()
+    hd = h_ref * keep
+    tq = hd @ w_in.double().t()
+    logit = torch.einsum("blh,bh->bl", ctx.double(), tq)
+    mask = torch.arange(L, device=dev).unsqueeze(0) >= lengths.unsqueeze(1)
+    a_ref = torch.softmax(logit.masked_fill(mask, float("-inf")), 1)
+    w_ref = torch.einsum("bl,blh->bh", a_ref, ctx.double())
+    assert relerr(h1.double(), h_ref) < 1e-5 and relerr(c1.double(), c_ref) < 1e-5
+    assert relerr(acts.double(), torch.cat((i, f, gg, o), 1)) < 1e-5
+    assert relerr(wh[:, H:].double(), hd) < 1e-5
+    assert relerr(attn.double(), a_ref) < 1e-4 and bool((attn[mask] == 0).all())
+    assert relerr(wh[:, :H].double(), w_ref) < 1e-4
+    # ---- backward ----
+    dwh = r(B, 2 * H)
+    d_h1x, d_c1 = r(B, H), r(B, H)
+    d_gates, d_c0, dlogit = torch.empty(B, 4 * H, device=dev), torch.empty(B, H, device=dev), torch.empty(B, L, device=dev)
+    ops._call("vln_envdrop_ctx_step_bwd", ops._ptr(ctx), ops._ptr(cw), ops._ptr(lengths), ops._ptr(attn), ops._ptr(dwh), 2 * H,
+              ops._ptr(dlogit), ops._ptr(acts), ops._ptr(c0), ops._ptr(c1), ops._ptr(d_h1x), ops._ptr(d_c1), ops._ptr(d_gates),
+              ops._ptr(d_c0), B, L, H, p, rng.ptr, off, ops._stream())
+    a64 = attn.double()
+    rr = torch.einsum("blh,bh->bl", ctx.double(), dwh[:, :H].double())
+    dl_ref = a64 * (rr - (a64 * rr).sum(1, keepdim=True))
+    dl_ref = dl_ref.masked_fill(mask, 0.0)
+    dhd = dwh[:, H:].double() + torch.einsum("bl,blh->bh", dl_ref, cw.double())
+    dh = dhd * keep + d_h1x.double()
+    tc = torch.tanh(c1.double())
+    ia, fa, ga, oa = acts.double().chunk(4, 1)
+    dc = d_c1.double() + dh * oa * (1 - tc * tc)
+    dg_ref = torch.cat((dc * ga * ia * (1 - ia), dc * c0.double() * fa * (1 - fa), dc * ia * (1 - ga * ga), dh * tc * oa * (1 - oa)), 1)
+    assert relerr(dlogit.double(), dl_ref) < 1e-4
+    assert relerr(d_gates.double(), dg_ref) < 1e-4
+    assert relerr(d_c0.double(), dc * fa) < 1e-4

@@ -70,6 +70,17 @@ def main():
             lines.append("")
             lines.append(f"{k} durations (us bucket: launches/iter): " +
                          ", ".join(f"{b}-{b + 1}: {h[b] / n_it:.0f}" for b in sorted(h)))
+    # raw timeline of the first profiled iteration (start offset us, duration us, stream, kernel) for gap analysis
+    tl = os.environ.get("VLN_TIMELINE")
+    if tl:
+        per = len(evs) // n_it
+        rows = sorted((e.time_range.start, e.time_range.end - e.time_range.start,
+                       e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("<")[0].split("(")[0])
+                      for e in evs)[:per + 8]
+        t0 = rows[0][0]
+        with open(tl, "w") as f:
+            for a, d, nm in rows:
+                f.write(f"{a - t0:.2f},{d:.2f},{nm[:60]}\n")
     text = "\n".join(lines)
     print(text)
     if len(sys.argv) > 1:
