@@ -57,6 +57,8 @@ _SIGS = {
     "vln_lstm_pointwise_drop_bwd": ([_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p, _u64, _p], _i),
     "vln_envdrop_ctx_step_fwd": ([_p] * 6 + [_i] + [_p] * 4 + [_i, _i, _i, _f, _p, _u64, _i, _p], _i),
     "vln_envdrop_ctx_step_bwd": ([_p] * 5 + [_i] + [_p] * 8 + [_i, _i, _i, _f, _p, _u64, _p], _i),
+    "vln_linear_state_fwd": ([_p, _p, _i, _i, _p, _i, _i, _p, _i, _p, _i, _p, _p, _f, _p, _u64, _u64, _p, _p], _i),
+    "vln_linear_state_bwd": ([_p, _p, _i, _i, _p, _i, _i, _p, _i, _p, _p, _i, _p, _i, _p, _f, _p, _u64, _u64, _p, _p], _i),
     "vln_envdrop_state_fwd": ([_p, _i, _p, _i, _p, _p, _i, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_envdrop_state_bwd": ([_p, _p, _i, _p, _p, _i, _i, _p, _i, _i, _f, _p, _u64, _u64, _p], _i),
     "vln_envdrop_act_fwd": ([_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _u64, _p], _i),

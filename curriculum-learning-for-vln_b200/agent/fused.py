@@ -34,6 +34,8 @@ H_ACT = 64
 FUSE_TAIL = [__import__("os").environ.get("VLN_FUSE_TAIL", "1") != "0"]   # candidate logits + policy/env/act as one launch
 # LSTM pointwise + text attention as one launch per step, linear_in folded into the context (csrc/ctx_step.cu)
 CTX_STEP = [__import__("os").environ.get("VLN_CTX_STEP", "1") != "0"]
+# tanh / dropout glue around h~ as a tile epilogue of its producer GEMM (vln_linear_state_fwd / _bwd, csrc/gemm.cu)
+EPI_STATE = [__import__("os").environ.get("VLN_EPI_STATE", "1") != "0"]
 
 
 def _p(t, off=0):
@@ -122,6 +124,7 @@ class FusedDecoder:
         self._prep = None
         self.async_wgrad = False       # set by TrainStep (which always differentiates with .backward() into .grad buffers)
         self._wgrad_stream = None
+        self.counters = None           # arrive / depart counters of the GEMM tile epilogues (zero between launches)
 
     def params(self):
         d = self.dec
@@ -139,6 +142,8 @@ class FusedDecoder:
         pf = dec.feat_drop_ratio if dec.training else 0.0
         fb = ops.FEEDBACK[feedback]
         S = T + (1 if bootstrap else 0)
+        if self.counters is None:
+            self.counters = torch.zeros(16, dtype=torch.int32, device=device)
         offs = []
         for t in range(S):
             d = dict(act=0, img=0, cand=0, hprev=0, h1=0, ht=0, sample=0)
@@ -252,6 +257,7 @@ class _Rollout(torch.autograd.Function):
         # text-attention stage as one launch (csrc/ctx_step.cu): CW = ctx W_in once per rollout replaces the per-step
         # query projection tq = W_in drop(h_1)  (logit_l = ctx_l . tq = CW_l . drop(h_1))
         use_cs = CTX_STEP[0] and H == 512 and L <= 80
+        use_epi = EPI_STATE[0] and B <= 128 and fd.counters is not None
         CW = ops._tc_matmul_tall(ctx.view(B * L, H), s_tin.hi_t, s_tin.lo_t, H, H).view(B, L, H) if use_cs else None
 
         def visual_and_lstm(t, need_drop, q_done=False, pointwise=True):
@@ -283,11 +289,16 @@ class _Rollout(torch.autograd.Function):
                 _gemm(s_tin.hi, s_tin.lo, H, H, _p(WH[t], H), 2 * H, Bt, None, _p(TQ[t]), H)
                 _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, Bt,
                       L, H, 1 if t > 0 else 0, _stream())
-            _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, Bt, None, _p(PRE[t]), H)
             more = t + 1 < S
-            _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
-                  _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), Bt, H, p, rp,
-                  offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _stream())
+            if use_epi:     # pre = W_out [weighted | drop(h)], then h~ = tanh(pre) and its two dropout sites as the tile epilogue
+                _call("vln_linear_state_fwd", _ptr(s_out.hi), _ptr(s_out.lo), H, 2 * H, _p(WH[t]), 2 * H, Bt, _p(PRE[t]), H,
+                      _p(XH[t + 1], H_ACT + F), KX, _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), p, rp,
+                      offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _ptr(fd.counters), _stream())
+            else:
+                _gemm(s_out.hi, s_out.lo, H, 2 * H, _p(WH[t]), 2 * H, Bt, None, _p(PRE[t]), H)
+                _call("vln_envdrop_state_fwd", _ptr(PRE[t]), 1, _p(XH[t + 1], H_ACT + F), KX,
+                      _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), Bt, H, p, rp,
+                      offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _stream())
             if paired and more:      # tgt_t = W_cand hc_t and q_{t+1} = W_vin hq_{t+1} both only wait for h~_t: one launch
                 _call("vln_linear_bf16x3_pair", _ptr(s_cand.hi), _ptr(s_cand.lo), _ptr(HC[t]), _ptr(TGT[t]), _ptr(s_vin.hi),
                       _ptr(s_vin.lo), _ptr(HQ[t + 1]), _ptr(Q[t + 1]), F, H, H, Bt, F, _stream())
@@ -329,7 +340,7 @@ class _Rollout(torch.autograd.Function):
         fd.last = dict(LOGIT=LOGIT, ACTION=ACTION, TEACH=TEACH, n=n)
 
         fctx.fd, fctx.st, fctx.rp, fctx.MB, fctx.bwd_bufs = fd, st, rp, MB, bb_
-        fctx.cfg = (n, B, L, H, p, pf, split, offs, B_main, T_pair, use_cs)
+        fctx.cfg = (n, B, L, H, p, pf, split, offs, B_main, T_pair, use_cs, use_epi)
         fctx.splits = (s_cat, s_vin, s_tin, s_out, s_cand)
         fctx.save_for_backward(ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, CW if use_cs else TQ, PROBS, ENT,
                                ACTION, TEACH)
@@ -341,13 +352,13 @@ class _Rollout(torch.autograd.Function):
     @staticmethod
     def backward(fctx, d_ce, d_logp, d_ent, d_h1, *_unused):
         ctx, lengths, XH, HQ, HC, ACT, ACTS, CS, WH, ATTV, ATTC, TQ, PROBS, ENT, ACTION, TEACH = fctx.saved_tensors
-        n, B, L, H, p, pf, split, offs, B_main, T_pair, use_cs = fctx.cfg
+        n, B, L, H, p, pf, split, offs, B_main, T_pair, use_cs, use_epi = fctx.cfg
         CW = TQ                                                 # (the saved slot holds CW = ctx W_in with use_cs)
 
         def rows(t):
             return B if t < T_pair else B_main
         s_cat, s_vin, s_tin, s_out, s_cand = fctx.splits
-        st, rp, MB = fctx.st, fctx.rp, fctx.MB
+        st, rp, MB, fd = fctx.st, fctx.rp, fctx.MB, fctx.fd
         store = st.store
         dev = ctx.device
         F, G4, KX = ops.F_DIM, 4 * H, H_ACT + ops.F_DIM + H
@@ -370,9 +381,10 @@ class _Rollout(torch.autograd.Function):
         for t in range(n - 1, -1, -1):
             last = t == n - 1
             Bt = rows(t)            # rows that sat out step t+1 see zero carried gradients (zero-filled slab / DC)
-            _call("vln_envdrop_state_bwd", _ptr(DHC[t]), None if last else _p(DXH[t + 1], OH), KX,
-                  None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), Bt, H, p, rp,
-                  0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
+            if last or not use_epi or rows(t + 1) != Bt:   # (else DPRE[t] came out of the epilogue of step t+1's last GEMM)
+                _call("vln_envdrop_state_bwd", _ptr(DHC[t]), None if last else _p(DXH[t + 1], OH), KX,
+                      None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), Bt, H, p, rp,
+                      0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
             _gemm(s_out.hi_t, s_out.lo_t, 2 * H, H, _p(DPRE[t]), H, Bt, None, _p(DWH[t]), 2 * H)
             if use_cs:      # text attention backward + d drop(h_1) += sum_l dlogit_l CW_l + LSTM pointwise backward: one launch
                 _call("vln_envdrop_ctx_step_bwd", _ptr(ctx), _ptr(CW), _ptr(lengths), _ptr(ATTC[t]), _ptr(DWH[t]), 2 * H,
@@ -390,7 +402,13 @@ class _Rollout(torch.autograd.Function):
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4),
                   _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, Bt, 1 | 2, pf, rp,
                   offs[t]["img"], _ptr(MB[t]) if MB is not None else None, split, _stream())
-            _gemm(s_vin.hi_t, s_vin.lo_t, H, F, _p(DQ[t]), F, Bt, None, _p(DHQ[t]), H)
+            if use_epi and t > 0 and rows(t - 1) == Bt:
+                # d_hq_t = dq_t W_vin, then the gradient of h~_{t-1} through tanh and its two dropout sites: the tile epilogue
+                _call("vln_linear_state_bwd", _ptr(s_vin.hi_t), _ptr(s_vin.lo_t), H, F, _p(DQ[t]), F, Bt, _p(DHQ[t]), H,
+                      _ptr(DHC[t - 1]), _p(DXH[t], OH), KX, _p(XH[t], OH), KX, _ptr(DPRE[t - 1]), p, rp,
+                      offs[t]["hprev"], offs[t - 1]["ht"], _ptr(fd.counters), _stream())
+            else:
+                _gemm(s_vin.hi_t, s_vin.lo_t, H, F, _p(DQ[t]), F, Bt, None, _p(DHQ[t]), H)
         _call("vln_envdrop_act_bwd", _ptr(DXH), KX, _ptr(ACT), _ptr(DACT), B, H_ACT, n, p, rp, offs[0]["act"],
               (offs[1]["act"] - offs[0]["act"]) if len(offs) > 1 else 0, _stream())
         d_h0 = torch.empty((B, H), device=dev)

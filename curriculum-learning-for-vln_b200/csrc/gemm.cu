@@ -114,13 +114,114 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {   // round-to-
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// ---- optional tile epilogue (the per-element glue of the decoder step, folded into its producer GEMM) ----
+// The split-K partials of a tile meet in y through reductions, so no CTA owns a finished output.  With an epilogue
+// the `splits` CTAs of a weight tile — all resident: the grid is at most one CTA per SM — count themselves in on a
+// per-tile counter after their reductions (fence + atomic), spin until the tile is complete, and then each applies
+// the epilogue to 1/splits of the tile's [M x 128] outputs, read back from L2.  That replaces a separate grid-wide
+// launch on the step's latency chain (state_fwd / state_bwd, csrc/step.cu: same arithmetic, same Philox streams).
+struct Epi {
+  int kind;                      // 0 none; 1 state_fwd on y = linear_out pre-activation; 2 state_bwd on y = d_hq_next
+  unsigned int* ctr;             // [2 * tiles] arrive / depart counters, zero between launches
+  float p;
+  const uint64_t* rng;
+  unsigned long long off_q, off_c;
+  float* xh_next; int ld_xh; float* hq_next; float* hc_cur;                                  // kind 1 outputs
+  const float* d_hc; const float* d_xh_next; int ld_dxh; const float* htilde; int ld_h;      // kind 2 inputs
+  float* d_src;                                                                               // kind 2 output
+};
+
+__device__ __forceinline__ void ldcg8(const float* p, float (&v)[8]) {
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+__device__ __forceinline__ void tile_epilogue(const Epi& e, const float* y, int ldy, int M, int N, int tile, int split,
+                                              int splits, int tid) {
+  unsigned int* arrive = e.ctr + 2 * tile;
+  unsigned int* depart = arrive + 1;
+  __threadfence();                                           // this thread's reductions into y are ordered before the count
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(arrive, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+    } while (seen < (unsigned int)splits);
+  }
+  __syncthreads();
+  __threadfence();
+  const int n_items = M * (kTileN / 8);                      // items of 8 consecutive outputs (one Philox block)
+  const int chunk = (n_items + splits - 1) / splits;
+  const int i0 = split * chunk, i1 = min(n_items, i0 + chunk);
+  const bool on = e.p > 0.f;
+  const uint32_t thr = drop_threshold(e.p);
+  const float sc = on ? 1.0f / (1.0f - e.p) : 1.0f;
+  const uint64_t seed = on ? e.rng[0] : 0, base = on ? e.rng[1] : 0;
+  for (int it = i0 + tid; it < i1; it += kThreads) {
+    const int m = it / (kTileN / 8), g = it - m * (kTileN / 8);
+    const int n = tile * kTileN + g * 8;
+    if (n >= N) continue;
+    float v[8], kq[8], kc[8];
+    ldcg8(y + (size_t)m * ldy + n, v);
+    const uint64_t blk = ((uint64_t)m * (uint64_t)N + (uint64_t)n) >> 3;
+    if (on) {
+      const Philox8 rq = philox8(seed, base + e.off_q, blk), rc = philox8(seed, base + e.off_c, blk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        kq[j] = philox_keep(rq, j, thr) ? sc : 0.f;
+        kc[j] = philox_keep(rc, j, thr) ? sc : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kq[j] = kc[j] = 1.f;
+    }
+    if (e.kind == 1) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tanhf(v[j]);
+      if (e.xh_next) st8(e.xh_next + (size_t)m * e.ld_xh + n, v);
+      if (e.hq_next) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v[j] * kq[j];
+        st8(e.hq_next + (size_t)m * N + n, o);
+      }
+      if (e.hc_cur) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v[j] * kc[j];
+        st8(e.hc_cur + (size_t)m * N + n, o);
+      }
+    } else {
+      float a[8], b[8], h[8], o[8];
+      ldcg8(e.d_hc + (size_t)m * N + n, a);
+      ldcg8(e.d_xh_next + (size_t)m * e.ld_dxh + n, b);
+      ldcg8(e.htilde + (size_t)m * e.ld_h + n, h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (a[j] * kc[j] + b[j] + v[j] * kq[j]) * (1.f - h[j] * h[j]);
+      st8(e.d_src + (size_t)m * N + n, o);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int d = atomicAdd(depart, 1u);
+    if (d == (unsigned int)splits - 1u) {                    // everyone has left the spin: counters back to zero
+      *arrive = 0u;
+      *depart = 0u;
+    }
+  }
+}
+
 template <int MP>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_constant__ CUtensorMap tm_lo0,
                      const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_hi1,
                      const __grid_constant__ CUtensorMap tm_lo1, const __grid_constant__ CUtensorMap tm_x1, int M, int N,
                      int K, const float* __restrict__ bias, float* __restrict__ y0, float* __restrict__ y1, int ldy,
-                     int splits, int accumulate, int mode, int dbg, int m_tiles) {
+                     int splits, int accumulate, int mode, int dbg, int m_tiles, const __grid_constant__ Epi epi) {
   // blockIdx.z selects one of two independent problems of identical shape (e.g. the candidate projection of
   // step t and the visual-attention query of step t+1, which both only wait for h~_t)
   const CUtensorMap& tm_hi = blockIdx.z == 0 ? tm_hi0 : tm_hi1;
@@ -296,6 +397,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
                      : "memory");
       }
     }
+    if (epi.kind != 0) tile_epilogue(epi, y, ldy, M, N, tile, split, splits, tid);
   } else {
     if (splits > 1) {
       cluster_arrive();
@@ -415,7 +517,8 @@ struct Second {                                            // second problem of 
 
 template <int MP>
 int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
-                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec = Second(), int m_tiles = 1) {
+                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec = Second(), int m_tiles = 1,
+                  Epi epi = Epi()) {
   CUtensorMap tm_hi, tm_lo;
   int rc = vln_make_tmap_2d(&tm_hi, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
   if (rc) return rc;
@@ -461,7 +564,7 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   cfg.numAttrs = na;
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP>, tm_hi, tm_lo, tm_x, tm_hi1, tm_lo1, tm_x1, M, N, K, bias, y,
                                     sec.y ? sec.y : y, ldy, splits,
-                                    accumulate, m_tiles > 1 ? 2 : mode, variant().dbg, m_tiles));
+                                    accumulate, m_tiles > 1 ? 2 : mode, variant().dbg, m_tiles, epi));
   return 0;
 }
 
@@ -485,6 +588,48 @@ extern "C" int vln_linear_bf16x3(const void* w_hi, const void* w_lo, int N, int 
   if (variant().mode == 2) s = splits;
   if (M <= 64) return launch_linear<64>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
   return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, s, accumulate, (cudaStream_t)stream);
+}
+
+// y += x W^T with a tile epilogue (see Epi): the shapes of the decoder step's H-wide products only (N = H outputs).
+static int linear_epi(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, float* y, int ldy,
+                      const Epi& epi, void* stream) {
+  VLN_REQUIRE(w_hi && w_lo && x && y && N > 0 && M > 0 && epi.ctr, "bad arguments");
+  VLN_REQUIRE(K > 0 && K % kBK == 0, "K must be a positive multiple of 64");
+  VLN_REQUIRE(M <= 128, "at most 128 activation rows");
+  VLN_REQUIRE(N % 8 == 0 && N <= 8 * kTileN, "epilogue shapes: N a multiple of 8, at most 8 weight tiles");
+  VLN_REQUIRE(((uintptr_t)x & 15) == 0 && ldx % 4 == 0 && ((uintptr_t)y & 15) == 0 && ldy % 4 == 0, "x / y rows must be 16-byte aligned");
+  VLN_REQUIRE(((uintptr_t)w_hi & 15) == 0 && ((uintptr_t)w_lo & 15) == 0, "weights must be 16-byte aligned");
+  VLN_REQUIRE(epi.p >= 0.f && epi.p < 1.f && (epi.p == 0.f || epi.rng), "dropout needs 0 <= p < 1 and an rng state");
+  VLN_REQUIRE(variant().mode == 2, "tile epilogues need the vector-reduction split-K merge");
+  const int nkb = K / kBK;
+  const int tiles = (N + kTileN - 1) / kTileN;
+  int splits = 148 / tiles;                                    // one CTA per SM, one wave: every CTA of a tile is resident
+  if (splits > nkb) splits = nkb;
+  if (M <= 64) return launch_linear<64>(w_hi, w_lo, N, K, x, ldx, M, nullptr, y, ldy, splits, 1, (cudaStream_t)stream, Second(), 1, epi);
+  return launch_linear<128>(w_hi, w_lo, N, K, x, ldx, M, nullptr, y, ldy, splits, 1, (cudaStream_t)stream, Second(), 1, epi);
+}
+
+extern "C" int vln_linear_state_fwd(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, float* y,
+                                    int ldy, float* xh_next, int ld_xh, float* hq_next, float* hc_cur, float p,
+                                    const uint64_t* rng, uint64_t off_q, uint64_t off_c, unsigned int* counters, void* stream) {
+  VLN_REQUIRE(!xh_next || (ld_xh % 4 == 0 && ((uintptr_t)xh_next & 15) == 0), "xh rows must be 16-byte aligned");
+  Epi e = Epi();
+  e.kind = 1; e.ctr = counters; e.p = p; e.rng = rng; e.off_q = off_q; e.off_c = off_c;
+  e.xh_next = xh_next; e.ld_xh = ld_xh; e.hq_next = hq_next; e.hc_cur = hc_cur;
+  return linear_epi(w_hi, w_lo, N, K, x, ldx, M, y, ldy, e, stream);
+}
+
+extern "C" int vln_linear_state_bwd(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, float* y,
+                                    int ldy, const float* d_hc, const float* d_xh_next, int ld_dxh, const float* htilde,
+                                    int ld_h, float* d_src, float p, const uint64_t* rng, uint64_t off_q, uint64_t off_c,
+                                    unsigned int* counters, void* stream) {
+  VLN_REQUIRE(d_hc && d_xh_next && htilde && d_src, "bad arguments");
+  VLN_REQUIRE(ld_dxh % 4 == 0 && ld_h % 4 == 0 && (((uintptr_t)d_hc | (uintptr_t)d_xh_next | (uintptr_t)htilde | (uintptr_t)d_src) & 15) == 0,
+              "operand rows must be 16-byte aligned");
+  Epi e = Epi();
+  e.kind = 2; e.ctr = counters; e.p = p; e.rng = rng; e.off_q = off_q; e.off_c = off_c;
+  e.d_hc = d_hc; e.d_xh_next = d_xh_next; e.ld_dxh = ld_dxh; e.htilde = htilde; e.ld_h = ld_h; e.d_src = d_src;
+  return linear_epi(w_hi, w_lo, N, K, x, ldx, M, y, ldy, e, stream);
 }
 
 // Tall activations (the encoder's input projection over all B*L token rows, units.py:58-63; the critic over all

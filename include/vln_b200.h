@@ -183,6 +183,21 @@ int vln_envdrop_ctx_step_bwd(const float* ctx, const float* cw, const int32_t* l
                              float* d_c0, int B, int L, int H, float p, const uint64_t* rng, uint64_t call_off,
                              void* stream);
 
+/* vln_linear_bf16x3 (accumulating into a zero-filled y [M,N], M <= 128, N = H) with the per-element glue that follows
+ * it in the EnvDrop decoder step folded in as a tile epilogue — one launch less on the step's latency chain each:
+ *   state_fwd: y = linear_out pre-activation (units.py:119-120) -> exactly vln_envdrop_state_fwd(y, apply_tanh = 1, ...);
+ *   state_bwd: y = d_hq_next (input gradient of visual_attn.linear_in of the NEXT step) -> exactly
+ *              vln_envdrop_state_bwd(d_hc, d_xh_next, d_hq_next = y, htilde, apply_tanh = 1, d_src, ...).
+ * `counters`: device uint32 [16], zero before the first launch (the kernel returns them to zero); launches that share
+ * a counter buffer must be ordered on one stream. */
+int vln_linear_state_fwd(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, float* y,
+                         int ldy, float* xh_next, int ld_xh, float* hq_next, float* hc_cur, float p,
+                         const uint64_t* rng, uint64_t off_q, uint64_t off_c, unsigned int* counters, void* stream);
+int vln_linear_state_bwd(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, float* y,
+                         int ldy, const float* d_hc, const float* d_xh_next, int ld_dxh, const float* htilde,
+                         int ld_h, float* d_src, float p, const uint64_t* rng, uint64_t off_q, uint64_t off_c,
+                         unsigned int* counters, void* stream);
+
 /* Glue of the fused EnvDrop decoder step (EnvDropDecoder.forward policy.py:208-246): everything between
  * two grid-wide kernels of the step, writing into the operand rows of the next GEMM.
  * state_fwd: h~ = apply_tanh ? tanh(src) : src  (src = linear_out pre-activation, units.py:120, or the

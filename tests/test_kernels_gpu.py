@@ -866,3 +866,63 @@ def test_ctx_step_equals_separate_kernels(setup, B, L, p):
     assert relerr(dlogit.double(), dl_ref) < 1e-4
     assert relerr(d_gates.double(), dg_ref) < 1e-4
     assert relerr(d_c0.double(), dc * fa) < 1e-4
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+@pytest.mark.parametrize("M", [64, 128, 37])
+def test_linear_state_epilogues_equal_separate_kernels(setup, M, p):
+    """vln_linear_state_fwd / _bwd (GEMM + tile epilogue, csrc/gemm.cu) == vln_linear_bf16x3 followed by
+    vln_envdrop_state_fwd / _bwd, bit for bit (same reductions into y are not ordered, so y itself to 1e-6)."""
+    import ctypes as C
+    world, store, ops, dev = setup
+    H, F, KX, OH = 512, 2176, 2752, 2240
+    g = torch.Generator().manual_seed(M)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)
+    rng = ops.Rng(5, dev)
+    ctr = torch.zeros(16, dtype=torch.int32, device=dev)
+    off_q, off_c = 3, 9
+    # ---- forward: pre = W_out wh; h~ = tanh(pre) -> xh_next / hq_next / hc ----
+    w = r(H, 2 * H) * 0.05
+    sw = ops._SplitWeight(w).fresh(w)
+    wh = r(M, 2 * H)
+    outs = []
+    for fused in (False, True):
+        pre = torch.zeros(M, H, device=dev)
+        xh, hq, hc = torch.zeros(M, KX, device=dev), torch.zeros(M, H, device=dev), torch.zeros(M, H, device=dev)
+        if fused:
+            for _ in range(2):          # twice: the counters must return to zero
+                pre.zero_()
+                ops._call("vln_linear_state_fwd", ops._ptr(sw.hi), ops._ptr(sw.lo), H, 2 * H, ops._ptr(wh), 2 * H, M, ops._ptr(pre), H,
+                          C.c_void_p(xh.data_ptr() + 4 * OH), KX, ops._ptr(hq), ops._ptr(hc), p, rng.ptr, off_q, off_c, ops._ptr(ctr),
+                          ops._stream())
+        else:
+            ops._call("vln_linear_bf16x3", ops._ptr(sw.hi), ops._ptr(sw.lo), H, 2 * H, ops._ptr(wh), 2 * H, M, None, ops._ptr(pre), H, 1, 0,
+                      ops._stream())
+            ops._call("vln_envdrop_state_fwd", ops._ptr(pre), 1, C.c_void_p(xh.data_ptr() + 4 * OH), KX, ops._ptr(hq), ops._ptr(hc), M, H, p,
+                      rng.ptr, off_q, off_c, ops._stream())
+        outs.append((pre, xh, hq, hc))
+    assert int(ctr.abs().sum()) == 0
+    for a, b in zip(*outs):
+        assert relerr(b, a) < 1e-5
+    assert torch.equal(outs[0][2] == 0, outs[1][2] == 0) and torch.equal(outs[0][3] == 0, outs[1][3] == 0)     # same masks
+    # ---- backward: d_hq = dq W_vin; d_pre = (drop_c'(d_hc) + d_xh_next + drop_q'(d_hq)) * (1 - h~^2) ----
+    wv = r(F, H) * 0.05
+    sv = ops._SplitWeight(wv).fresh(wv)
+    dq, d_hc = r(M, F), r(M, H)
+    dxh, xh_t = r(M, KX), torch.tanh(r(M, KX))
+    outs = []
+    for fused in (False, True):
+        dhq, dpre = torch.zeros(M, H, device=dev), torch.zeros(M, H, device=dev)
+        if fused:
+            ops._call("vln_linear_state_bwd", ops._ptr(sv.hi_t), ops._ptr(sv.lo_t), H, F, ops._ptr(dq), F, M, ops._ptr(dhq), H,
+                      ops._ptr(d_hc), C.c_void_p(dxh.data_ptr() + 4 * OH), KX, C.c_void_p(xh_t.data_ptr() + 4 * OH), KX, ops._ptr(dpre),
+                      p, rng.ptr, off_q, off_c, ops._ptr(ctr), ops._stream())
+        else:
+            ops._call("vln_linear_bf16x3", ops._ptr(sv.hi_t), ops._ptr(sv.lo_t), H, F, ops._ptr(dq), F, M, None, ops._ptr(dhq), H, 1, 0,
+                      ops._stream())
+            ops._call("vln_envdrop_state_bwd", ops._ptr(d_hc), C.c_void_p(dxh.data_ptr() + 4 * OH), KX, ops._ptr(dhq),
+                      C.c_void_p(xh_t.data_ptr() + 4 * OH), KX, 1, ops._ptr(dpre), M, H, p, rng.ptr, off_q, off_c, ops._stream())
+        outs.append((dhq, dpre))
+    assert int(ctr.abs().sum()) == 0
+    for a, b in zip(*outs):
+        assert relerr(b, a) < 1e-5
