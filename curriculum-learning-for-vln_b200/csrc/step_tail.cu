@@ -56,27 +56,44 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
   pdl_trigger();
   // Everything up to the wait reads data that was complete long before the preceding kernel (the GEMM that produces
-  // tgt) started: this step's state was written by the previous step's tail, nine kernels back, and the tables are
-  // constant.  So the index chain and the candidate rows are in flight while that GEMM is still finishing.
+  // tgt) started: this step's state was written by the previous step's tail, five grid-wide kernels back (each of
+  // which had to drain before the next could become resident), and the tables are constant.  So the index chain, the
+  // candidate rows and the whole speculative transition are in flight while that GEMM is still finishing.
   const int g = a.vp[b];
   const int vw_in = a.view[b];
   const int n = a.n_cand[g];
-  // ---- warp 0: action-independent inputs of the transition, requested before the candidate rows ----
-  int row_view = 0, row_vp = -1, gl = 0, tg = -1, vloc_g = 0;
+  // ---- warp 0: the transition, SPECULATIVELY for every action it could take.  Lane j < n stands for "move to
+  //      candidate j", every lane >= n for "stay" (STOP / ended / ignored): each lane fetches the tables of ITS next
+  //      viewpoint — distance to the goal, next hop, the teacher slot there — before the dependency wait, so that once
+  //      the action is known the outcome is a handful of shuffles instead of two dependent global round trips ----
+  int row_view = 0, sp_cur = g, sp_n2 = 0, sp_teach = 0, gl = 0, tg = -1;
+  float sp_d = 0.f, d_in = 0.f;
   bool was_ended = false;
-  float d_in = 0.f;
   if (j == 0) {
-    if (lane < VLN_CMAX) {
+    if (lane < n) {
       row_view = a.cand_view[(size_t)g * VLN_CMAX + lane];
-      row_vp = a.cand_vp[(size_t)g * VLN_CMAX + lane];
+      sp_cur = a.cand_vp[(size_t)g * VLN_CMAX + lane];
     }
     gl = a.goal[b];
     tg = a.target ? a.target[b] : -1;
     was_ended = a.ended_in[b] != 0;
     d_in = a.dist_in[b];
-    vloc_g = a.vp_local[gl];
+    const int vloc_g = a.vp_local[gl];
+    const int64_t so = a.sq_off[sp_cur];
+    sp_n2 = a.n_cand[sp_cur];
+    int c2[VLN_CMAX];
+#pragma unroll
+    for (int k = 0; k < VLN_CMAX; ++k) c2[k] = a.cand_vp[(size_t)sp_cur * VLN_CMAX + k];
+    sp_d = a.dist_tbl[so + vloc_g];
+    const int nh = a.next_hop[so + vloc_g];
+    sp_teach = sp_n2;                                          // base.py:174-177: STOP when no candidate leads on
+#pragma unroll
+    for (int k = VLN_CMAX - 1; k >= 0; --k)
+      if (k < sp_n2 && c2[k] == nh) sp_teach = k;              // first matching slot
+    if (sp_cur == gl) sp_teach = sp_n2;
   }
-  // this warp's candidate row (8 x 16 bytes per lane) and its angle feature
+  // this warp's candidate row (8 x 16 bytes per lane), its angle feature, and the feature-dropout keep mask
+  // (policy.py:226-231) applied in registers — none of it depends on the preceding kernel
   uint4 xr[8];
   float4 an = make_float4(0.f, 0.f, 0.f, 0.f);
   if (j < n) {
@@ -85,6 +102,15 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
     const uint4* src = reinterpret_cast<const uint4*>(a.table + ((size_t)g * VLN_V + cv) * VLN_IMG);
 #pragma unroll
     for (int it = 0; it < 8; ++it) xr[it] = __ldg(src + it * 32 + lane);
+    if (a.drop_p > 0.f) {
+      const uint32_t thr = drop_threshold(a.drop_p);
+      const uint64_t seed = a.rng[0], offset = a.rng[1] + a.off_cand;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const uint64_t e = (((uint64_t)b * VLN_NSLOT + j) * VLN_IMG + (uint64_t)(it * 32 + lane) * 8) >> 3;
+        xr[it] = apply_keep(xr[it], philox8(seed, offset, e), thr);
+      }
+    }
   }
   pdl_wait();
   // ---- candidate logits (cand_logits_fwd_kernel) ----
@@ -97,18 +123,11 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   __syncthreads();
   float res;
   if (j < n) {
-    const uint32_t thr = drop_threshold(a.drop_p);
-    uint64_t seed = 0, offset = 0;
-    if (a.drop_p > 0.f) { seed = a.rng[0]; offset = a.rng[1] + a.off_cand; }
     float acc = 0.f;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int vi = it * 32 + lane;
-      uint4 x = xr[it];
-      if (a.drop_p > 0.f) {
-        const uint64_t e = (((uint64_t)b * VLN_NSLOT + j) * VLN_IMG + (uint64_t)vi * 8) >> 3;
-        x = apply_keep(x, philox8(seed, offset, e), thr);
-      }
+      const uint4 x = xr[it];
       const float4 q0 = reinterpret_cast<const float4*>(ts)[vi * 2], q1 = reinterpret_cast<const float4*>(ts)[vi * 2 + 1];
       acc += bf16lo(x.x) * q0.x + bf16hi(x.x) * q0.y + bf16lo(x.y) * q0.z + bf16hi(x.y) * q0.w +
              bf16lo(x.z) * q1.x + bf16hi(x.z) * q1.y + bf16lo(x.w) * q1.z + bf16hi(x.w) * q1.w;
@@ -136,7 +155,6 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   const float p = e / s;
   const float lp = x - m - logf(s);
   const float ent = -warp_sum(p > 0.f ? p * lp : 0.f);
-  tg = __shfl_sync(0xffffffffu, tg, 0);
   const int t_from = a.feedback >> 8;
   const int mode = (t_from > 0 && b >= t_from - 1) ? 0 : (a.feedback & 3);
   int act_id;
@@ -160,22 +178,14 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   const float lp_a = __shfl_sync(0xffffffffu, lp, act_id >= 0 ? act_id : 0);
   if (lane < VLN_NSLOT) a.probs[(size_t)b * VLN_NSLOT + lane] = p;
 
-  // ---- simulator transition (env_step_kernel): the chosen slot's (viewpoint, view) come from the lanes' row ----
-  const bool stop = was_ended || act_id < 0 || act_id >= n;                // lane 0's flags are broadcast below
-  const bool stop0 = __shfl_sync(0xffffffffu, (int)stop, 0) != 0;
-  const int pick = (act_id >= 0 && act_id < VLN_CMAX) ? act_id : 0;
-  const int nv = __shfl_sync(0xffffffffu, row_view, pick), np_ = __shfl_sync(0xffffffffu, row_vp, pick);
-  const int cur = stop0 ? g : np_;
-  const int vw = stop0 ? vw_in : nv;
-  gl = __shfl_sync(0xffffffffu, gl, 0);
-  vloc_g = __shfl_sync(0xffffffffu, vloc_g, 0);
-  // tables of the new viewpoint, all lanes at once
-  const int64_t so = a.sq_off[cur];
-  const int n2 = a.n_cand[cur];
-  const int c2 = lane < VLN_CMAX ? a.cand_vp[(size_t)cur * VLN_CMAX + lane] : -1;
-  const float d = a.dist_tbl[so + vloc_g];
-  const int nh = a.next_hop[so + vloc_g];
-  const unsigned match = __ballot_sync(0xffffffffu, lane < n2 && c2 == nh);
+  // ---- simulator transition (env_step_kernel): pick the speculated outcome of the chosen action ----
+  const bool stop = was_ended || act_id < 0 || act_id >= n;
+  const int sel = stop ? 31 : act_id;                          // lane 31 always speculated "stay" (n <= 15)
+  const int cur = __shfl_sync(0xffffffffu, sp_cur, sel);
+  const int nv = __shfl_sync(0xffffffffu, row_view, sel);
+  const int vw = stop ? vw_in : nv;
+  const float d = __shfl_sync(0xffffffffu, sp_d, sel);
+  const int teach = __shfl_sync(0xffffffffu, sp_teach, sel);
   if (lane == 0) {
     a.ce[b] = tg >= 0 ? -lp_t : 0.f;
     a.action[b] = act_id;
@@ -193,7 +203,7 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
     a.dist_out[b] = d;
     const bool now_ended = was_ended || stop;
     a.ended_out[b] = now_ended ? 1 : 0;
-    a.teacher_out[b] = now_ended ? -1 : (cur == gl ? n2 : (match ? __ffs(match) - 1 : n2));
+    a.teacher_out[b] = now_ended ? -1 : teach;
     if (a.n_active && !now_ended) atomicAdd(a.n_active, 1);
   }
   // ---- next pass's action embedding for the new view (act_fwd_kernel) ----
