@@ -10,7 +10,10 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libvln_b200.so")
+# VLN_LIB_VARIANT=stamps selects a debug build (-DVLN_CHAIN_STAMPS: the step-chain kernels record globaltimer stamps,
+# tools/chain_stamps.py); the product library has none of it compiled in
+VARIANT = os.environ.get("VLN_LIB_VARIANT", "")
+LIB_PATH = os.path.join(CSRC, "libvln_b200%s.so" % (("_" + VARIANT) if VARIANT else ""))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "vln_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -24,7 +27,8 @@ def build(force=False, verbose=False):
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(p) for p in deps)):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    extra = ["-DVLN_CHAIN_STAMPS"] if VARIANT == "stamps" else []
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + srcs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=CSRC)

@@ -35,7 +35,11 @@ FUSE_TAIL = [__import__("os").environ.get("VLN_FUSE_TAIL", "1") != "0"]   # cand
 # LSTM pointwise + text attention as one launch per step, linear_in folded into the context (csrc/ctx_step.cu)
 CTX_STEP = [__import__("os").environ.get("VLN_CTX_STEP", "1") != "0"]
 # tanh / dropout glue around h~ as a tile epilogue of its producer GEMM (vln_linear_state_fwd / _bwd, csrc/gemm.cu)
-EPI_STATE = [__import__("os").environ.get("VLN_EPI_STATE", "1") != "0"]
+# (bit 0: forward state_fwd in the linear_out GEMM; bit 1: backward state_bwd in the visual_attn.linear_in gradient GEMM)
+# Default off: on the B = 64 iteration the separate state_fwd / state_bwd launches are FASTER (4.30 ms vs 4.41 ms with
+# both epilogues): a kernel boundary under programmatic dependent launch costs ~1 us, the fence + atomic + spin + L2
+# read-back of the tile epilogue ~2-4 us.  Kept selectable (VLN_EPI_STATE=1|2|3) and parity-tested.
+EPI_STATE = [int(__import__("os").environ.get("VLN_EPI_STATE", "0"))]
 
 
 def _p(t, off=0):
@@ -72,8 +76,11 @@ def _gemm(hi, lo, N, K, x, ldx, M, bias, y, ldy, accumulate=1):
         _call("vln_linear_bf16x3_tall", _ptr(hi), _ptr(lo), N, K, x, ldx, M, bias, y, ldy, accumulate, _stream())
 
 
+_EXP = __import__("os").environ.get("VLN_EXP", "")     # timing experiments only (wrong results): "nofill", "nomask"
+
+
 def _carver(total, dev):
-    slab = torch.zeros(total, device=dev)
+    slab = (torch.empty if "nofill" in _EXP else torch.zeros)(total, device=dev)
     cur = [0]
 
     def carve(*shape):
@@ -92,7 +99,7 @@ def _make_buffers(S, T, B, L, H, dev, paired_rollouts):
     out later steps must read as finite zeros in the stacked weight-gradient GEMMs).  ~0.5 GB of fills per
     iteration at B = 128: FusedDecoder.prepare issues them on the side stream, under the instruction encoder."""
     F, G4, KX = ops.F_DIM, 4 * H, H_ACT + ops.F_DIM + H
-    alloc = torch.zeros if paired_rollouts else torch.empty
+    alloc = torch.zeros if (paired_rollouts and "nofill" not in _EXP) else torch.empty
     c = _carver(S * B * (F + G4) + T * B * (H + H + F), dev)
     f = dict(Q=c(S, B, F), GATES=c(S, B, G4), TQ=c(T, B, H), PRE=c(T, B, H), TGT=c(T, B, F),
              XH=alloc((S + 1, B, KX), device=dev), HQ=alloc((S + 1, B, H), device=dev), HC=alloc((T, B, H), device=dev),
@@ -166,15 +173,21 @@ class FusedDecoder:
                 self._side = torch.cuda.Stream()
             side = self._side
             side.wait_stream(main)      # also orders this iteration's fills after every earlier use of recycled blocks
-        if pf > 0.0:
-            MB = torch.empty((S, B * ops.N_VIEWS, ops.IMG_DIM // 8), dtype=torch.uint8, device=device)   # owned by `main`
+        # Feature-dropout keep-bits (policy.py:226-231) of every decoder pass, packed, drawn by one kernel on the side
+        # stream.  (The panorama kernel can also draw a launch's bits itself ahead of its dependency wait — what it does
+        # for callers without pre-generated bits — but on the step chain that work is not hidden: it shares the SM with
+        # the predecessor's CTAs and slowed the chain by as much as the bulk kernel costs; measured 4.35 vs 4.37 ms.)
+        n_bits = S if pf > 0.0 else 0
+        if n_bits > 0:
+            MB = torch.empty((n_bits, B * ops.N_VIEWS, ops.IMG_DIM // 8), dtype=torch.uint8, device=device)   # owned by `main`
+        if n_bits > 0 and "nomask" not in _EXP:
             with torch.cuda.stream(side):
                 stride = offs[1]["img"] - offs[0]["img"] if S > 1 else 0
-                if pair is None:
-                    _call("vln_feature_mask_bits", _ptr(MB), B * ops.N_VIEWS, S, pf, rng.ptr, offs[0]["img"], stride, _stream())
+                V = ops.N_VIEWS
+                if pair is None or n_bits < S:
+                    _call("vln_feature_mask_bits", _ptr(MB), B * V, n_bits, pf, rng.ptr, offs[0]["img"], stride, _stream())
                 else:        # rows [0, B_main) for every pass, the teacher-forced rows only for their T_teacher steps
                     B_main, T_t = pair
-                    V = ops.N_VIEWS
                     _call("vln_feature_mask_bits_ld", _ptr(MB), B_main * V, B * V, 0, S, pf, rng.ptr, offs[0]["img"], stride,
                           _stream())
                     _call("vln_feature_mask_bits_ld", _ptr(MB), (B - B_main) * V, B * V, B_main * V, T_t, pf, rng.ptr,
@@ -257,7 +270,7 @@ class _Rollout(torch.autograd.Function):
         # text-attention stage as one launch (csrc/ctx_step.cu): CW = ctx W_in once per rollout replaces the per-step
         # query projection tq = W_in drop(h_1)  (logit_l = ctx_l . tq = CW_l . drop(h_1))
         use_cs = CTX_STEP[0] and H == 512 and L <= 80
-        use_epi = EPI_STATE[0] and B <= 128 and fd.counters is not None
+        use_epi = EPI_STATE[0] if (B <= 128 and fd.counters is not None) else 0
         CW = ops._tc_matmul_tall(ctx.view(B * L, H), s_tin.hi_t, s_tin.lo_t, H, H).view(B, L, H) if use_cs else None
 
         def visual_and_lstm(t, need_drop, q_done=False, pointwise=True):
@@ -266,7 +279,7 @@ class _Rollout(torch.autograd.Function):
                 _gemm(s_vin.hi, s_vin.lo, F, H, _p(HQ[t]), H, Bt, None, _p(Q[t]), F)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4), _ptr(Q[t]), F,
                   _ptr(ATTV[t]), None, F, _p(XH[t], H_ACT), KX, Bt, 0, pf, rp, offs[t]["img"],
-                  _ptr(MB[t]) if MB is not None else None, split, _stream())
+                  _ptr(MB[t]) if (MB is not None and t < MB.shape[0]) else None, split, _stream())
             _gemm(s_cat.hi, s_cat.lo, G4, KX, _p(XH[t]), KX, Bt, _ptr(bsum), _p(GATES[t]), G4)
             if not pointwise:
                 return
@@ -290,7 +303,7 @@ class _Rollout(torch.autograd.Function):
                 _call("vln_ctx_attn_fwd_ld", _ptr(ctx), _ptr(TQ[t]), _ptr(lengths), _ptr(ATTC[t]), _ptr(WH[t]), 2 * H, Bt,
                       L, H, 1 if t > 0 else 0, _stream())
             more = t + 1 < S
-            if use_epi:     # pre = W_out [weighted | drop(h)], then h~ = tanh(pre) and its two dropout sites as the tile epilogue
+            if use_epi & 1:     # pre = W_out [weighted | drop(h)], then h~ = tanh(pre) and its two dropout sites as the tile epilogue
                 _call("vln_linear_state_fwd", _ptr(s_out.hi), _ptr(s_out.lo), H, 2 * H, _p(WH[t]), 2 * H, Bt, _p(PRE[t]), H,
                       _p(XH[t + 1], H_ACT + F), KX, _ptr(HQ[t + 1]) if more else None, _ptr(HC[t]), p, rp,
                       offs[t + 1]["hprev"] if more else 0, offs[t]["ht"], _ptr(fd.counters), _stream())
@@ -381,7 +394,7 @@ class _Rollout(torch.autograd.Function):
         for t in range(n - 1, -1, -1):
             last = t == n - 1
             Bt = rows(t)            # rows that sat out step t+1 see zero carried gradients (zero-filled slab / DC)
-            if last or not use_epi or rows(t + 1) != Bt:   # (else DPRE[t] came out of the epilogue of step t+1's last GEMM)
+            if last or not (use_epi & 2) or rows(t + 1) != Bt:   # (else DPRE[t] came out of the epilogue of step t+1's last GEMM)
                 _call("vln_envdrop_state_bwd", _ptr(DHC[t]), None if last else _p(DXH[t + 1], OH), KX,
                       None if last else _ptr(DHQ[t + 1]), _p(XH[t + 1], OH), KX, 1, _ptr(DPRE[t]), Bt, H, p, rp,
                       0 if last else offs[t + 1]["hprev"], offs[t]["ht"], _stream())
@@ -401,8 +414,8 @@ class _Rollout(torch.autograd.Function):
             _gemm(s_cat.hi_t, s_cat.lo_t, KX, G4, _p(DGATES[t]), G4, Bt, None, _p(DXH[t]), KX)
             _call("vln_pano_attn_ld", store.handle, _ptr(st.vp[t]), _ptr(st.view[t]), _ptr(store.loc4),
                   _p(DXH[t], H_ACT), KX, _ptr(ATTV[t]), _p(XH[t], H_ACT), KX, _ptr(DQ[t]), F, Bt, 1 | 2, pf, rp,
-                  offs[t]["img"], _ptr(MB[t]) if MB is not None else None, split, _stream())
-            if use_epi and t > 0 and rows(t - 1) == Bt:
+                  offs[t]["img"], _ptr(MB[t]) if (MB is not None and t < MB.shape[0]) else None, split, _stream())
+            if (use_epi & 2) and t > 0 and rows(t - 1) == Bt:
                 # d_hq_t = dq_t W_vin, then the gradient of h~_{t-1} through tanh and its two dropout sites: the tile epilogue
                 _call("vln_linear_state_bwd", _ptr(s_vin.hi_t), _ptr(s_vin.lo_t), H, F, _p(DQ[t]), F, Bt, _p(DHQ[t]), H,
                       _ptr(DHC[t - 1]), _p(DXH[t], OH), KX, _p(XH[t], OH), KX, _ptr(DPRE[t - 1]), p, rp,

@@ -122,6 +122,42 @@ __host__ __device__ __forceinline__ float philox_uniform(const Philox8& r, int j
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ---- chain stamps (debug builds only: -DVLN_CHAIN_STAMPS, tools/chain_stamps.py) ---------------------------------
+// Block 0 / thread 0 of a step-chain kernel records {kernel id, globaltimer at its first instruction, after the
+// programmatic-dependency wait, at its last instruction} behind the rng state (ops.Rng allocates the room: word 2 =
+// enable flag, word 3 = running count, 4 words per record from word 4), so the residency / release / work phases of
+// the chain can be read off one clock across kernels.  Compiled out of the product library.
+#ifdef VLN_CHAIN_STAMPS
+__device__ __forceinline__ unsigned long long chain_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long* chain_begin(const uint64_t* rng, int kid) {
+  if (rng == nullptr || blockIdx.x != 0 || blockIdx.y != 0 || blockIdx.z != 0 || threadIdx.x != 0) return nullptr;
+  unsigned long long* r = (unsigned long long*)rng;
+  if (r[2] == 0ull) return nullptr;
+  unsigned long long* s = r + 4 + (atomicAdd(&r[3], 1ull) % 8192ull) * 4ull;
+  s[0] = (unsigned long long)kid;
+  s[1] = chain_gtimer();
+  s[2] = 0ull;
+  s[3] = 0ull;
+  return s;
+}
+#define CHAIN_BEGIN(rng, kid) unsigned long long* chain_s_ = chain_begin(rng, kid)
+#define CHAIN_MARK(i)                          \
+  do {                                         \
+    if (chain_s_) chain_s_[i] = chain_gtimer(); \
+  } while (0)
+#else
+#define CHAIN_BEGIN(rng, kid) \
+  do {                        \
+  } while (0)
+#define CHAIN_MARK(i) \
+  do {                \
+  } while (0)
+#endif
+
 // ---- warp helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int u = threadIdx.x, lane = u & 31, warp = u >> 5, b = blockIdx.x, L = a.L;
+  CHAIN_BEGIN(a.rng, 3);
   pdl_trigger();
   // ready: ctx / CW / lengths were complete before the preceding kernel started (every decoder step but the first),
   // so both tiles are requested before the dependency wait and land while the gates GEMM is still finishing
@@ -109,7 +110,9 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_
     for (int l = 0; l < kLmax; ++l) col[l] = l < len ? __ldg(cb + (size_t)l * kH) : 0.f;
   }
   if (u < kLmax + 16) sm.sc[u] = 0.f;
+  const float keep = keep_of(a.p, a.rng, a.call_off, b, u);     // (the Philox base moves only between iterations)
   if (a.ready) pdl_wait();
+  CHAIN_MARK(2);
   // ---- nn.LSTMCell pointwise half for hidden unit u (gate order i, f, g, o) + dropout of h_1 ----
   {
     const float* gr = a.gates + (size_t)b * 4 * kH + u;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_
     a.h1[i] = h;
     float* ar = a.acts + (size_t)b * 4 * kH + u;
     ar[0] = gi; ar[kH] = gf; ar[2 * kH] = gg; ar[3 * kH] = go;
-    const float hd = h * keep_of(a.p, a.rng, a.call_off, b, u);
+    const float hd = h * keep;
     a.wh[(size_t)b * a.ld_wh + kH + u] = hd;
     sm.vec[u] = hd;
   }
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_
   }
   __syncthreads();
   a.wh[(size_t)b * a.ld_wh + u] = col_weighted(sm.sc, col);      // weighted context, column u
+  CHAIN_MARK(3);
 }
 
 struct BwdArgs {
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int u = threadIdx.x, lane = u & 31, warp = u >> 5, b = blockIdx.x, L = a.L;
+  CHAIN_BEGIN(a.rng, 13);
   pdl_trigger();
   // everything read before the wait dates from the forward pass (tiles, lengths, saved attention / activations / cells)
   const int len = max(0, min(a.lengths[b], min(L, kLmax)));
@@ -188,7 +193,10 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_
   const float* ar = a.acts + (size_t)b * 4 * kH + u;
   const float gi = ar[0], gf = ar[kH], gg = ar[2 * kH], go = ar[3 * kH];
   const float cp = a.c0[i], cn = a.c1[i];
+  const float keep = keep_of(a.p, a.rng, a.call_off, b, u);
+  const float tc = tanhf(cn);
   pdl_wait();
+  CHAIN_MARK(2);
   sm.vec[u] = a.dwh[(size_t)b * a.ld_dwh + u];           // d_weighted (from the linear_out input-gradient GEMM)
   const float dhd_gemm = a.dwh[(size_t)b * a.ld_dwh + kH + u];
   __syncthreads();
@@ -216,10 +224,9 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_
   }
   __syncthreads();
   // d(drop(h_1))_u = (W_out^T dpre)_u [GEMM] + sum_l dlogit_l CW_lu ; through the dropout, + the critic's gradient on h_1
-  float dh = (dhd_gemm + col_weighted(sm.sc, col)) * keep_of(a.p, a.rng, a.call_off, b, u);
+  float dh = (dhd_gemm + col_weighted(sm.sc, col)) * keep;
   if (a.d_h1_extra) dh += a.d_h1_extra[i];
   // ---- LSTMCell pointwise backward ----
-  const float tc = tanhf(cn);
   const float dc = (a.d_c1 ? a.d_c1[i] : 0.f) + dh * go * (1.f - tc * tc);
   float* dg = a.d_gates + (size_t)b * 4 * kH + u;
   dg[0] = dc * gg * gi * (1.f - gi);
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_
   dg[2 * kH] = dc * gi * (1.f - gg * gg);
   dg[3 * kH] = dh * tc * go * (1.f - go);
   a.d_c0[i] = dc * gf;
+  CHAIN_MARK(3);
 }
 
 int configure() {

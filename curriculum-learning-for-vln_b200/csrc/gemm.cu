@@ -37,7 +37,8 @@ int vln_make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint
                          uint32_t box_cols, uint32_t box_rows);
 
 // ---- optional phase stamps (VLN_GEMM_STAMPS=1): CTA (0,0) records clock64 at 9 phase boundaries + globaltimer ----
-__device__ unsigned long long g_stamps[64 * 12];
+constexpr int kStampSlots = 1024;
+__device__ unsigned long long g_stamps[kStampSlots * 12];
 __device__ unsigned int g_stamp_n;
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -46,7 +47,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define STAMP(i)                                                                    \
   do {                                                                              \
-    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_stamps[(slot % 64) * 12 + (i)] = (unsigned long long)clock64(); \
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_stamps[(slot % kStampSlots) * 12 + (i)] = (unsigned long long)clock64(); \
   } while (0)
 
 namespace {
@@ -55,9 +56,13 @@ constexpr int kBK = 64;                 // k-block: 64 bf16 = one 128-byte swizz
 constexpr int kTileN = 128;             // weight rows per CTA (MMA M)
 constexpr int kThreads = 256;
 
-template <int MP>
+// ST ring stages: 3 (MP = 64) / 2 (MP = 128) for the deep-K layers; launches whose CTAs run only one or two k-blocks
+// (most of the step's GEMMs after split-K) take 1 or 2 stages = 65 / 130 KB instead of 193 KB of shared memory, so
+// that the CTAs of the NEXT kernel of the chain become resident while this one still runs and programmatic
+// dependent launch really overlaps their prologue + weight-tile requests with it.
+template <int MP, int ST>
 struct Cfg {
-  static constexpr int kStages = MP == 64 ? 3 : 2;
+  static constexpr int kStages = ST;
   static constexpr int kABytes = kTileN * kBK * 2;   // 16 KB per hi / lo weight tile
   static constexpr int kBBytes = MP * kBK * 2;       // 8 / 16 KB per hi / lo activation tile
   static constexpr int kXBytes = MP * kBK * 4;       // 16 / 32 KB raw fp32 activation tile (TMA destination)
@@ -215,7 +220,7 @@ __device__ __forceinline__ void tile_epilogue(const Epi& e, const float* y, int 
   }
 }
 
-template <int MP>
+template <int MP, int ST>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_constant__ CUtensorMap tm_lo0,
                      const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_hi1,
@@ -228,7 +233,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
   const CUtensorMap& tm_lo = blockIdx.z == 0 ? tm_lo0 : tm_lo1;
   const CUtensorMap& tm_x = blockIdx.z == 0 ? tm_x0 : tm_x1;
   float* __restrict__ y = blockIdx.z == 0 ? y0 : y1;
-  using C = Cfg<MP>;
+  using C = Cfg<MP, ST>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1 KB aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + C::kStages * C::kStageBytes);
@@ -245,8 +250,8 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
   if (dbg && blockIdx.x == 0 && blockIdx.y == 0) {
     if (tid == 0) {
       slot_s = atomicAdd(&g_stamp_n, 1u);
-      g_stamps[(slot_s % 64) * 12 + 10] = gtimer();
-      g_stamps[(slot_s % 64) * 12 + 0] = (unsigned long long)clock64();
+      g_stamps[(slot_s % kStampSlots) * 12 + 10] = gtimer();
+      g_stamps[(slot_s % kStampSlots) * 12 + 0] = (unsigned long long)clock64();
     }
     __syncthreads();
     slot = slot_s;
@@ -297,7 +302,10 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
           tma_load_2d(st + C::kABytes, &tm_lo, &full_w[s], (kb0 + it) * kBK, tile * kTileN);
           // the weight tiles were written before this chain of kernels started; the activations come from the
           // predecessor: everything downstream (conversion, MMA, epilogue) is ordered after this wait
-          if (it == 0) pdl_wait();
+          if (it == 0) {
+            pdl_wait();
+            if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_stamps[(slot % kStampSlots) * 12 + 9] = gtimer();
+          }
           tma_load_2d(st + 2 * C::kABytes + 2 * C::kBBytes, &tm_x, &full_w[s], (kb0 + it) * kBK, m0);
         }
       }
@@ -455,7 +463,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
   }
   if (tid == 0) {
     STAMP(8);
-    if (dbg && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[(slot % 64) * 12 + 11] = gtimer();
+    if (dbg && blockIdx.x == 0 && blockIdx.y == 0) g_stamps[(slot % kStampSlots) * 12 + 11] = gtimer();
   }
 }
 
@@ -515,10 +523,9 @@ struct Second {                                            // second problem of 
   float* y = nullptr;
 };
 
-template <int MP>
-int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
-                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec = Second(), int m_tiles = 1,
-                  Epi epi = Epi()) {
+template <int MP, int ST>
+int launch_linear_st(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
+                     float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec, int m_tiles, Epi epi) {
   CUtensorMap tm_hi, tm_lo;
   int rc = vln_make_tmap_2d(&tm_hi, w_hi, (uint64_t)N, (uint64_t)K, (uint64_t)K, kBK, kTileN, 1);
   if (rc) return rc;
@@ -535,7 +542,7 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   }
   static bool configured = false;
   if (!configured) {
-    VLN_CHECK_CUDA(cudaFuncSetAttribute(linear_bf16x3_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MP>::kSmem));
+    VLN_CHECK_CUDA(cudaFuncSetAttribute(linear_bf16x3_kernel<MP, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MP, ST>::kSmem));
     configured = true;
   }
   const int tiles = (N + kTileN - 1) / kTileN;
@@ -544,7 +551,7 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tiles, m_tiles > 1 ? m_tiles : splits, sec.y ? 2 : 1);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg<MP>::kSmem;
+  cfg.dynamicSmemBytes = Cfg<MP, ST>::kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
@@ -562,10 +569,26 @@ int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float*
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP>, tm_hi, tm_lo, tm_x, tm_hi1, tm_lo1, tm_x1, M, N, K, bias, y,
+  VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP, ST>, tm_hi, tm_lo, tm_x, tm_hi1, tm_lo1, tm_x1, M, N, K, bias, y,
                                     sec.y ? sec.y : y, ldy, splits,
                                     accumulate, m_tiles > 1 ? 2 : mode, variant().dbg, m_tiles, epi));
   return 0;
+}
+
+// ring depth by the k-blocks a CTA runs (see Cfg); VLN_GEMM_STAGES=0 always takes the deepest ring
+template <int MP>
+int launch_linear(const void* w_hi, const void* w_lo, int N, int K, const float* x, int ldx, int M, const float* bias,
+                  float* y, int ldy, int splits, int accumulate, cudaStream_t stream, Second sec = Second(), int m_tiles = 1,
+                  Epi epi = Epi()) {
+  static const bool adapt = !(getenv("VLN_GEMM_STAGES") && getenv("VLN_GEMM_STAGES")[0] == '0');
+  const int nkb = K / kBK;
+  const int n_iter = m_tiles > 1 ? nkb : (nkb + splits - 1) / splits;
+  constexpr int kDeep = MP == 64 ? 3 : 2;
+  if (adapt && n_iter == 1)
+    return launch_linear_st<MP, 1>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, splits, accumulate, stream, sec, m_tiles, epi);
+  if (adapt && n_iter == 2)
+    return launch_linear_st<MP, 2>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, splits, accumulate, stream, sec, m_tiles, epi);
+  return launch_linear_st<MP, kDeep>(w_hi, w_lo, N, K, x, ldx, M, bias, y, ldy, splits, accumulate, stream, sec, m_tiles, epi);
 }
 
 }  // namespace
@@ -670,7 +693,7 @@ extern "C" int vln_linear_bf16x3_pair(const void* w0_hi, const void* w0_lo, cons
 
 extern "C" int vln_debug_gemm_stamps(unsigned long long* out_host /*[64*12]*/, unsigned int* n) {
   VLN_CHECK_CUDA(cudaDeviceSynchronize());
-  VLN_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_stamps, sizeof(unsigned long long) * 64 * 12));
+  VLN_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_stamps, sizeof(unsigned long long) * kStampSlots * 12));
   VLN_CHECK_CUDA(cudaMemcpyFromSymbol(n, g_stamp_n, sizeof(unsigned int)));
   return 0;
 }

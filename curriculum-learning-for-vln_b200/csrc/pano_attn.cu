@@ -84,7 +84,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
                  const int32_t* __restrict__ view, const float* __restrict__ loc4, const float* __restrict__ vec,
                  float* __restrict__ attn_io, float* __restrict__ out, int B, int mode_in, float drop_p,
                  const uint64_t* __restrict__ rng, uint64_t call_off, int ld_vec, int ld_out,
-                 const uint8_t* __restrict__ mask_bits, int dbg) {
+                 const uint8_t* __restrict__ mask_bits, int gen_mask, int dbg) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,13 +99,33 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
 
   int it = 0;
   if (dbg && blockIdx.x == 0 && tid == 0) g_pano_stamps[0] = (unsigned long long)clock64();
+  CHAIN_BEGIN(rng, 1 + 10 * mode);
   pdl_trigger();
   if (tid < 2 * VLN_V) mbar_init(&sm.full[0][0] + tid, 1);
   if (tid >= 96 && tid < 98) mbar_init(&sm.xbar[tid - 96], 1);
   fence_mbar_init();
   cluster_arrive();                                        // (waited for just before the first DSMEM store)
+  // One unit per cluster (gen_mask): the keep-bits of this CTA's half panorama (the bytes vln_feature_mask_bits would
+  // write: Philox block c of dense row ep*36 + v at byte (c % 32) * 4 + (c % 128) / 32 of the half row) are drawn HERE,
+  // ahead of the dependency wait — the CTA is resident and idle while its predecessor runs, so the Philox rounds that
+  // made the inline variant ALU-bound stay off the step's chain, and no bits cross HBM.
+  auto draw_mask = [&]() {
+    const uint64_t g_seed = rng[0], g_off = rng[1] + call_off;
+    const uint32_t g_thr = drop_threshold(drop_p);
+    for (int w = tid; w < VLN_V * kMaskBytes; w += kThreads) {
+      const int v = w >> 7, wl = w & 127;
+      const int c = rank * 128 + (wl & 3) * 32 + (wl >> 2);
+      const Philox8 r = philox8(g_seed, g_off, ((uint64_t)cid * VLN_V + (uint64_t)v) * 256 + (uint64_t)c);
+      uint32_t bits = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bits |= (philox_keep(r, k, g_thr) ? 1u : 0u) << k;
+      sm.mask[0][w] = (uint8_t)bits;
+    }
+  };
+  if (gen_mask && cid < B && !early) draw_mask();           // (backward: after the rows have been requested, below)
   __syncthreads();
   if (!early) pdl_wait();                                  // viewpoints, query and mask bits come from predecessors
+  if (!early) CHAIN_MARK(2);
   if (dbg && blockIdx.x == 0 && tid == 0) g_pano_stamps[1] = (unsigned long long)clock64();
 
   // request row r of episode `ep` (this CTA's half, and its keep-bits) into unit buffer `ub`
@@ -120,7 +140,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   const uint32_t thr = drop_threshold(drop_p);
   uint64_t seed = 0, offset = 0;
-  if (drop_p > 0.f && !mask_bits) {
+  if (drop_p > 0.f && !mask_bits && !gen_mask) {
     seed = rng[0];
     offset = rng[1] + call_off;
   }
@@ -151,7 +171,9 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
     // every warp requests the three rows it will consume in phase 1 (one warp issuing all 36-72 bulk copies
     // serialised ~30 cycles apiece: the first vectors were ready 1 us later with keep-bits than without)
     if (cid < B && lane < VLN_V / kWarps) request_row(cid, g0, warp + lane * kWarps, 0);
+    if (gen_mask && cid < B && early) draw_mask();         // while the rows are in flight
     if (early) pdl_wait();                                 // the query / gradient vector comes from the predecessor
+    if (early) CHAIN_MARK(2);
     prefetch_unit(cid, vw0, 0);
   }
 
@@ -208,7 +230,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = rowp[j * 32 + lane];
         if (drop_p > 0.f) {
-          if (mask_bits) {
+          if (mask_bits || gen_mask) {
             // pre-generated keep-bits: byte j of this lane's 4-byte group covers the 8 features of x[j]
             const uint32_t mb = *reinterpret_cast<const uint32_t*>(sm.mask[ub] + (size_t)v * kMaskBytes + lane * 4);
 #pragma unroll
@@ -344,6 +366,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   // No CTA exits while its peer could still store into it: every unit's exchange was waited for above, and a
   // cluster without any unit (cid >= B) exchanges nothing; it only completes the initial cluster barrier.
   if (it == 0) cluster_wait();
+  CHAIN_MARK(3);
 }
 
 }  // namespace
@@ -379,6 +402,8 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
   }
   const int max_clusters = ctx->num_sms / 2;
   const int clusters = B < max_clusters ? B : max_clusters;
+  // dropout without pre-generated bits: one unit per cluster draws them in shared memory ahead of the dependency wait
+  const int gen_mask = (drop_p > 0.f && !mask_bits && B <= max_clusters) ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kThreads);
@@ -394,7 +419,7 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
   cfg.attrs = attr;
   cfg.numAttrs = vln_pdl_enabled() ? 2 : 1;
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pano_attn_kernel, ctx->table, vp, view, loc4, vec, attn_io, out, B, mode, drop_p, rng,
-                                    call_off, ld_vec, ld_out, mask_bits, (getenv("VLN_PANO_STAMPS") ? atoi(getenv("VLN_PANO_STAMPS")) : 0)));
+                                    call_off, ld_vec, ld_out, mask_bits, gen_mask, (getenv("VLN_PANO_STAMPS") ? atoi(getenv("VLN_PANO_STAMPS")) : 0)));
   return 0;
 }
 

@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   __shared__ __align__(16) float ts[VLN_F];
   __shared__ float ta[4];
   __shared__ float s_logit[VLN_NSLOT];
+  __shared__ __align__(16) float s_pose[VLN_V * 4];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
+  CHAIN_BEGIN(a.rng, 6);
   pdl_trigger();
   // Everything up to the wait reads data that was complete long before the preceding kernel (the GEMM that produces
   // tgt) started: this step's state was written by the previous step's tail, five grid-wide kernels back (each of
@@ -92,6 +94,32 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
       if (k < sp_n2 && c2[k] == nh) sp_teach = k;              // first matching slot
     if (sp_cur == gl) sp_teach = sp_n2;
   }
+  // the rest of what the post-action part reads and that no predecessor writes: the pose table, the sampling uniform,
+  // this lane's two rows of the action-embedding weights and their dropout keep-scales
+  if (tid >= 32 && tid < 32 + VLN_V && a.xh != nullptr)
+    reinterpret_cast<float4*>(s_pose)[tid - 32] = __ldg(reinterpret_cast<const float4*>(a.pose4) + (tid - 32));
+  float u_sample = 0.f;
+  float4 wa[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  float ba[2] = {0.f, 0.f}, ka[2] = {1.f, 1.f};
+  if (j == 0) {
+    if ((a.feedback & 3) == 2) u_sample = philox_uniform(philox8(a.rng[0], a.rng[1] + a.off_sample, (uint64_t)b), 0);
+    if (a.xh != nullptr) {
+      const bool on = a.p_act > 0.f;
+      const uint32_t thr_a = drop_threshold(a.p_act);
+      const float sc_a = on ? 1.0f / (1.0f - a.p_act) : 1.0f;
+      const uint64_t seed_a = on ? a.rng[0] : 0, off_a = on ? a.rng[1] + a.off_act : 0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int q = lane + 32 * r;
+        if (q < a.E) {
+          wa[r] = __ldg(reinterpret_cast<const float4*>(a.w_act + (size_t)q * 4));
+          ba[r] = a.b_act[q];
+          const int i = b * a.E + q;
+          if (on) ka[r] = philox_keep(philox8(seed_a, off_a, (uint64_t)(i >> 3)), i & 7, thr_a) ? sc_a : 0.f;
+        }
+      }
+    }
+  }
   // this warp's candidate row (8 x 16 bytes per lane), its angle feature, and the feature-dropout keep mask
   // (policy.py:226-231) applied in registers — none of it depends on the preceding kernel
   uint4 xr[8];
@@ -113,6 +141,7 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
     }
   }
   pdl_wait();
+  CHAIN_MARK(2);
   // ---- candidate logits (cand_logits_fwd_kernel) ----
   for (int i = tid; i < VLN_F; i += 512) ts[i] = a.tgt[(size_t)b * VLN_F + i];
   __syncthreads();
@@ -163,7 +192,7 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
   } else if (mode == 1) {
     act_id = __ffs(__ballot_sync(0xffffffffu, x == m)) - 1;
   } else {
-    const float u = philox_uniform(philox8(a.rng[0], a.rng[1] + a.off_sample, (uint64_t)b), 0);
+    const float u = u_sample;
     float cdf = p;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -206,20 +235,37 @@ __global__ void __launch_bounds__(512) cand_policy_env_act_kernel(const __grid_c
     a.teacher_out[b] = now_ended ? -1 : teach;
     if (a.n_active && !now_ended) atomicAdd(a.n_active, 1);
   }
-  // ---- next pass's action embedding for the new view (act_fwd_kernel) ----
-  if (a.xh == nullptr) return;
-  const bool on = a.p_act > 0.f;
-  const uint32_t thr_a = drop_threshold(a.p_act);
-  const float sc_a = on ? 1.0f / (1.0f - a.p_act) : 1.0f;
-  const uint64_t seed_a = on ? a.rng[0] : 0, off_a = on ? a.rng[1] + a.off_act : 0;
-  for (int q = lane; q < a.E; q += 32) {
-    const float v = act_embed_one(a.w_act + (size_t)q * 4, a.pose4 + (size_t)vw * 4, a.b_act[q]);
-    const int i = b * a.E + q;
-    a.act[i] = v;
-    float k = 1.f;
-    if (on) k = philox_keep(philox8(seed_a, off_a, (uint64_t)(i >> 3)), i & 7, thr_a) ? sc_a : 0.f;
-    a.xh[(size_t)b * a.ld_xh + q] = v * k;
+  // ---- next pass's action embedding for the new view (act_fwd_kernel; weights, bias, keep-scales fetched above) ----
+  if (a.xh == nullptr) {
+    CHAIN_MARK(3);
+    return;
   }
+  const float4 pz = *reinterpret_cast<const float4*>(s_pose + vw * 4);
+  if (a.E <= 64) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int q = lane + 32 * r;
+      if (q < a.E) {
+        const float v = tanhf(fmaf(pz.w, wa[r].w, fmaf(pz.z, wa[r].z, fmaf(pz.y, wa[r].y, fmaf(pz.x, wa[r].x, ba[r])))));
+        a.act[b * a.E + q] = v;
+        a.xh[(size_t)b * a.ld_xh + q] = v * ka[r];
+      }
+    }
+  } else {                                       // wider embeddings: the general loop
+    const bool on = a.p_act > 0.f;
+    const uint32_t thr_a = drop_threshold(a.p_act);
+    const float sc_a = on ? 1.0f / (1.0f - a.p_act) : 1.0f;
+    const uint64_t seed_a = on ? a.rng[0] : 0, off_a = on ? a.rng[1] + a.off_act : 0;
+    for (int q = lane; q < a.E; q += 32) {
+      const float v = act_embed_one(a.w_act + (size_t)q * 4, a.pose4 + (size_t)vw * 4, a.b_act[q]);
+      const int i = b * a.E + q;
+      a.act[i] = v;
+      float k = 1.f;
+      if (on) k = philox_keep(philox8(seed_a, off_a, (uint64_t)(i >> 3)), i & 7, thr_a) ? sc_a : 0.f;
+      a.xh[(size_t)b * a.ld_xh + q] = v * k;
+    }
+  }
+  CHAIN_MARK(3);
 }
 
 }  // namespace

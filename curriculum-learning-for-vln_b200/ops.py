@@ -51,7 +51,10 @@ class Rng:
     every dropout site so tests can regenerate the very same masks for the oracle."""
 
     def __init__(self, seed=2020, device="cuda"):
-        self.state = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        # words 0, 1 = {seed, base} (the C-ABI's rng state); the room behind them is only touched by the debug build's
+        # chain stamps (csrc/common.cuh CHAIN_BEGIN: word 2 = enable, word 3 = count, 4 words per record from word 4)
+        self.state = torch.zeros(4 + 4 * 8192, dtype=torch.int64, device=device)
+        self.state[0] = int(seed) & 0x7FFFFFFFFFFFFFFF
         self.off = 0
         self.log = None
 

@@ -88,7 +88,7 @@ def stamps():
     import ctypes as C
     from clvln_b200 import _lib
     L = _lib.lib()
-    buf = (C.c_ulonglong * (64 * 12))()
+    buf = (C.c_ulonglong * (1024 * 12))()
     n = C.c_uint()
     L.vln_debug_gemm_stamps.argtypes = [C.c_void_p, C.c_void_p]
     L.vln_debug_gemm_stamps(buf, C.byref(n))
