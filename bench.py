@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 METRIC = "train episodes/sec (EnvDrop IL+A2C iteration, B=64/GPU, L=80)"
 UNIT = "episodes/s"
 B_PER_GPU = 64
+WORKLOAD = ("EnvDrop IL+A2C training iteration (teacher rollout + 35-step sampled rollout + backward + clip + RMSprop), "
+            "B=%d/GPU, L=80, 36x2176 features, H=512")
 ALGO_BYTES_PER_EPISODE_STEP = 36 * 2048 * 2
 
 
@@ -209,7 +211,8 @@ def roofline_others(ops, torch, B, peaks):
     out.append({"kernel": "linear_bf16x3 (LSTMCell gates, %dx%dx%d, bf16x3 = 3 MMAs per product)" % (N, K, B), "bound": "l2",
                 "us_per_launch": round(t * 1e6, 2), "weight_GBs_from_l2": round(N * K * 4 / t / 1e9, 1),
                 "achieved_tflops": round(tf, 1), "peak_tflops": peak_tf, "tensor_frac": round(tf / peak_tf, 4),
-                "note": "skinny (M = batch): bound by streaming the L2-resident weights (+ the activation tile every N-tile CTA re-reads), not by the tensor pipe"})
+                "useful_tflops": round(tf / 3, 1), "tensor_frac_useful": round(tf / 3 / peak_tf, 4),
+                "note": "skinny (M = batch): bound by streaming the L2-resident weights (+ the activation tile every N-tile CTA re-reads), not by the tensor pipe; tensor_frac counts the three bf16 MMAs of every bf16x3 product, tensor_frac_useful counts 2*M*N*K once"})
     L, H = 80, 256
     xproj = [torch.randn(B, L, 4 * H, device=dev) * 0.1 for _ in range(2)]
     whh = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
@@ -220,6 +223,21 @@ def roofline_others(ops, torch, B, peaks):
                 "us_per_launch": round(t * 1e6, 1), "us_per_timestep": round(t * 1e6 / L, 3),
                 "achieved_tflops": round(tf, 2), "peak_tflops": peak_tf, "tensor_frac": round(tf / peak_tf, 5),
                 "note": "80 serial steps; per step and CTA 48 tcgen05.mma of 128x16x16 (8 cycles each) inside a ~2 900-cycle exchange / gate-math chain"})
+    # text-attention stage of a decoder step (csrc/ctx_step.cu): LSTM pointwise + masked softmax over the instruction +
+    # weighted context, one CTA per episode; algorithmic bytes = the episode's CW and ctx tiles, 2 x L x H x 4 B (L2-resident)
+    H = 512
+    gates, c0 = torch.randn(B, 4 * H, device=dev), torch.randn(B, H, device=dev)
+    h1, c1, acts = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev), torch.empty(B, 4 * H, device=dev)
+    wh, attn = torch.zeros(B, 2 * H, device=dev), torch.empty(B, L, device=dev)
+    ctx, cw = torch.randn(B, L, H, device=dev), torch.randn(B, L, H, device=dev) * 0.05
+    rng = ops.Rng(3, dev)
+    t = time_graph(lambda: ops._call("vln_envdrop_ctx_step_fwd", ops._ptr(gates), ops._ptr(c0), ops._ptr(h1), ops._ptr(c1),
+                                     ops._ptr(acts), ops._ptr(wh), 2 * H, ops._ptr(ctx), ops._ptr(cw), ops._ptr(lengths),
+                                     ops._ptr(attn), B, L, H, 0.5, rng.ptr, 1, 1, ops._stream()))
+    by = B * 2 * L * H * 4
+    out.append({"kernel": "ctx_step_fwd (LSTM pointwise + text attention, B=%d, L=%d, H=%d)" % (B, L, H), "bound": "l2",
+                "us_per_launch": round(t * 1e6, 2), "algorithmic_bytes": by, "achieved_GBs": round(by / t / 1e9, 1),
+                "note": "per-episode CTA: one bulk copy of the dotted tile into shared memory + the summed tile in registers; latency-bound at B=64 (21 MB per launch)"})
     return out
 
 
@@ -274,6 +292,60 @@ def cpu_iteration_factory(world_small, items, B, threads):
         opt.step()
         return float(loss)
     return iteration
+
+
+def reference_iteration_factory(world, items, B, threads):
+    """One EnvDrop training iteration of the UNMODIFIED reference (trainer.py:411-429: EnvDropAgent.rollout teacher +
+    sampled, backward, clip_grad_norm x2, RMSprop) on the host cores: the reference's own agent / decoder / R2RBatch code
+    from oracle/_ref (oracle/build_ref.py), with only its external inputs substituted (oracle/ref_harness.py: the
+    Matterport simulator -> a table-driven graph walker, dataset / connectivity loaders -> the synthetic world).
+    Returns None when oracle/_ref is not there."""
+    import contextlib
+    import random
+    import torch
+    from oracle import ref_loader, ref_harness as H
+    if not ref_loader.reference_available():
+        return None
+    torch.set_num_threads(threads)
+    with contextlib.redirect_stdout(sys.stderr):           # the reference prints progress lines; stdout carries ONE json line
+        src = H.install(world, {"train": items})
+        import src.environ as environ
+        import src.agent as agent_mod
+        tok = H.StubTokenizer(items)
+        fs = H.feature_store(world)
+        random.seed(2020)
+        torch.manual_seed(2020)
+        env = environ.R2RBatch(fs, batch_size=B, splits=["train"], tokenizer=tok)
+        cfg = H.model_cfg("ENVDROP")
+        ag = agent_mod.EnvDropAgent(cfg, 80, "/tmp", torch.device("cpu"), env, tok, episode_len=35)
+    ag.env = env
+    ag.train()
+    params = list(ag.encoder.parameters()) + list(ag.decoder.parameters()) + list(ag.critic.parameters())
+    opt = torch.optim.RMSprop(params, lr=1e-4)
+
+    def iteration():
+        with contextlib.redirect_stdout(sys.stderr):
+            ag.rollout(train_ml=True, train_rl=False, feedback="teacher")
+            ml = ag.loss["ml_loss"]
+            ag.rollout(train_ml=False, train_rl=True, restart=True, feedback="sample")
+            loss = ml + ag.loss["rl_loss"]
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(ag.encoder.parameters(), 40.0)
+            torch.nn.utils.clip_grad_norm_(ag.decoder.parameters(), 40.0)
+            opt.step()
+        return float(loss.detach())
+    return iteration
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 def cpu_per_op(B, threads, world, items):
@@ -374,27 +446,36 @@ def host_threads():
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python
-    reference itself cannot travel to the GPU box) on all host threads, same metric and config."""
+    """--impl reference: the reference's own CPU implementation of the iteration on all host threads, same metric and
+    workload — the UNMODIFIED reference agent from oracle/_ref when it is there (kind "reference": full 90-scan world,
+    the same 14 039 synthetic episodes as the CUDA arm), else the oracle port (kind "port", 8-scan world)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     threads = host_threads()
-    from clvln_b200.environ import make_world, make_items
-    world = make_world(n_scans=8, seed=2020)
+    from oracle import ref_loader
     B = args.batch
-    items = make_items(world, max(4 * B, 256), seed=2020, fixed_len=80)
-    it = cpu_iteration_factory(world, items, B, threads)
+    real = ref_loader.reference_available()
+    if real:
+        world, items = build_world(args.small, None, with_table=True, lengths="80")
+        make = lambda b: reference_iteration_factory(world, items, b, threads)
+        world_desc = "%d-viewpoint synthetic world (%d scans)" % (world.n_vp, len(world.scans))
+    else:
+        from clvln_b200.environ import make_world, make_items
+        world = make_world(n_scans=8, seed=2020)
+        items = make_items(world, max(4 * B, 256), seed=2020, fixed_len=80)
+        make = lambda b: cpu_iteration_factory(world, items, b, threads)
+        world_desc = "8-scan synthetic world"
+    it = make(B)
     t0 = time.time()
     it()                                                  # probe (also the first warm-up)
     probe = time.time() - t0
     budget = 200.0
     n_total = args.steps + args.warmup
-    if probe * n_total > budget and B > 16:               # bound the run: smaller per-step sample
+    if probe * n_total > budget and B > 16:               # bound the run: a step becomes a 16-episode sample of the batch
         B = 16
-        items = make_items(world, 256, seed=2020, fixed_len=80)
-        it = cpu_iteration_factory(world, items, B, threads)
+        it = make(B)
         it()
     for _ in range(max(0, args.warmup - 1)):
         it()
@@ -403,15 +484,19 @@ def run_reference(args):
         it()
     dt = time.time() - t0
     v = B * args.steps / dt
-    sample = f"{args.steps} full EnvDrop training iterations (teacher + 35-step sampled rollout + backward + clip + RMSprop) at B={B}, L=80, 8-scan synthetic world, fp32, {threads} torch threads"
+    what = "the unmodified reference (src/agent/envdrop.py rollout x2 + backward + clip_grad_norm x2 + RMSprop, oracle/_ref)" \
+        if real else "oracle CPU restatement of the reference"
+    sample = (f"{args.steps} full EnvDrop training iterations (teacher + 35-step sampled rollout + backward + clip + RMSprop) at "
+              f"B={B}, L=80, {world_desc}, fp32, {threads} torch threads: {what}")
     extra = {"per_op_ms": cpu_per_op(args.batch, threads, world, items)} if args.per_op else {}
-    print(json.dumps({**extra, 
+    print(json.dumps({**extra,
         "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "EnvDrop IL+A2C training iteration, B=%d/step, L=80, 36x2176 features, H=512, <=35 steps" % B,
-                   "device": "host CPU", "torch_threads": threads},
-        "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD % B, "device": "host CPU: " + cpu_model(), "torch_threads": threads,
+                   "world": world_desc},
+        "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": threads, "cpu": cpu_model(),
+                         "kind": "reference" if real else "port", "sample": sample},
         "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -491,9 +576,9 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": round(n_ep / t_dev, 2), "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(t_dev / args.steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16 feature table, fp32 accumulate)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 state/accumulate; bf16 feature table; forward + input-gradient GEMMs bf16x3 on tcgen05 (3 bf16 MMAs per product, ~2e-5 rel); weight-gradient GEMMs TF32",
         "data": "synthetic",
-        "config": {"workload": "EnvDrop IL+A2C training iteration (teacher rollout + 35-step sampled rollout + backward + clip + RMSprop), B=%d/GPU, L=80, 36x2176 features, H=512" % args.batch,
+        "config": {"workload": WORKLOAD % args.batch,
                    "global_batch": args.batch * world_size, "parallelism": f"dp{world_size}",
                    "table": "%d viewpoints x 36 x 2048 bf16 = %.2f GB in HBM" % (world.n_vp, world.n_vp * 36 * 2048 * 2 / 1e9),
                    "l2": "inputs larger than L2: every step gathers random viewpoints from the %.2f GB table" % (world.n_vp * 36 * 2048 * 2 / 1e9),
@@ -517,18 +602,26 @@ def run_b200(args):
             out["roofline"]["others"] = roofline_others(ops, torch, args.batch, peaks)
         if world_size == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            from clvln_b200.environ import make_world, make_items
-            w_small = make_world(n_scans=8, seed=2020)
+            from oracle import ref_loader
             B = args.batch
-            it = cpu_iteration_factory(w_small, make_items(w_small, 4 * B, seed=2020, fixed_len=80), B, threads)
+            real = ref_loader.reference_available()
+            if real:        # the unmodified reference (oracle/_ref) on this very world and episode set
+                it = reference_iteration_factory(world, items, B, threads)
+                desc = "%d-viewpoint world; the unmodified reference agent + trainer recipe from oracle/_ref" % world.n_vp
+            else:
+                from clvln_b200.environ import make_world, make_items
+                w_small = make_world(n_scans=8, seed=2020)
+                it = cpu_iteration_factory(w_small, make_items(w_small, 4 * B, seed=2020, fixed_len=80), B, threads)
+                desc = "8-scan synthetic world; oracle CPU restatement of the reference"
             it()
             n, t0 = 0, time.time()
-            while n < 2 or (time.time() - t0 < 12.0 and n < 50):
+            while n < 2 or (time.time() - t0 < 15.0 and n < 50):
                 it()
                 n += 1
             dt = time.time() - t0
-            out["cpu_baseline"] = {"value": round(B * n / dt, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                                   "sample": f"{n} full EnvDrop training iterations at B={B}, L=80 on an 8-scan synthetic world (oracle CPU restatement of the reference, fp32, {threads} torch threads, {dt:.1f} s)"}
+            out["cpu_baseline"] = {"value": round(B * n / dt, 3), "unit": UNIT, "cores": threads, "cpu": cpu_model(),
+                                   "kind": "reference" if real else "port",
+                                   "sample": f"{n} full EnvDrop training iterations at B={B}, L=80 ({desc}; fp32, {threads} torch threads, {dt:.1f} s)"}
         print(json.dumps(out), flush=True)
     if world_size > 1:
         dist.destroy_process_group()

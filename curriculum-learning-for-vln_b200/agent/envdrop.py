@@ -73,10 +73,14 @@ class EnvDropAgent(BaseAgent):
         ib2 = dataclasses.replace(ib, tokens=two(ib.tokens), lengths=two(ib.lengths), lengths_cpu=two(ib.lengths_cpu),
                                   vp=two(ib.vp), view=two(ib.view), goal=two(ib.goal), index=two(ib.index))
         prep = self._fused.prepare(self.rng, 2 * B, T, "sample", True, self.device, pair=(B, T_t), L=ib2.tokens.shape[1])
+        torch.cuda.nvtx.range_push("vln/encoder")
         ctx, h_t, c_t = self.encoder(ib2.tokens, ib2.lengths)
+        torch.cuda.nvtx.range_pop()
         st = RolloutState(store, ib2, T + 1)
+        torch.cuda.nvtx.range_push("vln/decoder_rollout")
         (ce, logps, ents, hiddens, logits, actions, targets, rewards, masks, last_h) = self._fused.run(
             self.rng, st, ctx, ib2.lengths, h_t, c_t, T, "sample", True, 0, self.split_for(2 * B), prep, pair=(B, T_t))
+        torch.cuda.nvtx.range_pop()
         n = st.steps
         ml = ce[:T_t, B:].sum(0) if train_cl else ce[:T_t, B:].sum()
         if self.trace is not None:

@@ -192,6 +192,11 @@ class FusedDecoder:
                           _stream())
                     _call("vln_feature_mask_bits_ld", _ptr(MB), (B - B_main) * V, B * V, B_main * V, T_t, pf, rng.ptr,
                           offs[0]["img"], stride, _stream())
+        if side is not None:            # this iteration's bf16 weight splits (they only depend on the weights): off the
+            with torch.cuda.stream(side):        # chain between encoder and decoder
+                self.cat.fresh(dec.lstm.weight_ih, dec.lstm.weight_hh)
+                for w in self.params()[6:10]:
+                    ops._split_of(w)
         if L is not None:               # the rollout's work buffers: allocated + zero-filled under the encoder
             with torch.cuda.stream(side):
                 bufs = _make_buffers(S, T, B, L, dec.hidden_size, device, pair is not None)

@@ -114,6 +114,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+// one row of a CTA's partial tile, shared -> global, added (split-K merge) or stored by the bulk-copy engine: the L2
+// performs the 512-byte row as whole-sector operations instead of 32 separate 16-byte REDs from the LSU
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_f32(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {   // round-to-nearest-even, a in the low half
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -378,6 +394,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) red[(cb * 32 + j) * kTileN + wq * 32 + lane] = __uint_as_float(v[j]);
       }
+      fence_proxy_async();                                   // the bulk-copy engine (async proxy) reads this tile below
     }
   }
   // ---------------- epilogue, part 2: cluster reduction through distributed shared memory ----------------
@@ -385,8 +402,36 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
   tc_fence_before();
   __syncthreads();
   if (tid == 0) STAMP(6);
-  if (mode == 2) {
-    // experiment: no cluster; partial tiles meet in y through 16-byte vector reductions (REDG.ADD.F32x4)
+  if (mode == 3) {
+    // (variant) split-K merge by the bulk-copy engine: one cp.reduce.async.bulk (add.f32) per row of the partial tile
+    // instead of the per-thread vector reductions below (which take 2-3 us of every launch in the step chain)
+    float* red = reinterpret_cast<float*>(base);
+    if (bias != nullptr && split == 0 && n_iter > 0) {       // (CTA-uniform) the bias joins the first split's tile
+      for (int item = tid; item < MP * (kTileN / 4); item += kThreads) {
+        const int m = item / (kTileN / 4), c = (item - m * (kTileN / 4)) * 4;
+        const int n = tile * kTileN + c;
+        if (n >= N) continue;
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+        float4* p = reinterpret_cast<float4*>(red + m * kTileN + c);
+        float4 a = *p;
+        a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
+        *p = a;
+      }
+      fence_proxy_async();
+      __syncthreads();
+    }
+    const int rows_here = min(MP, M - m0);
+    const int n0 = tile * kTileN;
+    const uint32_t row_bytes = (uint32_t)min(kTileN, N - n0) * 4u;
+    if (n_iter > 0 && tid < rows_here) {
+      float* dst = y + (size_t)(m0 + tid) * ldy + n0;
+      if (m_tiles > 1 && !accumulate) bulk_store_f32(dst, red + tid * kTileN, row_bytes);   // the only writer of this block
+      else bulk_reduce_add_f32(dst, red + tid * kTileN, row_bytes);
+      bulk_commit_wait_all();                                // complete (not merely read) before this thread goes on
+    }
+    if (epi.kind != 0) tile_epilogue(epi, y, ldy, M, N, tile, split, splits, tid);
+  } else if (mode == 2) {
+    // partial tiles meet in y through 16-byte vector reductions (REDG.ADD.F32x4); VLN_GEMM_BULK=0 selects this path
     const float* red = reinterpret_cast<const float*>(base);
     for (int item = tid; item < MP * (kTileN / 4); item += kThreads) {
       const int m = item / (kTileN / 4), c = (item - m * (kTileN / 4)) * 4;
@@ -500,9 +545,12 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __
 // split-K merge strategy (read once): VLN_GEMM_VARIANT = red4 (default: vector reductions into y) |
 // c8 | c4 | c2 | c1 (splits of a tile form a cluster and reduce through DSMEM; measured slower)
 struct Variant {
-  int cap = 8, mode = 2, dbg = 0;
+  int cap = 8, mode = 2, dbg = 0, bulk = 0;
   Variant() {
     dbg = getenv("VLN_GEMM_STAMPS") != nullptr;
+    // VLN_GEMM_BULK=1: split-K merge through cp.reduce.async.bulk rows instead of REDG.128 (measured slower in the
+    // iteration: 4.45 vs 4.36 ms, the wait for the bulk group's completion outweighs the shorter issue phase)
+    bulk = getenv("VLN_GEMM_BULK") && getenv("VLN_GEMM_BULK")[0] == '1';
     const char* e = getenv("VLN_GEMM_VARIANT");
     if (!e) return;
     if (!strcmp(e, "c8")) mode = 0;
@@ -571,7 +619,8 @@ int launch_linear_st(const void* w_hi, const void* w_lo, int N, int K, const flo
   cfg.numAttrs = na;
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP, ST>, tm_hi, tm_lo, tm_x, tm_hi1, tm_lo1, tm_x1, M, N, K, bias, y,
                                     sec.y ? sec.y : y, ldy, splits,
-                                    accumulate, m_tiles > 1 ? 2 : mode, variant().dbg, m_tiles, epi));
+                                    accumulate, (m_tiles > 1 || mode == 2) ? (variant().bulk ? 3 : 2) : mode, variant().dbg, m_tiles,
+                                    epi));
   return 0;
 }
 

@@ -80,12 +80,23 @@ class TrainStep:
 
     def __call__(self):
         ag = self.agent
+        nvtx = torch.cuda.nvtx if ag.device.type == "cuda" else None      # ranges for nsys / ncu --nvtx
         if ag.rng is not None:
             ag.rng.begin_iteration()
         self.opt.zero_grad()
+        if nvtx:
+            nvtx.range_push("vln/rollouts")
         loss, item = self.losses()
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push("vln/backward")
         loss.backward()
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push("vln/allreduce+clip+update")
         self.opt.step()
+        if nvtx:
+            nvtx.range_pop()
         if item is not None:
             self.weights.record(ag.last_batch.index, item)
         return loss.detach()

@@ -17,7 +17,11 @@ import types
 
 import torch
 
+# the reference itself where it exists (this container), else its unmodified copy under oracle/_ref (oracle/build_ref.py;
+# what reaches the GPU box)
 REF_ROOT = os.environ.get("VLN_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REF_ROOT, "tasks", "R2R-judy", "src", "model", "units.py")):
+    REF_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REF_TASK = os.path.join(REF_ROOT, "tasks", "R2R-judy")
 
 

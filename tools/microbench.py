@@ -51,6 +51,9 @@ def main():
     ap.add_argument("--drops", type=float, nargs="*", default=[0.0, 0.3])
     ap.add_argument("--modes", type=int, nargs="*", default=[0, 1], help="0 forward, 1 backward")
     ap.add_argument("--no-cand", action="store_true")
+    ap.add_argument("--cands", type=int, nargs="*", default=[1, 2, 4, 8, 12, 15],
+                    help="candidate counts of the cand_logits sweep (BASELINE config 5: candidates 1-16 incl. the END slot)")
+    ap.add_argument("--cand-batches", type=int, nargs="*", default=[64, 256, 1024])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peaks = {}
@@ -98,19 +101,35 @@ def main():
                                           drop=drop, us=round(t * 1e6, 2), algo_GBs=round(gbs, 1),
                                           frac_of_measured_peak=round(gbs / peak, 3))), flush=True)
             del bits
-        if args.no_cand:
-            continue
+    if args.no_cand:
+        return
+    # ---- candidate logits, fwd + bwd, swept over the number of navigable candidates per episode (config 5) ----
+    # every viewpoint of a launch has exactly n_cand candidates: algorithmic bytes = B * n_cand * 2048 * 2 each way
+    nc_tab = store.n_cand
+    for B in args.cand_batches:
+        vps = [torch.randint(0, n_vp, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(N_SETS)]
+        view = torch.randint(0, 36, (B,), device=dev, dtype=torch.int32, generator=g)
         tgt = torch.randn(B, 2176, device=dev) * 0.05
         logits = torch.empty(B, 16, device=dev)
-        ncs = sum(int(tables["n_cand"][v.long()].sum()) for v in vps) / N_SETS
+        dlogits = torch.randn(B, 16, device=dev)
+        d_tgt = torch.empty(B, 2176, device=dev)
+        for nc in args.cands:
+            nc_tab.fill_(nc)
+            for drop in (0.0, 0.3):
+                def run_f(k):
+                    ops._call("vln_cand_logits_fwd", store.handle, ops._ptr(vps[k]), ops._ptr(view), ops._ptr(store.cand_view),
+                              ops._ptr(store.cand_ang4), ops._ptr(nc_tab), ops._ptr(tgt), None, ops._ptr(logits), B, drop,
+                              rng.ptr, 3 + k, ops._stream())
 
-        def run_c(k):
-            ops._call("vln_cand_logits_fwd", store.handle, ops._ptr(vps[k]), ops._ptr(view), ops._ptr(store.cand_view),
-                      ops._ptr(store.cand_ang4), ops._ptr(store.n_cand), ops._ptr(tgt), None, ops._ptr(logits), B, 0.0,
-                      None, 0, ops._stream())
-        t = time_graph(run_c)
-        print(json.dumps(dict(kernel="cand_logits_fwd", B=B, us=round(t * 1e6, 2),
-                              algo_GBs=round(ncs * 4096 / t / 1e9, 1))), flush=True)
+                def run_b(k):
+                    ops._call("vln_cand_logits_bwd", store.handle, ops._ptr(vps[k]), ops._ptr(view), ops._ptr(store.cand_view),
+                              ops._ptr(store.cand_ang4), ops._ptr(nc_tab), ops._ptr(dlogits), ops._ptr(d_tgt), None, B, drop,
+                              rng.ptr, 3 + k, ops._stream())
+                for name, fn in (("cand_logits_fwd", run_f), ("cand_logits_bwd", run_b)):
+                    t = time_graph(fn)
+                    gbs = B * nc * 4096 / t / 1e9
+                    print(json.dumps(dict(kernel=name, B=B, n_cand=nc, drop=drop, us=round(t * 1e6, 2), algo_GBs=round(gbs, 1),
+                                          frac_of_measured_peak=round(gbs / peak, 4))), flush=True)
 
 
 if __name__ == "__main__":
