@@ -132,6 +132,8 @@ class FusedDecoder:
         self.async_wgrad = False       # set by TrainStep (which always differentiates with .backward() into .grad buffers)
         self._wgrad_stream = None
         self.counters = None           # arrive / depart counters of the GEMM tile epilogues (zero between launches)
+        self.on_grads_ready = None     # set by TrainStep under data parallelism: called (on the stream that accumulated them)
+        #                                once this node's weight gradients are final -> early all-reduce of their bucket
 
     def params(self):
         d = self.dec
@@ -477,6 +479,8 @@ class _Rollout(torch.autograd.Function):
                 grads = weight_grads()
                 for q, g_ in zip(params, grads):
                     q.grad.add_(g_)
+                if fd.on_grads_ready is not None:
+                    fd.on_grads_ready()
             keep = [grads, DGATES, XH, WH, HQ, HC, DTQ, DPRE, DQ, DTGT, DACT, dCW, ctx]    # alive until the join (allocator safety)
 
             def join():

@@ -49,6 +49,7 @@ class GraphedTrainStep(TrainStep):
         self.opt.zero_grad()
         loss, item = self.losses()
         loss.backward()
+        self.opt.finish_reduce()            # data parallel: the rest of the gradient all-reduce, inside the graph
         self.agent.rng.advance()
         return loss.detach(), item
 
@@ -113,6 +114,8 @@ class GraphedTrainStep(TrainStep):
             g, loss, item, n_calls, stat, refs = self.graphs[key]
             g.replay()
             ops.CALLS[0] += n_calls
+            if self.opt.world > 1:
+                self.opt._reduced = [(0, self.opt.grad.numel())]      # the replayed graph all-reduced the whole buffer
             ag.last_state, ag.last_batch = refs[0], refs[1]
             if getattr(ag, "_fused", None) is not None:
                 ag._fused.last = refs[2]

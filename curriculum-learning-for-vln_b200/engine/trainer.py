@@ -44,6 +44,13 @@ class TrainStep:
         if agent.device.type == "cuda":           # same for the encoder's leaf gradients (ops._leaf_grads_async)
             from .. import ops
             ops.ASYNC_LEAF_GRADS[0] = os.environ.get("VLN_ASYNC_WGRAD", "1") != "0"
+        # data parallel: the decoder's + critic's gradient bucket is all-reduced as soon as the decoder's backward through
+        # time has produced it, under the encoder's backward (engine/optim.py reduce_range); groups = [encoder, decoder, critic]
+        fd = getattr(agent, "_fused", None)
+        if (fd is not None and getattr(self.opt, "world", 1) > 1 and fd.async_wgrad and self.name == "ENVDROP"
+                and os.environ.get("VLN_EARLY_ALLREDUCE", "1") != "0"):
+            lo, hi = self.opt.group_offsets[1], self.opt.grad.numel()
+            fd.on_grads_ready = lambda: self.opt.reduce_range(lo, hi)
 
     def losses(self):
         """Run the rollouts; return (loss to differentiate, per-item loss record or None)."""

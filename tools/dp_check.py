@@ -54,13 +54,26 @@ def main():
     B = 8
     # ---- data-parallel run: this rank's shard, gradient all-reduced by the optimiser's own call ----
     cfg, env, agent, step = make(rank, ws, dev, B)
+    hook, agent._fused.on_grads_ready = agent._fused.on_grads_ready, None      # first without the early bucket: local gradient
     step.opt.zero_grad()
     loss, _ = step.losses()
     loss.backward()
     torch.cuda.synchronize()
     g_local = step.opt.grad.clone()
-    dist.all_reduce(step.opt.grad, op=dist.ReduceOp.SUM)            # what FlatOptimizer.step does first
+    # the same minibatch again through the optimiser's own path: decoder + critic bucket all-reduced from inside the
+    # backward pass (under the encoder's BPTT), the encoder's bucket by finish_reduce
+    agent._fused.on_grads_ready = hook
+    assert hook is not None, "TrainStep did not install the early all-reduce hook"
+    env.reset_index = (lambda orig: (lambda **kw: orig(restart=True)))(env.reset_index)
+    step.opt.zero_grad()
+    loss, _ = step.losses()
+    loss.backward()
+    step.opt.finish_reduce()
+    torch.cuda.synchronize()
     g_dp = step.opt.grad / ws
+    g_sum = g_local.clone()
+    dist.all_reduce(g_sum, op=dist.ReduceOp.SUM)
+    bucket_err = float((g_dp - g_sum / ws).abs().max() / (g_sum / ws).abs().max())
     shard_ids = [it["instr_id"] for it in env.batch]
     out = {}
     if rank == 0:
@@ -84,7 +97,7 @@ def main():
         g_ref = g_sum / ws
         cos = float(torch.dot(g_dp, g_ref) / (g_dp.norm() * g_ref.norm()))
         rel = float((g_dp - g_ref).abs().max() / g_ref.abs().max())
-        out.update(grad_cosine=cos, grad_max_rel=rel, local_vs_mean_cosine=float(torch.dot(g_local, g_ref) / (g_local.norm() * g_ref.norm())))
+        out.update(grad_cosine=cos, grad_max_rel=rel, bucketed_vs_single_allreduce_max_rel=bucket_err, local_vs_mean_cosine=float(torch.dot(g_local, g_ref) / (g_local.norm() * g_ref.norm())))
     # ---- three real optimiser steps: parameters must stay identical on every rank ----
     cfg, env, agent, step = make(rank, ws, dev, B)
     losses = [float(step()) for _ in range(3)]
