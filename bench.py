@@ -624,7 +624,17 @@ def run_b200(args):
                                    "sample": f"{n} full EnvDrop training iterations at B={B}, L=80 ({desc}; fp32, {threads} torch threads, {dt:.1f} s)"}
         print(json.dumps(out), flush=True)
     if world_size > 1:
+        # the iteration graphs hold captured NCCL kernels: release them before the communicator, and never let a stuck
+        # teardown keep the job alive (the result line is out)
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        torch.cuda.synchronize()
+        if hasattr(step, "graphs"):
+            step.graphs.clear()
+        del step
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

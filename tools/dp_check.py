@@ -79,6 +79,7 @@ def main():
     if rank == 0:
         # ---- single process: the same global minibatch, each rank's shard in turn, mean of the gradients ----
         cfg1, env1, agent1, step1 = make(0, 1, dev, B * ws)
+        agent1._fused.on_grads_ready = None                 # single-process reference: no collective may be issued here
         env1._next_minibatch()
         glob = list(env1.batch)
         assert [it["instr_id"] for it in glob[0::ws]] == shard_ids, "shard 0 is not rows 0::world of the sorted global batch"
@@ -110,7 +111,8 @@ def main():
         out.update(world_size=ws, params_identical_after_3_steps=bool(same.item()), rank0_losses=[round(x, 4) for x in losses])
         print(json.dumps(out), flush=True)
         assert out["grad_cosine"] > 0.99999 and out["grad_max_rel"] < 1e-3 and out["params_identical_after_3_steps"]
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
