@@ -415,8 +415,17 @@ __device__ __forceinline__ int group_of(const Groups& gr, int64_t i) {
   return k;
 }
 
+// Per-group sum of squares, DETERMINISTIC: every block writes its partial sums to a scratch slot, the last block to
+// arrive (ticket) adds the slots in index order.  (A plain atomicAdd per block gives an order-dependent fp32 sum:
+// under data parallelism the ranks then compute clip coefficients that differ in the last bit and their parameters
+// drift apart by an ulp per step — found by tools/dp_check.py.)
+constexpr int kSqBlocks = 296;
+__device__ float g_sq_partials[kSqBlocks * 4];
+__device__ unsigned int g_sq_ticket;
+
 __global__ void sqnorm_kernel(const float* __restrict__ grad, Groups gr, float scale, float* __restrict__ sqnorm) {
   __shared__ float red[4][32];
+  __shared__ bool last;
   const int64_t n4 = gr.off[gr.n] >> 2;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -439,8 +448,20 @@ __global__ void sqnorm_kernel(const float* __restrict__ grad, Groups gr, float s
     for (int k = 0; k < 4; ++k) {
       float s = lane < (blockDim.x >> 5) ? red[k][lane] : 0.f;
       s = warp_sum(s);
-      if (lane == 0 && k < gr.n) atomicAdd(sqnorm + k, s);
+      if (lane == 0) g_sq_partials[blockIdx.x * 4 + k] = s;
     }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&g_sq_ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 4) {                                    // fixed order: block 0, 1, 2, ...
+    float s = 0.f;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&g_sq_partials[b * 4 + threadIdx.x]);
+    if ((int)threadIdx.x < gr.n) sqnorm[threadIdx.x] = s;
+    if (threadIdx.x == 0) g_sq_ticket = 0;                  // ready for the next launch
   }
 }
 
@@ -671,8 +692,7 @@ extern "C" int vln_grad_sqnorm(const float* grad, const int64_t* group_off, int 
   VLN_REQUIRE(make_groups(&g, group_off, nullptr, n_groups) == 0, "1..4 groups supported");
   for (int i = 0; i <= n_groups; ++i) VLN_REQUIRE(group_off[i] % 4 == 0, "group offsets must be multiples of 4 floats");
   VLN_REQUIRE(((uintptr_t)grad & 15) == 0, "grad must be 16-byte aligned");
-  VLN_CHECK_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(float) * n_groups, STREAM));
-  sqnorm_kernel<<<296, 256, 0, STREAM>>>(grad, g, grad_scale, sqnorm);
+  sqnorm_kernel<<<kSqBlocks, 256, 0, STREAM>>>(grad, g, grad_scale, sqnorm);
   VLN_LAUNCH_OK();
   return 0;
 }

@@ -63,7 +63,8 @@ def main():
     # the same minibatch again through the optimiser's own path: decoder + critic bucket all-reduced from inside the
     # backward pass (under the encoder's BPTT), the encoder's bucket by finish_reduce
     agent._fused.on_grads_ready = hook
-    assert hook is not None, "TrainStep did not install the early all-reduce hook"
+    early = os.environ.get("VLN_EARLY_ALLREDUCE", "1") != "0"
+    assert (hook is not None) == early, "early all-reduce hook: installed exactly when enabled"
     env.reset_index = (lambda orig: (lambda **kw: orig(restart=True)))(env.reset_index)
     step.opt.zero_grad()
     loss, _ = step.losses()
@@ -107,6 +108,16 @@ def main():
     dist.broadcast(ref, src=0)
     same = torch.tensor([float(torch.equal(flat, ref))], device=dev)
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    differing = {}
+    if rank == 1:
+        o = 0
+        names = [(m_name, n_, p_) for m_name, m in zip(("encoder", "decoder", "critic"), agent._modules()) for n_, p_ in m.named_parameters()]
+        for m_name, n_, p_ in names:
+            off = (p_.data_ptr() - step.opt.flat.data_ptr()) // 4
+            a, b = flat[off:off + p_.numel()], ref[off:off + p_.numel()]
+            if not torch.equal(a, b):
+                differing[f"{m_name}.{n_}"] = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        print("RANK1 differing parameters:", json.dumps(differing), flush=True)
     if rank == 0:
         out.update(world_size=ws, params_identical_after_3_steps=bool(same.item()), rank0_losses=[round(x, 4) for x in losses])
         print(json.dumps(out), flush=True)
