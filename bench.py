@@ -133,9 +133,9 @@ def roofline_pano(store, ops, torch, B, split, peaks):
         bits = torch.empty((n_sets, B * 36, 256), dtype=torch.uint8, device=dev)
         ops._call("vln_feature_mask_bits", ops._ptr(bits), B * 36, n_sets, 0.3, rng.ptr, 1, 7, ops._stream())
 
-    def launch(k):
+    def launch(k, mode=0):
         ops._call("vln_pano_attn_ld", store.handle, ops._ptr(vps[k]), ops._ptr(view), ops._ptr(store.loc4), ops._ptr(q),
-                  2176, ops._ptr(attn), None, 2176, C.c_void_p(out.data_ptr() + 256), 2752, B, 0, 0.3, rng.ptr, 1 + 7 * k,
+                  2176, ops._ptr(attn), None, 2176, C.c_void_p(out.data_ptr() + 256), 2752, B, mode, 0.3, rng.ptr, 1 + 7 * k,
                   ops._ptr(bits[k]) if use_bits else None, split, ops._stream())
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
@@ -158,6 +158,25 @@ def roofline_pano(store, ops, torch, B, split, peaks):
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / (reps * n_sets)
+    # latency floor of a launch of this shape: the same kernel, same grid / cluster / shared memory / dependency chain,
+    # stopping after its dependent index load and ONE row's HBM round trip per CTA (mode bit 2)
+    floor = None
+    if B <= torch.cuda.get_device_properties(dev).multi_processor_count // 2:
+        gf = torch.cuda.CUDAGraph()
+        launch(0, 4)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(gf):
+            for k in range(n_sets):
+                launch(k, 4)
+        for _ in range(3):
+            gf.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            gf.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        floor = e0.elapsed_time(e1) * 1e-3 / (reps * n_sets)
     achieved = B * ALGO_BYTES_PER_EPISODE_STEP / t / 1e9
     peak = float(peaks.get("hbm_gbs", 6650.0))
     return {"bound": "hbm", "kernel": "pano_attn fwd (fused gather + feature dropout + 36-view soft-dot attention)",
@@ -165,6 +184,11 @@ def roofline_pano(store, ops, torch, B, split, peaks):
             "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback",
             "peak_spec": 8000.0, "frac_of_spec": round(achieved / 8000.0, 4),      # both denominators
             "us_per_launch": round(t * 1e6, 2), "episodes_per_launch": B, "split": split, "traffic": None,
+            **({"latency_floor_us": round(floor * 1e6, 2),
+                "transfer_us_at_peak": round(B * ALGO_BYTES_PER_EPISODE_STEP / (float(peaks.get("hbm_gbs", 6650.0)) * 1e9) * 1e6, 2),
+                "frac_of_floor_plus_transfer": round((floor + B * ALGO_BYTES_PER_EPISODE_STEP / (float(peaks.get("hbm_gbs", 6650.0)) * 1e9)) / t, 4),
+                "floor_note": "latency_floor_us = this kernel's launch (same grid, 2-CTA clusters, 216 KB shared memory, same dependency chain) + the dependent index load + one row's HBM round trip per CTA, no payload; a launch cannot beat floor + bytes/peak"}
+               if floor is not None else {}),
             "keep_bits": "pre-generated, streamed (9 216 B / episode)" if use_bits else "drawn in shared memory ahead of the dependency wait",
             "note": "B=64 episodes per launch is the north-star shape: 9.4 MB per launch = 1.4 us at peak, so the launch is latency-bound; tools/microbench.py sweeps B up to 2048"}
 

@@ -8,11 +8,11 @@ of the reference's tasks/R2R-judy/src interface for this path).
 from . import environ  # noqa: F401
 from . import utils  # noqa: F401
 
-__all__ = ["environ", "utils", "ops", "model", "agent", "engine"]
+__all__ = ["environ", "utils", "ops", "model", "agent", "engine", "compat"]
 
 
 def __getattr__(name):
-    if name in ("ops", "model", "agent", "engine"):
+    if name in ("ops", "model", "agent", "engine", "compat"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

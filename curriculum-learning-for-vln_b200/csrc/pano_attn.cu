@@ -92,6 +92,9 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   const int cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int col0 = rank * kHalf;
   const int mode = mode_in & 1;
+  // mode bit 2: latency-floor probe — the launch, the dependency wait, the dependent index load and ONE row's bulk copy
+  // (one HBM round trip per CTA), nothing else: what a launch of this shape costs before a single useful byte moves
+  const bool probe = (mode_in & 4) != 0;
   // mode bit 1: the indices, keep-bits and (backward) the saved attention were complete before the PRECEDING kernel
   // started (backward pass: they date from the forward pass) — the first unit's rows are then requested before the
   // programmatic-dependency wait, and the HBM round trip overlaps the predecessor's tail
@@ -170,6 +173,15 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
     }
     // every warp requests the three rows it will consume in phase 1 (one warp issuing all 36-72 bulk copies
     // serialised ~30 cycles apiece: the first vectors were ready 1 us later with keep-bits than without)
+    if (probe) {
+      if (cid < B && tid == 0) {
+        request_row(cid, g0, 0, 0);
+        mbar_wait(&sm.full[0][0], 0);
+        attn_io[(size_t)cid * VLN_V] = (float)sm.rows[0][0];
+      }
+      cluster_wait();
+      return;
+    }
     if (cid < B && lane < VLN_V / kWarps) request_row(cid, g0, warp + lane * kWarps, 0);
     if (gen_mask && cid < B && early) draw_mask();         // while the rows are in flight
     if (early) pdl_wait();                                 // the query / gradient vector comes from the predecessor
@@ -377,7 +389,7 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
                                 uint64_t call_off, const uint8_t* mask_bits, int split, void* stream) {
   VLN_REQUIRE(ctx && vp && view && loc4 && vec && attn_io && out && B > 0, "bad arguments");
   VLN_REQUIRE(split == 1 || split == 2 || split == 4, "split (kernel variant) must be 1 = automatic, 2 = cluster, 4 = streaming");
-  VLN_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (forward) or 1 (backward), + 2 = indices complete before the predecessor");
+  VLN_REQUIRE(mode >= 0 && mode <= 7, "mode must be 0 (forward) or 1 (backward), + 2 = indices complete before the predecessor, + 4 = latency-floor probe");
   VLN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "drop_p out of range");
   VLN_REQUIRE(drop_p == 0.f || rng || mask_bits, "dropout needs an rng state or pre-generated keep-bits");
   VLN_REQUIRE(!mask_bits || (drop_p > 0.f && ((uintptr_t)mask_bits & 15) == 0), "mask_bits: 16-byte aligned, with drop_p > 0");
@@ -390,7 +402,7 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
   // episodes (the rollout's B = 64), the streaming kernel (pano_stream.cu) maximises bytes in flight for many.
   static const int stream_min_b = getenv("VLN_PANO_STREAM_MIN_B") ? atoi(getenv("VLN_PANO_STREAM_MIN_B")) : 128;
   const bool stream_ok = drop_p == 0.f || mask_bits;        // the streaming kernel has no inline Philox
-  if (stream_ok && (split == 4 || (split == 1 && B >= stream_min_b))) {
+  if (stream_ok && !(mode & 4) && (split == 4 || (split == 1 && B >= stream_min_b))) {
     VLN_CHECK_CUDA(vln_pano_stream_launch(ctx, vp, view, loc4, vec, ld_vec, attn_io, out, ld_out, B, mode & 1, drop_p, mask_bits,
                                           (cudaStream_t)stream));
     return 0;

@@ -148,7 +148,7 @@ class ClassicTrainer:
                 bump = isinstance(self, ClassicTrainer) and type(self) is ClassicTrainer and \
                     cfg.MODEL.NAME in ("SELF-MONITOR", "ENVDROP")
                 start = ckpt["last_epoch"] + (1 if bump else 0)
-        step = self.make_step(cfg, agent)
+        step = None                                   # built at the first iteration (it allocates the flat GPU buffers)
         best = {k: 0.0 for k in (valid_env or {})}
         history = []
         t0 = time.time()
@@ -158,6 +158,8 @@ class ClassicTrainer:
             agent.reset_loss()
             rec = []
             for it in range(tc.ITER_PER_EPOCH):
+                if step is None:
+                    step = self.make_step(cfg, agent)
                 if hasattr(step, "prefetch_next"):           # stage the next minibatch under this iteration's GPU work,
                     step.prefetch_next = it + 1 < tc.ITER_PER_EPOCH      # except across the epoch boundary (eval / env switch)
                 rec.append(step())

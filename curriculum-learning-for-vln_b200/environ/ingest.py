@@ -298,3 +298,64 @@ def heading_to_start_view(heading):
     """viewIndex after newEpisode(scan, vp, heading, 0): the simulator snaps the heading to the 30-degree grid
     on elevation row 1; what R2RBatch does with each item's `heading`."""
     return heading_to_view(heading)
+
+
+# ---- the inverse direction: a World + episodes written in the reference's on-disk formats ------------------------
+def write_connectivity(world, conn_dir, seed=0):
+    """connectivity/<scan>_connectivity.json files for a World (fixtures / tests): every viewpoint gets a random 3-D
+    position, `unobstructed` is the World's adjacency; load_nav_graphs recomputes edge lengths from the poses, so a
+    world loaded back from these files is self-consistent (distances follow the written poses)."""
+    rng = np.random.RandomState(seed)
+    os.makedirs(conn_dir, exist_ok=True)
+    for s, scan in enumerate(world.scans):
+        n = len(world.vp_names[s])
+        pos = rng.uniform(0, 20, size=(n, 3))
+        nbr = [set() for _ in range(n)]
+        for (u, v) in world.edge_len[s]:
+            nbr[u].add(v), nbr[v].add(u)
+        data = []
+        for u in range(n):
+            pose = [0.0] * 16
+            pose[3], pose[7], pose[11] = (float(x) for x in pos[u])
+            data.append({"image_id": world.vp_names[s][u], "pose": pose, "included": True,
+                         "unobstructed": [v in nbr[u] for v in range(n)]})
+        with open(os.path.join(conn_dir, f"{scan}_connectivity.json"), "w") as f:
+            json.dump(data, f)
+
+
+def synthetic_vocab(vocab=992):
+    """<PAD> <UNK> <EOS> <BOS> w4 ... w991: the vocabulary under which make_items' token ids are ordinary words."""
+    return ["<PAD>", "<UNK>", "<EOS>", "<BOS>"] + ["w%d" % i for i in range(4, vocab)]
+
+
+def write_reference_dataset(world, splits, root, dataset="R2R", data_dir="tasks/R2R-judy/data", vocab=992, seed=0):
+    """Everything the reference's main.py reads, for a (synthetic) World and {split name: episode items}: under `root`
+    connectivity/*.json, img_features/ResNet-152-imagenet.tsv (+ candidates.json next to it: the candidate cache the
+    Matterport simulator would produce), <data_dir>/<dataset>_<split>.json with the instructions as text, and the two
+    vocabulary files.  Returns the paths main.py's config needs."""
+    write_connectivity(world, os.path.join(root, "connectivity"), seed)
+    feat_dir = os.path.join(root, "img_features")
+    os.makedirs(feat_dir, exist_ok=True)
+    tsv = os.path.join(feat_dir, "ResNet-152-imagenet.tsv")
+    write_feature_tsv(tsv, {world.long_id(g): world.table[g].float().cpu().numpy() for g in range(world.n_vp)})
+    with open(os.path.join(feat_dir, "candidates.json"), "w") as f:
+        json.dump(dump_candidates(world), f)
+    ddir = os.path.join(root, data_dir)
+    os.makedirs(ddir, exist_ok=True)
+    for split, items in splits.items():
+        by_path = {}
+        for it in items:
+            text = " ".join("w%d" % int(t) for t in it["instr_encoding"][1:it["instr_length"] - 1])
+            d = by_path.setdefault(it["path_id"], {"scan": it["scan"], "path_id": it["path_id"], "path": list(it["path"]),
+                                                   "heading": float(it["heading"]), "distance": float(it["distance"]),
+                                                   "instructions": []})
+            d["instructions"].append(text)
+        with open(os.path.join(ddir, "%s_%s.json" % (dataset, split)), "w") as f:
+            json.dump(list(by_path.values()), f)
+    words = synthetic_vocab(vocab)
+    out = {"tsv": tsv, "data_dir": ddir}
+    for name in ("train_vocab.txt", "trainval_vocab.txt"):
+        out[name] = os.path.join(ddir if dataset == "R2R" else os.path.dirname(ddir), name)
+        with open(out[name], "w") as f:
+            f.write("\n".join(words) + "\n")
+    return out

@@ -29,12 +29,24 @@ class CfgNode(dict):
     def freeze(self):
         return self
 
+    @staticmethod
+    def _decode(v):
+        """yacs' _decode_cfg_value: strings that are Python literals become them ("(1024, )" -> (1024,), as
+        configs/monitor/*.yaml write MLP_HIDDEN); anything else stays a string."""
+        if isinstance(v, str):
+            import ast
+            try:
+                return ast.literal_eval(v)
+            except Exception:
+                return v
+        return v
+
     def merge_from_other(self, other):
         for k, v in other.items():
             if isinstance(v, dict) and isinstance(self.get(k), dict):
                 self[k].merge_from_other(v)
             else:
-                self[k] = v
+                self[k] = CfgNode(v) if isinstance(v, dict) else self._decode(v)
 
     def merge_from_file(self, path):
         import yaml
@@ -49,12 +61,7 @@ class CfgNode(dict):
             parts = key.split(".")
             for p in parts[:-1]:
                 node = node[p]
-            if isinstance(val, str):
-                try:
-                    val = ast.literal_eval(val)
-                except Exception:
-                    pass
-            node[parts[-1]] = val
+            node[parts[-1]] = self._decode(val)
 
 
 def get_cfg_defaults():
