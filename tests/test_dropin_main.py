@@ -106,7 +106,8 @@ def test_main_py_sequence_trains_evaluates_and_checkpoints(tmp_path, monkeypatch
     monkeypatch.chdir(tmp_path)
     src = compat.install_as_src()
     utils, engine, environ = src.utils, src.engine, src.environ
-    cfg = utils.get_cfg_defaults()
+    from clvln_b200.utils import agent_cfg
+    cfg = agent_cfg("ENVDROP")              # get_cfg_defaults() + the values of configs/envdrop/envdrop_config.yaml (not on this box)
     cfg.merge_from_list(_overrides(tmp_path, paths) + ["MODEL.NAME", "ENVDROP", "TRAIN.OPTIM", "rms", "TRAIN.MAX_EPOCH", "1",
                                                        "TRAIN.ITER_PER_EPOCH", "3", "TRAIN.EVAL_INTERVAL", "1",
                                                        "AGENT.MAX_EPISODE_LEN", "10", "AGENT.FEEDBACK", "sample"])
