@@ -138,7 +138,11 @@ class ClassicTrainer:
         checkpoints are written under OUTPUT.CKPT_DIR."""
         tc = cfg.TRAIN
         if valid_env and evaluator is None:
-            from .evaluator import evaluate as evaluator
+            from .evaluator import evaluate as _evaluate
+            if agent.device.type == "cuda":           # the whole split in one kernel launch on the HBM distance table
+                evaluator = lambda env, results: _evaluate(env, results, store=agent.store_of(env))
+            else:
+                evaluator = _evaluate
         rank0 = not _is_dist() or dist.get_rank() == 0
         start = tc.START_EPOCH
         if cfg.OUTPUT.RESUME:

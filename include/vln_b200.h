@@ -401,6 +401,14 @@ int vln_optim_step(float* param, const float* grad, float* state1, float* state2
                    const int64_t* group_off, const float* max_norm, int n_groups,
                    const float* sqnorm, float grad_scale, int kind, float lr, int step, void* stream);
 
+/* Evaluation.score (src/engine/evaluator.py:41-146; DTW src/utils/dtw.py:60-82; CLS src/utils/cls.py:62-90) for N
+ * trajectories in one launch, float64 on the fp32 all-pairs distance table of the environment kernels.
+ * pred int32 [N,P] / ref int32 [N,R] hold global viewpoint indices (first pred_len[n] / ref_len[n] entries valid, R <= 16);
+ * out float64 [N,8] = {nav_error, oracle_error, steps, trajectory length, SPL term, nDTW, SDTW, CLS}. */
+int vln_eval_paths(const int32_t* pred, const int32_t* pred_len, int P, const int32_t* ref, const int32_t* ref_len,
+                   int R, const float* dist_tbl, const int64_t* sq_off, const int32_t* vp_local, double margin,
+                   double* out, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

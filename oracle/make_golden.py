@@ -140,12 +140,44 @@ def rollout_cases():
     return out
 
 
+def eval_cases():
+    """Random-walk trajectories on a seeded synthetic world scored by the reference's own Evaluation.score
+    (src/engine/evaluator.py:101-146): the summary and the per-trajectory lists travel as tests/golden/eval.json."""
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_items, make_world
+    from oracle import ref_harness as H
+    w = make_world(n_scans=3, seed=4)
+    items = make_items(w, 60, seed=4, instr_per_path=3)
+    H.install(w, {"val": items})
+    import src.engine.evaluator as RE
+    ref_eval = RE.Evaluation(["val"], data_name="R2R")
+    rng = random.Random(7)
+    results = []
+    for it in items:
+        traj = [it["path_g"][0]]
+        if rng.random() < 0.5:
+            traj = list(it["path_g"][:rng.randint(1, len(it["path_g"]))])
+        for _ in range(rng.randint(0, 6)):
+            g = traj[-1]
+            traj.append(int(w.cand_vp[g, rng.randrange(int(w.n_cand[g]))]))
+        s = it["scan_idx"]
+        o = int(w.scan_off[s])
+        results.append({"instr_id": it["instr_id"], "trajectory": [[w.vp_names[s][g - o], 0.0, 0.0] for g in traj]})
+    summary, scores = ref_eval.score(results)
+    return {"world": {"n_scans": 3, "seed": 4}, "items": {"n": 60, "seed": 4, "instr_per_path": 3}, "results": results,
+            "summary": {k: float(v) for k, v in summary.items()},
+            "scores": {k: [float(x) for x in v] for k, v in scores.items()}}
+
+
 def main():
     from oracle import ref_loader
     assert ref_loader.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.save(module_cases(), os.path.join(OUT, "modules.pt"))
     torch.save(rollout_cases(), os.path.join(OUT, "rollouts.pt"))
+    import json
+    with open(os.path.join(OUT, "eval.json"), "w") as f:
+        json.dump(eval_cases(), f)
     for f in os.listdir(OUT):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

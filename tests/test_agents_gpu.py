@@ -472,3 +472,33 @@ def test_classic_trainer_with_validation_and_checkpoints(tmp_path):
     trainer2 = build_trainer(cfg, train_env, dev)
     trainer2.train(cfg, agent, None, train_env, None, log=lambda *_: None)
     assert [h["epoch"] for h in trainer2.history] == [3, 4]
+
+
+def test_device_evaluation_matches_host_scores():
+    """engine.Evaluation.score_device (ONE launch of vln_eval_paths over the whole split: nav / oracle error, SPL, nDTW,
+    SDTW, CLS per trajectory in float64 on the HBM distance table) == Evaluation.score (the host restatement that
+    tests/_ref_check_eval.py pins against the reference's Evaluation.score and whose DTW / CLS reproduce the reference's
+    doctest values) on random walks of every length, incl. trajectories that never leave the start."""
+    from clvln_b200.engine import Evaluation
+    agent, pag, env, penv, sds, cfg = _setup("ENVDROP", B=8, n_items=60)
+    w = env.world
+    rs = np.random.RandomState(3)
+    results = []
+    for it in env.data:
+        g = it["path_g"][0]
+        traj = [(env._vp_name(g), 0.0, 0.0)]
+        for _ in range(int(rs.randint(0, 12))):
+            n = int(w.n_cand[g])
+            if n == 0:
+                break
+            g = int(w.cand_vp[g, rs.randint(0, n)])
+            traj.append((env._vp_name(g), 0.0, 0.0))
+        if rs.rand() < 0.3:                                   # some follow the ground truth exactly
+            traj = [(env._vp_name(x), 0.0, 0.0) for x in it["path_g"]]
+        results.append({"instr_id": it["instr_id"], "trajectory": traj})
+    ev = Evaluation(env)
+    host, per = ev.score(results)
+    devs, m = ev.score_device(results, agent.store_of(env))
+    for k in host:
+        assert abs(host[k] - devs[k]) <= 1e-9 * max(1.0, abs(host[k])), (k, host[k], devs[k])
+    assert np.allclose(m[:, 5], per["ndtws"], rtol=1e-12, atol=0) and np.allclose(m[:, 7], per["clss"], rtol=1e-12, atol=0)

@@ -128,3 +128,51 @@ def test_port_rollouts_match_reference_golden(roll, kind):
     assert len(gn) == len(g["grad_norms"])
     for a, b in zip(gn, g["grad_norms"]):
         assert abs(a - b) <= 1e-4 * max(1e-3, abs(b)), (a, b)
+
+
+def _eval_fixture():
+    import json
+    import random
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import R2RBatch, make_items, make_world
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval.json")))
+    w = make_world(**d["world"])
+    items = make_items(w, d["items"]["n"], seed=d["items"]["seed"], instr_per_path=d["items"]["instr_per_path"])
+    random.seed(0)
+    return d, w, items
+
+
+def test_host_evaluation_matches_reference_golden():
+    """engine.Evaluation.score (host) == the reference's Evaluation.score outputs committed in tests/golden/eval.json
+    (generated by oracle/make_golden.py from the unmodified src/engine/evaluator.py on a seeded synthetic world)."""
+    import numpy as np
+    from clvln_b200.engine import Evaluation
+    from clvln_b200.environ import R2RBatch
+    d, w, items = _eval_fixture()
+    env = R2RBatch(w, items, batch_size=8, name="val")
+    summary, per = Evaluation(env).score(d["results"])
+    for k, v in d["summary"].items():
+        assert np.isclose(summary[k], v, rtol=2e-6, atol=1e-6), (k, summary[k], v)
+    for k in ("ndtws", "sdtws", "clss", "nav_errors", "success_path_length"):
+        assert np.allclose(per[k], d["scores"][k], rtol=2e-6, atol=1e-6), k
+
+
+@pytest.mark.gpu
+def test_device_evaluation_matches_reference_golden():
+    """The batched GPU scorer (csrc/eval.cu, Evaluation.score_device) against the same reference outputs; the tolerance
+    is the fp32 storage of the distance table (the reference keeps float64 distances)."""
+    import numpy as np
+    import torch
+    from clvln_b200 import ops
+    from clvln_b200.engine import Evaluation
+    from clvln_b200.environ import R2RBatch
+    d, w, items = _eval_fixture()
+    dev = torch.device("cuda:0")
+    env = R2RBatch(w, items, batch_size=8, name="val", device=dev)
+    store = ops.FeatureStore.from_world(w, dev)
+    summary, m = Evaluation(env).score_device(d["results"], store)
+    for k, v in d["summary"].items():
+        assert np.isclose(summary[k], v, rtol=2e-6, atol=1e-6), (k, summary[k], v)
+    for col, k in ((0, "nav_errors"), (1, "oracle_errors"), (3, "trajectory_lengths"), (4, "success_path_length"),
+                   (5, "ndtws"), (6, "sdtws"), (7, "clss")):
+        assert np.allclose(m[:, col], d["scores"][k], rtol=2e-6, atol=1e-6), k
