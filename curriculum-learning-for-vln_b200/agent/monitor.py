@@ -51,10 +51,10 @@ class SelfMonitorAgent(BaseAgent):
         ml, prog_log = 0.0, torch.zeros((), device=self.device)
         for t in range(T):
             cands, lens = ops.gather_cand(store, st.vp[t], st.view[t])
-            # the reference pads candidates to the longest row of the batch (base.py:150-151) and its
-            # BatchNorm statistics run over exactly those rows, so the width must match
-            C = int(lens.max().item())
-            cands = cands[:, :C].contiguous()
+            # the reference pads candidates to the longest row of the batch (base.py:150-151) and its BatchNorm
+            # statistics run over exactly those rows: the decoder takes that width from `lens` on the device
+            # (masked statistics over all 16 slots), so the rollout never reads it back to the host
+            C = ops.NSLOT
             cmask = LengthMask(lens, C)
             (logit, prog), (h_t, c_t), _ = self.decoder(None, a_prev, cands, h_t, c_t, ctx, ctx_mask, cmask)
             logit = logit.masked_fill(cmask.dense(), float("-inf"))

@@ -119,10 +119,12 @@ class ClassicTrainer:
         return train_env
 
     def make_step(self, cfg, agent, weights=None):
-        """The iteration body: CUDA-graph replay for the fused EnvDrop rollout on a GPU (engine/graphs.py), the
-        eager TrainStep otherwise (drop-in module path of Follower / Self-Monitor, CPU-side tests)."""
-        if (cfg.MODEL.NAME == "ENVDROP" and getattr(agent, "fused", False) and agent.device.type == "cuda"
-                and os.environ.get("VLN_TRAIN_GRAPH", "1") != "0"):
+        """The iteration body: CUDA-graph replay on a GPU (engine/graphs.py) — the fused EnvDrop rollout, and the module
+        path of Follower / Self-Monitor (their rollouts are free of host read-backs: device-side candidate width, fixed
+        step count with masks) — the eager TrainStep otherwise (VLN_TRAIN_GRAPH=0, CPU-side tests)."""
+        graphable = getattr(agent, "fused", False) if cfg.MODEL.NAME == "ENVDROP" else \
+            os.environ.get("VLN_TRAIN_GRAPH_MODULES", "1") != "0"
+        if graphable and agent.device.type == "cuda" and os.environ.get("VLN_TRAIN_GRAPH", "1") != "0":
             from .graphs import GraphedTrainStep
             agent.sync_every = 0                  # fixed-length sampled rollouts (ended episodes are masked): no host polls
             return GraphedTrainStep(cfg, agent, weights=weights)

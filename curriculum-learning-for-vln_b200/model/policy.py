@@ -79,7 +79,15 @@ class MonitorDecoder(U.KernelModule):
         B, C, _ = a_t_cands.shape
         cm = candidate_mask.dense() if isinstance(candidate_mask, U.LengthMask) else candidate_mask
         proj_prev = self.proj_navigable_mlp(a_t_prev)
-        proj_cands = self.proj_navigable_mlp(a_t_cands.reshape(-1, self.action_embed_size)).view(B, C, -1)
+        if isinstance(candidate_mask, U.LengthMask) and self.training:
+            # all C slots go through the MLP; its BatchNorm statistics cover the slots j < max(lengths) — the width the
+            # reference pads to — taken from the device-side lengths (no host read-back per step)
+            width = candidate_mask.lengths.max()
+            w = (torch.arange(C, device=a_t_cands.device) < width).to(a_t_cands.dtype).repeat(B)
+            proj_cands = self.proj_navigable_mlp(a_t_cands.reshape(-1, self.action_embed_size), row_weight=w,
+                                                 n_rows=(width * B).to(a_t_cands.dtype)).view(B, C, -1)
+        else:
+            proj_cands = self.proj_navigable_mlp(a_t_cands.reshape(-1, self.action_embed_size)).view(B, C, -1)
         proj_cands = proj_cands * (1 - cm.float()).unsqueeze(2)
         positioned = self.position(ctx)
         weighted_ctx, ctx_attn = self.text_attn(h_0, positioned, ctx_mask)

@@ -250,5 +250,33 @@ class MLPwithBN(KernelModule):
             self.out_size = out_size
         self.mlp = nn.Sequential(*layers)
 
-    def forward(self, x):
-        return self.mlp(x)
+    def forward(self, x, row_weight=None, n_rows=None):
+        """``row_weight`` [rows] (0/1) + ``n_rows`` (0-dim tensor = its sum): the BatchNorm statistics run over the
+        weighted rows only.  The reference pads candidates to the batch's widest row and normalises over exactly those
+        B x C rows (policy.py:144-149); here the candidate tensor always has 16 slots and the width C is a DEVICE value,
+        so no host read-back sits in the rollout (the statistics, running averages included, are the same numbers)."""
+        if row_weight is None:
+            return self.mlp(x)
+        for layer in self.mlp:
+            if isinstance(layer, nn.BatchNorm1d) and layer.training:
+                x = _masked_batch_norm(layer, x, row_weight, n_rows)
+            else:
+                x = layer(x)
+        return x
+
+
+def _masked_batch_norm(bn, x, w, n):
+    """nn.BatchNorm1d in training mode over the rows with weight 1: batch mean / biased variance for the output,
+    running_mean / running_var (unbiased, momentum) / num_batches_tracked updated as torch does."""
+    wc = w.unsqueeze(1)
+    mean = (x * wc).sum(0) / n
+    d = (x - mean) * wc
+    var = (d * d).sum(0) / n
+    with torch.no_grad():
+        m = bn.momentum if bn.momentum is not None else 0.1
+        # (.data: like the fused batch-norm kernels, the update must not bump the buffers' autograd version counters —
+        #  the standard BatchNorm call on the previous-action rows has saved them for its backward)
+        bn.running_mean.data.mul_(1 - m).add_(mean.detach() * m)
+        bn.running_var.data.mul_(1 - m).add_(var.detach() * (n / (n - 1).clamp(min=1)) * m)
+        bn.num_batches_tracked.data.add_(1)
+    return (x - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias

@@ -159,6 +159,8 @@ class _WidthDrop:
         if p <= 0.0:
             return x
         keep = self.masks[tag].pop(0)
+        if keep.dim() == 3 and x.dim() == 2:            # [B, 16 slots, n] mask for the oracle's flattened [B * C, n] rows
+            keep = keep[:, :x.shape[0] // keep.shape[0]].reshape(x.shape[0], -1)
         if keep.shape != x.shape:
             keep = keep[tuple(slice(0, s) for s in x.shape)]
         return x * keep.to(x.dtype) * (1.0 / (1.0 - p))
@@ -186,6 +188,10 @@ def test_follower_monitor_rollouts_match_oracle(kind, mode):
         feed = _mask_feed(agent)
         if "mlp" in feed:           # MLPwithBN runs twice per step: previous action, then the candidates
             feed["mlp_prev"], feed["mlp_cand"] = feed["mlp"][0::2], feed["mlp"][1::2]
+            # the product runs all 16 candidate slots through the MLP (device-side width, masked BatchNorm statistics);
+            # the oracle's tensor is [B * max(n_cand + 1), 1024]: hand the masks over per (episode, slot)
+            nb = feed["mlp_prev"][0].shape[0]
+            feed["mlp_cand"] = [m.view(nb, -1, m.shape[-1]) for m in feed["mlp_cand"]]
         drop = _WidthDrop(feed)
     forced = [t["action"].cpu().numpy() for t in tr2]
     roll = PR.rollout_follower if kind == "FOLLOWER" else PR.rollout_monitor

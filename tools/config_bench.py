@@ -96,8 +96,9 @@ def main():
                           "episodes_per_s": round(n_ep / float(t), 1), "ms_per_iteration": round(float(t) / args.steps * 1e3, 3),
                           "step": type(step).__name__, "loss": float(loss), "steps": args.steps,
                           "table_viewpoints": world.n_vp}), flush=True)
-    if world_size > 1:
-        dist.destroy_process_group()
+    if world_size > 1:                      # (iteration graphs hold captured NCCL kernels: no graceful communicator teardown)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
