@@ -96,6 +96,9 @@ _SIGS = {
     "vln_a2c_fwd": ([_p] * 7 + [_f, _f] + [_p] * 4 + [_i, _i, _p], _i),
     "vln_a2c_bwd": ([_p] * 4 + [_f] + [_p] * 3 + [_i, _i, _p], _i),
     "vln_env_observe": ([_p] * 11 + [_i, _p], _i),
+    "vln_wgrad_tf32": ([_p, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i64, _p], _i),
+    "vln_dgrad_tf32": ([_p, _i, _p, _i, _i, _i, _i, _p, _i, _p], _i),
+    "vln_seq_outer_sum": ([_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _p, _i, _p], _i),
     "vln_eval_paths": ([_p, _p, _i, _p, _p, _i, _p, _p, _p, C.c_double, _p, _i, _p], _i),
     "vln_grad_sqnorm": ([_p, C.POINTER(_i64), _i, _p, _f, _p], _i),
     "vln_optim_step": ([_p, _p, _p, _p, C.POINTER(_i64), C.POINTER(_f), _i, _p, _f, _i, _f, _i, _p], _i),

@@ -437,13 +437,13 @@ class _Rollout(torch.autograd.Function):
         d_c0 = DC[0]
 
         # ---- d_ctx[b] = sum_t attn_t^T d_weighted_t + dlogit_t^T tq_t: one batched GEMM pair over all steps ----
-        d_ctx = torch.bmm(ATTC[:n].permute(1, 2, 0), DWH[:, :, :H].transpose(0, 1))
+        d_ctx = ops.seq_outer_sum(ATTC[:n], DWH[:n, :, :H])
         dCW = None
         if use_cs:          # through CW = ctx W_in:  dCW = sum_t dlogit_t (x) drop(h_1)_t ,  d_ctx += dCW W_in^T
-            dCW = torch.bmm(DLC.permute(1, 2, 0), WH[:n, :, H:].transpose(0, 1))
+            dCW = ops.seq_outer_sum(DLC[:n], WH[:n, :, H:])
             _gemm(s_tin.hi, s_tin.lo, H, H, _p(dCW), H, B * L, None, _p(d_ctx), H, accumulate=1)
         else:
-            d_ctx.baddbmm_(DLC.permute(1, 2, 0), TQ[:n].transpose(0, 1))
+            ops.seq_outer_sum(DLC[:n], TQ[:n], out=d_ctx)
 
         # ---- weight gradients: one GEMM per weight over all n*B rows ----
         def weight_grads():

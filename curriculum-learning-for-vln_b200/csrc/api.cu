@@ -98,6 +98,36 @@ int vln_make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint
   return 0;
 }
 
+// 2-D fp32 row-major tensor map with a 128-byte swizzle (box_cols = 32 floats = one swizzle row): MN-major tf32 operands
+// of the weight-gradient kernel (csrc/wgrad.cu).  atom32: 32-byte chunks are permuted within the 128-byte span (the only
+// shared-memory layout tcgen05 takes for MN-major 32-bit operands), else the common 16-byte chunks.
+int vln_make_tmap_2d_f32_sw(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                            uint32_t box_cols, uint32_t box_rows, int atom32) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    vln_set_error("cuTensorMapEncodeTiled entry point not available");
+    return -4;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld_elems * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);                                               // (see vln_make_tmap_2d)
+  }
+  if (r != CUDA_SUCCESS) {
+    vln_set_error("cuTensorMapEncodeTiled(f32, swizzle 128B) failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)",
+                  (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_cols, box_rows);
+    return -5;
+  }
+  return 0;
+}
+
 extern "C" int vln_ctx_create(vln_ctx** out, const void* table_bf16, int n_vp, int device) {
   VLN_REQUIRE(out && table_bf16 && n_vp > 0, "null table or n_vp <= 0");
   VLN_REQUIRE(((uintptr_t)table_bf16 & 15) == 0, "table must be 16-byte aligned");

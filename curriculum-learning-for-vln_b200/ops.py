@@ -225,13 +225,90 @@ class _LinearTC(torch.autograd.Function):
         return dx, dw, db, (dy if ctx.has_acc else None)
 
 
+_announced = set()
+
+
+def _announce_library(what, why):
+    """Say ONCE per call site when a product falls to a library GEMM instead of the package's own kernels."""
+    if what not in _announced:
+        _announced.add(what)
+        import warnings
+        warnings.warn("clvln_b200.ops.%s: library GEMM (%s); the tcgen05 kernels take fp32 2-D operands whose inner sizes "
+                      "are multiples of 4" % (what, why), RuntimeWarning, stacklevel=3)
+
+
 WGRAD_TF32 = [True]       # weight-gradient GEMMs ([N x T*B] x [T*B x K], library calls) on TF32 tensor cores
 
 
+WGRAD_TC = [__import__("os").environ.get("VLN_WGRAD_TC", "1") != "0"]   # hand-written tcgen05 kind::tf32 kernel (csrc/wgrad.cu)
+_wgrad_scratch = {}
+
+
+def _wgrad_ws(dev):
+    """Scratch slab of the split-row merge, one per (device, stream): weight gradients of the decoder and of the encoder
+    run on different side streams at the same time."""
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _wgrad_scratch.get(key)
+    if ws is None:
+        ws = _wgrad_scratch[key] = torch.empty(4 << 20, device=dev)
+    return ws
+
+
+def _rows_view(t):
+    """[R, C] fp32 with unit column stride and 16-byte aligned rows (row stride free) — what the kernel's TMA needs."""
+    if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16 or t.dtype != torch.float32:
+        t = t.contiguous().float()
+    return t
+
+
+def wgrad_tc(dy, x, out=None):
+    """dW[M,N] = dY^T X on the tcgen05 kernel; accumulated into `out` (a .grad view) when given."""
+    dy, x = _rows_view(dy), _rows_view(x)
+    R, M = dy.shape
+    N = x.shape[1]
+    acc = out is not None
+    if out is None:
+        out = torch.empty((M, N), device=dy.device)
+    assert out.stride(1) == 1 and out.stride(0) % 4 == 0
+    scratch = _wgrad_ws(dy.device)
+    _call("vln_wgrad_tf32", _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), R, M, N, _ptr(out), out.stride(0), 1 if acc else 0,
+          _ptr(scratch), scratch.numel(), _stream())
+    return out
+
+
+def dgrad_tc(dy, w):
+    """dX[M,K] = dY[M,N] W[N,K] on the tcgen05 kind::tf32 kernel (dY as the K-major operand)."""
+    dy, w = _rows_view(dy), _rows_view(w)
+    M, N = dy.shape
+    K = w.shape[1]
+    out = torch.empty((M, K), device=dy.device)
+    _call("vln_dgrad_tf32", _ptr(dy), dy.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def seq_outer_sum(a, v, out=None):
+    """out[b,l,j] (+)= sum_t a[t,b,l] v[t,b,j] (fp32): a [n,B,L], v [n,B,H] views with unit last stride -> [B,L,H]."""
+    n, B, L = a.shape
+    H = v.shape[2]
+    assert a.stride(2) == 1 and v.stride(2) == 1 and v.shape[:2] == (n, B)
+    acc = out is not None
+    if out is None:
+        out = torch.empty((B, L, H), device=a.device)
+    assert out.is_contiguous()
+    _call("vln_seq_outer_sum", _ptr(a), a.stride(0), a.stride(1), _ptr(v), v.stride(0), v.stride(1), n, B, L, H, _ptr(out),
+          1 if acc else 0, _stream())
+    return out
+
+
 def wgrad(dy, x):
-    """dW = dY^T X over all stacked rows (one library GEMM per weight and iteration).  TF32 inputs with
-    fp32 accumulation: the rounding of the 10-bit mantissas averages out over the T*B-long sums
-    (measured gradient cosine vs the fp32 oracle stays >= 0.9999, tests/test_agents_gpu.py)."""
+    """dW = dY^T X over all stacked rows (one GEMM per weight and iteration) with TF32 inputs and fp32 accumulation: the
+    rounding of the 10-bit mantissas averages out over the T*B-long sums (measured gradient cosine vs the fp32 oracle stays
+    >= 0.9999, tests/test_agents_gpu.py).  The hand-written tcgen05 kernel (csrc/wgrad.cu) when the shapes allow it (M, N
+    multiples of 4); with WGRAD_TF32 off (the fp32 comparison of the kernel tests) the library fp32 GEMM."""
+    if WGRAD_TC[0] and WGRAD_TF32[0] and dy.is_cuda and dy.shape[1] % 4 == 0 and x.shape[1] % 4 == 0:
+        return wgrad_tc(dy, x)
+    if WGRAD_TF32[0]:
+        _announce_library("wgrad", "dY^T X with shape %s x %s" % (tuple(dy.shape), tuple(x.shape)))
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = bool(WGRAD_TF32[0])
     try:
@@ -301,13 +378,8 @@ class _LinearTall(torch.autograd.Function):
         N, K = w.shape
         dx = None
         if ctx.needs_input_grad[0]:
-            if ctx.dx_tf32 and WGRAD_TF32[0]:
-                prev = torch.backends.cuda.matmul.allow_tf32
-                torch.backends.cuda.matmul.allow_tf32 = True
-                try:
-                    dx = dy @ w.detach()
-                finally:
-                    torch.backends.cuda.matmul.allow_tf32 = prev
+            if ctx.dx_tf32 and WGRAD_TF32[0] and WGRAD_TC[0] and K % 4 == 0:
+                dx = dgrad_tc(dy, w.detach())
             else:
                 dx = _tc_matmul_tall(dy, ctx.sw.hi_t, ctx.sw.lo_t, K, N)
         dw = None
@@ -345,11 +417,18 @@ def linear(x, w, b=None, acc=None, dx_tf32=False):
     assert x.is_cuda, "ops.linear runs on the GPU only (there is no CPU path in this package)"
     ok = (USE_TC_LINEAR[0] and x.dim() == 2 and w.shape[1] % 64 == 0 and w.shape[0] % 4 == 0
           and x.dtype == torch.float32)
+    if (not ok and USE_TC_LINEAR[0] and x.dim() == 2 and x.dtype == torch.float32 and w.shape[0] % 4 == 0
+            and w.shape[1] % 64 != 0):
+        # inner size not a multiple of 64 (the Follower's 300-wide word embeddings): zero columns up to the next multiple;
+        # F.pad is differentiable, so the gradients come back sliced
+        pad = 64 - w.shape[1] % 64
+        return linear(F.pad(x, (0, pad)), F.pad(w, (0, pad)), b, acc, dx_tf32)
     if ok and x.shape[0] <= 128:
         return _LinearTC.apply(x, w, b, acc)
     if ok and w.shape[0] % 64 == 0:
         y = _LinearTall.apply(x, w, b, dx_tf32)
         return y if acc is None else y + acc
+    _announce_library("linear", "x %s, weight %s" % (tuple(x.shape), tuple(w.shape)))
     y = _LinearLib.apply(x, w, b) if x.dim() == 2 else F.linear(x, w, b)
     return y if acc is None else y + acc
 

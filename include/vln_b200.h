@@ -401,6 +401,27 @@ int vln_optim_step(float* param, const float* grad, float* state1, float* state2
                    const int64_t* group_off, const float* max_norm, int n_groups,
                    const float* sqnorm, float grad_scale, int kind, float lr, int step, void* stream);
 
+/* Weight gradient of every nn.Linear / nn.LSTMCell of the path (what autograd computes as dY.t() @ X for policy.py:238,
+ * units.py:58-60, 107, 119): dw[M,N] (+)= sum_r dy[r,m] * x[r,n] over the R stacked rows of a rollout, on tcgen05
+ * (kind::tf32, both operands MN-major straight from TMA, fp32 accumulation in tensor memory).  dy [R, ld_dy], x [R, ld_x],
+ * dw [M, ld_dw] fp32, M / N / strides multiples of 4.  accumulate != 0 adds into dw (e.g. a .grad buffer).  `scratch`
+ * (scratch_floats fp32) is optional: with it small outputs are split over row ranges so that the launch fills the SMs; the
+ * partial blocks are merged in range order by a second launch (the result does not depend on scheduling). */
+int vln_wgrad_tf32(const float* dy, int ld_dy, const float* x, int ld_x, int R, int M, int N, float* dw, int ld_dw,
+                   int accumulate, float* scratch, int64_t scratch_floats, void* stream);
+
+/* Input gradient of a tall nn.Linear (autograd's dY @ W for units.py:58-60, the encoder's input projection, whose dx only
+ * feeds the embedding gradient): dx[M,N] = dy[M,R] w[R,N], same tcgen05 kind::tf32 kernel with dy as the K-major operand.
+ * fp32, R / N / strides multiples of 4. */
+int vln_dgrad_tf32(const float* dy, int ld_dy, const float* w, int ld_w, int M, int R, int N, float* dx, int ld_dx,
+                   void* stream);
+
+/* Gradient of the instruction context accumulated over the n decoder steps of a rollout (autograd through
+ * SoftDotAttention, units.py:107-118, n times): out[b,l,j] (+)= sum_t a[t,b,l] * v[t,b,j], fp32 FMAs.
+ * a at a + t*a_step + b*lda + l (l < L), v at v + t*v_step + b*ldv + j (j < H), out [B,L,H] contiguous. */
+int vln_seq_outer_sum(const float* a, int64_t a_step, int lda, const float* v, int64_t v_step, int ldv, int n, int B,
+                      int L, int H, float* out, int accumulate, void* stream);
+
 /* Evaluation.score (src/engine/evaluator.py:41-146; DTW src/utils/dtw.py:60-82; CLS src/utils/cls.py:62-90) for N
  * trajectories in one launch, float64 on the fp32 all-pairs distance table of the environment kernels.
  * pred int32 [N,P] / ref int32 [N,R] hold global viewpoint indices (first pred_len[n] / ref_len[n] entries valid, R <= 16);

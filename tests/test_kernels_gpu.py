@@ -926,3 +926,59 @@ def test_linear_state_epilogues_equal_separate_kernels(setup, M, p):
     assert int(ctr.abs().sum()) == 0
     for a, b in zip(*outs):
         assert relerr(b, a) < 1e-5
+
+
+@pytest.mark.parametrize("R,M,N", [(2688, 2048, 2752), (5376, 2176, 512), (2688, 512, 1024), (10240, 512, 512), (300, 64, 128),
+                                   (77, 132, 260), (2688, 2048, 512)])
+def test_wgrad_tcgen05(setup, R, M, N):
+    """vln_wgrad_tf32 (csrc/wgrad.cu: dW = dY^T X on tcgen05 kind::tf32, operands MN-major straight from TMA) against
+    the float64 product: TF32 inputs, fp32 accumulation -> max-rel <= 2e-3, cosine > 1 - 1e-6; strided operand views,
+    accumulation into an existing buffer, ragged edges; identical bits on every run (ordered merge of the row ranges)."""
+    world, store, ops, dev = setup
+    g = torch.Generator().manual_seed(R + M)
+    big_dy = torch.randn(R, M + 8, generator=g).to(dev)
+    big_x = torch.randn(R, N + 12, generator=g).to(dev)
+    dy, x = big_dy[:, 4:4 + M], big_x[:, 8:8 + N]              # row-strided views with 16-byte aligned rows
+    ref = dy.double().t() @ x.double()
+    out = ops.wgrad_tc(dy, x)
+    assert relerr(out.double(), ref) < 2e-3
+    cos = torch.dot(out.double().flatten(), ref.flatten()) / (out.double().norm() * ref.norm())
+    assert float(cos) > 1 - 1e-6
+    again = ops.wgrad_tc(dy, x)
+    assert torch.equal(out, again)
+    base = torch.randn(M, N, generator=g).to(dev)
+    acc = base.clone()
+    ops.wgrad_tc(dy, x, out=acc)
+    assert relerr(acc.double(), ref + base.double()) < 2e-3
+
+
+@pytest.mark.parametrize("M,R,N", [(5120, 1024, 256), (1280, 1024, 256), (300, 132, 260), (129, 64, 128)])
+def test_dgrad_tcgen05(setup, M, R, N):
+    """vln_dgrad_tf32 (dX = dY W, dY as the K-major tf32 operand of the same tcgen05 kernel) against the float64 product."""
+    world, store, ops, dev = setup
+    g = torch.Generator().manual_seed(M + N)
+    dy = torch.randn(M, R + 4, generator=g).to(dev)[:, :R]
+    w = torch.randn(R, N + 8, generator=g).to(dev)[:, 4:4 + N]
+    ref = dy.double() @ w.double()
+    out = ops.dgrad_tc(dy, w)
+    assert relerr(out.double(), ref) < 2e-3
+    cos = torch.dot(out.double().flatten(), ref.flatten()) / (out.double().norm() * ref.norm())
+    assert float(cos) > 1 - 1e-6
+    assert torch.equal(out, ops.dgrad_tc(dy, w))
+
+
+@pytest.mark.parametrize("n,B,L,H", [(35, 128, 80, 512), (70, 64, 80, 512), (5, 3, 17, 100), (1, 2, 41, 129)])
+def test_seq_outer_sum(setup, n, B, L, H):
+    """vln_seq_outer_sum (d_ctx over the steps of a rollout) equals the batched fp32 product; strided views; accumulation."""
+    world, store, ops, dev = setup
+    g = torch.Generator().manual_seed(n * B)
+    a = torch.randn(n, B, L, generator=g).to(dev)
+    big = torch.randn(n, B, 2 * H, generator=g).to(dev)
+    v = big[:, :, H:]
+    ref = torch.bmm(a.double().permute(1, 2, 0), v.double().transpose(0, 1))
+    out = ops.seq_outer_sum(a, v)
+    assert relerr(out.double(), ref) < 1e-5
+    base = torch.randn(B, L, H, generator=g).to(dev)
+    acc = base.clone()
+    ops.seq_outer_sum(a, v, out=acc)
+    assert relerr(acc.double(), ref + base.double()) < 1e-5
