@@ -97,6 +97,8 @@ _SIGS = {
     "vln_a2c_bwd": ([_p] * 4 + [_f] + [_p] * 3 + [_i, _i, _p], _i),
     "vln_env_observe": ([_p] * 11 + [_i, _p], _i),
     "vln_wgrad_tf32": ([_p, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _i64, _p], _i),
+    "vln_chain_begin": ([_p, _i, _p], _i),
+    "vln_chain_end": ([], _i),
     "vln_dgrad_tf32": ([_p, _i, _p, _i, _i, _i, _i, _p, _i, _p], _i),
     "vln_seq_outer_sum": ([_p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _p, _i, _p], _i),
     "vln_eval_paths": ([_p, _p, _i, _p, _p, _i, _p, _p, _p, C.c_double, _p, _i, _p], _i),

@@ -131,6 +131,7 @@ class FusedDecoder:
         self._prep = None
         self.async_wgrad = False       # set by TrainStep (which always differentiates with .backward() into .grad buffers)
         self._wgrad_stream = None
+        self.chain_flags = None        # counters of the chain links (ops.chain_begin)
         self.counters = None           # arrive / depart counters of the GEMM tile epilogues (zero between launches)
         self.on_grads_ready = None     # set by TrainStep under data parallelism: called (on the stream that accumulated them)
         #                                once this node's weight gradients are final -> early all-reduce of their bucket
@@ -293,6 +294,9 @@ class _Rollout(torch.autograd.Function):
             _call("vln_lstm_pointwise_drop_fwd", _ptr(GATES[t]), _ptr(CS[t]), _ptr(H1[t]), _ptr(CS[t + 1]),
                   _ptr(ACTS[t]), _p(WH[t], H) if need_drop else None, 2 * H, Bt, H, p, rp, offs[t]["h1"], _stream())
 
+        # from here to the end of the rollout every launch is a kernel of this package: their grid-to-grid dependencies
+        # are resolved through device-side counters (chain links, csrc/common.cuh) instead of grid completion
+        ops.chain_begin(fd)
         _call("vln_envdrop_state_fwd", _ptr(h0), 0, _p(XH[0], H_ACT + F), KX, _ptr(HQ[0]), None, B, H, p, rp,
               offs[0]["hprev"], 0, _stream())
         act_embed(0)
@@ -355,6 +359,7 @@ class _Rollout(torch.autograd.Function):
                 break
         if bootstrap:                                           # envdrop.py:225-237: h_1 of the state after the last step
             visual_and_lstm(n, False, q_done=paired and n > 0)
+        ops.chain_end()
         st.teacher = TEACH[n]
         # kept alive for inspection (tests read a CUDA-graph replay's logits / actions from these static buffers)
         fd.last = dict(LOGIT=LOGIT, ACTION=ACTION, TEACH=TEACH, n=n)
@@ -393,6 +398,7 @@ class _Rollout(torch.autograd.Function):
         # ---- off the recursion: candidate-logit backward of ALL steps in one launch, then d(h~_drop) = dtgt W_cand
         #      as a stack of 128-row GEMMs (none of it depends on the backward-in-time chain) ----
         stride = (offs[1]["cand"] - offs[0]["cand"]) if len(offs) > 1 else 0
+        ops.chain_begin(fd)
         _call("vln_cand_logits_bwd_policy", store.handle, _ptr(st.vp), _ptr(st.view), _ptr(store.cand_view),
               _ptr(store.cand_ang4), _ptr(store.n_cand), _ptr(PROBS), _ptr(TEACH), _ptr(ACTION), _ptr(ENT),
               _ptr(d_ce) if d_ce is not None else None, _ptr(d_logp) if d_logp is not None else None,
@@ -434,6 +440,7 @@ class _Rollout(torch.autograd.Function):
         d_h0 = torch.empty((B, H), device=dev)
         _call("vln_envdrop_state_bwd", None, _p(DXH[0], OH), KX, _ptr(DHQ[0]), None, 0, 0, _ptr(d_h0), B, H, p, rp,
               offs[0]["hprev"], 0, _stream())
+        ops.chain_end()
         d_c0 = DC[0]
 
         # ---- d_ctx[b] = sum_t attn_t^T d_weighted_t + dlogit_t^T tq_t: one batched GEMM pair over all steps ----

@@ -24,6 +24,71 @@ bool vln_pdl_enabled() {
   return on != 0;
 }
 
+// ---- chain links (common.cuh): host-side bookkeeping of one region at a time ----
+namespace {
+struct ChainState {
+  bool active = false, prev_valid = false;
+  cudaStream_t stream = nullptr;
+  unsigned int* flags = nullptr;
+  int n = 0, next = 0;
+  unsigned int prev_signals = 0;
+} g_chain;
+bool chain_flags_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    // off unless VLN_CHAIN_FLAGS=1: measured on B200 the counters lose to griddepcontrol.wait (4.81 vs 4.42 ms per
+    // iteration): the hardware releases a dependent grid ~0.8 us after the primary's last CTA retires, a fence + atomic
+    // + polling round trip costs more than that; most of the "gap" between two step kernels is the primary's own
+    // reduction traffic draining
+    const char* e = getenv("VLN_CHAIN_FLAGS");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0 && vln_pdl_enabled();
+}
+}  // namespace
+
+ChainLink vln_chain_link(cudaStream_t stream, unsigned int signals) {
+  ChainLink l{nullptr, nullptr, nullptr, 0u};
+  if (!g_chain.active || stream != g_chain.stream) return l;
+  if (g_chain.next >= g_chain.n - 1) {                       // out of counters: plain dependencies from here on
+    g_chain.prev_valid = false;
+    return l;
+  }
+  l.err = g_chain.flags + (g_chain.n - 1);
+  if (g_chain.prev_valid) {
+    l.wait_flag = g_chain.flags + (g_chain.next - 1);
+    l.wait_n = g_chain.prev_signals;
+  }
+  l.done_flag = g_chain.flags + g_chain.next;
+  g_chain.next++;
+  g_chain.prev_signals = signals;
+  g_chain.prev_valid = true;
+  return l;
+}
+void vln_chain_break(cudaStream_t stream) {
+  if (g_chain.active && stream == g_chain.stream) g_chain.prev_valid = false;
+}
+
+extern "C" int vln_chain_begin(unsigned int* flags, int n_flags, void* stream) {
+  VLN_REQUIRE(flags && n_flags >= 16, "need an array of at least 16 counters");
+  g_chain.active = false;
+  if (!chain_flags_enabled()) return 0;
+  VLN_CHECK_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_flags * sizeof(unsigned int), (cudaStream_t)stream));
+  g_chain.active = true;
+  g_chain.prev_valid = false;
+  g_chain.stream = (cudaStream_t)stream;
+  g_chain.flags = flags;
+  g_chain.n = n_flags;
+  g_chain.next = 0;
+  return 0;
+}
+extern "C" int vln_chain_end(void) {
+  const int used = g_chain.active ? g_chain.next : 0;
+  g_chain.active = false;
+  g_chain.prev_valid = false;
+  return used;
+}
+
 extern "C" const char* vln_last_error(void) { return g_err; }
 extern "C" int vln_version(void) { return 100; }
 

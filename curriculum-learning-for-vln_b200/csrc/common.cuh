@@ -41,8 +41,45 @@ void vln_set_error(const char* fmt, ...);
 // (barrier init, TMEM allocation, weight-tile TMA) concurrently with the predecessor's tail and blocks in
 // pdl_wait() before it touches anything a predecessor writes.  VLN_PDL=0 turns the attribute off.
 bool vln_pdl_enabled();
+
+// ---- chain links: grid-to-grid dependencies resolved by device-side counters ---------------------------------------
+// Between two dependent kernels of the decoder step, griddepcontrol.wait returns only after the predecessor grid has
+// COMPLETED and its memory has been flushed: measured 2-3.5 us from the predecessor's last store to the successor's
+// release (tools/chain_stamps.py), 14 of the 38 us of a decoder step.  Inside a chain region (vln_chain_begin ...
+// vln_chain_end on one stream) consecutive launches are linked through a zeroed array of counters instead: every CTA
+// (or warp) of the producer adds 1 to its launch's counter after its last global access (fence + atomic), and the
+// successor — already resident, it was launched programmatically — polls that counter with ld.acquire.gpu until all
+// `wait_n` arrivals are in.  A launch that is not link-aware breaks the chain (its successor falls back to
+// griddepcontrol.wait, which is always correct).  The counters live in caller memory and are zeroed by a memset node at
+// the head of the region, so a captured graph replays the protocol unchanged.
+struct ChainLink {
+  const unsigned int* wait_flag;   // predecessor's counter, nullptr: griddepcontrol.wait
+  unsigned int* done_flag;         // this launch's counter, nullptr: nothing to signal
+  unsigned int* err;               // incremented when a poll times out (a protocol bug; read by vln_chain_end)
+  unsigned int wait_n;             // arrivals the predecessor's launch produces
+};
+// `signals`: how many arrivals THIS launch will add to its counter (CTAs, or warps, as the kernel signals)
+ChainLink vln_chain_link(cudaStream_t stream, unsigned int signals);
+void vln_chain_break(cudaStream_t stream);
+
+template <typename K, typename... Args>
+inline cudaError_t vln_launch_linked(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = vln_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+// launch of a kernel that does not take part in the link protocol
 template <typename K, typename... Args>
 inline cudaError_t vln_launch_chain(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  vln_chain_break(stream);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -122,6 +159,56 @@ __host__ __device__ __forceinline__ float philox_uniform(const Philox8& r, int j
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ---- chain links, device side ----
+__device__ __forceinline__ void chain_spin(const ChainLink& c) {
+  const long long t0 = clock64();
+  unsigned int v;
+  while (true) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.wait_flag) : "memory");
+    if (v >= c.wait_n) break;
+    if (clock64() - t0 > (1ll << 31)) {                      // ~1 s: never in a correct chain; do not hang the device
+      atomicAdd(c.err, 1u);
+      break;
+    }
+  }
+}
+// replaces a pdl_wait() that every thread of the CTA executes at the same point
+__device__ __forceinline__ void chain_wait_cta(const ChainLink& c) {
+  if (c.wait_flag == nullptr) {
+    pdl_wait();
+    return;
+  }
+  if (threadIdx.x == 0) chain_spin(c);
+  __syncthreads();
+}
+// replaces a pdl_wait() executed by ONE thread that then issues TMA / bulk copies of the predecessor's output
+__device__ __forceinline__ void chain_wait_thread(const ChainLink& c) {
+  if (c.wait_flag == nullptr) {
+    pdl_wait();
+    return;
+  }
+  chain_spin(c);
+  asm volatile("fence.proxy.async;" ::: "memory");           // generic-proxy observation before async-proxy reads
+}
+// after the CTA's last global access (all threads, converged): one arrival per CTA
+__device__ __forceinline__ void chain_signal_cta(const ChainLink& c) {
+  if (c.done_flag == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");         // bulk reductions / stores of this CTA (async proxy)
+    __threadfence();
+    atomicAdd(c.done_flag, 1u);
+  }
+}
+// one arrival per WARP (kernels whose warps retire at different points)
+__device__ __forceinline__ void chain_signal_warp(const ChainLink& c) {
+  if (c.done_flag == nullptr) return;
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence();
+    atomicAdd(c.done_flag, 1u);
+  }
+}
 // ---- chain stamps (debug builds only: -DVLN_CHAIN_STAMPS, tools/chain_stamps.py) ---------------------------------
 // Block 0 / thread 0 of a step-chain kernel records {kernel id, globaltimer at its first instruction, after the
 // programmatic-dependency wait, at its last instruction} behind the rng state (ops.Rng allocates the room: word 2 =

@@ -85,7 +85,8 @@ struct FwdArgs {
   int L; float p; const uint64_t* rng; uint64_t call_off; int ready;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_constant__ FwdArgs a,
+                                                                   const __grid_constant__ ChainLink link) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int u = threadIdx.x, lane = u & 31, warp = u >> 5, b = blockIdx.x, L = a.L;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_
   pdl_trigger();
   // ready: ctx / CW / lengths were complete before the preceding kernel started (every decoder step but the first),
   // so both tiles are requested before the dependency wait and land while the gates GEMM is still finishing
-  if (!a.ready) pdl_wait();
+  if (!a.ready) chain_wait_cta(link);
   const int len = max(0, min(a.lengths[b], min(L, kLmax)));
   if (u == 0) {
     mbar_init(&sm.bar, 1);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_
   }
   if (u < kLmax + 16) sm.sc[u] = 0.f;
   const float keep = keep_of(a.p, a.rng, a.call_off, b, u);     // (the Philox base moves only between iterations)
-  if (a.ready) pdl_wait();
+  if (a.ready) chain_wait_cta(link);
   CHAIN_MARK(2);
   // ---- nn.LSTMCell pointwise half for hidden unit u (gate order i, f, g, o) + dropout of h_1 ----
   {
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_fwd_kernel(const __grid_
   }
   __syncthreads();
   a.wh[(size_t)b * a.ld_wh + u] = col_weighted(sm.sc, col);      // weighted context, column u
+  chain_signal_cta(link);
   CHAIN_MARK(3);
 }
 
@@ -163,7 +165,8 @@ struct BwdArgs {
   float* d_gates; float* d_c0; int L; float p; const uint64_t* rng; uint64_t call_off;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_constant__ BwdArgs a,
+                                                                   const __grid_constant__ ChainLink link) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int u = threadIdx.x, lane = u & 31, warp = u >> 5, b = blockIdx.x, L = a.L;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_
   const float cp = a.c0[i], cn = a.c1[i];
   const float keep = keep_of(a.p, a.rng, a.call_off, b, u);
   const float tc = tanhf(cn);
-  pdl_wait();
+  chain_wait_cta(link);
   CHAIN_MARK(2);
   sm.vec[u] = a.dwh[(size_t)b * a.ld_dwh + u];           // d_weighted (from the linear_out input-gradient GEMM)
   const float dhd_gemm = a.dwh[(size_t)b * a.ld_dwh + kH + u];
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) ctx_step_bwd_kernel(const __grid_
   dg[2 * kH] = dc * gi * (1.f - gg * gg);
   dg[3 * kH] = dh * tc * go * (1.f - go);
   a.d_c0[i] = dc * gf;
+  chain_signal_cta(link);
   CHAIN_MARK(3);
 }
 
@@ -261,7 +265,8 @@ extern "C" int vln_envdrop_ctx_step_fwd(const float* gates, const float* c0, flo
   VLN_REQUIRE((((uintptr_t)ctx | (uintptr_t)cw) & 15) == 0, "ctx / cw must be 16-byte aligned");
   if (int rc = configure()) return rc;
   FwdArgs a{gates, c0, h1, c1, acts, wh, ld_wh, ctx, cw, lengths, attn, L, p, rng, call_off, tiles_ready ? 1 : 0};
-  VLN_CHECK_CUDA(vln_launch_chain(ctx_step_fwd_kernel, dim3(B), dim3(kThreads), sizeof(Smem), (cudaStream_t)stream, a));
+  const ChainLink link = vln_chain_link((cudaStream_t)stream, (unsigned int)B);
+  VLN_CHECK_CUDA(vln_launch_linked(ctx_step_fwd_kernel, dim3(B), dim3(kThreads), sizeof(Smem), (cudaStream_t)stream, a, link));
   return 0;
 }
 
@@ -279,6 +284,7 @@ extern "C" int vln_envdrop_ctx_step_bwd(const float* ctx, const float* cw, const
   VLN_REQUIRE((((uintptr_t)ctx | (uintptr_t)cw) & 15) == 0, "ctx / cw must be 16-byte aligned");
   if (int rc = configure()) return rc;
   BwdArgs a{ctx, cw, lengths, attn, dwh, ld_dwh, dlogit_out, acts, c0, c1, d_h1_extra, d_c1, d_gates, d_c0, L, p, rng, call_off};
-  VLN_CHECK_CUDA(vln_launch_chain(ctx_step_bwd_kernel, dim3(B), dim3(kThreads), sizeof(Smem), (cudaStream_t)stream, a));
+  const ChainLink link = vln_chain_link((cudaStream_t)stream, (unsigned int)B);
+  VLN_CHECK_CUDA(vln_launch_linked(ctx_step_bwd_kernel, dim3(B), dim3(kThreads), sizeof(Smem), (cudaStream_t)stream, a, link));
   return 0;
 }

@@ -242,7 +242,8 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
                      const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_hi1,
                      const __grid_constant__ CUtensorMap tm_lo1, const __grid_constant__ CUtensorMap tm_x1, int M, int N,
                      int K, const float* __restrict__ bias, float* __restrict__ y0, float* __restrict__ y1, int ldy,
-                     int splits, int accumulate, int mode, int dbg, int m_tiles, const __grid_constant__ Epi epi) {
+                     int splits, int accumulate, int mode, int dbg, int m_tiles, const __grid_constant__ Epi epi,
+                     const __grid_constant__ ChainLink link) {
   // blockIdx.z selects one of two independent problems of identical shape (e.g. the candidate projection of
   // step t and the visual-attention query of step t+1, which both only wait for h~_t)
   const CUtensorMap& tm_hi = blockIdx.z == 0 ? tm_hi0 : tm_hi1;
@@ -319,7 +320,7 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
           // the weight tiles were written before this chain of kernels started; the activations come from the
           // predecessor: everything downstream (conversion, MMA, epilogue) is ordered after this wait
           if (it == 0) {
-            pdl_wait();
+            chain_wait_thread(link);
             if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_stamps[(slot % kStampSlots) * 12 + 9] = gtimer();
           }
           tma_load_2d(st + 2 * C::kABytes + 2 * C::kBBytes, &tm_x, &full_w[s], (kb0 + it) * kBK, m0);
@@ -427,7 +428,12 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
       float* dst = y + (size_t)(m0 + tid) * ldy + n0;
       if (m_tiles > 1 && !accumulate) bulk_store_f32(dst, red + tid * kTileN, row_bytes);   // the only writer of this block
       else bulk_reduce_add_f32(dst, red + tid * kTileN, row_bytes);
-      bulk_commit_wait_all();                                // complete (not merely read) before this thread goes on
+      if (epi.kind != 0) {
+        bulk_commit_wait_all();                              // complete (not merely read): the tile epilogue re-reads y
+      } else {                                               // the source rows have been read; grid completion covers the rest
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
     }
     if (epi.kind != 0) tile_epilogue(epi, y, ldy, M, N, tile, split, splits, tid);
   } else if (mode == 2) {
@@ -502,6 +508,11 @@ linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_hi0, const __grid_co
   if (tid == 0) STAMP(7);
   tc_fence_before();
   __syncthreads();
+  if (tid == 32 && link.done_flag != nullptr) {              // every global access of this CTA precedes the barrier above
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    atomicAdd(link.done_flag, 1u);
+  }
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(MP) : "memory");
@@ -617,10 +628,12 @@ int launch_linear_st(const void* w_hi, const void* w_lo, int N, int K, const flo
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if (!(accumulate && vln_pdl_enabled())) vln_chain_break(stream);   // behind a memset / plain stream order: nothing to poll
+  const ChainLink link = vln_chain_link(stream, cfg.gridDim.x * cfg.gridDim.y * cfg.gridDim.z);
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, linear_bf16x3_kernel<MP, ST>, tm_hi, tm_lo, tm_x, tm_hi1, tm_lo1, tm_x1, M, N, K, bias, y,
                                     sec.y ? sec.y : y, ldy, splits,
                                     accumulate, (m_tiles > 1 || mode == 2) ? (variant().bulk ? 3 : 2) : mode, variant().dbg, m_tiles,
-                                    epi));
+                                    epi, link));
   return 0;
 }
 

@@ -84,7 +84,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
                  const int32_t* __restrict__ view, const float* __restrict__ loc4, const float* __restrict__ vec,
                  float* __restrict__ attn_io, float* __restrict__ out, int B, int mode_in, float drop_p,
                  const uint64_t* __restrict__ rng, uint64_t call_off, int ld_vec, int ld_out,
-                 const uint8_t* __restrict__ mask_bits, int gen_mask, int dbg) {
+                 const uint8_t* __restrict__ mask_bits, int gen_mask, int dbg, const __grid_constant__ ChainLink link) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -127,7 +127,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   };
   if (gen_mask && cid < B && !early) draw_mask();           // (backward: after the rows have been requested, below)
   __syncthreads();
-  if (!early) pdl_wait();                                  // viewpoints, query and mask bits come from predecessors
+  if (!early) chain_wait_cta(link);                        // viewpoints, query and mask bits come from predecessors
   if (!early) CHAIN_MARK(2);
   if (dbg && blockIdx.x == 0 && tid == 0) g_pano_stamps[1] = (unsigned long long)clock64();
 
@@ -180,11 +180,12 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
         attn_io[(size_t)cid * VLN_V] = (float)sm.rows[0][0];
       }
       cluster_wait();
+      chain_signal_cta(link);
       return;
     }
     if (cid < B && lane < VLN_V / kWarps) request_row(cid, g0, warp + lane * kWarps, 0);
     if (gen_mask && cid < B && early) draw_mask();         // while the rows are in flight
-    if (early) pdl_wait();                                 // the query / gradient vector comes from the predecessor
+    if (early) chain_wait_cta(link);                       // the query / gradient vector comes from the predecessor
     if (early) CHAIN_MARK(2);
     prefetch_unit(cid, vw0, 0);
   }
@@ -378,6 +379,7 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
   // No CTA exits while its peer could still store into it: every unit's exchange was waited for above, and a
   // cluster without any unit (cid >= B) exchanges nothing; it only completes the initial cluster barrier.
   if (it == 0) cluster_wait();
+  chain_signal_cta(link);
   CHAIN_MARK(3);
 }
 
@@ -430,8 +432,10 @@ extern "C" int vln_pano_attn_ld(const vln_ctx* ctx, const int32_t* vp, const int
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = vln_pdl_enabled() ? 2 : 1;
+  const ChainLink link = vln_chain_link((cudaStream_t)stream, (unsigned int)(2 * clusters));
   VLN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pano_attn_kernel, ctx->table, vp, view, loc4, vec, attn_io, out, B, mode, drop_p, rng,
-                                    call_off, ld_vec, ld_out, mask_bits, gen_mask, (getenv("VLN_PANO_STAMPS") ? atoi(getenv("VLN_PANO_STAMPS")) : 0)));
+                                    call_off, ld_vec, ld_out, mask_bits, gen_mask, (getenv("VLN_PANO_STAMPS") ? atoi(getenv("VLN_PANO_STAMPS")) : 0),
+                                    link));
   return 0;
 }
 

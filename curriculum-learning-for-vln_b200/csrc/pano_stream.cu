@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128, kCtas)
 pano_stream_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restrict__ vp,
                    const int32_t* __restrict__ view, const float* __restrict__ loc4, const float* __restrict__ vec,
                    float* __restrict__ attn_io, float* __restrict__ out, int B, float scale, int ld_vec, int ld_out,
-                   const uint8_t* __restrict__ mask_bits) {
+                   const uint8_t* __restrict__ mask_bits, const __grid_constant__ ChainLink link) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   SmemS<kS>& sm = *reinterpret_cast<SmemS<kS>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,11 +86,14 @@ pano_stream_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __res
   if (tid < kS) mbar_init(&sm.full[tid], 1);
   fence_mbar_init();
   __syncthreads();
-  pdl_wait();                                              // viewpoints, query and keep-bits come from predecessors
+  chain_wait_cta(link);                                    // viewpoints, query and keep-bits come from predecessors
 
   const int stride = gridDim.x;
   int e = blockIdx.x;
-  if (e >= B) return;
+  if (e >= B) {
+    chain_signal_cta(link);
+    return;
+  }
   // one thread feeds the ring: chunk c of episode `ep` (viewpoint g) into `slot`
   auto issue = [&](int ep, int g, int c, int slot) {
     uint64_t* bar = &sm.full[slot];
@@ -323,6 +326,7 @@ pano_stream_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __res
     }
     g_cur = g_next;
   }
+  chain_signal_cta(link);
 }
 
 template <int MODE, bool MASK, int kS, int kCtas>
@@ -338,8 +342,9 @@ cudaError_t launch_stream_cfg(const vln_ctx* ctx, const int32_t* vp, const int32
   }
   const int max_ctas = ctx->num_sms * kCtas;
   const int grid = B < max_ctas ? B : max_ctas;
-  return vln_launch_chain(pano_stream_kernel<MODE, MASK, kS, kCtas>, dim3(grid), dim3(128), sizeof(SmemS<kS>), stream, ctx->table, vp, view,
-                          loc4, vec, attn_io, out, B, scale, ld_vec, ld_out, mask_bits);
+  const ChainLink link = vln_chain_link(stream, (unsigned int)grid);
+  return vln_launch_linked(pano_stream_kernel<MODE, MASK, kS, kCtas>, dim3(grid), dim3(128), sizeof(SmemS<kS>), stream, ctx->table, vp, view,
+                           loc4, vec, attn_io, out, B, scale, ld_vec, ld_out, mask_bits, link);
 }
 
 template <int MODE, bool MASK>

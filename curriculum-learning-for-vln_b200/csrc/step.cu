@@ -84,11 +84,9 @@ __device__ __forceinline__ void stE(float* p, const float (&v)[kE]) { *reinterpr
   const int sub = h & 7
 
 // ---- h~ state: tanh + the two dropout sites that consume it -------------------------------------
-__global__ void state_fwd_kernel(const float* __restrict__ src, int apply_tanh, float* __restrict__ xh_next, int ld_xh,
-                                 float* __restrict__ hq_next, float* __restrict__ hc_cur, int B, int H, float p,
-                                 const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
-  pdl_trigger();
-  pdl_wait();
+__device__ __forceinline__ void state_fwd_body(const float* __restrict__ src, int apply_tanh, float* __restrict__ xh_next,
+                                               int ld_xh, float* __restrict__ hq_next, float* __restrict__ hc_cur, int B, int H,
+                                               float p, const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
   ELEM_INDEX();
   float v[kE], k[kE], o[kE];
   ldE(src + (size_t)b * H + h, v);
@@ -111,13 +109,21 @@ __global__ void state_fwd_kernel(const float* __restrict__ src, int apply_tanh, 
   }
 }
 
-// d_src = (drop_c'(d_hc) + d_xh_next + drop_q'(d_hq_next)) * (apply_tanh ? 1 - h~^2 : 1)
-__global__ void state_bwd_kernel(const float* __restrict__ d_hc, const float* __restrict__ d_xh_next, int ld_dxh,
-                                 const float* __restrict__ d_hq_next, const float* __restrict__ htilde, int ld_h,
-                                 int apply_tanh, float* __restrict__ d_src, int B, int H, float p,
-                                 const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
+__global__ void state_fwd_kernel(const float* __restrict__ src, int apply_tanh, float* __restrict__ xh_next, int ld_xh,
+                                 float* __restrict__ hq_next, float* __restrict__ hc_cur, int B, int H, float p,
+                                 const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c,
+                                 const __grid_constant__ ChainLink link) {
   pdl_trigger();
-  pdl_wait();
+  chain_wait_cta(link);
+  state_fwd_body(src, apply_tanh, xh_next, ld_xh, hq_next, hc_cur, B, H, p, rng, off_q, off_c);
+  chain_signal_cta(link);
+}
+
+// d_src = (drop_c'(d_hc) + d_xh_next + drop_q'(d_hq_next)) * (apply_tanh ? 1 - h~^2 : 1)
+__device__ __forceinline__ void state_bwd_body(const float* __restrict__ d_hc, const float* __restrict__ d_xh_next, int ld_dxh,
+                                               const float* __restrict__ d_hq_next, const float* __restrict__ htilde, int ld_h,
+                                               int apply_tanh, float* __restrict__ d_src, int B, int H, float p,
+                                               const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c) {
   ELEM_INDEX();
   float g[kE] = {0.f, 0.f}, v[kE], k[kE];
   if (d_hc) {
@@ -143,6 +149,16 @@ __global__ void state_bwd_kernel(const float* __restrict__ d_hc, const float* __
     for (int j = 0; j < kE; ++j) g[j] *= 1.f - v[j] * v[j];
   }
   stE(d_src + (size_t)b * H + h, g);
+}
+__global__ void state_bwd_kernel(const float* __restrict__ d_hc, const float* __restrict__ d_xh_next, int ld_dxh,
+                                 const float* __restrict__ d_hq_next, const float* __restrict__ htilde, int ld_h,
+                                 int apply_tanh, float* __restrict__ d_src, int B, int H, float p,
+                                 const uint64_t* __restrict__ rng, uint64_t off_q, uint64_t off_c,
+                                 const __grid_constant__ ChainLink link) {
+  pdl_trigger();
+  chain_wait_cta(link);
+  state_bwd_body(d_hc, d_xh_next, ld_dxh, d_hq_next, htilde, ld_h, apply_tanh, d_src, B, H, p, rng, off_q, off_c);
+  chain_signal_cta(link);
 }
 
 // ---- action embedding of the agent's pose: drop(tanh(W_a angle128(view) + b_a)) ------------------
@@ -386,8 +402,9 @@ extern "C" int vln_envdrop_state_fwd(const float* src, int apply_tanh, float* xh
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
   VLN_REQUIRE(!xh_next || ld_xh % 4 == 0, "xh rows must be 16-byte aligned");
   const int n = B * (H / kE);                              // one thread per kE consecutive elements
-  VLN_CHECK_CUDA(vln_launch_chain(state_fwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, src, apply_tanh, xh_next,
-                                  ld_xh, hq_next, hc_cur, B, H, p, rng, off_q, off_c));
+  const ChainLink link = vln_chain_link(STREAM, (unsigned int)((n + 127) / 128));
+  VLN_CHECK_CUDA(vln_launch_linked(state_fwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, src, apply_tanh, xh_next,
+                                   ld_xh, hq_next, hc_cur, B, H, p, rng, off_q, off_c, link));
   return 0;
 }
 
@@ -398,8 +415,9 @@ extern "C" int vln_envdrop_state_bwd(const float* d_hc, const float* d_xh_next, 
   VLN_REQUIRE(!apply_tanh || htilde, "tanh backward needs the saved h~");
   VLN_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || rng), "dropout needs 0 <= p < 1 and an rng state");
   const int n = B * (H / kE);                              // one thread per kE consecutive elements
-  VLN_CHECK_CUDA(vln_launch_chain(state_bwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, d_hc, d_xh_next, ld_dxh,
-                                  d_hq_next, htilde, ld_h, apply_tanh, d_src, B, H, p, rng, off_q, off_c));
+  const ChainLink link = vln_chain_link(STREAM, (unsigned int)((n + 127) / 128));
+  VLN_CHECK_CUDA(vln_launch_linked(state_bwd_kernel, dim3((n + 127) / 128), dim3(128), 0, STREAM, d_hc, d_xh_next, ld_dxh,
+                                   d_hq_next, htilde, ld_h, apply_tanh, d_src, B, H, p, rng, off_q, off_c, link));
   return 0;
 }
 

@@ -43,6 +43,27 @@ def _call(name, *args):
     _lib.check(getattr(_lib.lib(), name)(*args), name)
 
 
+CHAIN_FLAGS_N = 4096
+
+
+def chain_begin(owner):
+    """Open a chain region on the current stream (include/vln_b200.h: vln_chain_begin): until chain_end() consecutive
+    kernels of this package hand over through device-side counters kept in ``owner.chain_flags``."""
+    if getattr(owner, "chain_flags", None) is None:
+        owner.chain_flags = torch.zeros(CHAIN_FLAGS_N, dtype=torch.int32, device=torch.cuda.current_device())
+    _call("vln_chain_begin", _ptr(owner.chain_flags), CHAIN_FLAGS_N, _stream())
+
+
+def chain_end():
+    return _lib.lib().vln_chain_end()
+
+
+def chain_timeouts(owner):
+    """Polls that gave up (must be 0: a non-zero count means a producer signalled fewer arrivals than announced)."""
+    f = getattr(owner, "chain_flags", None)
+    return 0 if f is None else int(f[-1])
+
+
 class Rng:
     """Philox stream bookkeeping.  ``state`` is a device int64[2] = {seed, base}; every dropout /
     sampling call site takes the next ``call_off`` and its kernel draws from stream

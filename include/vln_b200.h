@@ -410,6 +410,16 @@ int vln_optim_step(float* param, const float* grad, float* state1, float* state2
 int vln_wgrad_tf32(const float* dy, int ld_dy, const float* x, int ld_x, int R, int M, int N, float* dw, int ld_dw,
                    int accumulate, float* scratch, int64_t scratch_floats, void* stream);
 
+/* Chain regions.  The kernels of a decoder step (policy.py:208-246 and its backward) form a chain of grid-wide
+ * dependencies; between vln_chain_begin and vln_chain_end consecutive launches on `stream` resolve them through counters in
+ * `flags` (n_flags uint32 in device memory, zeroed here by a memset on the stream; the last one counts poll time-outs and must
+ * read 0) instead of waiting for the predecessor grid to complete (same results).  Regions do not
+ * nest; a launch on another stream, or of a kernel that is not link-aware, simply falls back to the plain dependency.
+ * vln_chain_end returns the number of counters used.  An experiment kept behind VLN_CHAIN_FLAGS=1 (default off: on B200
+ * griddepcontrol.wait measured faster, 4.42 vs 4.81 ms per EnvDrop iteration); with it off both calls do nothing. */
+int vln_chain_begin(unsigned int* flags, int n_flags, void* stream);
+int vln_chain_end(void);
+
 /* Input gradient of a tall nn.Linear (autograd's dY @ W for units.py:58-60, the encoder's input projection, whose dx only
  * feeds the embedding gradient): dx[M,N] = dy[M,R] w[R,N], same tcgen05 kind::tf32 kernel with dy as the K-major operand.
  * fp32, R / N / strides multiples of 4. */

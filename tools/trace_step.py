@@ -26,7 +26,7 @@ def main():
     world, items = bench.build_world(False, dev)
     cfg = utils.agent_cfg("ENVDROP")
     random.seed(2020)
-    env = R2RBatch(world, items, batch_size=64, device=dev)
+    env = R2RBatch(world, items, batch_size=int(os.environ.get("VLN_TRACE_BATCH", "64")), device=dev)
     torch.manual_seed(2020)
     agent = build_agent(cfg, utils.StubTokenizer(), dev)
     agent.env = env
