@@ -444,6 +444,15 @@ def linear(x, w, b=None, acc=None, dx_tf32=False):
         # F.pad is differentiable, so the gradients come back sliced
         pad = 64 - w.shape[1] % 64
         return linear(F.pad(x, (0, pad)), F.pad(w, (0, pad)), b, acc, dx_tf32)
+    if USE_TC_LINEAR[0] and x.dim() == 2 and x.dtype == torch.float32 and w.shape[1] % 64 == 0:
+        # output width the kernels do not take (the critic's single value): zero weight rows up to the next multiple
+        # of 4 (skinny) / 64 (tall launches), the extra outputs sliced away; differentiable like the padding above
+        N = w.shape[0]
+        need = 4 if x.shape[0] <= 128 else 64
+        if N % need != 0:
+            pad = need - N % need
+            y = linear(x, F.pad(w, (0, 0, 0, pad)), None if b is None else F.pad(b, (0, pad)), None, dx_tf32)[:, :N]
+            return y if acc is None else y + acc
     if ok and x.shape[0] <= 128:
         return _LinearTC.apply(x, w, b, acc)
     if ok and w.shape[0] % 64 == 0:
