@@ -3,6 +3,7 @@ from .base import BaseAgent, RolloutState
 from .envdrop import EnvDropAgent
 from .follower import FollowerAgent
 from .monitor import SelfMonitorAgent
+from .speaker import Speaker
 
 
 def build_agent(cfg, tokenizer, device, **kwargs):
@@ -21,4 +22,4 @@ def build_agent(cfg, tokenizer, device, **kwargs):
     raise NotImplementedError(name)
 
 
-__all__ = ["BaseAgent", "RolloutState", "EnvDropAgent", "FollowerAgent", "SelfMonitorAgent", "build_agent"]
+__all__ = ["BaseAgent", "RolloutState", "EnvDropAgent", "FollowerAgent", "SelfMonitorAgent", "Speaker", "build_agent"]

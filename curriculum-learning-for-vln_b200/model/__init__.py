@@ -2,6 +2,8 @@
 from .units import (EncoderLSTM, SoftDotAttention, VisualSoftDotAttention, ActionScoring, PositionalEncoding,
                     MLPwithBN, LengthMask, use_rng)
 from .policy import AttnDecoderLSTM, MonitorDecoder, EnvDropDecoder, Critic
+from .speaker import SpeakerEncoder, SpeakerDecoder
 
 __all__ = ["EncoderLSTM", "SoftDotAttention", "VisualSoftDotAttention", "ActionScoring", "PositionalEncoding",
-           "MLPwithBN", "LengthMask", "use_rng", "AttnDecoderLSTM", "MonitorDecoder", "EnvDropDecoder", "Critic"]
+           "MLPwithBN", "LengthMask", "use_rng", "AttnDecoderLSTM", "MonitorDecoder", "EnvDropDecoder", "Critic",
+           "SpeakerEncoder", "SpeakerDecoder"]

@@ -85,6 +85,8 @@ def get_cfg_defaults():
                      MLP_HIDDEN=(128,)),
         ENVDROP=dict(WORD_EMB_SIZE=0, ACT_EMB_SIZE=0, HIDDEN_SIZE=0, DROP_RATE=0.5, FEAT_DROP_RATE=0.3,
                      ENC_BIDIRECTION=True, ENC_LAYERS=1, ML_WEIGHT=0.0, GAMMA=0.0, RL_NORMALIZE="none")))
+    cfg.AIDE = C(dict(SPEAKER=dict(RNN_DIM=512, DROPOUT=0.6, FEAT_DROPOUT=0.3, BI_DIRECTION=True, WEMB=256, LR=1e-4,
+                                   FAST_TRAIN=False, IGNORE_ID=-1, MAX_DECODE=120, LOAD_OPTIM=False)))    # config.py:109-119
     return cfg
 
 

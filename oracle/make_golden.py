@@ -8,12 +8,14 @@ inputs; the committed fixtures then pin oracle/port_*.py wherever /root/referenc
   modules.pt   small-dimension instances of EncoderLSTM (3 layouts), EnvDropDecoder,
                AttnDecoderLSTM, MonitorDecoder (eval and BN-training), Critic: state_dict, inputs,
                outputs — a few hundred KB.
+  speaker.pt   the real Speaker class (shipped sizes, eval mode) on the seeded world: path lengths, loss / accuracies,
+               beam-search scores, greedy words, gradient norms.
   rollouts.pt  the three real agents (shipped model sizes) on a seeded synthetic world:
                teacher + forced-action rollouts in eval mode: per-step logits/targets, losses,
                per-parameter gradient norms, trajectories, and the minibatch order over a
                wrap-around.  World and weights are regenerated from seeds by the test.
 
-usage: python -m oracle.make_golden
+usage: python -m oracle.make_golden [speaker]
 """
 import os
 import random
@@ -140,6 +142,79 @@ def rollout_cases():
     return out
 
 
+def speaker_cases():
+    """The real Speaker class (shipped sizes) on the seeded synthetic world, eval mode: path lengths, teacher-forcing loss /
+    accuracies, the per-word scores of the beam-search entry point, greedy words, gradient norms of the eval-mode loss;
+    world and weights are regenerated from the seeds by the tests (weight checksums guard the init order).  Driven through
+    the key-renaming adapter of tests/_ref_check_speaker.py (the class reads observation keys its own env lacks)."""
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items
+    from oracle import ref_harness as H, ref_loader
+    w = make_world(n_scans=3, seed=1)
+    items = make_items(w, 40, seed=1)
+    H.install(w, {"train": items})
+    import src.agent.speaker as ref_speaker
+    import src.environ as environ
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    ref_speaker.Variable = torch.autograd.Variable
+    if not hasattr(np, "bool"):
+        np.bool = bool
+
+    class OldKeys:
+        def __init__(self, r2r):
+            self.r2r, self.env = r2r, r2r.env
+            self.feature_size, self.batch_size = r2r.feature_size, r2r.batch_size
+
+        def reset(self, **kw):
+            return self._wrap(self.r2r.reset(**kw))
+
+        def _get_obs(self):
+            return self._wrap(self.r2r.observe())
+
+        @staticmethod
+        def _wrap(obs):
+            return [dict(ob, viewpoint=ob["viewpointId"],
+                         candidate=[dict(c, pointId=c["absViewIndex"], viewpointId=c["nextViewpointId"]) for c in ob["candidates"]])
+                    for ob in obs]
+
+    tok = H.StubTokenizer(items)
+    cfg = ref_loader.AttrDict(RNN_DIM=512, DROPOUT=0.6, FEAT_DROPOUT=0.3, BI_DIRECTION=True, WEMB=256, LR=1e-4,
+                              FAST_TRAIN=False, IGNORE_ID=-1, MAX_DECODE=24, LOAD_OPTIM=False)
+    random.seed(2020)
+    torch.manual_seed(2020)
+    renv = environ.R2RBatch(H.feature_store(w), batch_size=8, splits=["train"], tokenizer=tok)
+    H.warm_candidate_buffer(renv)
+    spk = ref_speaker.Speaker(cfg, torch.device("cpu"), tok, env=OldKeys(renv))
+    mods = [spk.encoder, spk.decoder]
+    out = {"world": dict(n_scans=3, seed=1, n_items=40, B=8), "max_decode": 24,
+           "w_checksum": [float(p.detach().double().sum()) for m in mods for p in m.parameters()], "batches": []}
+    random.seed(1)
+    for _ in range(2):
+        obs = spk.env.reset()
+        (img, can), lens = spk.from_shortest_path()
+        insts = torch.from_numpy(np.array([ob["instr_encoding"] for ob in obs]))
+        spk.env.reset(restart=True)
+        loss, wa, sa = spk.teacher_forcing(train=False)
+        scores = spk.teacher_forcing(train=False, features=((img, can), lens), insts=insts, for_listener=True).detach()
+        for m in mods:
+            m.zero_grad()
+        spk.encoder.eval(), spk.decoder.eval()
+        # gradients of the eval-mode loss (train=True would switch torch's dropout on): the class's own modules and criterion
+        ctx = spk.encoder(can.clone(), img.clone(), lens, already_dropfeat=True)
+        z = torch.zeros(1, len(lens), 512)
+        logits, _, _ = spk.decoder(insts, ctx, ref_speaker.utils.length2mask(lens, torch.device("cpu")), z, z)
+        l2 = spk.softmax_loss(input=logits.permute(0, 2, 1)[:, :, :-1], target=insts[:, 1:])
+        l2.backward()
+        gn = [float(p.grad.norm()) if p.grad is not None else 0.0 for m in mods for p in m.parameters()]
+        spk.env.reset(restart=True)
+        words = spk.infer_batch()
+        out["batches"].append(dict(instr_ids=[ob["instr_id"] for ob in obs], lengths=np.asarray(lens).tolist(), loss=float(loss),
+                                   word_accu=float(wa), sent_accu=float(sa), scores=scores, loss_grad=float(l2),
+                                   grad_norms=gn, words=torch.from_numpy(words.astype(np.int64)),
+                                   can_sum=float(can.double().sum()), img_sum=float(img.double().sum())))
+    return out
+
+
 def eval_cases():
     """Random-walk trajectories on a seeded synthetic world scored by the reference's own Evaluation.score
     (src/engine/evaluator.py:101-146): the summary and the per-trajectory lists travel as tests/golden/eval.json."""
@@ -173,6 +248,11 @@ def main():
     from oracle import ref_loader
     assert ref_loader.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "speaker":          # only the speaker fixture (the others are unchanged)
+        torch.save(speaker_cases(), os.path.join(OUT, "speaker.pt"))
+        print("speaker.pt", os.path.getsize(os.path.join(OUT, "speaker.pt")))
+        return
+    torch.save(speaker_cases(), os.path.join(OUT, "speaker.pt"))
     torch.save(module_cases(), os.path.join(OUT, "modules.pt"))
     torch.save(rollout_cases(), os.path.join(OUT, "rollouts.pt"))
     import json

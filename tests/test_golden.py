@@ -176,3 +176,62 @@ def test_device_evaluation_matches_reference_golden():
     for col, k in ((0, "nav_errors"), (1, "oracle_errors"), (3, "trajectory_lengths"), (4, "success_path_length"),
                    (5, "ndtws"), (6, "sdtws"), (7, "clss")):
         assert np.allclose(m[:, col], d["scores"][k], rtol=2e-6, atol=1e-6), k
+
+
+# ---- speaker --------------------------------------------------------------------------------------------------------
+def _speaker_golden():
+    return torch.load(os.path.join(G, "speaker.pt"), weights_only=False)
+
+
+def _speaker_world(g):
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items
+    w = g["world"]
+    world = make_world(n_scans=w["n_scans"], seed=w["seed"])
+    return world, make_items(world, w["n_items"], seed=w["seed"])
+
+
+def test_port_speaker_matches_reference_golden():
+    """oracle/port_speaker.py on the regenerated world + weights reproduces what the REAL Speaker class produced
+    (tests/golden/speaker.pt, oracle/make_golden.py): path lengths, feature checksums, eval loss / accuracies,
+    beam-search scores, greedy words, gradient norms of the eval-mode loss."""
+    import numpy as np
+    from clvln_b200.model import SpeakerEncoder, SpeakerDecoder
+    from oracle import port_env as PE, port_speaker as PS
+    g = _speaker_golden()
+    world, items = _speaker_world(g)
+    random.seed(2020)
+    torch.manual_seed(2020)
+    penv = PE.R2RBatchPort(PE.WorldView(world), items, batch_size=g["world"]["B"])
+    # the reference builds encoder then decoder under this seed; the product modules have the same parameter containers
+    # in the same order, so the regenerated weights are the reference's
+    mods = [SpeakerEncoder(2176, 512, 0.6, True, 128, 0.3), SpeakerDecoder(992, 256, 0, 512, 0.6)]
+    chk = [float(p.detach().double().sum()) for m in mods for p in m.parameters()]
+    assert len(chk) == len(g["w_checksum"]) and max(abs(a - b) for a, b in zip(chk, g["w_checksum"])) < 1e-6
+    sds = [{k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in m.state_dict().items()} for m in mods]
+    port = PS.SpeakerPort(sds[0], sds[1], max_decode=g["max_decode"])
+    random.seed(1)
+    for ref in g["batches"]:
+        obs = penv.reset()
+        assert [ob["instr_id"] for ob in obs] == ref["instr_ids"]
+        (img, can), lens, _ = PS.from_shortest_path(penv, obs)
+        assert lens.tolist() == ref["lengths"]
+        assert abs(float(can.double().sum()) - ref["can_sum"]) < 1e-6 * max(1.0, abs(ref["can_sum"]))
+        assert abs(float(img.double().sum()) - ref["img_sum"]) < 1e-6 * max(1.0, abs(ref["img_sum"]))
+        insts = torch.from_numpy(np.array([ob["instr_encoding"] for ob in obs]))
+        feats = ((img, can), lens)
+        loss, wa, sa, _ = port.teacher_forcing(feats, insts, train=False)
+        assert abs(loss - ref["loss"]) < 1e-5 * max(1.0, abs(ref["loss"])) and abs(wa - ref["word_accu"]) < 1e-9 and sa == ref["sent_accu"]
+        close(port.teacher_forcing(feats, insts, train=False, for_listener=True).detach(), ref["scores"], 1e-5)
+        for sd in sds:
+            for v in sd.values():
+                v.grad = None
+        l2 = port.teacher_forcing(feats, insts, train=True, drop=None)
+        l2.backward()
+        assert abs(float(l2) - ref["loss_grad"]) < 1e-5 * max(1.0, abs(ref["loss_grad"]))
+        names = [(0, n) for n, _ in mods[0].named_parameters()] + [(1, n) for n, _ in mods[1].named_parameters()]
+        gn = [float(sds[k][n].grad.norm()) if sds[k][n].grad is not None else 0.0 for k, n in names]
+        for a, b in zip(gn, ref["grad_norms"]):
+            assert abs(a - b) <= 1e-4 * max(1e-3, abs(b)), (a, b)
+        words, _ = port.infer_batch(feats)
+        assert torch.equal(torch.from_numpy(words), ref["words"])

@@ -28,6 +28,12 @@ def test_port_rollouts_match_reference_agents():
     runpy.run_path(os.path.join(HERE, "_ref_check_rollout.py"), run_name="__main__")
 
 
+def test_port_speaker_matches_reference_speaker():
+    """Real SpeakerEncoder / SpeakerDecoder (eval, RNG-matched train, gradients) and the real Speaker class
+    (from_shortest_path, teacher_forcing incl. the beam-search entry point, greedy infer_batch) == oracle/port_speaker.py."""
+    runpy.run_path(os.path.join(HERE, "_ref_check_speaker.py"), run_name="__main__")
+
+
 def test_ingest_matches_reference_loaders():
     """environ/ingest.py == ImageFeatures.read_in, load_nav_graphs + networkx paths (ties), Tokenizer."""
     runpy.run_path(os.path.join(HERE, "_ref_check_ingest.py"), run_name="__main__")
