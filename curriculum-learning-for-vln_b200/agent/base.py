@@ -132,6 +132,35 @@ class BaseAgent:
     def rollout(self, **kw):
         raise NotImplementedError
 
+    # ---- beam search (base.py:183-482; agent/beam.py) ---------------------------------------------------------------
+    def running_state(self, h_t, c_t, extra=None, **kw):
+        """What a search state carries between expansions (the agents' overrides, e.g. envdrop.py:280-281)."""
+        if extra is None:
+            extra = kw.get("h_tilde", kw.get("a_t_prev"))
+        return (h_t, c_t, extra)
+
+    def beam_start_state(self, h_t):
+        """The third element of the start states' running state ([B, .])."""
+        raise NotImplementedError
+
+    def decode_observation(self, store, vp, view, h_t, c_t, extra, ctx, ctx_mask, ended):
+        """One decoder step for a batch of (viewpoint, view) states -> (masked logits [B, 16], h_t, c_t, extra)."""
+        raise NotImplementedError
+
+    decode_obervation = decode_observation                   # (the reference's spelling, base.py:472)
+
+    def _dijkstra(self, max_candidates):
+        from . import beam
+        return beam.dijkstra(self, max_candidates)
+
+    def beam_rollout(self, speaker, beam_size):
+        from . import beam
+        return beam.beam_rollout(self, speaker, beam_size)
+
+    def beam_search(self, speaker, beam_size=30):
+        from . import beam
+        return beam.beam_search(self, speaker, beam_size)
+
     def test(self, iters=None, **kw):
         """base.py:63-82: roll out until an instr_id repeats (or `iters` batches)."""
         self.env.reset_epoch(shuffle=(iters is not None))

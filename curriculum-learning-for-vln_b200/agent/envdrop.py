@@ -55,6 +55,18 @@ class EnvDropAgent(BaseAgent):
         logit, (h_t, c_t), h_tilde = self.decoder(pose, pano, cands, h_tilde, h_t, c_t, ctx, ctx_mask)
         return logit, h_t, c_t, h_tilde
 
+    # ---- beam search hooks (envdrop.py:280-297) ------------------------------------------------------------------------
+    def beam_start_state(self, h_t):
+        return h_t                                            # h_tilde starts as the encoder's h_t (base.py:236)
+
+    def decode_observation(self, store, vp, view, h_t, c_t, h_tilde, ctx, ctx_mask, ended=None):
+        pano, cands = ops.PanoView(store, vp, view), ops.CandView(store, vp, view)
+        pano.split = self.split_for(vp.shape[0])
+        logit, (h_t, c_t), h_tilde = self.decoder(ops.pose_feature(store, view), pano, cands, h_tilde, h_t, c_t, ctx, ctx_mask)
+        return logit, h_t, c_t, h_tilde
+
+    decode_obervation = decode_observation
+
     def rollout_pair(self, train_cl=False):
         """The two rollouts of one EnvDrop training iteration (trainer.py:411-421: teacher-forced for the imitation
         loss, then sampled on the SAME minibatch for A2C) stepped as ONE batch of 2B episodes: rows [0,B) sample,

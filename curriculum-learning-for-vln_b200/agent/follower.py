@@ -19,6 +19,15 @@ def masked_mean_ce(ce, target):
     return ce.sum() / n
 
 
+def _beam_next_action(store, vp, logit, ended):
+    """follower.py:190-195: the argmax slot, -1 for STOP (slot n_cand) and for rows whose search has ended."""
+    action = logit.argmax(1).to(torch.int32)
+    stop = action == store.n_cand[vp.long()]
+    if ended is not None:
+        stop = stop | torch.as_tensor(ended, dtype=torch.bool, device=logit.device)
+    return torch.where(stop, torch.full_like(action, -1), action)
+
+
 class FollowerAgent(BaseAgent):
     def __init__(self, model_cfg, results_dir, device, env, tokenizer, glove=None, episode_len=10):
         super().__init__(results_dir, device, env, tokenizer, episode_len=episode_len)
@@ -34,6 +43,19 @@ class FollowerAgent(BaseAgent):
 
     def _modules(self):
         return [self.encoder, self.decoder]
+
+    # ---- beam search hooks (follower.py:175-198) ----------------------------------------------------------------------
+    def beam_start_state(self, h_t):
+        return torch.zeros(h_t.shape[0], self.action_emb_size, device=self.device)
+
+    def decode_observation(self, store, vp, view, h_t, c_t, a_prev, ctx, ctx_mask, ended=None):
+        pano = ops.PanoView(store, vp, view)
+        pano.split = self.split_for(vp.shape[0])
+        logit, (h_t, c_t), _ = self.decoder(pano, a_prev, ops.CandView(store, vp, view), h_t, c_t, ctx, ctx_mask)
+        action = _beam_next_action(store, vp, logit, ended)
+        return logit, h_t, c_t, ops.gather_action_feat(store, vp, view, action, None).detach()
+
+    decode_obervation = decode_observation
 
     def rollout(self, train_ml=True, train_rl=False, train_cl=False, reset=True, restart=False, speaker=None,
                 avoid_cyclic=False, feedback="sample", return_traj=None):

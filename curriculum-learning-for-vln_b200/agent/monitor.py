@@ -35,6 +35,23 @@ class SelfMonitorAgent(BaseAgent):
         self.losses = []
         self.progress_losses = []
 
+    # ---- beam search hooks (monitor.py:201-225) -----------------------------------------------------------------------
+    beam_full_length = True            # the decoder's progress head needs the full-width instruction (rollout, above)
+
+    def beam_start_state(self, h_t):
+        return torch.zeros(h_t.shape[0], self.action_emb_size, device=self.device)
+
+    def decode_observation(self, store, vp, view, h_t, c_t, a_prev, ctx, ctx_mask, ended=None):
+        from .follower import _beam_next_action
+        cands, lens = ops.gather_cand(store, vp, view)
+        cmask = LengthMask(lens, ops.NSLOT)
+        (logit, _), (h_t, c_t), _ = self.decoder(None, a_prev, cands, h_t, c_t, ctx, ctx_mask, cmask)
+        logit = logit.masked_fill(cmask.dense(), float("-inf"))
+        action = _beam_next_action(store, vp, logit, ended)
+        return logit, h_t, c_t, ops.gather_action_feat(store, vp, view, action, None).detach()
+
+    decode_obervation = decode_observation
+
     def rollout(self, train_ml=True, train_cl=False, reset=True, restart=False, lamb=0.5, speaker=None,
                 avoid_cyclic=False, feedback="sample", return_traj=None):
         assert speaker is None and not avoid_cyclic, "speaker / avoid_cyclic paths are not part of this build"

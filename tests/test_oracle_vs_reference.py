@@ -34,6 +34,12 @@ def test_port_speaker_matches_reference_speaker():
     runpy.run_path(os.path.join(HERE, "_ref_check_speaker.py"), run_name="__main__")
 
 
+def test_port_beam_search_matches_reference_dijkstra():
+    """Real EnvDrop / Follower agents' _dijkstra (K best listener paths, base.py:183-397) == oracle/port_beam.py: paths,
+    actions, scores, visual features, dijk_path."""
+    runpy.run_path(os.path.join(HERE, "_ref_check_beam.py"), run_name="__main__")
+
+
 def test_ingest_matches_reference_loaders():
     """environ/ingest.py == ImageFeatures.read_in, load_nav_graphs + networkx paths (ties), Tokenizer."""
     runpy.run_path(os.path.join(HERE, "_ref_check_ingest.py"), run_name="__main__")
