@@ -262,6 +262,19 @@ def roofline_others(ops, torch, B, peaks):
     out.append({"kernel": "ctx_step_fwd (LSTM pointwise + text attention, B=%d, L=%d, H=%d)" % (B, L, H), "bound": "l2",
                 "us_per_launch": round(t * 1e6, 2), "algorithmic_bytes": by, "achieved_GBs": round(by / t / 1e9, 1),
                 "note": "per-episode CTA: one bulk copy of the dotted tile into shared memory + the summed tile in registers; latency-bound at B=64 (21 MB per launch)"})
+    # weight gradient of the LSTMCell gates over the stacked rows of the paired rollout (csrc/wgrad.cu: tcgen05 kind::tf32,
+    # both operands MN-major straight from TMA): the largest of the backward pass's dY^T X products
+    R, M, Nw = 35 * 2 * B, 2048, 2752
+    dy, xs = torch.randn(R, M, device=dev), torch.randn(R, Nw, device=dev)
+    t = time_graph(lambda: ops.wgrad_tc(dy, xs), n_in=4, reps=5)
+    tf = 2 * R * M * Nw / t / 1e12
+    out.append({"kernel": "wgrad_tf32 (dW = dY^T X of the LSTMCell gates, R=%d rows, %dx%d, tcgen05 kind::tf32)" % (R, M, Nw),
+                "bound": "l2", "us_per_launch": round(t * 1e6, 1), "achieved_tflops": round(tf, 1),
+                "peak_tflops_tf32": round(peak_tf / 2, 1), "tensor_frac_tf32": round(tf / (peak_tf / 2), 4),
+                "operand_GBs_from_l2": round((M // 128) * ((Nw + 127) // 128) * R * 1024 / t / 1e9, 1),
+                "note": "fp32 operands as tf32: a 128x128 block needs 1 KB of operands per reduction row for 16 384 MACs, so "
+                        "the launch is bound by L2 -> shared-memory traffic (operand_GBs_from_l2), not by the tensor pipe; "
+                        "tf32 peak taken as half the measured dense bf16 rate"})
     return out
 
 
@@ -600,7 +613,7 @@ def run_b200(args):
     out = {
         "metric": METRIC, "value": round(n_ep / t_dev, 2), "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": round(t_dev / args.steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 state/accumulate; bf16 feature table; forward + input-gradient GEMMs bf16x3 on tcgen05 (3 bf16 MMAs per product, ~2e-5 rel); weight-gradient GEMMs TF32",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 state/accumulate; bf16 feature table; forward + input-gradient GEMMs bf16x3 on tcgen05 (3 bf16 MMAs per product, ~2e-5 rel); weight-gradient GEMMs and the encoder's embedding-side input gradient tcgen05 kind::tf32 (csrc/wgrad.cu, fp32 accumulate); no library GEMM in the iteration",
         "data": "synthetic",
         "config": {"workload": WORKLOAD % args.batch,
                    "global_batch": args.batch * world_size, "parallelism": f"dp{world_size}",
