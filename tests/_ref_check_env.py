@@ -45,4 +45,30 @@ for step in range(8):
         acts.append(a)
     obs = env.step(np.array(acts), obs, traj)
 print([ob['distance'] for ob in obs])
+# ---- first-visit observations.  make_candidate's first visit to a viewpoint computes a candidate's
+# relative heading as (state.heading - base) + rel_heading (common_env.py:249-256); every later visit reads the buffer and
+# computes (state.heading + rel_heading) - base (:283-285).  The two associations differ by at most one fp64 rounding of the
+# heading, i.e. after float32(sin / cos) by at most one unit in the last place of the 128 angle features; the image half,
+# the candidate order and the view indices are identical.  The product tables (and the checks above) hold the BUFFERED
+# arithmetic, the one every observation but a viewpoint's very first uses.
+env2 = environ.R2RBatch(fs, batch_size=8, splits=["train"], tokenizer=tok)          # cold buffer
+worst, n_diff, n_tot = 0.0, 0, 0
+for long_id, f in list(fs.items())[:200]:
+    scan, vp = long_id.split("_", 1)
+    if scan not in env2.scans:
+        continue
+    for view in (12, 17, 23):
+        env2.buffered_state_dict.pop(long_id, None)
+        first = env2.make_candidate(f, scan, vp, view)
+        again = env2.make_candidate(f, scan, vp, view)
+        assert [c["nextViewpointId"] for c in first] == [c["nextViewpointId"] for c in again]
+        assert [c["absViewIndex"] for c in first] == [c["absViewIndex"] for c in again]
+        for a, b in zip(first, again):
+            assert np.array_equal(a["feature"][:2048], b["feature"][:2048])
+            d = np.abs(a["feature"][2048:].astype(np.float64) - b["feature"][2048:].astype(np.float64)).max()
+            worst = max(worst, d)
+            n_diff += int(d > 0)
+            n_tot += 1
+print(f"first-visit vs buffered angle features: {n_diff}/{n_tot} candidates differ, max abs difference {worst:.3e}")
+assert worst <= 2 ** -23                                    # one ulp of a float32 in [0.5, 1)
 print("harness OK")
