@@ -549,7 +549,9 @@ def run_b200(args):
     if world_size > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps the version banner off stdout (one JSON line)
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that does not complete aborts the job after 3 minutes instead of NCCL's default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     import clvln_b200  # noqa: F401
     from clvln_b200 import ops, utils, _lib
     from clvln_b200.agent import build_agent

@@ -183,7 +183,9 @@ pano_attn_kernel(const __nv_bfloat16* __restrict__ table, const int32_t* __restr
       chain_signal_cta(link);
       return;
     }
+    if (dbg && blockIdx.x == 0 && tid == 0 && g0 >= 0) g_pano_stamps[9] = (unsigned long long)clock64();    // index in hand
     if (cid < B && lane < VLN_V / kWarps) request_row(cid, g0, warp + lane * kWarps, 0);
+    if (dbg && blockIdx.x == 0 && tid == 0) g_pano_stamps[10] = (unsigned long long)clock64();             // rows requested
     if (gen_mask && cid < B && early) draw_mask();         // while the rows are in flight
     if (early) chain_wait_cta(link);                       // the query / gradient vector comes from the predecessor
     if (early) CHAIN_MARK(2);

@@ -6,7 +6,7 @@ Python/launch path, not by the GPU.  ``GraphedTrainStep`` captures zero_grad -> 
 backward once per teacher-rollout length into a CUDA graph and replays it: the minibatch's index
 tensors are copied into static buffers, the Philox base lives in device memory and is advanced
 inside the graph, so every replay sees new data and new dropout masks / samples.  The gradient
-all-reduce and the fused clip + update stay outside the graph (3 launches).
+all-reduce (by default, see ``dp_in_graph``) and the fused clip + update stay outside the graph (3 launches).
 """
 import torch
 
@@ -39,6 +39,20 @@ class GraphedTrainStep(TrainStep):
         # minibatches is unchanged; callers switch it off for the last iteration before they touch the env / the
         # global `random` stream themselves (epoch end: evaluation, curriculum round switch).
         self.prefetch_next = False
+        # Data parallel.  Default: the gradient all-reduce stays OUTSIDE the captured graph — `opt.step()` issues exactly
+        # one all-reduce of the flat buffer per iteration on every rank, whatever mix of warm-up / capture / replay the
+        # ranks are in (the round-1 scheme, measured at 8 GPUs).  VLN_DP_INGRAPH=1 captures the bucketed, overlapped
+        # all-reduce into the graph instead (decoder + critic bucket under the encoder's backward): then warm-up
+        # iterations all-reduce for real and capture iterations do not, so it is only correct when every rank meets new
+        # graph keys at the same iterations — which environ/batch.py guarantees by taking the teacher-rollout length over
+        # the GLOBAL minibatch.  (Before that guarantee a 4-GPU run hung: one rank had warmed up a new length while its
+        # peers replayed, and the collectives no longer paired up.)  Measured at 2 GPUs the in-graph variant is not faster
+        # (4.62 vs 4.49 ms single; round 1 outside the graph: 4.89 vs 4.78), so it is opt-in.
+        import os
+        self.dp_in_graph = os.environ.get("VLN_DP_INGRAPH", "0") == "1"
+        fd = getattr(agent, "_fused", None)
+        if fd is not None and not self.dp_in_graph:
+            fd.on_grads_ready = None        # (TrainStep set the early-bucket hook; it must not be captured)
         # warm-up iterations run on a side stream and the capture on its own: the AccumulateGrad nodes of the (persistent)
         # parameters then see a different stream than the one they were created on; intended here, so silence the notice
         fn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
@@ -49,7 +63,8 @@ class GraphedTrainStep(TrainStep):
         self.opt.zero_grad()
         loss, item = self.losses()
         loss.backward()
-        self.opt.finish_reduce()            # data parallel: the rest of the gradient all-reduce, inside the graph
+        if self.dp_in_graph:
+            self.opt.finish_reduce()        # data parallel, opt-in: the rest of the gradient all-reduce, inside the graph
         self.agent.rng.advance()
         return loss.detach(), item
 
@@ -115,7 +130,10 @@ class GraphedTrainStep(TrainStep):
             g.replay()
             ops.CALLS[0] += n_calls
             if self.opt.world > 1:
-                self.opt._reduced = [(0, self.opt.grad.numel())]      # the replayed graph all-reduced the whole buffer
+                if self.dp_in_graph:
+                    self.opt._reduced = [(0, self.opt.grad.numel())]  # the replayed graph all-reduced the whole buffer
+                else:
+                    self.opt._pending, self.opt._reduced = [], []     # nothing reduced yet: opt.step() all-reduces once
             ag.last_state, ag.last_batch = refs[0], refs[1]
             if getattr(ag, "_fused", None) is not None:
                 ag._fused.last = refs[2]

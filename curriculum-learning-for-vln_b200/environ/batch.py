@@ -92,6 +92,7 @@ class R2RBatch:
             batch = sorted(batch, key=lambda it: it["instr_length"], reverse=True)
         self.global_batch = batch
         self.batch = batch[self.rank::self.world_size] if self.world_size > 1 else batch
+        self._batch_is_shard = True
 
     def reset_epoch(self, shuffle=False):
         if shuffle:
@@ -106,8 +107,10 @@ class R2RBatch:
         elif inject:
             self._next_minibatch(**kw)
             self.batch[:len(batch)] = batch
+            self._batch_is_shard = False
         else:
             self.batch = batch
+            self._batch_is_shard = False
 
     # ---- index face -----------------------------------------------------------------------------
     def reset_index(self, batch=None, inject=False, restart=False, full_length=False, **kw):
@@ -131,6 +134,18 @@ class R2RBatch:
             self._next_minibatch()
             self._staged.append((self.batch, self._make_index_batch(full_length)))
 
+    def _hops_of(self, item):
+        """Hops of the item's shortest path (start -> goal), cached on the item."""
+        n = item.get("_hops")
+        if n is None:
+            w = self.world
+            cur, goal, n = int(item["path_g"][0]), int(item["path_g"][-1]), 0
+            while cur != goal:
+                cur = w.hop(cur, goal)
+                n += 1
+            item["_hops"] = n
+        return n
+
     def _make_index_batch(self, full_length=False):
         b = self.batch
         w = self.world
@@ -143,13 +158,13 @@ class R2RBatch:
         view = np.array([heading_to_view(it["heading"]) for it in b], np.int32)
         index = np.array([self.index(it) for it in b], np.int64) if hasattr(self, "item2idx") else \
             np.zeros(len(b), np.int64)
-        hops = 0
-        for s, g in zip(vp, goal):
-            cur, n = int(s), 0
-            while cur != int(g):
-                cur = w.hop(cur, int(g))
-                n += 1
-            hops = max(hops, n)
+        # Length of the teacher-forced rollout.  Under data parallelism it is taken over the GLOBAL minibatch (every rank
+        # draws the same one and keeps rows rank::world), not over this rank's shard: the trainers key their captured CUDA
+        # graphs on it, and a rank that met a new length would run warm-up + capture iterations — with their gradient
+        # all-reduces — while its peers replay, i.e. the ranks would issue different numbers of collectives and hang.
+        # Rows that reach their goal earlier are masked exactly as before, so losses are unchanged.
+        rows = self.global_batch if (self.world_size > 1 and getattr(self, "_batch_is_shard", False)) else b
+        hops = max((self._hops_of(it) for it in rows), default=0)
         dev = self.device
         nb = 0
 

@@ -114,6 +114,39 @@ def test_sharding_reassembles_global_batch():
             assert [it["instr_id"] for it in e.global_batch] == ids
 
 
+@pytest.mark.parametrize("world_size", [2, 4, 8])
+def test_teacher_rollout_length_is_global_under_data_parallelism(world_size):
+    """Every rank must report the SAME teacher_steps for a minibatch (the maximum over the global batch): the trainers key
+    their captured CUDA graphs on it, and ranks that disagreed would run warm-up / capture iterations — whose gradient
+    all-reduces the replaying peers do not issue — at different steps and hang in NCCL (seen at 4 GPUs, where one rank
+    had issued three iterations' worth of collectives more than the others).  Also through the staged (prefetch) path,
+    and back to the local maximum when a batch is handed in explicitly."""
+    from clvln_b200.environ import R2RBatch
+    world, items = _world(160)
+    ranks = []
+    for r in range(world_size):
+        random.seed(21)
+        ranks.append(R2RBatch(world, items, batch_size=4, rank=r, world_size=world_size))
+    local_differs = False
+    for step in range(12):                                         # crosses a wrap-around
+        st = random.getstate()
+        got, local = [], []
+        for e in ranks:
+            random.setstate(st)
+            if step % 3 == 2:
+                e.prefetch(1)
+            ib = e.reset_index()
+            got.append(ib.teacher_steps)
+            local.append(1 + max(e._hops_of(it) for it in e.batch))
+        assert len(set(got)) == 1, got
+        assert got[0] == max(local) == 1 + max(ranks[0]._hops_of(it) for it in ranks[0].global_batch)
+        local_differs |= len(set(local)) > 1
+    assert local_differs                                           # (the shards themselves do disagree: the case that hung)
+    e = ranks[0]
+    mine = list(e.batch)
+    assert e.reset_index(batch=mine).teacher_steps == 1 + max(e._hops_of(it) for it in mine)
+
+
 def test_curriculum_env_matches_oracle():
     from clvln_b200.environ import CLR2RBatch, split_rounds
     from oracle import port_env as PE

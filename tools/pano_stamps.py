@@ -43,4 +43,4 @@ for B in [int(a) for a in sys.argv[1:]] or [16, 64, 2048]:
         buf = (C.c_ulonglong * 16)()
         L.vln_debug_pano_stamps(buf)
         d = [buf[i] - buf[0] for i in range(1, 8)]
-        print(f"B={B} mask_bits={bits}: " + ", ".join(f"{n}={v}" for n, v in zip(names, d)) + f" | unit starts at {buf[8] - buf[0]}")
+        print(f"B={B} mask_bits={bits}: " + ", ".join(f"{n}={v}" for n, v in zip(names, d)) + f" | unit starts at {buf[8] - buf[0]}, index in hand at {buf[9] - buf[0]}, rows requested at {buf[10] - buf[0]}")

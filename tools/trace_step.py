@@ -24,7 +24,7 @@ def main():
     from clvln_b200.environ import R2RBatch
     torch.backends.cuda.matmul.allow_tf32 = False
     world, items = bench.build_world(False, dev)
-    cfg = utils.agent_cfg("ENVDROP")
+    cfg = utils.agent_cfg(os.environ.get("VLN_TRACE_AGENT", "ENVDROP"))
     random.seed(2020)
     env = R2RBatch(world, items, batch_size=int(os.environ.get("VLN_TRACE_BATCH", "64")), device=dev)
     torch.manual_seed(2020)
