@@ -10,12 +10,13 @@ inputs; the committed fixtures then pin oracle/port_*.py wherever /root/referenc
                outputs — a few hundred KB.
   speaker.pt   the real Speaker class (shipped sizes, eval mode) on the seeded world: path lengths, loss / accuracies,
                beam-search scores, greedy words, gradient norms.
+  beam.pt      the real EnvDrop / Follower agents' _dijkstra (K = 3): paths, actions, listener scores, dijk_path.
   rollouts.pt  the three real agents (shipped model sizes) on a seeded synthetic world:
                teacher + forced-action rollouts in eval mode: per-step logits/targets, losses,
                per-parameter gradient norms, trajectories, and the minibatch order over a
                wrap-around.  World and weights are regenerated from seeds by the test.
 
-usage: python -m oracle.make_golden [speaker]
+usage: python -m oracle.make_golden [speaker|beam]
 """
 import os
 import random
@@ -215,6 +216,46 @@ def speaker_cases():
     return out
 
 
+def beam_cases():
+    """The real EnvDrop and Follower agents' ``_dijkstra`` (base.py:183-397; K = 3) on the seeded synthetic world, eval mode:
+    per episode the K best paths (poses, actions, listener scores) and the navigation path; world and weights are regenerated
+    from the seeds by the test."""
+    import clvln_b200  # noqa: F401
+    from clvln_b200.environ import make_world, make_items
+    from oracle import ref_harness as H
+    w = make_world(n_scans=3, seed=1)
+    items = make_items(w, 40, seed=1)
+    H.install(w, {"train": items})
+    import src.agent as agent_mod
+    import src.environ as environ
+    tok = H.StubTokenizer(items)
+    fs = H.feature_store(w)
+    dev = torch.device("cpu")
+    out = {"world": dict(n_scans=3, seed=1, n_items=40, B=6), "K": 3}
+    for kind in ("ENVDROP", "FOLLOWER"):
+        random.seed(2020)
+        torch.manual_seed(2020)
+        renv = environ.R2RBatch(fs, batch_size=6, splits=["train"], tokenizer=tok)
+        H.warm_candidate_buffer(renv)
+        cfg = H.model_cfg(kind)
+        if kind == "ENVDROP":
+            ag = agent_mod.EnvDropAgent(cfg, 80, "/tmp", dev, renv, tok, episode_len=12)
+        else:
+            ag = agent_mod.FollowerAgent(cfg, "/tmp", dev, renv, tok, episode_len=10)
+        ag.env = renv
+        ag.eval()
+        mods = [ag.encoder, ag.decoder] + ([ag.critic] if kind == "ENVDROP" else [])
+        with torch.no_grad():
+            res = ag._dijkstra(3)
+        out[kind] = dict(w_checksum=[float(p.detach().double().sum()) for m in mods for p in m.parameters()],
+                         results=[dict(instr_id=r["instr_id"], dijk_path=list(r["dijk_path"]),
+                                       paths=[dict(trajectory=[tuple(x) for x in p["trajectory"]], action=list(p["action"]),
+                                                   listener_scores=[float(x) for x in p["listener_scores"]],
+                                                   listener_actions=list(p["listener_actions"])) for p in r["paths"]])
+                                  for r in res])
+    return out
+
+
 def eval_cases():
     """Random-walk trajectories on a seeded synthetic world scored by the reference's own Evaluation.score
     (src/engine/evaluator.py:101-146): the summary and the per-trajectory lists travel as tests/golden/eval.json."""
@@ -248,11 +289,13 @@ def main():
     from oracle import ref_loader
     assert ref_loader.reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] == "speaker":          # only the speaker fixture (the others are unchanged)
-        torch.save(speaker_cases(), os.path.join(OUT, "speaker.pt"))
-        print("speaker.pt", os.path.getsize(os.path.join(OUT, "speaker.pt")))
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only in ("speaker", "beam"):                             # only that fixture (the others are unchanged)
+        torch.save({"speaker": speaker_cases, "beam": beam_cases}[only](), os.path.join(OUT, only + ".pt"))
+        print(only + ".pt", os.path.getsize(os.path.join(OUT, only + ".pt")))
         return
     torch.save(speaker_cases(), os.path.join(OUT, "speaker.pt"))
+    torch.save(beam_cases(), os.path.join(OUT, "beam.pt"))
     torch.save(module_cases(), os.path.join(OUT, "modules.pt"))
     torch.save(rollout_cases(), os.path.join(OUT, "rollouts.pt"))
     import json

@@ -235,3 +235,42 @@ def test_port_speaker_matches_reference_golden():
             assert abs(a - b) <= 1e-4 * max(1e-3, abs(b)), (a, b)
         words, _ = port.infer_batch(feats)
         assert torch.equal(torch.from_numpy(words), ref["words"])
+
+
+# ---- beam search ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["ENVDROP", "FOLLOWER"])
+def test_port_beam_search_matches_reference_golden(kind):
+    """oracle/port_beam.py on the regenerated world + weights finds the K best listener paths the REAL agents' _dijkstra
+    found (tests/golden/beam.pt, oracle/make_golden.py): same poses, actions, navigation path; scores to 1e-5."""
+    import numpy as np
+    from clvln_b200.model import EncoderLSTM, EnvDropDecoder, AttnDecoderLSTM, Critic
+    from oracle import port_beam as PB, port_env as PE, port_rollout as PR
+    g = torch.load(os.path.join(G, "beam.pt"), weights_only=False)
+    world, items = _speaker_world(g)
+    random.seed(2020)
+    torch.manual_seed(2020)
+    penv = PE.R2RBatchPort(PE.WorldView(world), items, batch_size=g["world"]["B"])
+    if kind == "ENVDROP":
+        mods = [EncoderLSTM(992, 256, 512, 0, 0.5, True, 1), EnvDropDecoder(512, 0.5, 0.3, 64, 128, 2176), Critic(512, 0.5)]
+        kw = dict(hidden=512, bidirectional=True, enc_layers=1, episode_len=12)
+    else:
+        mods = [EncoderLSTM(992, 300, 256, 0, 0.5, True, 2), AttnDecoderLSTM(256, 0.5, 2176, 2176)]
+        kw = dict(hidden=256, bidirectional=True, enc_layers=2, episode_len=10)
+    ref = g[kind]
+    chk = [float(p.detach().double().sum()) for m in mods for p in m.parameters()]
+    assert len(chk) == len(ref["w_checksum"]) and max(abs(a - b) for a, b in zip(chk, ref["w_checksum"])) < 1e-6
+    sds = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in mods]
+    ag = PR.Agent(kind, sds[0], sds[1], sds[2] if len(sds) > 2 else None, **kw)
+    random.seed(1)                                         # (the reference agent's constructor re-seeds `random`, base.py:28)
+    with torch.no_grad():
+        got = PB.dijkstra(ag, penv, g["K"])
+    assert [r["instr_id"] for r in got] == [r["instr_id"] for r in ref["results"]]
+    key = lambda p: (tuple(p["action"]), tuple(x[0] for x in p["trajectory"]))        # noqa: E731
+    for a, b in zip(got, ref["results"]):
+        assert a["dijk_path"] == b["dijk_path"]
+        pa, pb = sorted(a["paths"], key=key), sorted(b["paths"], key=key)
+        assert len(pa) == len(pb)
+        for x, y in zip(pa, pb):
+            assert [tuple(t) for t in x["trajectory"]] == y["trajectory"]
+            assert x["action"] == y["action"] and x["listener_actions"] == y["listener_actions"]
+            assert np.allclose(x["listener_scores"], y["listener_scores"], rtol=1e-5, atol=1e-6)
