@@ -24,44 +24,62 @@ from ..model.units import LengthMask
 START = -95                                                  # action id of the start state (base.py:241)
 
 
-class FloydGraph:
-    """misc.py:493-541: incremental all-pairs shortest paths over the viewpoints seen so far (only shapes ``dijk_path``)."""
+class SeenGraph:
+    """All-pairs shortest routes over the viewpoints the search has seen so far, grown one expanded viewpoint at a time
+    (the role of ``utils.FloydGraph``, misc.py:493-541; it only shapes ``dijk_path``, the walk a robot would make between
+    consecutive expansions).  Dense tables over node numbers in order of first appearance: ``_d[i][j]`` the best known
+    length, ``_via[i][j]`` the intermediate viewpoint of that route (-1 = the direct edge).  ``relax`` is one Floyd-Warshall
+    round through a newly expanded viewpoint, scanning pairs in first-appearance order with in-place symmetric updates,
+    which is what decides ties between equally long routes."""
+    FAR = 95959595
 
     def __init__(self):
-        self._dis = defaultdict(lambda: defaultdict(lambda: 95959595))
-        self._point = defaultdict(lambda: defaultdict(lambda: ""))
-        self._visited = set()
+        self._num, self._names = {}, []
+        self._d, self._via = [], []
+        self._expanded = set()
 
-    def distance(self, x, y):
-        return 0 if x == y else self._dis[x][y]
+    def _node(self, name):
+        i = self._num.get(name)
+        if i is None:
+            i = self._num[name] = len(self._names)
+            self._names.append(name)
+            for row in self._d:
+                row.append(self.FAR)
+            for row in self._via:
+                row.append(-1)
+            self._d.append([self.FAR] * (i + 1))
+            self._via.append([-1] * (i + 1))
+        return i
 
-    def add_edge(self, x, y, dis):
-        if dis < self._dis[x][y]:
-            self._dis[x][y] = dis
-            self._dis[y][x] = dis
-            self._point[x][y] = ""
-            self._point[y][x] = ""
+    def link(self, a, b, length):
+        i, j = self._node(a), self._node(b)
+        if length < self._d[i][j]:
+            self._d[i][j] = self._d[j][i] = length
+            self._via[i][j] = self._via[j][i] = -1
 
-    def update(self, k):
-        for x in self._dis:
-            for y in self._dis:
-                if x != y and self._dis[x][k] + self._dis[k][y] < self._dis[x][y]:
-                    self._dis[x][y] = self._dis[x][k] + self._dis[k][y]
-                    self._dis[y][x] = self._dis[x][y]
-                    self._point[x][y] = k
-                    self._point[y][x] = k
-        self._visited.add(k)
+    def relax(self, name):
+        k = self._num.get(name)
+        if k is not None:
+            d, via, n = self._d, self._via, len(self._names)
+            for i in range(n):
+                for j in range(n):
+                    if i != j and d[i][k] + d[k][j] < d[i][j]:
+                        d[i][j] = d[j][i] = d[i][k] + d[k][j]
+                        via[i][j] = via[j][i] = k
+        self._expanded.add(name)
 
-    def visited(self, k):
-        return k in self._visited
+    def seen(self, name):
+        return name in self._expanded
 
-    def path(self, x, y):
-        if x == y:
+    def route(self, a, b):
+        """Viewpoints to walk through from a to b, b included (empty when a == b)."""
+        if a == b:
             return []
-        if self._point[x][y] == "":
-            return [y]
-        k = self._point[x][y]
-        return self.path(x, k) + self.path(k, y)
+        i, j = self._num.get(a), self._num.get(b)
+        if i is None or j is None or self._via[i][j] < 0:
+            return [b]
+        mid = self._names[self._via[i][j]]
+        return self.route(a, mid) + self.route(mid, b)
 
 
 def dijkstra(agent, max_candidates, max_expansions=500):
@@ -97,7 +115,7 @@ def dijkstra(agent, max_candidates, max_expansions=500):
                                    "scores": [], "actions": []}} for i in range(B)]
     visited = [set() for _ in range(B)]
     finished = [set() for _ in range(B)]
-    graphs = [FloydGraph() for _ in range(B)]
+    graphs = [SeenGraph() for _ in range(B)]
     ended = np.array([False] * B)
     for _ in range(max_expansions):
         pick = [max(((sid, s) for sid, s in id2state[i].items() if sid not in visited[i]), key=lambda kv: kv[1]["score"])
@@ -124,12 +142,12 @@ def dijkstra(agent, max_candidates, max_expansions=500):
         view_t = torch.tensor(views, dtype=torch.int32, device=dev)
         for i, g in enumerate(cur):                          # navigation graph of what has been seen (dijk_path only)
             vn = name(g)
-            if not graphs[i].visited(vn):
+            if not graphs[i].seen(vn):
                 for j in range(int(n_cand[g])):
                     nxt = int(cand_vp[g, j])
-                    graphs[i].add_edge(vn, name(nxt), float(world.distance(g, nxt)))
-                graphs[i].update(vn)
-            results[i]["dijk_path"].extend(graphs[i].path(results[i]["dijk_path"][-1], vn))
+                    graphs[i].link(vn, name(nxt), float(world.distance(g, nxt)))
+                graphs[i].relax(vn)
+            results[i]["dijk_path"].extend(graphs[i].route(results[i]["dijk_path"][-1], vn))
         logits, h_b, c_b, x_b = agent.decode_observation(store, vp_t, view_t, h_b, c_b, x_b, ctx, ctx_mask, tmp_ended)
         log_probs = F.log_softmax(logits, 1).detach().cpu().numpy()
         for i, g in enumerate(cur):
@@ -156,7 +174,7 @@ def dijkstra(agent, max_candidates, max_expansions=500):
         if ended.all():
             break
     for i in range(B):
-        results[i]["dijk_path"].extend(graphs[i].path(results[i]["dijk_path"][-1], results[i]["dijk_path"][0]))
+        results[i]["dijk_path"].extend(graphs[i].route(results[i]["dijk_path"][-1], results[i]["dijk_path"][0]))
     for i, result in enumerate(results):
         assert len(finished[i]) <= max_candidates
         for sid in finished[i]:

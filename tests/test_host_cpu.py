@@ -344,3 +344,38 @@ def test_product_package_never_imports_the_oracle():
     entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
     build_src = entry[entry.index("def build()"):entry.index("def smoke()")]
     assert not re.search(r"(from|import)\s+oracle\b", build_src)          # build() compiles and imports the product only
+
+
+def test_seen_graph_routes_match_the_reference_floyd_graph():
+    """agent/beam.py's SeenGraph (dense tables over node numbers) gives the routes of the reference's FloydGraph
+    (misc.py:493-541, restated in oracle/port_beam.py and pinned there through dijk_path) for the way beam search uses it:
+    edges of an expanded viewpoint, one relaxation, then routes between arbitrary seen viewpoints; ties included."""
+    import clvln_b200  # noqa: F401
+    from clvln_b200.agent.beam import SeenGraph
+    from oracle.port_beam import FloydGraph
+    rng = random.Random(7)
+    for trial in range(30):
+        n = rng.randint(4, 14)
+        names = ["v%d" % i for i in range(n)]
+        nbrs = {a: rng.sample([b for b in names if b != a], rng.randint(1, min(4, n - 1))) for a in names}
+        length = {}
+        for a in names:
+            for b in nbrs[a]:
+                length.setdefault(frozenset((a, b)), rng.choice([1.0, 1.0, 2.0, 1.5, 3.25]))     # equal lengths: ties
+        mine, ref = SeenGraph(), FloydGraph()
+        order = names[:]
+        rng.shuffle(order)
+        seen = []
+        for a in order + order[:3]:                                # re-expanding a viewpoint is a no-op in the search
+            assert mine.seen(a) == ref.visited(a)
+            if not ref.visited(a):
+                for b in nbrs[a]:
+                    d = length[frozenset((a, b))]
+                    mine.link(a, b, d)
+                    ref.add_edge(a, b, d)
+                mine.relax(a)
+                ref.update(a)
+                seen.append(a)
+            for _ in range(6):
+                x, y = rng.choice(names), rng.choice(names)
+                assert mine.route(x, y) == ref.path(x, y), (trial, x, y)
