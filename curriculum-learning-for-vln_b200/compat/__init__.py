@@ -32,7 +32,7 @@ def install_as_src():
         sys.modules[f"src.{name}"] = getattr(pkg, name)
     model = types.ModuleType("src.model")
     from .. import model as _model
-    for k in ("EncoderLSTM", "AttnDecoderLSTM", "MonitorDecoder", "EnvDropDecoder", "Critic"):
+    for k in ("EncoderLSTM", "AttnDecoderLSTM", "MonitorDecoder", "EnvDropDecoder", "Critic", "SpeakerEncoder", "SpeakerDecoder"):
         setattr(model, k, getattr(_model, k))
     sys.modules["src.model"] = model
     pkg.model = model
