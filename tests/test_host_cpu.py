@@ -379,3 +379,72 @@ def test_seen_graph_routes_match_the_reference_floyd_graph():
             for _ in range(6):
                 x, y = rng.choice(names), rng.choice(names)
                 assert mine.route(x, y) == ref.path(x, y), (trial, x, y)
+
+
+def test_product_beam_search_host_logic_matches_oracle_on_cpu():
+    """agent/beam.py's search (state dictionary, tie rule, poses, SeenGraph routes, index-form visual features) against
+    oracle/port_beam.py with the SAME decoder arithmetic: a stand-in agent whose encoder / decoder step are the oracle's CPU
+    modules, so only the product's host-side search logic is under test here (the CUDA decoder step is compared on the
+    GPU in tests/test_beam_gpu.py)."""
+    import clvln_b200  # noqa: F401
+    from clvln_b200.agent import beam
+    from clvln_b200.environ import R2RBatch
+    from clvln_b200.model import EncoderLSTM, EnvDropDecoder, Critic
+    from oracle import port_beam as PB, port_env as PE, port_modules as P, port_rollout as PR
+    world, items = _world(40, seed=1)
+    torch.manual_seed(5)
+    mods = [EncoderLSTM(992, 256, 512, 0, 0.5, True, 1), EnvDropDecoder(512, 0.5, 0.3, 64, 128, 2176), Critic(512, 0.5)]
+    sds = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in mods]
+    pag = PR.Agent("ENVDROP", sds[0], sds[1], sds[2], hidden=512, bidirectional=True, enc_layers=1, episode_len=12)
+    view = PE.WorldView(world)
+
+    class StandIn:
+        """The agent surface beam.dijkstra uses, with the oracle's arithmetic behind it."""
+        device = torch.device("cpu")
+
+        def __init__(self, env):
+            self.env = env
+            self.scratch = PE.R2RBatchPort(view, items, batch_size=env.batch_size)      # only its observe() is used
+
+        def store_of(self, env):
+            return None
+
+        def encoder(self, tokens, lengths):
+            return P.encoder_lstm(pag.enc, tokens, lengths.long(), bidirectional=True, num_layers=1, drop_ratio=0.5, drop=None)
+
+        def beam_start_state(self, h_t):
+            return h_t
+
+        def decode_observation(self, store, vp, view_idx, h_t, c_t, extra, ctx, ctx_mask, ended):
+            self.scratch.batch = self.env.batch
+            self.scratch.state = [[world.scans[int(world.vp_scan[g])], self.env._vp_name(g), v]
+                                  for g, v in zip(vp.tolist(), view_idx.tolist())]
+            obs = self.scratch.observe()
+            logit, h_t, c_t, extra, _, _ = PB.decode_observation(pag, obs, h_t, c_t, extra, ctx, ctx_mask.dense(), ended)
+            pad = torch.full((logit.shape[0], 16 - logit.shape[1]), -float("inf"))
+            return torch.cat((logit, pad), 1), h_t, c_t, extra
+
+    random.seed(2020)
+    env = R2RBatch(world, items, batch_size=5)
+    random.seed(2020)
+    penv = PE.R2RBatchPort(view, items, batch_size=5)
+    random.seed(1)
+    agent = StandIn(env)
+    with torch.no_grad():
+        for K in (2, 4):
+            got = beam.dijkstra(agent, K)
+            ref = PB.dijkstra(pag, penv, K)
+            assert [r["instr_id"] for r in got] == [r["instr_id"] for r in ref]
+            key = lambda p: (tuple(p["action"]), tuple(x[0] for x in p["trajectory"]))      # noqa: E731
+            for g, r in zip(got, ref):
+                assert g["dijk_path"] == r["dijk_path"]
+                gp, rp = sorted(g["paths"], key=key), sorted(r["paths"], key=key)
+                assert len(gp) == len(rp)
+                for a, b in zip(gp, rp):
+                    assert [tuple(t) for t in a["trajectory"]] == [tuple(t) for t in b["trajectory"]]
+                    assert a["action"] == b["action"] and a["listener_actions"] == b["listener_actions"]
+                    assert np.allclose(a["listener_scores"], b["listener_scores"], rtol=1e-6, atol=1e-7)
+                    # index-form features name the panorama / candidate the oracle kept as tensors
+                    for (gv, vw, slot), (f, c) in zip(a["visual_feature"], b["visual_feature"]):
+                        assert torch.equal(torch.from_numpy(world.table[gv].float().numpy())[:, :8], f[:, :8])
+                        assert (slot == int(world.n_cand[gv])) == bool((c == 0).all())
