@@ -217,7 +217,7 @@ def speaker_cases():
 
 
 def beam_cases():
-    """The real EnvDrop and Follower agents' ``_dijkstra`` (base.py:183-397; K = 3) on the seeded synthetic world, eval mode:
+    """The real EnvDrop, Follower and Self-Monitor agents' ``_dijkstra`` (base.py:183-397; K = 3) on the seeded synthetic world, eval mode:
     per episode the K best paths (poses, actions, listener scores) and the navigation path; world and weights are regenerated
     from the seeds by the test."""
     import clvln_b200  # noqa: F401
@@ -232,7 +232,7 @@ def beam_cases():
     fs = H.feature_store(w)
     dev = torch.device("cpu")
     out = {"world": dict(n_scans=3, seed=1, n_items=40, B=6), "K": 3}
-    for kind in ("ENVDROP", "FOLLOWER"):
+    for kind in ("ENVDROP", "FOLLOWER", "MONITOR"):
         random.seed(2020)
         torch.manual_seed(2020)
         renv = environ.R2RBatch(fs, batch_size=6, splits=["train"], tokenizer=tok)
@@ -240,8 +240,11 @@ def beam_cases():
         cfg = H.model_cfg(kind)
         if kind == "ENVDROP":
             ag = agent_mod.EnvDropAgent(cfg, 80, "/tmp", dev, renv, tok, episode_len=12)
-        else:
+        elif kind == "FOLLOWER":
             ag = agent_mod.FollowerAgent(cfg, "/tmp", dev, renv, tok, episode_len=10)
+        else:
+            ag = agent_mod.SelfMonitorAgent(cfg, 80, "/tmp", dev, renv, tok, episode_len=10)
+            ag.reset_loss()
         ag.env = renv
         ag.eval()
         mods = [ag.encoder, ag.decoder] + ([ag.critic] if kind == "ENVDROP" else [])

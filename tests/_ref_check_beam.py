@@ -1,5 +1,5 @@
 """Container-only: oracle/port_beam.py against the UNMODIFIED reference agents' ``_dijkstra`` (src/agent/base.py:183-397)
-for EnvDrop and Follower on the FakeSim world: the same K best paths per episode — trajectories, actions, listener scores,
+for EnvDrop, Follower and Self-Monitor on the FakeSim world: the same K best paths per episode — trajectories, actions, listener scores,
 visual features — and the same navigation path (``dijk_path``)."""
 import random
 import sys
@@ -22,7 +22,7 @@ tok = H.StubTokenizer(items)
 fs = H.feature_store(w)
 view = PE.WorldView(w)
 dev = torch.device("cpu")
-for kind in ("ENVDROP", "FOLLOWER"):
+for kind in ("ENVDROP", "FOLLOWER", "MONITOR"):
     random.seed(2020)
     torch.manual_seed(2020)
     renv = environ.R2RBatch(fs, batch_size=6, splits=["train"], tokenizer=tok)
@@ -30,8 +30,11 @@ for kind in ("ENVDROP", "FOLLOWER"):
     cfg = H.model_cfg(kind)
     if kind == "ENVDROP":
         ag = agent_mod.EnvDropAgent(cfg, 80, "/tmp", dev, renv, tok, episode_len=12)
-    else:
+    elif kind == "FOLLOWER":
         ag = agent_mod.FollowerAgent(cfg, "/tmp", dev, renv, tok, episode_len=10)
+    else:
+        ag = agent_mod.SelfMonitorAgent(cfg, 80, "/tmp", dev, renv, tok, episode_len=10)
+        ag.reset_loss()
     ag.env = renv
     ag.eval()
     st = random.getstate()
@@ -45,7 +48,7 @@ for kind in ("ENVDROP", "FOLLOWER"):
     for K in (3, 5):
         with torch.no_grad():
             ref = ag._dijkstra(K)
-            got = PB.dijkstra(pag, penv, K)
+            got = PB.dijkstra(pag, penv, K, full_length=(kind == "MONITOR"))   # monitor.py:68-87: always the full 80 tokens
         assert [r["instr_id"] for r in ref] == [r["instr_id"] for r in got]
         n_paths = 0
         for r, g in zip(ref, got):

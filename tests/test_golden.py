@@ -238,12 +238,12 @@ def test_port_speaker_matches_reference_golden():
 
 
 # ---- beam search ----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind", ["ENVDROP", "FOLLOWER"])
+@pytest.mark.parametrize("kind", ["ENVDROP", "FOLLOWER", "MONITOR"])
 def test_port_beam_search_matches_reference_golden(kind):
     """oracle/port_beam.py on the regenerated world + weights finds the K best listener paths the REAL agents' _dijkstra
     found (tests/golden/beam.pt, oracle/make_golden.py): same poses, actions, navigation path; scores to 1e-5."""
     import numpy as np
-    from clvln_b200.model import EncoderLSTM, EnvDropDecoder, AttnDecoderLSTM, Critic
+    from clvln_b200.model import EncoderLSTM, EnvDropDecoder, AttnDecoderLSTM, MonitorDecoder, Critic
     from oracle import port_beam as PB, port_env as PE, port_rollout as PR
     g = torch.load(os.path.join(G, "beam.pt"), weights_only=False)
     world, items = _speaker_world(g)
@@ -253,9 +253,12 @@ def test_port_beam_search_matches_reference_golden(kind):
     if kind == "ENVDROP":
         mods = [EncoderLSTM(992, 256, 512, 0, 0.5, True, 1), EnvDropDecoder(512, 0.5, 0.3, 64, 128, 2176), Critic(512, 0.5)]
         kw = dict(hidden=512, bidirectional=True, enc_layers=1, episode_len=12)
-    else:
+    elif kind == "FOLLOWER":
         mods = [EncoderLSTM(992, 300, 256, 0, 0.5, True, 2), AttnDecoderLSTM(256, 0.5, 2176, 2176)]
         kw = dict(hidden=256, bidirectional=True, enc_layers=2, episode_len=10)
+    else:
+        mods = [EncoderLSTM(992, 256, 512, 0, 0.5, False, 1), MonitorDecoder(512, 0.5, 80, [1024], 2176, 2176)]
+        kw = dict(hidden=512, bidirectional=False, enc_layers=1, episode_len=10)
     ref = g[kind]
     chk = [float(p.detach().double().sum()) for m in mods for p in m.parameters()]
     assert len(chk) == len(ref["w_checksum"]) and max(abs(a - b) for a, b in zip(chk, ref["w_checksum"])) < 1e-6
@@ -263,7 +266,7 @@ def test_port_beam_search_matches_reference_golden(kind):
     ag = PR.Agent(kind, sds[0], sds[1], sds[2] if len(sds) > 2 else None, **kw)
     random.seed(1)                                         # (the reference agent's constructor re-seeds `random`, base.py:28)
     with torch.no_grad():
-        got = PB.dijkstra(ag, penv, g["K"])
+        got = PB.dijkstra(ag, penv, g["K"], full_length=(kind == "MONITOR"))
     assert [r["instr_id"] for r in got] == [r["instr_id"] for r in ref["results"]]
     key = lambda p: (tuple(p["action"]), tuple(x[0] for x in p["trajectory"]))        # noqa: E731
     for a, b in zip(got, ref["results"]):

@@ -381,26 +381,39 @@ def test_seen_graph_routes_match_the_reference_floyd_graph():
                 assert mine.route(x, y) == ref.path(x, y), (trial, x, y)
 
 
-def test_product_beam_search_host_logic_matches_oracle_on_cpu():
-    """agent/beam.py's search (state dictionary, tie rule, poses, SeenGraph routes, index-form visual features) against
-    oracle/port_beam.py with the SAME decoder arithmetic: a stand-in agent whose encoder / decoder step are the oracle's CPU
-    modules, so only the product's host-side search logic is under test here (the CUDA decoder step is compared on the
-    GPU in tests/test_beam_gpu.py)."""
+@pytest.mark.parametrize("kind", ["ENVDROP", "FOLLOWER", "MONITOR"])
+def test_product_beam_search_host_logic_matches_oracle_on_cpu(kind):
+    """agent/beam.py's search (state dictionary, tie rule, poses, SeenGraph routes, index-form visual features, the
+    Self-Monitor's full-width instruction) against oracle/port_beam.py with the SAME decoder arithmetic: a stand-in agent
+    whose encoder / decoder step are the oracle's CPU modules, so only the product's host-side search logic is under test
+    here (the CUDA decoder step is compared on the GPU in tests/test_beam_gpu.py)."""
     import clvln_b200  # noqa: F401
     from clvln_b200.agent import beam
     from clvln_b200.environ import R2RBatch
-    from clvln_b200.model import EncoderLSTM, EnvDropDecoder, Critic
+    from clvln_b200.model import AttnDecoderLSTM, Critic, EncoderLSTM, EnvDropDecoder, MonitorDecoder
     from oracle import port_beam as PB, port_env as PE, port_modules as P, port_rollout as PR
     world, items = _world(40, seed=1)
     torch.manual_seed(5)
-    mods = [EncoderLSTM(992, 256, 512, 0, 0.5, True, 1), EnvDropDecoder(512, 0.5, 0.3, 64, 128, 2176), Critic(512, 0.5)]
+    if kind == "ENVDROP":
+        mods = [EncoderLSTM(992, 256, 512, 0, 0.5, True, 1), EnvDropDecoder(512, 0.5, 0.3, 64, 128, 2176), Critic(512, 0.5)]
+        kw = dict(hidden=512, bidirectional=True, enc_layers=1, episode_len=12)
+    elif kind == "FOLLOWER":
+        mods = [EncoderLSTM(992, 300, 256, 0, 0.5, True, 2), AttnDecoderLSTM(256, 0.5, 2176, 2176)]
+        kw = dict(hidden=256, bidirectional=True, enc_layers=2, episode_len=10)
+    else:
+        mods = [EncoderLSTM(992, 256, 512, 0, 0.5, False, 1), MonitorDecoder(512, 0.5, 80, [1024], 2176, 2176)]
+        kw = dict(hidden=512, bidirectional=False, enc_layers=1, episode_len=10)
+    for m in mods:
+        m.eval()
     sds = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in mods]
-    pag = PR.Agent("ENVDROP", sds[0], sds[1], sds[2], hidden=512, bidirectional=True, enc_layers=1, episode_len=12)
+    pag = PR.Agent(kind, sds[0], sds[1], sds[2] if len(sds) > 2 else None, **kw)
     view = PE.WorldView(world)
+    full = kind == "MONITOR"
 
     class StandIn:
         """The agent surface beam.dijkstra uses, with the oracle's arithmetic behind it."""
         device = torch.device("cpu")
+        beam_full_length = full
 
         def __init__(self, env):
             self.env = env
@@ -410,10 +423,11 @@ def test_product_beam_search_host_logic_matches_oracle_on_cpu():
             return None
 
         def encoder(self, tokens, lengths):
-            return P.encoder_lstm(pag.enc, tokens, lengths.long(), bidirectional=True, num_layers=1, drop_ratio=0.5, drop=None)
+            return P.encoder_lstm(pag.enc, tokens, lengths.long(), bidirectional=pag.bi, num_layers=pag.layers, drop_ratio=0.5,
+                                  drop=None)
 
         def beam_start_state(self, h_t):
-            return h_t
+            return h_t if kind == "ENVDROP" else torch.zeros(h_t.shape[0], 2176)
 
         def decode_observation(self, store, vp, view_idx, h_t, c_t, extra, ctx, ctx_mask, ended):
             self.scratch.batch = self.env.batch
@@ -433,7 +447,7 @@ def test_product_beam_search_host_logic_matches_oracle_on_cpu():
     with torch.no_grad():
         for K in (2, 4):
             got = beam.dijkstra(agent, K)
-            ref = PB.dijkstra(pag, penv, K)
+            ref = PB.dijkstra(pag, penv, K, full_length=full)
             assert [r["instr_id"] for r in got] == [r["instr_id"] for r in ref]
             key = lambda p: (tuple(p["action"]), tuple(x[0] for x in p["trajectory"]))      # noqa: E731
             for g, r in zip(got, ref):
